@@ -1,0 +1,322 @@
+"""cuda-qr_b200 -- B200 (sm_100a) drop-in for the QR hot path of brian-kelley/CUDA-QR.
+
+The product is ``libcudaqr_b200.so`` (hand-written CUDA behind the C ABI declared in
+``include/cudaqr_b200.h``).  This module is the thin host-side mirror of the reference's
+interface over that ABI:
+
+* legacy, host-pointer entry points with the reference's names and argument meaning
+  (``mmqr``, ``explicitQR``, ``dgemm``, ``identity``, ``getPanelDims``, ``printMat``;
+  qr.c:15-18,47,55 / qr.cu:30-31,49,475) operating on column-major numpy arrays;
+* ``Context``: the device-resident API on raw device pointers (torch tensors are only the
+  allocator here -- ``tensor.data_ptr()`` is what crosses the boundary).
+
+There is NO CPU fallback: if the shared library is missing this import raises, and every
+compute call needs a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libcudaqr_b200.so")
+_FP = ctypes.POINTER(ctypes.c_float)
+_IP = ctypes.POINTER(ctypes.c_int)
+_VP = ctypes.c_void_p
+
+OPT_GEMM, OPT_OUTER_BLOCK, OPT_TILE_ROWS, OPT_SPLITK = 1, 2, 3, 4
+GEMM_SIMT, GEMM_TF32X3 = 0, 1
+
+# Every symbol include/cudaqr_b200.h declares (tests check the .so exports all of them).
+EXPORTS = [
+    "getPanelDims", "mmqr", "mmqr_alloc", "explicitQR", "dgemm", "identity", "printMat",
+    "cqr_create", "cqr_destroy", "cqr_set_stream", "cqr_set_option", "cqr_get_option", "cqr_synchronize",
+    "cqr_error_string", "cqr_launch_count", "cqr_reserve", "cqr_geqrf", "cqr_extract_r", "cqr_form_q",
+    "cqr_apply_q", "cqr_tsqr_r", "cqr_tsqr_factor", "cqr_tsqr_form_q", "cqr_stack_qr", "cqr_stack_form_q",
+    "cqr_geqrf_batched", "cqr_gemm", "cqr_set_identity", "cqr_version",
+]
+
+
+def build_library(force: bool = False) -> str:
+    """nvcc-compile csrc/*.cu for sm_100a into libcudaqr_b200.so (cross-compiles without a GPU)."""
+    src_dir = os.path.join(_HERE, "csrc")
+    if force:
+        subprocess.check_call(["make", "-C", src_dir, "clean"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", src_dir, "-j8"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+class CudaQRError(RuntimeError):
+    pass
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C cuda-qr_b200/csrc). There is no CPU fallback.")
+    lib = ctypes.CDLL(_LIB_PATH)
+    i, ll, f = ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+    lib.getPanelDims.argtypes = [i, i, _IP, _IP]
+    lib.mmqr.argtypes = [_FP, _FP, i, i]
+    lib.mmqr_alloc.argtypes = [_FP, ctypes.POINTER(_FP), i, i]
+    lib.explicitQR.argtypes = [_FP, _FP, _FP, _FP, i, i]
+    lib.dgemm.argtypes = [_FP, _FP, _FP, i, i, i]
+    lib.identity.argtypes = [_FP, i]
+    lib.printMat.argtypes = [_FP, i, i]
+    lib.cqr_create.argtypes = [ctypes.POINTER(_VP), i]
+    lib.cqr_destroy.argtypes = [_VP]
+    lib.cqr_set_stream.argtypes = [_VP, _VP]
+    lib.cqr_set_option.argtypes = [_VP, i, i]
+    lib.cqr_get_option.argtypes = [_VP, i, _IP]
+    lib.cqr_synchronize.argtypes = [_VP]
+    lib.cqr_error_string.argtypes = [i]
+    lib.cqr_error_string.restype = ctypes.c_char_p
+    lib.cqr_launch_count.argtypes = [_VP]
+    lib.cqr_launch_count.restype = ll
+    lib.cqr_reserve.argtypes = [_VP, ctypes.c_size_t]
+    lib.cqr_geqrf.argtypes = [_VP, _VP, i, i, i, _VP]
+    lib.cqr_extract_r.argtypes = [_VP, _VP, i, i, i, _VP, i, i]
+    lib.cqr_form_q.argtypes = [_VP, _VP, i, i, i, _VP, _VP, i, i]
+    lib.cqr_apply_q.argtypes = [_VP, i, _VP, i, i, i, _VP, _VP, i, i]
+    lib.cqr_tsqr_r.argtypes = [_VP, _VP, i, ll, i, _VP, i]
+    lib.cqr_tsqr_factor.argtypes = [_VP, _VP, i, ll, i, _VP, i]
+    lib.cqr_tsqr_form_q.argtypes = [_VP, _VP, i, _VP, i]
+    lib.cqr_stack_qr.argtypes = [_VP, _VP, i, i, i, _VP, _VP, i]
+    lib.cqr_stack_form_q.argtypes = [_VP, _VP, i, i, i, _VP, _VP, i, _VP, i]
+    lib.cqr_geqrf_batched.argtypes = [_VP, _VP, i, ll, i, i, i, _VP]
+    lib.cqr_gemm.argtypes = [_VP, i, i, i, i, f, _VP, i, _VP, i, f, _VP, i]
+    lib.cqr_set_identity.argtypes = [_VP, _VP, i, i, i]
+    lib.cqr_version.restype = ctypes.c_char_p
+    return lib
+
+
+lib = _load()
+
+
+def version() -> str:
+    return lib.cqr_version().decode()
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise CudaQRError(f"{what} failed: {lib.cqr_error_string(rc).decode()} (status {rc})")
+
+
+def _host(a: np.ndarray, shape=None) -> np.ndarray:
+    if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and (a.flags["F_CONTIGUOUS"] or a.ndim == 1)):
+        raise TypeError("expected a column-major (Fortran-order) float32 numpy array")
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(_FP)
+
+
+# ----------------------------------------------------------------------------------------------
+# Legacy interface (host buffers; same names / argument meaning / blocking behaviour as the reference)
+# ----------------------------------------------------------------------------------------------
+def getPanelDims(m: int, n: int):
+    """qr.cu:49-55 -> (rowPanels, colPanels); tau buffers hold rowPanels*colPanels*4 floats (qr.cu:764)."""
+    rp, cp = ctypes.c_int(), ctypes.c_int()
+    lib.getPanelDims(m, n, ctypes.byref(rp), ctypes.byref(cp))
+    return rp.value, cp.value
+
+
+def tau_size(m: int, n: int) -> int:
+    rp, cp = getPanelDims(m, n)
+    return rp * cp * 4
+
+
+def mmqr(mat: np.ndarray, tau: np.ndarray | None = None) -> np.ndarray:
+    """qr.cu:475 -- factor `mat` (m x n, column-major float32) IN PLACE; returns tau (caller-sized
+    via getPanelDims when given).  Includes the H2D / D2H copies, like the reference."""
+    _host(mat)
+    m, n = mat.shape
+    if m < n or n < 1:
+        raise ValueError("mmqr needs m >= n >= 1 (qr.cu:736)")
+    if tau is None:
+        tau = np.empty(tau_size(m, n), dtype=np.float32)
+    elif tau.size < tau_size(m, n) or tau.dtype != np.float32:
+        raise ValueError("tau must hold rowPanels*colPanels*4 float32 values (getPanelDims)")
+    lib.mmqr(_p(mat), _p(tau), m, n)
+    return tau
+
+
+def explicitQR(A: np.ndarray, tau: np.ndarray):
+    """qr.c:330 -- (Q m x m, R m x n) from mmqr's in-place storage and tau."""
+    _host(A)
+    m, n = A.shape
+    Q = np.empty((m, m), dtype=np.float32, order="F")
+    R = np.empty((m, n), dtype=np.float32, order="F")
+    lib.explicitQR(_p(A), _p(np.ascontiguousarray(tau, dtype=np.float32)), _p(Q), _p(R), m, n)
+    return Q, R
+
+
+def dgemm(A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """qr.c:443 -- C(k x n) = A(k x m) B(m x n), fp32."""
+    _host(A), _host(B)
+    k, m = A.shape
+    if B.shape[0] != m:
+        raise ValueError("inner dimensions differ")
+    n = B.shape[1]
+    C = np.empty((k, n), dtype=np.float32, order="F")
+    lib.dgemm(_p(A), _p(B), _p(C), k, m, n)
+    return C
+
+
+def identity(m: int) -> np.ndarray:
+    """qr.c:316."""
+    A = np.empty((m, m), dtype=np.float32, order="F")
+    lib.identity(_p(A), m)
+    return A
+
+
+def printMat(mat: np.ndarray) -> None:
+    """qr.c:21 (prints through C stdio)."""
+    _host(mat)
+    lib.printMat(_p(mat), mat.shape[0], mat.shape[1])
+
+
+# ----------------------------------------------------------------------------------------------
+# Device-resident API
+# ----------------------------------------------------------------------------------------------
+def _dptr(t) -> int:
+    """Device pointer of a torch CUDA tensor (or a raw int)."""
+    if isinstance(t, int):
+        return t
+    if t is None:
+        return 0
+    if not t.is_cuda or str(t.dtype) != "torch.float32":
+        raise TypeError("expected a float32 CUDA tensor")
+    return t.data_ptr()
+
+
+def colmajor(m: int, n: int, device="cuda", ld: int | None = None):
+    """Allocate an m x n column-major fp32 device matrix as a torch view (ld >= m): returns a tensor
+    `a` with a[i, j] at offset i + j*ld, i.e. a = storage(n, ld).T[:m]."""
+    import torch
+    ld = ld or m
+    return torch.empty((n, ld), dtype=torch.float32, device=device).t()[:m]
+
+
+def to_colmajor(x, ld: int | None = None):
+    """Copy a 2-D torch tensor into column-major device storage."""
+    out = colmajor(x.shape[0], x.shape[1], device=x.device, ld=ld)
+    out.copy_(x)
+    return out
+
+
+def _ld(t) -> int:
+    if t.dim() != 2 or t.stride(0) != 1:
+        raise ValueError("expected a column-major 2-D tensor (stride(0) == 1); see colmajor()")
+    return t.stride(1) if t.shape[1] > 1 else max(t.shape[0], t.stride(1))
+
+
+class Context:
+    """Owns a cqr_context (workspace + stream) on one device."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        h = _VP()
+        _check(lib.cqr_create(ctypes.byref(h), device), "cqr_create")
+        self.h = h
+        self.device = device
+        if stream is not None:
+            self.set_stream(stream)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.cqr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int):
+        _check(lib.cqr_set_stream(self.h, _VP(cuda_stream)), "cqr_set_stream")
+
+    def use_torch_stream(self):
+        import torch
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_option(self, opt: int, value: int):
+        _check(lib.cqr_set_option(self.h, opt, value), "cqr_set_option")
+
+    def get_option(self, opt: int) -> int:
+        v = ctypes.c_int()
+        _check(lib.cqr_get_option(self.h, opt, ctypes.byref(v)), "cqr_get_option")
+        return v.value
+
+    def synchronize(self):
+        _check(lib.cqr_synchronize(self.h), "cqr_synchronize")
+
+    def launch_count(self) -> int:
+        return int(lib.cqr_launch_count(self.h))
+
+    def reserve(self, nbytes: int):
+        _check(lib.cqr_reserve(self.h, nbytes), "cqr_reserve")
+
+    # -- blocked Householder QR -----------------------------------------------------------
+    def geqrf(self, A, tau):
+        m, n = A.shape
+        _check(lib.cqr_geqrf(self.h, _dptr(A), _ld(A), m, n, _dptr(tau)), "cqr_geqrf")
+
+    def extract_r(self, A, R):
+        m, n = A.shape
+        _check(lib.cqr_extract_r(self.h, _dptr(A), _ld(A), m, n, _dptr(R), _ld(R), R.shape[0]), "cqr_extract_r")
+
+    def form_q(self, A, tau, Q):
+        m, n = A.shape
+        _check(lib.cqr_form_q(self.h, _dptr(A), _ld(A), m, n, _dptr(tau), _dptr(Q), _ld(Q), Q.shape[1]), "cqr_form_q")
+
+    def apply_q(self, A, tau, C, trans: bool):
+        m, n = A.shape
+        _check(lib.cqr_apply_q(self.h, 1 if trans else 0, _dptr(A), _ld(A), m, n, _dptr(tau), _dptr(C), _ld(C),
+                               C.shape[1]), "cqr_apply_q")
+
+    # -- TSQR -----------------------------------------------------------------------------
+    def tsqr_r(self, A, R):
+        m, n = A.shape
+        _check(lib.cqr_tsqr_r(self.h, _dptr(A), _ld(A), m, n, _dptr(R), _ld(R)), "cqr_tsqr_r")
+
+    def tsqr_factor(self, A, R):
+        m, n = A.shape
+        _check(lib.cqr_tsqr_factor(self.h, _dptr(A), _ld(A), m, n, _dptr(R), _ld(R)), "cqr_tsqr_factor")
+
+    def tsqr_form_q(self, Q, X=None):
+        _check(lib.cqr_tsqr_form_q(self.h, _dptr(X), _ld(X) if X is not None else 0, _dptr(Q), _ld(Q)),
+               "cqr_tsqr_form_q")
+
+    def stack_qr(self, Rs, n: int, tau, R):
+        rows = Rs.shape[0]
+        _check(lib.cqr_stack_qr(self.h, _dptr(Rs), _ld(Rs), rows // n, n, _dptr(tau), _dptr(R), _ld(R)), "cqr_stack_qr")
+
+    def stack_form_q(self, Rs, n: int, tau, Qs, X=None):
+        rows = Rs.shape[0]
+        _check(lib.cqr_stack_form_q(self.h, _dptr(Rs), _ld(Rs), rows // n, n, _dptr(tau), _dptr(X),
+                                    _ld(X) if X is not None else 0, _dptr(Qs), _ld(Qs)), "cqr_stack_form_q")
+
+    # -- batched --------------------------------------------------------------------------
+    def geqrf_batched(self, A3, tau):
+        """A3: torch tensor of shape (batch, n, lda) holding column-major matrices (A3[b].T[:m] is matrix b)."""
+        batch, n, lda = A3.shape
+        m = lda
+        _check(lib.cqr_geqrf_batched(self.h, _dptr(A3), lda, A3.stride(0), m, n, batch, _dptr(tau)),
+               "cqr_geqrf_batched")
+
+    def gemm(self, A, B, D, trans_a: bool = False, alpha: float = 1.0, beta: float = 0.0):
+        M, N = D.shape
+        K = A.shape[0] if trans_a else A.shape[1]
+        _check(lib.cqr_gemm(self.h, 1 if trans_a else 0, M, N, K, alpha, _dptr(A), _ld(A), _dptr(B), _ld(B), beta,
+                            _dptr(D), _ld(D)), "cqr_gemm")
+
+    def set_identity(self, A):
+        _check(lib.cqr_set_identity(self.h, _dptr(A), _ld(A), A.shape[0], A.shape[1]), "cqr_set_identity")

@@ -1,0 +1,119 @@
+// common.cuh -- shared device helpers and kernel launch declarations (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#ifndef CQR_SLOT
+#define CQR_SLOT 64            // panel width / height of one R slot in the TSQR tree
+#endif
+
+namespace cqr {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// x = hi + lo with hi carrying the top 11 significand bits (the TF32 payload, low 13 bits
+// zero) and lo the exact remainder: the operand split behind the 3xTF32 tensor-core GEMMs.
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_lo(float x) { return x - tf32_hi(x); }
+
+// ---- tile (TSQR leaf / tree node / batched) Householder kernels: tile_qr.cu ------------
+struct TileSrc {
+  float* base;          // tile t starts at base + t * tile_stride
+  long long tile_stride;
+  long long ld;
+  long long rows_total; // rows in tile t = clamp(rows_total - t*TH, 0, TH)
+};
+
+struct TileQRParams {
+  TileSrc a;            // tiles to factor
+  int ncols;            // reflectors per tile (<= 64)
+  int write_back;       // store V (and the tile's R) over the source tile
+  float* tau;           // [tiles][64]
+  float* r_out;         // R of tile t -> r_out + (t / fan) * r_tile_stride + (t % fan) * 64, ld = r_ld
+  long long r_tile_stride;
+  long long r_ld;
+  int r_rows;           // rows of the R slot to write (64 inside the tree, ncols for the root)
+  int fan;              // tiles stacked per parent tile (TH / 64)
+  // batched mode: tau row stride other than 64 and no R output
+  int tau_stride;
+};
+
+struct TileApplyParams {
+  TileSrc v;            // reflector tiles (as written by tile_qr with write_back)
+  const float* tau;     // [tiles][64]
+  int nref;             // reflectors per tile
+  int nc;               // columns of the block being transformed (<= 64)
+  const float* x;       // seed: tile t reads the 64-row slot x + (t / fan)*x_tile_stride + (t % fan)*64, ld x_ld
+  long long x_tile_stride;
+  long long x_ld;
+  int x_rows;           // valid seed rows (<= 64); x == nullptr means identity
+  int fan;
+  TileSrc out;          // output tiles: rows_total masks ragged stores
+};
+
+void launch_tile_qr(const TileQRParams& p, int tiles, int tile_rows, cudaStream_t s);
+void launch_tile_apply_q(const TileApplyParams& p, int tiles, int tile_rows, cudaStream_t s);
+
+// ---- Householder reconstruction + T builder: reconstruct.cu ---------------------------------
+struct HrParams {
+  const float* q;  long long ldq;     // thin Q of the panel (mp x b)
+  const float* rt; long long ldrt;    // R from TSQR (b x b upper)
+  float* a;        long long lda;     // panel of A (mp x b): Y below the diagonal, S*R on/above
+  float* tau;                         // b
+  float* t;        long long ldt;     // b x b compact-WY T (upper)
+  float* uinv;                        // 64 x 64 scratch: inverse of the LU's U factor
+  float* vbuf;     long long ldv;     // explicit Y (unit diagonal, zeros above), mp x b
+  float* vlo;                         // optional: Y - tf32_hi(Y) (nullptr = skip)
+  long long mp; int b;
+};
+void launch_hr_top(const HrParams& p, cudaStream_t s);
+void launch_hr_rows(const HrParams& p, cudaStream_t s);
+
+// T(kb x kb) from the Gram matrix G = V^T V and tau.  If have_diag != 0 the 64 x 64
+// diagonal blocks of T are already in place and only the off-diagonal blocks are built.
+void launch_build_t(const float* g, long long ldg, const float* tau, float* t, long long ldt, int kb,
+                    int have_diag, cudaStream_t s);
+
+// ---- fp32 SIMT GEMMs and element-wise utilities: gemm_simt.cu -------------------------------
+// D[z](M x N) = A(:, z-th K chunk)^T * B(z-th K chunk, :) ; D[z] = d + z * d_split_stride
+void launch_gemm_tn_simt(int M, int N, int K, const float* a, long long lda, const float* b, long long ldb,
+                         float* d, long long ldd, int splits, long long d_split_stride, cudaStream_t s);
+// D = alpha * A * B + beta * D ; optional d_lo = D - tf32_hi(D)
+void launch_gemm_nn_simt(int M, int N, int K, float alpha, const float* a, long long lda, const float* b,
+                         long long ldb, float beta, float* d, long long ldd, float* d_lo, long long ldd_lo,
+                         cudaStream_t s);
+// out = sum_z part[z] (M x N, part ld = ldp, stride between parts = stride); optional lo output
+void launch_reduce_splits(int M, int N, const float* part, long long ldp, long long stride, int splits, float* out,
+                          long long ldo, float* out_lo, long long ldo_lo, cudaStream_t s);
+void launch_split_lo(int M, int N, const float* a, long long lda, float* lo, long long ldlo, cudaStream_t s);
+void launch_set_identity(float* a, long long lda, int m, int n, cudaStream_t s);
+void launch_fill_zero(float* a, long long lda, long long m, int n, cudaStream_t s);
+void launch_copy_matrix(long long m, int n, const float* a, long long lda, float* b, long long ldb, cudaStream_t s);
+// R extraction: r(i,j) = (i <= j) ? a(i,j) : 0 for i < r_rows
+void launch_extract_r(const float* a, long long lda, int m, int n, float* r, long long ldr, int r_rows,
+                      cudaStream_t s);
+// V extraction from LAPACK-format storage: v(i,j) = i<j ? 0 : i==j ? 1 : a(i,j), for a panel whose
+// diagonal starts at local row d0 of the mp x b block; optional lo copy
+void launch_extract_v(const float* a, long long lda, long long mp, int b, int d0, float* v, long long ldv,
+                      float* vlo, cudaStream_t s);
+
+// ---- tcgen05 3xTF32 GEMMs: gemm_umma.cu -------------------------------------------------------
+// Both return false (nothing launched) when shape/alignment rules out the TMA path.
+bool umma_available();
+bool launch_gemm_tn_umma(int M, int N, int K, const float* a, const float* a_lo, long long lda, const float* b,
+                         const float* b_lo, long long ldb, float* d, long long ldd, int splits,
+                         long long d_split_stride, cudaStream_t s);
+bool launch_gemm_nn_umma(int M, int N, int K, float alpha, const float* a, const float* a_lo, long long lda,
+                         const float* b, const float* b_lo, long long ldb, float beta, float* d, long long ldd,
+                         float* d_lo, long long ldd_lo, cudaStream_t s);
+
+// global launch counter (gpu_launches evidence)
+extern long long g_launches;
+
+}  // namespace cqr

@@ -1,0 +1,673 @@
+// driver.cu -- host side of libcudaqr_b200.so: context, workspace, the TSQR plan, the blocked
+// Householder driver and the reference's legacy entry points (include/cudaqr_b200.h).
+//
+// Replaces the reference's host driver mmqr (qr.cu:475-553): instead of two launches per
+// 64 x 4 window (70 516 launches for 4084^2), a panel is one TSQR tree (a handful of launches
+// over all row tiles at once), reconstructed to a single (Y, T), and the trailing matrix is
+// updated once per aggregated block of panels by GEMMs.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#pragma GCC visibility push(default)   // the C ABI is the only exported surface (-fvisibility=hidden elsewhere)
+#include "../../include/cudaqr_b200.h"
+#pragma GCC visibility pop
+#include "common.cuh"
+
+using namespace cqr;
+
+namespace {
+
+constexpr int kLegacyPR = 64;   // qr.cu:21
+constexpr int kLegacyPC = 4;    // qr.cu:23
+
+inline long long round_up(long long x, long long a) { return (x + a - 1) / a * a; }
+
+struct TsqrLevel {
+  int tiles = 0;
+  long long rows_total = 0;
+  float* store = nullptr;   // level >= 1: tiles x (TH x 64) tile storage (also holds V after factor)
+  float* tau = nullptr;     // tiles x 64
+  float* xbuf = nullptr;    // level >= 1: output of this level's apply-Q (seeds of the level below)
+};
+
+struct TsqrPlan {
+  long long m = 0;
+  int n = 0, th = 256, fan = 4;
+  std::vector<TsqrLevel> lv;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct cqr_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  // scratch arena (re-carved by every top-level call)
+  char* ws = nullptr;
+  size_t ws_bytes = 0, ws_off = 0;
+  // persistent TSQR state (cqr_tsqr_factor -> cqr_tsqr_form_q)
+  char* ts = nullptr;
+  size_t ts_bytes = 0;
+  TsqrPlan ts_plan;
+  float* ts_a = nullptr;
+  long long ts_lda = 0;
+  bool ts_valid = false;
+  int opt_gemm = 1, opt_outer = 256, opt_tile_rows = 256, opt_splitk = 0;
+  long long launches0 = 0;
+  cudaError_t last = cudaSuccess;
+};
+
+namespace {
+
+#define CQR_CUDA(x)                          \
+  do {                                       \
+    cudaError_t e__ = (x);                   \
+    if (e__ != cudaSuccess) return (int)e__; \
+  } while (0)
+
+int ws_ensure(cqr_context* c, size_t bytes) {
+  if (bytes <= c->ws_bytes) { c->ws_off = 0; return 0; }
+  CQR_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->ws) cudaFree(c->ws);
+  c->ws = nullptr; c->ws_bytes = 0;
+  bytes = (size_t)round_up((long long)bytes, 1 << 20);
+  cudaError_t e = cudaMalloc((void**)&c->ws, bytes);
+  if (e != cudaSuccess) { cudaGetLastError(); return CQR_ENOMEM; }
+  c->ws_bytes = bytes; c->ws_off = 0;
+  return 0;
+}
+
+struct Carver {   // size pass (base == nullptr) and carve pass share one code path
+  char* base; size_t off = 0;
+  explicit Carver(char* b) : base(b) {}
+  float* take(long long floats) {
+    size_t bytes = (size_t)round_up(floats * 4, 256);
+    float* p = base ? (float*)(base + off) : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+// ---- TSQR plan ---------------------------------------------------------------------------
+void plan_tsqr(TsqrPlan& P, long long m, int n, int th, Carver& cv) {
+  P.m = m; P.n = n; P.th = th; P.fan = th / CQR_SLOT;
+  P.lv.clear();
+  TsqrLevel l0;
+  l0.tiles = (int)((m + th - 1) / th);
+  l0.rows_total = m;
+  l0.tau = cv.take((long long)l0.tiles * 64);
+  P.lv.push_back(l0);
+  while (P.lv.back().tiles > 1) {
+    const int prev = P.lv.back().tiles;
+    TsqrLevel l;
+    l.tiles = (prev + P.fan - 1) / P.fan;
+    l.rows_total = (long long)prev * CQR_SLOT;
+    l.store = cv.take((long long)l.tiles * th * 64);
+    l.xbuf = cv.take((long long)l.tiles * th * 64);
+    l.tau = cv.take((long long)l.tiles * 64);
+    P.lv.push_back(l);
+  }
+}
+
+TileSrc level_src(const TsqrPlan& P, int l, float* a, long long lda) {
+  TileSrc s;
+  if (l == 0) { s.base = a; s.tile_stride = P.th; s.ld = lda; }
+  else { s.base = P.lv[l].store; s.tile_stride = (long long)P.th * 64; s.ld = P.th; }
+  s.rows_total = P.lv[l].rows_total;
+  return s;
+}
+
+// Factor: leaves read `a` (m x n, lda).  keep_q: write reflectors back (leaves into a).
+void run_tsqr_factor(cqr_context* c, const TsqrPlan& P, float* a, long long lda, bool keep_q, float* r,
+                     long long ldr) {
+  const int L = (int)P.lv.size();
+  for (int l = 0; l < L; ++l) {
+    TileQRParams p{};
+    p.a = level_src(P, l, a, lda);
+    p.ncols = P.n;
+    p.write_back = keep_q ? 1 : 0;
+    p.tau = P.lv[l].tau;
+    p.tau_stride = 64;
+    p.fan = P.fan;
+    if (l == L - 1) { p.r_out = r; p.r_tile_stride = 0; p.r_ld = ldr; p.r_rows = P.n; p.fan = 1; }
+    else { p.r_out = P.lv[l + 1].store; p.r_tile_stride = (long long)P.th * 64; p.r_ld = P.th; p.r_rows = CQR_SLOT; }
+    launch_tile_qr(p, P.lv[l].tiles, P.th, c->stream);
+  }
+}
+
+// Expand: q (m x nc, ldq) = Q * [X; 0], X = nc-column seed (n rows, ldx) or identity.
+void run_tsqr_form_q(cqr_context* c, const TsqrPlan& P, const float* a, long long lda, const float* x, long long ldx,
+                     int nc, float* q, long long ldq) {
+  const int L = (int)P.lv.size();
+  for (int l = L - 1; l >= 0; --l) {
+    TileApplyParams p{};
+    p.v = level_src(P, l, const_cast<float*>(a), lda);
+    p.tau = P.lv[l].tau;
+    p.nref = P.n;
+    p.nc = nc;
+    if (l == L - 1) { p.x = x; p.x_tile_stride = 0; p.x_ld = ldx; p.x_rows = P.n; p.fan = 1; }
+    else { p.x = P.lv[l + 1].xbuf; p.x_tile_stride = (long long)P.th * 64; p.x_ld = P.th; p.x_rows = P.n; p.fan = P.fan; }
+    if (l == 0) { p.out.base = q; p.out.tile_stride = P.th; p.out.ld = ldq; p.out.rows_total = P.m; }
+    else { p.out.base = P.lv[l].xbuf; p.out.tile_stride = (long long)P.th * 64; p.out.ld = P.th; p.out.rows_total = P.lv[l].rows_total; }
+    launch_tile_apply_q(p, P.lv[l].tiles, P.th, c->stream);
+  }
+}
+
+// ---- GEMM dispatch (tcgen05 3xTF32 when the shape allows, else fp32 SIMT) ---------------------
+int pick_splits(cqr_context* c, int M, int N, int K, int tile_m, int tile_n) {
+  if (c->opt_splitk > 0) return c->opt_splitk;
+  const long long tiles = (long long)((M + tile_m - 1) / tile_m) * ((N + tile_n - 1) / tile_n);
+  long long s = (2LL * c->sm_count + tiles - 1) / tiles;
+  const long long kmax = K / 512 > 0 ? K / 512 : 1;
+  if (s > kmax) s = kmax;
+  if (s > 32) s = 32;
+  return s < 1 ? 1 : (int)s;
+}
+
+struct Operand { const float* hi; const float* lo; long long ld; };
+
+// d(M x N) = A^T B through a split-K partial buffer + reduction (also emits d_lo when asked)
+void gemm_tn(cqr_context* c, int M, int N, int K, Operand A, Operand B, float* part, float* d, long long ldd,
+             float* d_lo, int max_splits) {
+  int splits = pick_splits(c, M, N, K, 128, 128);
+  if (splits > max_splits) splits = max_splits;
+  const long long ldp = round_up(M, 4);
+  const long long stride = ldp * N;
+  bool done = false;
+  if (c->opt_gemm == 1 && A.lo && B.lo)
+    done = launch_gemm_tn_umma(M, N, K, A.hi, A.lo, A.ld, B.hi, B.lo, B.ld, part, ldp, splits, stride, c->stream);
+  if (!done) launch_gemm_tn_simt(M, N, K, A.hi, A.ld, B.hi, B.ld, part, ldp, splits, stride, c->stream);
+  launch_reduce_splits(M, N, part, ldp, stride, splits, d, ldd, d_lo, ldd, c->stream);
+}
+
+void gemm_nn(cqr_context* c, int M, int N, int K, float alpha, Operand A, Operand B, float beta, float* d,
+             long long ldd, float* d_lo) {
+  bool done = false;
+  if (c->opt_gemm == 1 && A.lo && B.lo)
+    done = launch_gemm_nn_umma(M, N, K, alpha, A.hi, A.lo, A.ld, B.hi, B.lo, B.ld, beta, d, ldd, d_lo, ldd, c->stream);
+  if (!done) launch_gemm_nn_simt(M, N, K, alpha, A.hi, A.ld, B.hi, B.ld, beta, d, ldd, d_lo, ldd, c->stream);
+}
+
+constexpr int kMaxSplits = 32;
+
+struct BlockWs {   // scratch of one block-reflector application with kb reflectors on nc columns
+  float *part, *w, *w_lo, *x, *x_lo;
+  long long ldw;
+};
+
+BlockWs carve_block_ws(Carver& cv, int kb, int nc, bool lo) {
+  BlockWs b{};
+  b.ldw = round_up(kb, 4);
+  b.part = cv.take(b.ldw * (long long)nc * kMaxSplits);
+  b.w = cv.take(b.ldw * nc);
+  b.x = cv.take(b.ldw * nc);
+  b.w_lo = lo ? cv.take(b.ldw * nc) : nullptr;
+  b.x_lo = lo ? cv.take(b.ldw * nc) : nullptr;
+  return b;
+}
+
+// C <- (I - V op(T) V^T) C.   trans_t = 1: op(T) = T^T (this is Q^T C), 0: op(T) = T (Q C).
+// Replaces trailingUpdateKernel (qr.cu:335-465) and the CPU loop qr.c:255-293.
+void apply_block(cqr_context* c, long long mk, int kb, int nc, Operand V, Operand T, float* C, float* C_lo,
+                 long long ldc, int trans_t, BlockWs& ws) {
+  if (nc <= 0 || kb <= 0) return;
+  Operand Cop{C, C_lo, ldc};
+  gemm_tn(c, kb, nc, (int)mk, V, Cop, ws.part, ws.w, ws.ldw, ws.w_lo, kMaxSplits);        // W = V^T C
+  Operand W{ws.w, ws.w_lo, ws.ldw};
+  if (trans_t) gemm_tn(c, kb, nc, kb, T, W, ws.part, ws.x, ws.ldw, ws.x_lo, 1);             // X = T^T W
+  else gemm_nn(c, kb, nc, kb, 1.f, T, W, 0.f, ws.x, ws.ldw, ws.x_lo);                       // X = T W
+  Operand X{ws.x, ws.x_lo, ws.ldw};
+  gemm_nn(c, (int)mk, nc, kb, -1.f, V, X, 1.f, C, ldc, C_lo);                               // C -= V X
+}
+
+bool tensor_ok(cqr_context* c, const void* a, long long lda) {
+  return c->opt_gemm == 1 && umma_available() && lda % 4 == 0 && ((uintptr_t)a % 16) == 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+// Device-resident API
+// ================================================================================================
+extern "C" {
+
+const char* cqr_version(void) { return "cudaqr_b200 0.1;sm_100a;tsqr+hr+wy;tcgen05-3xtf32"; }
+
+const char* cqr_error_string(int status) {
+  switch (status) {
+    case CQR_OK: return "ok";
+    case CQR_EINVAL: return "invalid argument";
+    case CQR_ENOMEM: return "workspace allocation failed";
+    case CQR_ESTATE: return "call out of order";
+    case CQR_EUNSUPPORTED: return "unsupported shape";
+    default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown";
+  }
+}
+
+int cqr_create(cqr_context** out, int device) {
+  if (!out) return CQR_EINVAL;
+  int ndev = 0;
+  CQR_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return CQR_EINVAL;
+  CQR_CUDA(cudaSetDevice(device));
+  cqr_context* c = new cqr_context();
+  c->device = device;
+  cudaDeviceProp prop;
+  CQR_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  if (prop.major != 10) {   // sm_100a-only binary: fail loudly instead of faulting at first launch
+    delete c;
+    return (int)cudaErrorNoKernelImageForDevice;
+  }
+  c->launches0 = g_launches;
+  *out = c;
+  return 0;
+}
+
+int cqr_destroy(cqr_context* c) {
+  if (!c) return CQR_EINVAL;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->ws) cudaFree(c->ws);
+  if (c->ts) cudaFree(c->ts);
+  delete c;
+  return 0;
+}
+
+int cqr_set_stream(cqr_context* c, void* s) { if (!c) return CQR_EINVAL; c->stream = (cudaStream_t)s; return 0; }
+
+int cqr_set_option(cqr_context* c, int opt, int v) {
+  if (!c) return CQR_EINVAL;
+  switch (opt) {
+    case CQR_OPT_GEMM: if (v != 0 && v != 1) return CQR_EINVAL; c->opt_gemm = v; return 0;
+    case CQR_OPT_OUTER_BLOCK: if (v < 64 || v > 512 || v % 64) return CQR_EINVAL; c->opt_outer = v; return 0;
+    case CQR_OPT_TILE_ROWS: if (v != 128 && v != 256) return CQR_EINVAL; c->opt_tile_rows = v; return 0;
+    case CQR_OPT_SPLITK: if (v < 0 || v > kMaxSplits) return CQR_EINVAL; c->opt_splitk = v; return 0;
+  }
+  return CQR_EINVAL;
+}
+
+int cqr_get_option(cqr_context* c, int opt, int* v) {
+  if (!c || !v) return CQR_EINVAL;
+  switch (opt) {
+    case CQR_OPT_GEMM: *v = c->opt_gemm; return 0;
+    case CQR_OPT_OUTER_BLOCK: *v = c->opt_outer; return 0;
+    case CQR_OPT_TILE_ROWS: *v = c->opt_tile_rows; return 0;
+    case CQR_OPT_SPLITK: *v = c->opt_splitk; return 0;
+  }
+  return CQR_EINVAL;
+}
+
+int cqr_synchronize(cqr_context* c) {
+  if (!c) return CQR_EINVAL;
+  CQR_CUDA(cudaStreamSynchronize(c->stream));
+  CQR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+long long cqr_launch_count(cqr_context* c) { return c ? g_launches - c->launches0 : 0; }
+
+int cqr_reserve(cqr_context* c, size_t bytes) { if (!c) return CQR_EINVAL; cudaSetDevice(c->device); return ws_ensure(c, bytes); }
+
+int cqr_set_identity(cqr_context* c, float* dA, int lda, int m, int n) {
+  if (!c || !dA || m < 1 || n < 1 || lda < m) return CQR_EINVAL;
+  launch_set_identity(dA, lda, m, n, c->stream);
+  return (int)cudaGetLastError();
+}
+
+int cqr_extract_r(cqr_context* c, const float* dA, int lda, int m, int n, float* dR, int ldr, int r_rows) {
+  if (!c || !dA || !dR || m < 1 || n < 1 || lda < m || r_rows < 1 || ldr < r_rows) return CQR_EINVAL;
+  launch_extract_r(dA, lda, m, n, dR, ldr, r_rows, c->stream);
+  return (int)cudaGetLastError();
+}
+
+int cqr_gemm(cqr_context* c, int transA, int M, int N, int K, float alpha, const float* dA, int lda, const float* dB,
+             int ldb, float beta, float* dD, int ldd) {
+  if (!c || !dA || !dB || !dD || M < 1 || N < 1 || K < 1 || ldd < M || ldb < K) return CQR_EINVAL;
+  if (transA ? lda < K : lda < M) return CQR_EINVAL;
+  cudaSetDevice(c->device);
+  if (!transA) {
+    launch_gemm_nn_simt(M, N, K, alpha, dA, lda, dB, ldb, beta, dD, ldd, nullptr, 0, c->stream);
+  } else {
+    if (alpha != 1.f || beta != 0.f) return CQR_EUNSUPPORTED;
+    launch_gemm_tn_simt(M, N, K, dA, lda, dB, ldb, dD, ldd, 1, 0, c->stream);
+  }
+  return (int)cudaGetLastError();
+}
+
+// ---- blocked Householder QR ----------------------------------------------------------------------
+int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
+  if (!c || !dA || !dtau || n < 1 || m < n || lda < m) return CQR_EINVAL;
+  cudaSetDevice(c->device);
+  cudaStream_t st = c->stream;
+  const int th = c->opt_tile_rows;
+  const int KB = c->opt_outer < n ? c->opt_outer : (int)round_up(n, 64);
+  const bool tensor = tensor_ok(c, dA, lda) && m >= 128 && n > 64;
+  const long long ldv = round_up(m, 4);
+  const int ncmax = n > 64 ? n - 64 : 1;
+
+  TsqrPlan plan;
+  float *vbuf = nullptr, *vlo = nullptr, *tbig = nullptr, *tlo = nullptr, *gram = nullptr, *gpart = nullptr;
+  float *qthin = nullptr, *rt = nullptr, *uinv = nullptr, *alo = nullptr;
+  BlockWs bw{};
+  for (int pass = 0; pass < 2; ++pass) {
+    Carver cv(pass ? c->ws : nullptr);
+    plan_tsqr(plan, m, n < 64 ? n : 64, th, cv);
+    vbuf = cv.take(ldv * KB);
+    vlo = tensor ? cv.take(ldv * KB) : nullptr;
+    tbig = cv.take((long long)KB * KB);
+    tlo = tensor ? cv.take((long long)KB * KB) : nullptr;
+    gram = cv.take((long long)KB * KB);
+    gpart = cv.take((long long)KB * KB * kMaxSplits);
+    qthin = cv.take(ldv * 64);
+    rt = cv.take(64 * 64);
+    uinv = cv.take(64 * 64);
+    alo = tensor ? cv.take((long long)lda * n) : nullptr;
+    bw = carve_block_ws(cv, KB, ncmax, tensor);
+    if (!pass) { int rc = ws_ensure(c, cv.off); if (rc) return rc; }
+  }
+  if (tensor) launch_split_lo(m, n, dA, lda, alo, lda, st);
+
+  for (int K0 = 0; K0 < n; K0 += KB) {
+    const int kbw = (n - K0 < KB) ? n - K0 : KB;
+    const long long mK = m - K0;
+    launch_fill_zero(vbuf, ldv, mK, kbw, st);
+    if (vlo) launch_fill_zero(vlo, ldv, mK, kbw, st);
+    for (int j0 = K0; j0 < K0 + kbw; j0 += 64) {
+      const int b = (K0 + kbw - j0 < 64) ? K0 + kbw - j0 : 64;
+      const long long mp = m - j0;
+      float* ap = dA + j0 + (long long)j0 * lda;
+      // (1) panel TSQR: R_tsqr + implicit Q   (2) explicit thin Q   (3) Householder reconstruction
+      TsqrPlan pp;
+      { Carver cv2(c->ws); plan_tsqr(pp, mp, b, th, cv2); }   // same carve order => same buffers, sized for mp <= m
+      run_tsqr_factor(c, pp, ap, lda, true, rt, 64);
+      run_tsqr_form_q(c, pp, ap, lda, nullptr, 0, b, qthin, ldv);
+      HrParams hp{};
+      hp.q = qthin; hp.ldq = ldv; hp.rt = rt; hp.ldrt = 64; hp.a = ap; hp.lda = lda; hp.tau = dtau + j0;
+      hp.t = tbig + (j0 - K0) + (long long)(j0 - K0) * KB; hp.ldt = KB; hp.uinv = uinv;
+      hp.vbuf = vbuf + (j0 - K0) + (long long)(j0 - K0) * ldv; hp.ldv = ldv;
+      hp.vlo = vlo ? vlo + (j0 - K0) + (long long)(j0 - K0) * ldv : nullptr;
+      hp.mp = mp; hp.b = b;
+      launch_hr_top(hp, st);
+      launch_hr_rows(hp, st);
+      // (4) inner update: remaining columns of this outer block
+      const int ninner = K0 + kbw - (j0 + b);
+      if (ninner > 0) {
+        float* cp = dA + j0 + (long long)(j0 + b) * lda;
+        float* cpl = alo ? alo + j0 + (long long)(j0 + b) * lda : nullptr;
+        if (tlo) launch_split_lo(b, b, hp.t, KB, tlo + (j0 - K0) + (long long)(j0 - K0) * KB, KB, st);
+        Operand V{hp.vbuf, hp.vlo, ldv};
+        Operand T{hp.t, tlo ? tlo + (j0 - K0) + (long long)(j0 - K0) * KB : nullptr, KB};
+        apply_block(c, mp, b, ninner, V, T, cp, cpl, lda, 1, bw);
+      }
+    }
+    // (5) outer update with the aggregated (V, T) of the whole block
+    const int nrest = n - (K0 + kbw);
+    if (nrest > 0) {
+      Operand V{vbuf, vlo, ldv};
+      if (kbw > 64) {
+        gemm_tn(c, kbw, kbw, (int)mK, V, V, gpart, gram, KB, nullptr, kMaxSplits);
+        launch_build_t(gram, KB, dtau + K0, tbig, KB, kbw, 1, st);
+      }
+      if (tlo) launch_split_lo(kbw, kbw, tbig, KB, tlo, KB, st);
+      Operand T{tbig, tlo, KB};
+      float* cp = dA + K0 + (long long)(K0 + kbw) * lda;
+      float* cpl = alo ? alo + K0 + (long long)(K0 + kbw) * lda : nullptr;
+      apply_block(c, mK, kbw, nrest, V, T, cp, cpl, lda, 1, bw);
+    }
+  }
+  return (int)cudaGetLastError();
+}
+
+// Shared by form_q / apply_q: walk the outer blocks, rebuild (V, T) from LAPACK-format storage.
+static int apply_q_impl(cqr_context* c, int trans, const float* dA, int lda, int m, int n, const float* dtau,
+                        float* dC, int ldc, int nc, bool c_is_identity_start) {
+  cudaSetDevice(c->device);
+  cudaStream_t st = c->stream;
+  const int KB = c->opt_outer < n ? c->opt_outer : (int)round_up(n, 64);
+  const bool tensor = tensor_ok(c, dC, ldc) && m >= 128 && nc >= 64 && n >= 64;
+  const long long ldv = round_up(m, 4);
+  float *vbuf = nullptr, *vlo = nullptr, *tbig = nullptr, *tlo = nullptr, *gram = nullptr, *gpart = nullptr, *clo = nullptr;
+  BlockWs bw{};
+  for (int pass = 0; pass < 2; ++pass) {
+    Carver cv(pass ? c->ws : nullptr);
+    vbuf = cv.take(ldv * KB);
+    vlo = tensor ? cv.take(ldv * KB) : nullptr;
+    tbig = cv.take((long long)KB * KB);
+    tlo = tensor ? cv.take((long long)KB * KB) : nullptr;
+    gram = cv.take((long long)KB * KB);
+    gpart = cv.take((long long)KB * KB * kMaxSplits);
+    clo = tensor ? cv.take((long long)ldc * nc) : nullptr;
+    bw = carve_block_ws(cv, KB, nc, tensor);
+    if (!pass) { int rc = ws_ensure(c, cv.off); if (rc) return rc; }
+  }
+  if (tensor) launch_split_lo(m, nc, dC, ldc, clo, ldc, st);
+  const int nblk = (n + KB - 1) / KB;
+  for (int bi = 0; bi < nblk; ++bi) {
+    const int K0 = (trans ? bi : nblk - 1 - bi) * KB;
+    const int kbw = (n - K0 < KB) ? n - K0 : KB;
+    const long long mK = m - K0;
+    launch_extract_v(dA + K0 + (long long)K0 * lda, lda, mK, kbw, 0, vbuf, ldv, vlo, st);
+    Operand V{vbuf, vlo, ldv};
+    gemm_tn(c, kbw, kbw, (int)mK, V, V, gpart, gram, KB, nullptr, kMaxSplits);
+    launch_build_t(gram, KB, dtau + K0, tbig, KB, kbw, 0, st);
+    if (tlo) launch_split_lo(kbw, kbw, tbig, KB, tlo, KB, st);
+    Operand T{tbig, tlo, KB};
+    // Q = H_0..H_{n-1} applied to [I; 0]: block K0 only touches rows >= K0, and (backward
+    // accumulation from the identity) only columns >= K0 are non-zero there.
+    const int cskip = (c_is_identity_start && !trans) ? (K0 < nc ? K0 : nc) : 0;
+    float* cp = dC + K0 + (long long)cskip * ldc;
+    float* cpl = clo ? clo + K0 + (long long)cskip * ldc : nullptr;
+    apply_block(c, mK, kbw, nc - cskip, V, T, cp, cpl, ldc, trans ? 1 : 0, bw);
+  }
+  return (int)cudaGetLastError();
+}
+
+int cqr_form_q(cqr_context* c, const float* dA, int lda, int m, int n, const float* dtau, float* dQ, int ldq,
+               int q_cols) {
+  if (!c || !dA || !dtau || !dQ || n < 1 || m < n || lda < m || ldq < m || q_cols < 1 || q_cols > m) return CQR_EINVAL;
+  cudaSetDevice(c->device);
+  launch_set_identity(dQ, ldq, m, q_cols, c->stream);
+  return apply_q_impl(c, 0, dA, lda, m, n, dtau, dQ, ldq, q_cols, true);
+}
+
+int cqr_apply_q(cqr_context* c, int trans, const float* dA, int lda, int m, int n, const float* dtau, float* dC,
+                int ldc, int nc) {
+  if (!c || !dA || !dtau || !dC || n < 1 || m < n || lda < m || ldc < m || nc < 1) return CQR_EINVAL;
+  return apply_q_impl(c, trans ? 1 : 0, dA, lda, m, n, dtau, dC, ldc, nc, false);
+}
+
+// ---- TSQR ---------------------------------------------------------------------------------------
+static int tsqr_common(cqr_context* c, float* dA, int lda, long long m, int n, float* dR, int ldr, bool keep) {
+  if (!c || !dA || !dR || n < 1 || n > 64 || m < n || lda < m || ldr < n) return CQR_EINVAL;
+  cudaSetDevice(c->device);
+  const int th = c->opt_tile_rows;
+  TsqrPlan plan;
+  for (int pass = 0; pass < 2; ++pass) {
+    Carver cv(pass ? (keep ? c->ts : c->ws) : nullptr);
+    plan_tsqr(plan, m, n, th, cv);
+    if (!pass) {
+      if (keep) {
+        if (cv.off > c->ts_bytes) {
+          CQR_CUDA(cudaStreamSynchronize(c->stream));
+          if (c->ts) cudaFree(c->ts);
+          c->ts = nullptr; c->ts_bytes = 0;
+          if (cudaMalloc((void**)&c->ts, cv.off) != cudaSuccess) { cudaGetLastError(); return CQR_ENOMEM; }
+          c->ts_bytes = cv.off;
+        }
+      } else {
+        int rc = ws_ensure(c, cv.off); if (rc) return rc;
+      }
+    }
+  }
+  run_tsqr_factor(c, plan, dA, lda, keep, dR, ldr);
+  if (keep) { c->ts_plan = plan; c->ts_a = dA; c->ts_lda = lda; c->ts_valid = true; }
+  return (int)cudaGetLastError();
+}
+
+int cqr_tsqr_r(cqr_context* c, const float* dA, int lda, long long m, int n, float* dR, int ldr) {
+  return tsqr_common(c, const_cast<float*>(dA), lda, m, n, dR, ldr, false);
+}
+
+int cqr_tsqr_factor(cqr_context* c, float* dA, int lda, long long m, int n, float* dR, int ldr) {
+  return tsqr_common(c, dA, lda, m, n, dR, ldr, true);
+}
+
+int cqr_tsqr_form_q(cqr_context* c, const float* dX, int ldx, float* dQ, int ldq) {
+  if (!c || !dQ) return CQR_EINVAL;
+  if (!c->ts_valid) return CQR_ESTATE;
+  const TsqrPlan& P = c->ts_plan;
+  if (ldq < P.m || (dX && ldx < P.n)) return CQR_EINVAL;
+  cudaSetDevice(c->device);
+  run_tsqr_form_q(c, P, c->ts_a, c->ts_lda, dX, ldx, P.n, dQ, ldq);
+  return (int)cudaGetLastError();
+}
+
+int cqr_stack_qr(cqr_context* c, float* dRs, int ldrs, int nblk, int n, float* dtau, float* dR, int ldr) {
+  if (!c || !dRs || !dtau || !dR || n < 1 || n > 64 || nblk < 1 || ldrs < nblk * n || ldr < n) return CQR_EINVAL;
+  if (nblk * n > 256) return CQR_EUNSUPPORTED;
+  cudaSetDevice(c->device);
+  TileQRParams p{};
+  p.a.base = dRs; p.a.tile_stride = 0; p.a.ld = ldrs; p.a.rows_total = (long long)nblk * n;
+  p.ncols = n; p.write_back = 1; p.tau = dtau; p.tau_stride = 64;
+  p.r_out = dR; p.r_tile_stride = 0; p.r_ld = ldr; p.r_rows = n; p.fan = 1;
+  launch_tile_qr(p, 1, nblk * n <= 64 ? 64 : (nblk * n <= 128 ? 128 : 256), c->stream);
+  return (int)cudaGetLastError();
+}
+
+int cqr_stack_form_q(cqr_context* c, const float* dRs, int ldrs, int nblk, int n, const float* dtau, const float* dX,
+                     int ldx, float* dQs, int ldqs) {
+  if (!c || !dRs || !dtau || !dQs || n < 1 || n > 64 || nblk < 1 || ldrs < nblk * n || ldqs < nblk * n) return CQR_EINVAL;
+  if (nblk * n > 256) return CQR_EUNSUPPORTED;
+  cudaSetDevice(c->device);
+  TileApplyParams p{};
+  p.v.base = const_cast<float*>(dRs); p.v.tile_stride = 0; p.v.ld = ldrs; p.v.rows_total = (long long)nblk * n;
+  p.tau = dtau; p.nref = n; p.nc = n;
+  p.x = dX; p.x_tile_stride = 0; p.x_ld = ldx; p.x_rows = n; p.fan = 1;
+  p.out.base = dQs; p.out.tile_stride = 0; p.out.ld = ldqs; p.out.rows_total = (long long)nblk * n;
+  launch_tile_apply_q(p, 1, nblk * n <= 64 ? 64 : (nblk * n <= 128 ? 128 : 256), c->stream);
+  return (int)cudaGetLastError();
+}
+
+int cqr_geqrf_batched(cqr_context* c, float* dA, int lda, long long stride, int m, int n, int batch, float* dtau) {
+  if (!c || !dA || !dtau || n < 1 || n > 64 || m < n || m > 256 || lda < m || batch < 1) return CQR_EINVAL;
+  cudaSetDevice(c->device);
+  const int th = m <= 64 ? 64 : (m <= 128 ? 128 : 256);
+  // tiles are addressed as base + t*stride with every tile m rows tall: rows_total = m + t*TH keeps
+  // the kernel's clamp(rows_total - t*TH) at m only for t = 0, so batch tiles use fixed_rows instead.
+  TileQRParams p{};
+  p.a.base = dA; p.a.tile_stride = stride; p.a.ld = lda; p.a.rows_total = -(long long)m;
+  p.ncols = n; p.write_back = 1; p.tau = dtau; p.tau_stride = n; p.r_out = nullptr; p.fan = 1;
+  launch_tile_qr(p, batch, th, c->stream);
+  return (int)cudaGetLastError();
+}
+
+// ================================================================================================
+// Legacy entry points (host pointers, blocking, print + exit(1) on failure like qr.cu:467-471)
+// ================================================================================================
+static cqr_context* legacy_ctx() {
+  static cqr_context* c = nullptr;
+  if (!c) {
+    int rc = cqr_create(&c, 0);   // device 0 hard-wired, qr.cu:480,711
+    if (rc) { printf("CUDA error on line %i: %d\n", __LINE__, rc); exit(1); }
+  }
+  return c;
+}
+
+#define LEGACY_CHECK(x)                                                          \
+  do {                                                                           \
+    int rc__ = (int)(x);                                                         \
+    if (rc__) { printf("CUDA error on line %i: %d\n", __LINE__, rc__); exit(1); } \
+  } while (0)
+
+void getPanelDims(int m, int n, int* rowPanels, int* colPanels) {
+  *colPanels = n / kLegacyPC + (n % kLegacyPC != 0);
+  *rowPanels = 1;
+  if (m > kLegacyPR) *rowPanels += (m - kLegacyPR) / (kLegacyPR - kLegacyPC) + ((m - kLegacyPR) % (kLegacyPR - kLegacyPC) != 0);
+}
+
+void mmqr(float* mat, float* tau, int m, int n) {
+  if (!(m && n && m >= n)) { printf("mmqr: need m >= n >= 1 (got %d x %d)\n", m, n); exit(1); }   // qr.cu:736
+  cqr_context* c = legacy_ctx();
+  int rp, cp;
+  getPanelDims(m, n, &rp, &cp);
+  const size_t tau_count = (size_t)rp * cp * kLegacyPC;
+  const long long lda = round_up(m, 4);
+  float *dA = nullptr, *dtau = nullptr;
+  LEGACY_CHECK(cudaMalloc((void**)&dA, (size_t)lda * n * sizeof(float)));
+  LEGACY_CHECK(cudaMalloc((void**)&dtau, (size_t)n * sizeof(float)));
+  LEGACY_CHECK(cudaMemcpy2D(dA, lda * sizeof(float), mat, (size_t)m * sizeof(float), (size_t)m * sizeof(float), n,
+                            cudaMemcpyHostToDevice));
+  LEGACY_CHECK(cqr_geqrf(c, dA, (int)lda, m, n, dtau));
+  LEGACY_CHECK(cudaMemcpy2D(mat, (size_t)m * sizeof(float), dA, lda * sizeof(float), (size_t)m * sizeof(float), n,
+                            cudaMemcpyDeviceToHost));
+  memset(tau, 0, tau_count * sizeof(float));   // unused slots zero, qr.c:62
+  LEGACY_CHECK(cudaMemcpy(tau, dtau, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+  cudaFree(dA);
+  cudaFree(dtau);
+}
+
+void mmqr_alloc(float* mat, float** tau, int m, int n) {
+  int rp, cp;
+  getPanelDims(m, n, &rp, &cp);
+  *tau = (float*)malloc((size_t)rp * cp * kLegacyPC * sizeof(float));   // qr.c:61
+  if (!*tau) { puts("mmqr: out of host memory"); exit(1); }
+  mmqr(mat, *tau, m, n);
+}
+
+void explicitQR(float* A, float* tau, float* Q, float* R, int m, int n) {
+  if (!(m && n && m >= n)) { printf("explicitQR: need m >= n >= 1 (got %d x %d)\n", m, n); exit(1); }
+  cqr_context* c = legacy_ctx();
+  const long long ld = round_up(m, 4);
+  float *dA = nullptr, *dtau = nullptr, *dQ = nullptr, *dR = nullptr;
+  LEGACY_CHECK(cudaMalloc((void**)&dA, (size_t)ld * n * sizeof(float)));
+  LEGACY_CHECK(cudaMalloc((void**)&dR, (size_t)ld * n * sizeof(float)));
+  LEGACY_CHECK(cudaMalloc((void**)&dQ, (size_t)ld * m * sizeof(float)));
+  LEGACY_CHECK(cudaMalloc((void**)&dtau, (size_t)n * sizeof(float)));
+  LEGACY_CHECK(cudaMemcpy2D(dA, ld * sizeof(float), A, (size_t)m * sizeof(float), (size_t)m * sizeof(float), n,
+                            cudaMemcpyHostToDevice));
+  LEGACY_CHECK(cudaMemcpy(dtau, tau, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+  LEGACY_CHECK(cqr_extract_r(c, dA, (int)ld, m, n, dR, (int)ld, m));
+  LEGACY_CHECK(cqr_form_q(c, dA, (int)ld, m, n, dtau, dQ, (int)ld, m));
+  LEGACY_CHECK(cudaMemcpy2D(R, (size_t)m * sizeof(float), dR, ld * sizeof(float), (size_t)m * sizeof(float), n,
+                            cudaMemcpyDeviceToHost));
+  LEGACY_CHECK(cudaMemcpy2D(Q, (size_t)m * sizeof(float), dQ, ld * sizeof(float), (size_t)m * sizeof(float), m,
+                            cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dR); cudaFree(dQ); cudaFree(dtau);
+}
+
+void dgemm(float* A, float* B, float* C, int k, int m, int n) {
+  cqr_context* c = legacy_ctx();
+  float *dA = nullptr, *dB = nullptr, *dC = nullptr;
+  LEGACY_CHECK(cudaMalloc((void**)&dA, (size_t)k * m * sizeof(float)));
+  LEGACY_CHECK(cudaMalloc((void**)&dB, (size_t)m * n * sizeof(float)));
+  LEGACY_CHECK(cudaMalloc((void**)&dC, (size_t)k * n * sizeof(float)));
+  LEGACY_CHECK(cudaMemcpy(dA, A, (size_t)k * m * sizeof(float), cudaMemcpyHostToDevice));
+  LEGACY_CHECK(cudaMemcpy(dB, B, (size_t)m * n * sizeof(float), cudaMemcpyHostToDevice));
+  LEGACY_CHECK(cqr_gemm(c, 0, k, n, m, 1.f, dA, k, dB, m, 0.f, dC, k));
+  LEGACY_CHECK(cudaMemcpy(C, dC, (size_t)k * n * sizeof(float), cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dB); cudaFree(dC);
+}
+
+void identity(float* A, int m) {
+  cqr_context* c = legacy_ctx();
+  float* dA = nullptr;
+  LEGACY_CHECK(cudaMalloc((void**)&dA, (size_t)m * m * sizeof(float)));
+  LEGACY_CHECK(cqr_set_identity(c, dA, m, m, m));
+  LEGACY_CHECK(cudaMemcpy(A, dA, (size_t)m * m * sizeof(float), cudaMemcpyDeviceToHost));
+  cudaFree(dA);
+}
+
+void printMat(float* mat, int m, int n) {   // same text as qr.c:21-33
+  printf("Matrix %d x %d, row by row:\n", m, n);
+  for (int i = 0; i < m; i++) {
+    for (int j = 0; j < n; j++) printf("%9f ", mat[(size_t)j * m + i]);
+    putchar('\n');
+  }
+  putchar('\n');
+}
+
+}  // extern "C"

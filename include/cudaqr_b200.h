@@ -1,0 +1,137 @@
+/*
+ * cudaqr_b200.h -- C ABI of libcudaqr_b200.so: a B200 (sm_100a) drop-in for the QR hot
+ * path of brian-kelley/CUDA-QR (qr.c / qr.cu).
+ *
+ * Part 1 re-exports the reference's own entry points with identical signatures and data
+ * contract (host pointers, column-major, lda = m, fp32, m >= n, blocking, errors print
+ * and exit(1) as qr.cu:467-471 does).  Part 2 is the device-resident API those wrappers
+ * are built on (what benchmarks time; no host copies, explicit stream, int status).
+ *
+ * No torch types, no C++ types: plain pointers and sizes only.
+ */
+#ifndef CUDAQR_B200_H
+#define CUDAQR_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------
+ * Part 1 -- legacy entry points (replace the same-named functions of the reference)
+ * ---------------------------------------------------------------------------------- */
+
+/* Replaces getPanelDims, qr.cu:49-55 (qr.c:47-53 with PR=64, PC=4, qr.cu:21-23).
+ * Callers size tau as rowPanels*colPanels*4 floats (qr.cu:764); that is always >= n,
+ * which is what this library's tau (one value per column) needs. */
+void getPanelDims(int m, int n, int* rowPanels, int* colPanels);
+
+/* Replaces mmqr, qr.cu:475-553.  In place: on return `mat` holds R on and above the
+ * diagonal and the Householder vectors below it (unit diagonal implicit); tau[0..n)
+ * holds the reflector scalars, the rest of the caller's rowPanels*colPanels*4 buffer is
+ * zero-filled (qr.c:62).  tau's layout is this library's own: only the
+ * mmqr -> explicitQR round trip is contractual.  Any m >= n >= 1 is legal (the
+ * reference silently mis-factors shapes off its window grid). */
+void mmqr(float* mat, float* tau, int m, int n);
+
+/* Replaces the CPU variant mmqr, qr.c:55-313: callee malloc()s *tau, caller free()s. */
+void mmqr_alloc(float* mat, float** tau, int m, int n);
+
+/* Replaces explicitQR, qr.c:330-438 / qr.cu:582-686.  Q is m x m, R is m x n (zero
+ * below the diagonal), A = Q*R; all column-major host buffers owned by the caller. */
+void explicitQR(float* A, float* tau, float* Q, float* R, int m, int n);
+
+/* Replaces dgemm, qr.c:443-459 / qr.cu:691-707: C(k x n) = A(k x m) * B(m x n). */
+void dgemm(float* A, float* B, float* C, int k, int m, int n);
+
+/* Replaces identity, qr.c:316-324 / qr.cu:568-576. */
+void identity(float* A, int m);
+
+/* Replaces printMat, qr.c:21-33 / qr.cu:35-47 (same text format). */
+void printMat(float* mat, int m, int n);
+
+/* ------------------------------------------------------------------------------------
+ * Part 2 -- device-resident API.  All matrix pointers are DEVICE pointers, column-major.
+ * Every function returns 0 on success, a negative CQR_E* on bad arguments, or a
+ * positive cudaError_t.  Work is enqueued on the context's stream; nothing synchronises
+ * unless stated.
+ * ---------------------------------------------------------------------------------- */
+typedef struct cqr_context cqr_context;
+
+enum {
+  CQR_OK = 0,
+  CQR_EINVAL = -1,      /* bad shape / pointer / leading dimension            */
+  CQR_ENOMEM = -2,      /* workspace allocation failed                        */
+  CQR_ESTATE = -3,      /* call order (e.g. tsqr_form_q without tsqr_factor)  */
+  CQR_EUNSUPPORTED = -4
+};
+
+/* Options for cqr_set_option. */
+enum {
+  CQR_OPT_GEMM = 1,         /* 0 = fp32 SIMT GEMMs, 1 = tcgen05 3xTF32 (default when shapes allow) */
+  CQR_OPT_OUTER_BLOCK = 2,  /* aggregated block width for the trailing update: 64..512 (default 256) */
+  CQR_OPT_TILE_ROWS = 3,    /* TSQR leaf height: 128 or 256 (default 256)                            */
+  CQR_OPT_SPLITK = 4        /* 0 = automatic                                                        */
+};
+
+int cqr_create(cqr_context** ctx, int device);
+int cqr_destroy(cqr_context* ctx);
+int cqr_set_stream(cqr_context* ctx, void* cuda_stream);   /* cudaStream_t; NULL = default stream */
+int cqr_set_option(cqr_context* ctx, int option, int value);
+int cqr_get_option(cqr_context* ctx, int option, int* value);
+int cqr_synchronize(cqr_context* ctx);
+const char* cqr_error_string(int status);
+/* Kernels this context has launched since creation (bench.py's gpu_launches). */
+long long cqr_launch_count(cqr_context* ctx);
+/* Pre-size the internal workspace (bytes) so no allocation happens in a timed region. */
+int cqr_reserve(cqr_context* ctx, size_t bytes);
+
+/* Blocked Householder QR (device core of mmqr).  A: m x n, lda >= m.  tau: n floats. */
+int cqr_geqrf(cqr_context* ctx, float* dA, int lda, int m, int n, float* dtau);
+
+/* R = triu(A) into dR (r_rows x n, r_rows = m reproduces explicitQR's m x n R; r_rows = n
+ * gives the square factor). */
+int cqr_extract_r(cqr_context* ctx, const float* dA, int lda, int m, int n, float* dR, int ldr, int r_rows);
+
+/* Q = H_0 H_1 ... H_{n-1} restricted to its first q_cols columns (q_cols = m: the
+ * reference's explicit m x m Q; q_cols = n: thin Q).  dQ must not alias dA. */
+int cqr_form_q(cqr_context* ctx, const float* dA, int lda, int m, int n, const float* dtau,
+               float* dQ, int ldq, int q_cols);
+
+/* C <- Q*C (trans = 0) or Q^T*C (trans = 1); C is m x nc. */
+int cqr_apply_q(cqr_context* ctx, int trans, const float* dA, int lda, int m, int n, const float* dtau,
+                float* dC, int ldc, int nc);
+
+/* Communication-avoiding tall-skinny QR (n <= 64).  R-only: A is read once, never written. */
+int cqr_tsqr_r(cqr_context* ctx, const float* dA, int lda, long long m, int n, float* dR, int ldr);
+/* Factor keeping the implicit Q: leaf reflectors overwrite A, tree levels live in the context. */
+int cqr_tsqr_factor(cqr_context* ctx, float* dA, int lda, long long m, int n, float* dR, int ldr);
+/* Thin Q (m x n) of the last cqr_tsqr_factor on this context times the n x n seed dX
+ * (NULL = identity): dQ = Q * [X; 0].  Used by the multi-GPU R-tree to push the tree's
+ * own Q blocks down into each rank's local Q. */
+int cqr_tsqr_form_q(cqr_context* ctx, const float* dX, int ldx, float* dQ, int ldq);
+/* QR of nblk stacked n x n upper-triangular blocks (dRs: (nblk*n) x n, ld = ldrs); keeps
+ * the reflectors so cqr_stack_form_q can expand it.  The combine step of the R-tree. */
+int cqr_stack_qr(cqr_context* ctx, float* dRs, int ldrs, int nblk, int n, float* dtau, float* dR, int ldr);
+int cqr_stack_form_q(cqr_context* ctx, const float* dRs, int ldrs, int nblk, int n, const float* dtau,
+                     const float* dX, int ldx, float* dQs, int ldqs);
+
+/* `batch` independent m x n matrices (m <= 256, n <= 64, m >= n), one CTA each; matrix i
+ * starts at dA + i*stride, lda >= m.  tau: batch x n. */
+int cqr_geqrf_batched(cqr_context* ctx, float* dA, int lda, long long stride, int m, int n, int batch, float* dtau);
+
+/* D = alpha * op(A) * B + beta * D, fp32, column-major (device core of dgemm).
+ * transA = 0: A is M x K; transA = 1: A is K x M. */
+int cqr_gemm(cqr_context* ctx, int transA, int M, int N, int K, float alpha, const float* dA, int lda,
+             const float* dB, int ldb, float beta, float* dD, int ldd);
+
+int cqr_set_identity(cqr_context* ctx, float* dA, int lda, int m, int n);
+
+/* Library build info: "sm_100a;<date>;<features>" */
+const char* cqr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUDAQR_B200_H */

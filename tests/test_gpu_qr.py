@@ -1,0 +1,380 @@
+"""GPU parity tests (pytest -m gpu): every call goes through the C ABI of libcudaqr_b200.so and is
+checked against the oracle (oracle/: the reference's algorithm restated, pinned in test_oracle.py),
+against golden vectors produced by the unmodified reference, and -- at sizes the oracle cannot
+reach -- through size-independent fp64 properties.
+
+Tolerances are BASELINE.json's (north_star): backward error ||A-QR||/(||A|| n eps) <= 10,
+orthogonality ||Q^T Q - I||/(n eps) <= 10, sign-normalised R within 1e-4 (normwise) of the
+reference's R; eps = 2^-23.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import metrics
+from conftest import load_pkg
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return load_pkg()
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def ctx(pkg, torch):
+    c = pkg.Context(0)
+    c.use_torch_stream()
+    yield c
+    c.close()
+
+
+def check_factorisation(A, Q, R, r_ref=None):
+    """The three north_star acceptance numbers."""
+    be = metrics.backward_error(A, Q, R)
+    orth = metrics.orthogonality(Q)
+    assert be <= metrics.TOL_BACKWARD, f"backward error {be}"
+    assert orth <= metrics.TOL_ORTH, f"orthogonality {orth}"
+    if r_ref is not None:
+        d = metrics.r_rel_diff(R, r_ref)
+        assert d <= metrics.TOL_R, f"R differs from the reference's by {d}"
+    return be, orth
+
+
+# ---------------------------------------------------------------------------------------------
+# legacy entry points (host buffers), as the reference's own main() drives them (qr.c:461-523)
+# ---------------------------------------------------------------------------------------------
+def test_legacy_demo_6x4_matches_reference_known_answer(pkg, port):
+    A = oracle.rand_matrix(6, 4, 12)
+    RV = A.copy(order="F")
+    tau = pkg.mmqr(RV)
+    assert tau.size == pkg.tau_size(6, 4)
+    Q, R = pkg.explicitQR(RV, tau)
+    rv_ref, _ = port.mmqr(A, 4, 2)
+    check_factorisation(A, Q, R, rv_ref)
+    QR = pkg.dgemm(Q, R)
+    resid = float(np.sqrt(np.sum((QR - A) ** 2, dtype=np.float32)))
+    assert resid < 2e-6   # the reference prints 3.788e-07 for this input (qr.c:515)
+    # R above the diagonal, reflectors below: explicit R is exactly triu of the storage
+    assert np.array_equal(np.triu(RV)[:4], R[:4])
+    assert np.all(R[4:] == 0)
+
+
+@pytest.mark.parametrize("PR,PC,m,n", [(4, 2, 64, 32), (64, 4, 64, 64), (64, 4, 124, 64), (64, 4, 244, 124),
+                                       (64, 8, 512, 512)])
+def test_legacy_mmqr_explicitqr_vs_reference_golden(pkg, PR, PC, m, n):
+    """R parity against golden vectors written by the UNMODIFIED reference (tests/golden/make_golden.py)."""
+    gold = np.load(os.path.join(GOLD, "ref_cases.npz"))
+    key = f"pr{PR}_pc{PC}_{m}x{n}"
+    A = oracle.rand_matrix(m, n, 12)
+    RV = A.copy(order="F")
+    tau = pkg.mmqr(RV)
+    Q, R = pkg.explicitQR(RV, tau)
+    R_ref = np.zeros((n, n), dtype=np.float32)
+    R_ref[np.triu_indices(n)] = gold[key + "_Rpacked"]
+    check_factorisation(A, Q, R, R_ref)
+    assert Q.shape == (m, m) and R.shape == (m, n)
+
+
+@pytest.mark.parametrize("PR,PC,m,n,seed", [(64, 4, 184, 64, 3), (64, 8, 176, 96, 4), (4, 2, 34, 34, 2),
+                                            (64, 4, 484, 484, 7), (64, 4, 1024 - 60 * 0 + 0, 256, 9)])
+def test_legacy_vs_oracle_on_seeded_inputs(pkg, port, PR, PC, m, n, seed):
+    if not oracle.legal_shape(m, n, PR, PC):
+        m = PR + ((m - PR) // (PR - PC)) * (PR - PC)   # snap to the reference's window grid (qr.cu:722-734)
+    A = oracle.rand_matrix(m, n, seed)
+    rv_ref, _ = port.mmqr(A, PR, PC)
+    RV = A.copy(order="F")
+    tau = pkg.mmqr(RV)
+    Q, R = pkg.explicitQR(RV, tau)
+    check_factorisation(A, Q, R, rv_ref)
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (5, 1), (7, 7), (100, 37), (300, 70), (257, 129), (1000, 200), (65, 64)])
+def test_legacy_ragged_shapes_any_m_ge_n(pkg, m, n):
+    """Shapes off the reference's window grid (it silently mis-factors them); here any
+    m >= n must work.  Checked against fp64 Householder (numpy/LAPACK)."""
+    rng = np.random.default_rng(m * 1000 + n)
+    A = np.asfortranarray(rng.random((m, n), dtype=np.float32))
+    RV = A.copy(order="F")
+    tau = pkg.mmqr(RV)
+    Q, R = pkg.explicitQR(RV, tau)
+    R64 = np.linalg.qr(A.astype(np.float64), mode="r")
+    check_factorisation(A, Q, R, R64)
+
+
+def test_legacy_edge_cases(pkg):
+    # zero matrix: no NaN (the reference divides by a zero norm)
+    A = np.zeros((70, 9), dtype=np.float32, order="F")
+    RV = A.copy(order="F")
+    tau = pkg.mmqr(RV)
+    Q, R = pkg.explicitQR(RV, tau)
+    assert np.all(np.isfinite(Q)) and np.all(np.isfinite(R)) and np.all(np.isfinite(tau))
+    assert metrics.orthogonality(Q) <= metrics.TOL_ORTH
+    assert np.abs(Q @ R).max() < 1e-6
+    # rank-deficient (duplicated columns) and badly scaled
+    rng = np.random.default_rng(3)
+    B = rng.standard_normal((200, 20)).astype(np.float32)
+    A = np.asfortranarray(np.hstack([B, B, 1e-4 * B[:, :8]]).astype(np.float32))
+    RV = A.copy(order="F")
+    tau = pkg.mmqr(RV)
+    Q, R = pkg.explicitQR(RV, tau)
+    assert metrics.backward_error(A, Q, R) <= metrics.TOL_BACKWARD
+    assert metrics.orthogonality(Q) <= metrics.TOL_ORTH
+    # already upper-triangular input
+    A = np.asfortranarray(np.triu(rng.standard_normal((64, 64))).astype(np.float32))
+    RV = A.copy(order="F")
+    tau = pkg.mmqr(RV)
+    Q, R = pkg.explicitQR(RV, tau)
+    check_factorisation(A, Q, R, A)
+
+
+def test_legacy_dgemm_and_identity_vs_oracle(pkg, port):
+    rng = np.random.default_rng(0)
+    for k, m, n in [(6, 6, 4), (33, 70, 129), (200, 64, 200), (1, 5, 1)]:
+        A = np.asfortranarray(rng.standard_normal((k, m)).astype(np.float32))
+        B = np.asfortranarray(rng.standard_normal((m, n)).astype(np.float32))
+        C = pkg.dgemm(A, B)
+        C_ref = port.dgemm(A, B)          # qr.c:443-459 restated
+        C64 = A.astype(np.float64) @ B.astype(np.float64)
+        scale = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64)
+        # both are fp32 sums in different orders: within m*eps of the exact product, like the oracle
+        assert np.all(np.abs(C - C64) <= 2 * m * metrics.EPS32 * scale + 1e-30)
+        assert np.all(np.abs(C_ref - C64) <= 2 * m * metrics.EPS32 * scale + 1e-30)
+    I = pkg.identity(37)
+    assert np.array_equal(I, np.eye(37, dtype=np.float32))
+
+
+# ---------------------------------------------------------------------------------------------
+# device-resident API
+# ---------------------------------------------------------------------------------------------
+def dev(pkg, torch, A_np):
+    return pkg.to_colmajor(torch.from_numpy(np.ascontiguousarray(A_np)).cuda())
+
+
+def host(t):
+    return np.asfortranarray(t.cpu().numpy())
+
+
+@pytest.mark.parametrize("gemm_mode", [0, 1])
+@pytest.mark.parametrize("m,n", [(512, 512), (1024, 768), (2048, 2048), (3000, 1000)])
+def test_geqrf_device_both_gemm_paths(pkg, torch, ctx, port, gemm_mode, m, n):
+    ctx.set_option(pkg.OPT_GEMM, gemm_mode)
+    A = oracle.rand_matrix(m, n, 12)
+    dA = dev(pkg, torch, A)
+    tau = torch.zeros(n, device="cuda")
+    ctx.geqrf(dA, tau)
+    Q = pkg.colmajor(m, n)
+    ctx.form_q(dA, tau, Q)           # thin Q
+    R = pkg.colmajor(n, n)
+    ctx.extract_r(dA, R)
+    ctx.synchronize()
+    r_ref = None
+    if (m, n) == (512, 512):
+        r_ref, _ = port.mmqr(A, 64, 8)
+    else:
+        r_ref = np.linalg.qr(A.astype(np.float64), mode="r")
+    check_factorisation(A, host(Q), host(R), r_ref)
+    ctx.set_option(pkg.OPT_GEMM, 1)
+
+
+@pytest.mark.parametrize("outer", [64, 128, 256, 512])
+def test_geqrf_outer_block_widths_agree(pkg, torch, ctx, outer):
+    ctx.set_option(pkg.OPT_OUTER_BLOCK, outer)
+    m, n = 1536, 1100
+    A = oracle.rand_matrix(m, n, 5)
+    dA = dev(pkg, torch, A)
+    tau = torch.zeros(n, device="cuda")
+    ctx.geqrf(dA, tau)
+    Q = pkg.colmajor(m, n)
+    ctx.form_q(dA, tau, Q)
+    R = pkg.colmajor(n, n)
+    ctx.extract_r(dA, R)
+    ctx.synchronize()
+    check_factorisation(A, host(Q), host(R), np.linalg.qr(A.astype(np.float64), mode="r"))
+    ctx.set_option(pkg.OPT_OUTER_BLOCK, 256)
+
+
+def test_apply_q_and_qt_roundtrip(pkg, torch, ctx):
+    m, n, nc = 1500, 300, 77
+    rng = np.random.default_rng(1)
+    A = np.asfortranarray(rng.standard_normal((m, n)).astype(np.float32))
+    C = np.asfortranarray(rng.standard_normal((m, nc)).astype(np.float32))
+    dA = dev(pkg, torch, A)
+    tau = torch.zeros(n, device="cuda")
+    ctx.geqrf(dA, tau)
+    dC = dev(pkg, torch, C)
+    ctx.apply_q(dA, tau, dC, trans=True)
+    QtC = host(dC)
+    ctx.apply_q(dA, tau, dC, trans=False)
+    ctx.synchronize()
+    back = host(dC)
+    assert np.linalg.norm(back - C) / np.linalg.norm(C) < 50 * metrics.EPS32
+    # Q^T A = R: apply Q^T to A itself
+    dA2 = dev(pkg, torch, A)
+    ctx.apply_q(dA, tau, dA2, trans=True)
+    R = pkg.colmajor(n, n)
+    ctx.extract_r(dA, R)
+    ctx.synchronize()
+    QtA = host(dA2)
+    assert np.linalg.norm(QtA[:n] - np.triu(host(R))) / np.linalg.norm(A) < 10 * n * metrics.EPS32
+    assert np.linalg.norm(QtA[n:]) / np.linalg.norm(A) < 10 * n * metrics.EPS32
+    # least squares through Q^T b and back-substitution agrees with fp64 lstsq
+    x_ref = np.linalg.lstsq(A.astype(np.float64), C[:, :3].astype(np.float64), rcond=None)[0]
+    x = np.linalg.solve(np.triu(host(R)).astype(np.float64), QtC[:n, :3].astype(np.float64))
+    assert np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# TSQR (config 3), batched (config 4)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,n", [(544, 64), (4144, 64), (65536, 64), (100000, 33), (300, 4), (64, 64), (1 << 20, 64)])
+def test_tsqr_r_and_thin_q(pkg, torch, ctx, port, m, n):
+    if m <= 65536:
+        A = oracle.rand_matrix(m, n, 12)
+    else:
+        A = np.asfortranarray(np.random.default_rng(2).random((m, n), dtype=np.float32))
+    dA = dev(pkg, torch, A)
+    R1 = pkg.colmajor(n, n)
+    ctx.tsqr_r(dA, R1)                   # R-only, A untouched
+    ctx.synchronize()
+    assert np.array_equal(host(dA), A)
+    R2 = pkg.colmajor(n, n)
+    ctx.tsqr_factor(dA, R2)              # implicit Q kept
+    Q = pkg.colmajor(m, n)
+    ctx.tsqr_form_q(Q)
+    ctx.synchronize()
+    assert np.array_equal(host(R1), host(R2))
+    if oracle.legal_shape(m, n, 64, 4) and m <= 5000:
+        r_ref, _ = port.mmqr(A, 64, 4)   # the reference's own flat-tree TSQR on the same input
+    else:
+        r_ref = np.linalg.qr(A.astype(np.float64), mode="r")
+    check_factorisation(A, host(Q), host(R1), r_ref)
+    assert metrics.gram_error(A, host(R1)) < 1e-5
+
+
+def test_tsqr_seeded_form_q_is_linear(pkg, torch, ctx):
+    """form_q(X) = Q X: the hook the multi-GPU R-tree uses to push its own Q blocks down."""
+    m, n = 5000, 48
+    rng = np.random.default_rng(4)
+    A = np.asfortranarray(rng.standard_normal((m, n)).astype(np.float32))
+    X = np.asfortranarray(rng.standard_normal((n, n)).astype(np.float32))
+    dA = dev(pkg, torch, A)
+    R = pkg.colmajor(n, n)
+    ctx.tsqr_factor(dA, R)
+    Q = pkg.colmajor(m, n)
+    ctx.tsqr_form_q(Q)
+    QX = pkg.colmajor(m, n)
+    ctx.tsqr_form_q(QX, dev(pkg, torch, X))
+    ctx.synchronize()
+    want = host(Q).astype(np.float64) @ X.astype(np.float64)
+    assert np.linalg.norm(host(QX) - want) / np.linalg.norm(want) < 20 * metrics.EPS32
+
+
+def test_stack_qr_combines_two_r_factors(pkg, torch, ctx):
+    n = 64
+    rng = np.random.default_rng(5)
+    R1 = np.triu(rng.standard_normal((n, n))).astype(np.float32)
+    R2 = np.triu(rng.standard_normal((n, n))).astype(np.float32)
+    S = np.asfortranarray(np.vstack([R1, R2]))
+    dS = dev(pkg, torch, S)
+    tau = torch.zeros(64, device="cuda")
+    R = pkg.colmajor(n, n)
+    ctx.stack_qr(dS, n, tau, R)
+    Qs = pkg.colmajor(2 * n, n)
+    ctx.stack_form_q(dS, n, tau, Qs)
+    ctx.synchronize()
+    check_factorisation(S, host(Qs), host(R), np.linalg.qr(S.astype(np.float64), mode="r"))
+
+
+@pytest.mark.parametrize("m,n,batch", [(64, 64, 1000), (64, 64, 65536), (100, 40, 300), (256, 64, 50), (8, 8, 10)])
+def test_batched_geqrf(pkg, torch, ctx, port, m, n, batch):
+    g = torch.Generator(device="cuda").manual_seed(12)
+    A3 = torch.rand((batch, n, m), device="cuda", generator=g)      # A3[b].T is matrix b (column-major, lda = m)
+    if (m, n) == (64, 64):
+        A3[0].copy_(torch.from_numpy(oracle.rand_matrix(64, 64, 12).T.copy()).cuda())
+    orig = A3.clone()
+    tau = torch.zeros((batch, n), device="cuda")
+    ctx.geqrf_batched(A3, tau)
+    ctx.synchronize()
+    # fp64 check of a sample of matrices (all of them when the batch is small)
+    idx = list(range(batch)) if batch <= 300 else [0, 1, batch // 2, batch - 1] + list(range(7, batch, batch // 50))
+    for b in idx:
+        A = orig[b].t().cpu().numpy()
+        V = A3[b].t().cpu().numpy()
+        Q = metrics.householder_q(V, tau[b].cpu().numpy(), full=False)
+        R = np.triu(V[:n])
+        r_ref = np.linalg.qr(A.astype(np.float64), mode="r")
+        if b == 0 and (m, n) == (64, 64):
+            r_ref, _ = port.mmqr(np.asfortranarray(A), 64, 4)       # the reference's single-window case
+        check_factorisation(A, Q, R, r_ref)
+    # whole-batch property on device: R^T R == A^T A for every matrix (fp64 on the GPU)
+    Rd = torch.triu(A3.transpose(1, 2)[:, :n, :].double())
+    G = orig.double() @ orig.double().transpose(1, 2)
+    err = (Rd.transpose(1, 2) @ Rd - G).flatten(1).norm(dim=1) / G.flatten(1).norm(dim=1)
+    assert float(err.max()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE-size property checks (the oracle cannot reach these)
+# ---------------------------------------------------------------------------------------------
+def test_tsqr_full_size_8m_by_64_properties(pkg, torch, ctx):
+    m, n = 8388608, 64
+    g = torch.Generator(device="cuda").manual_seed(12)
+    A = pkg.colmajor(m, n)
+    A.copy_(torch.rand((m, n), device="cuda", generator=g))
+    R = pkg.colmajor(n, n)
+    ctx.tsqr_r(A, R)
+    ctx.synchronize()
+    G = (A.t().double() @ A.double())
+    Rd = torch.triu(R.double())
+    gram = float((Rd.t() @ Rd - G).norm() / G.norm())
+    assert gram < 1e-5
+    # thin Q: orthogonality and A = Q R, evaluated on device in fp64
+    A0 = A.clone()
+    ctx.tsqr_factor(A, R)
+    Q = pkg.colmajor(m, n)
+    ctx.tsqr_form_q(Q)
+    ctx.synchronize()
+    orth = float(((Q.t().double() @ Q.double()) - torch.eye(n, device="cuda", dtype=torch.float64)).norm()) / (n * metrics.EPS32)
+    be = float((A0.double() - Q.double() @ torch.triu(R.double())).norm() / A0.double().norm()) / (n * metrics.EPS32)
+    assert orth <= metrics.TOL_ORTH and be <= metrics.TOL_BACKWARD
+
+
+def test_square_8192_properties(pkg, torch, ctx):
+    """Down-scaled instance of config 2's code path with full acceptance metrics on device (fp64)."""
+    m = n = 8192
+    g = torch.Generator(device="cuda").manual_seed(12)
+    A = pkg.colmajor(m, n)
+    A.copy_(torch.rand((m, n), device="cuda", generator=g))
+    A0 = A.clone()
+    tau = torch.zeros(n, device="cuda")
+    ctx.geqrf(A, tau)
+    R = pkg.colmajor(n, n)
+    ctx.extract_r(A, R)
+    QR = R.clone()                               # Q (R) via apply_q: no dense Q needed
+    QRfull = pkg.colmajor(m, n)
+    QRfull.copy_(QR)
+    ctx.apply_q(A, tau, QRfull, trans=False)
+    ctx.synchronize()
+    be = float((A0.double() - QRfull.double()).norm() / A0.double().norm()) / (n * metrics.EPS32)
+    assert be <= metrics.TOL_BACKWARD
+    G = A0.t().double() @ A0.double()
+    Rd = R.double()
+    assert float((Rd.t() @ Rd - G).norm() / G.norm()) < 1e-5
+    Q = pkg.colmajor(m, 256)
+    ctx.form_q(A, tau, Q)                        # first 256 columns of Q
+    ctx.synchronize()
+    orth = float((Q.t().double() @ Q.double() - torch.eye(256, device="cuda", dtype=torch.float64)).norm()) / (256 * metrics.EPS32)
+    assert orth <= metrics.TOL_ORTH

@@ -106,6 +106,7 @@ void launch_extract_v(const float* a, long long lda, long long mp, int b, int d0
 // ---- tcgen05 3xTF32 GEMMs: gemm_umma.cu -------------------------------------------------------
 // Both return false (nothing launched) when shape/alignment rules out the TMA path.
 bool umma_available();
+int umma_effective_splits(int K, int splits);   // K splits the tensor kernel really uses for a request
 bool launch_gemm_tn_umma(int M, int N, int K, const float* a, const float* a_lo, long long lda, const float* b,
                          const float* b_lo, long long ldb, float* d, long long ldd, int splits,
                          long long d_split_stride, cudaStream_t s);

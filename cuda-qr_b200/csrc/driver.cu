@@ -174,6 +174,7 @@ void gemm_tn(cqr_context* c, int M, int N, int K, Operand A, Operand B, float* p
              float* d_lo, int max_splits) {
   int splits = pick_splits(c, M, N, K, 128, 128);
   if (splits > max_splits) splits = max_splits;
+  splits = umma_effective_splits(K, splits);   // no empty K ranges; the reduction below must agree
   const long long ldp = round_up(M, 4);
   const long long stride = ldp * N;
   bool done = false;
@@ -263,6 +264,7 @@ int cqr_create(cqr_context** out, int device) {
     return (int)cudaErrorNoKernelImageForDevice;
   }
   c->launches0 = g_launches;
+  if (const char* e = getenv("CQR_GEMM")) c->opt_gemm = (strcmp(e, "simt") == 0) ? 0 : 1;   // debugging aid
   *out = c;
   return 0;
 }
@@ -335,6 +337,38 @@ int cqr_gemm(cqr_context* c, int transA, int M, int N, int K, float alpha, const
     if (alpha != 1.f || beta != 0.f) return CQR_EUNSUPPORTED;
     launch_gemm_tn_simt(M, N, K, dA, lda, dB, ldb, dD, ldd, 1, 0, c->stream);
   }
+  return (int)cudaGetLastError();
+}
+
+// D = op(A) B on the tcgen05 3xTF32 kernels (operands split into hi/lo in workspace).  Returns
+// CQR_EUNSUPPORTED when the shape/alignment rules out the TMA path (no silent fallback here).
+int cqr_gemm_tf32x3(cqr_context* c, int transA, int M, int N, int K, const float* dA, int lda, const float* dB, int ldb,
+                    float* dD, int ldd) {
+  if (!c || !dA || !dB || !dD || M < 1 || N < 1 || K < 1 || ldd < M || ldb < K) return CQR_EINVAL;
+  if (transA ? lda < K : lda < M) return CQR_EINVAL;
+  cudaSetDevice(c->device);
+  if (!umma_available()) return CQR_EUNSUPPORTED;
+  const int arows = transA ? K : M, acols = transA ? M : K;
+  float *alo = nullptr, *blo = nullptr, *part = nullptr;
+  int splits = transA ? umma_effective_splits(K, pick_splits(c, M, N, K, 128, 128)) : 1;
+  const long long ldp = round_up(M, 4);
+  for (int pass = 0; pass < 2; ++pass) {
+    Carver cv(pass ? c->ws : nullptr);
+    alo = cv.take((long long)lda * acols);
+    blo = cv.take((long long)ldb * N);
+    part = cv.take(ldp * N * splits);
+    if (!pass) { int rc = ws_ensure(c, cv.off); if (rc) return rc; }
+  }
+  launch_split_lo(arows, acols, dA, lda, alo, lda, c->stream);
+  launch_split_lo(K, N, dB, ldb, blo, ldb, c->stream);
+  bool ok;
+  if (transA) {
+    ok = launch_gemm_tn_umma(M, N, K, dA, alo, lda, dB, blo, ldb, part, ldp, splits, ldp * N, c->stream);
+    if (ok) launch_reduce_splits(M, N, part, ldp, ldp * N, splits, dD, ldd, nullptr, 0, c->stream);
+  } else {
+    ok = launch_gemm_nn_umma(M, N, K, 1.f, dA, alo, lda, dB, blo, ldb, 0.f, dD, ldd, nullptr, 0, c->stream);
+  }
+  if (!ok) return CQR_EUNSUPPORTED;
   return (int)cudaGetLastError();
 }
 

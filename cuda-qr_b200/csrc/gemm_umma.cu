@@ -1,9 +1,342 @@
-// gemm_umma.cu -- tcgen05 / TMEM / TMA 3xTF32 GEMMs (placeholder until the kernels land).
+// gemm_umma.cu -- tcgen05 / TMEM / TMA GEMMs for the trailing update (north_star item 3):
+//     TN:  D[z] = A(Kz,:)^T B(Kz,:)          W = V^T C, X = T^T W, Gram = V^T V   (split-K partials)
+//     NN:  D    = alpha A B + beta D (+ D_lo)  C -= V X, X = T W
+// fp32 fidelity on a tensor pipe that has no fp32 MMA comes from the 3xTF32 split: every
+// operand is held as hi + lo (hi = top 11 significand bits, lo = exact remainder, see
+// common.cuh) and each K step issues  A_hi B_hi + A_lo B_hi + A_hi B_lo  into the same TMEM
+// accumulator (the dropped lo*lo term is 2^-22 relative).  Operands are pre-split in global
+// memory by their producers, so the kernel is a plain TMA -> smem -> tcgen05.mma pipeline:
+//   warp 0   : TMA producer (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx)
+//   warp 1   : MMA issuer   (one elected lane, tcgen05.mma kind::tf32, M=128, N=BN, K=8)
+//   warps 2-5: epilogue     (tcgen05.ld 32x32b -> registers -> coalesced column-major stores)
+// A is K-major for TN (columns of V are contiguous along K) and MN-major for NN (V itself);
+// B is always K-major.  Ragged M/N/K edges rely on TMA zero fill plus masked stores.
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace cqr {
-bool umma_available() { return false; }
-bool launch_gemm_tn_umma(int, int, int, const float*, const float*, long long, const float*, const float*, long long,
-                         float*, long long, int, long long, cudaStream_t) { return false; }
-bool launch_gemm_nn_umma(int, int, int, float, const float*, const float*, long long, const float*, const float*,
-                         long long, float, float*, long long, float*, long long, cudaStream_t) { return false; }
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;               // fp32 elements per 128-byte swizzle row
+constexpr int kThreads = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Shared-memory matrix descriptor, 128B swizzle, Blackwell version bit set.
+//   K-major : rows of 128 B, 8-row atoms 1024 B apart (SBO); LBO unused (1)
+//   MN-major: 32-element chunks along M at LBO, 8-deep K groups at SBO = 1024
+//             tf32 MN-major operands must use the "128B swizzle, 32B atom" mode (layout type 1,
+//             TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 4-deep K groups of 128 B rows, 512 B apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (sm_100)
+  d |= (uint64_t)layout << 61;   // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+  return d;
+}
+
+// kind::tf32 instruction descriptor: F32 accumulate, TF32 A/B, M = 128, N = BN.
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(BM >> 4) << 24);
+}
+
+struct Epilogue {
+  float* d;
+  long long ldd;
+  long long split_stride;   // TN: partial z at d + z*split_stride
+  float* d_lo;              // NN: optional tf32 remainder of the result
+  long long ldd_lo;
+  float alpha, beta;
+};
+
+template <int BN, bool kAMn>
+__global__ void __launch_bounds__(kThreads, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, Epilogue ep,
+                 int M, int N, int K, int kper) {
+  constexpr int kStages = (BN == 256) ? 2 : 3;
+  constexpr uint32_t kABytes = BM * BK * 4;            // 16 KB per hi or lo tile
+  constexpr uint32_t kBBytes = BN * BK * 4;
+  constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kStages, tfull = full0 + 16 * kStages;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int kbeg = blockIdx.z * kper;
+  const int kend = min(K, kbeg + kper);
+  const int nkb = (kend - kbeg + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const uint32_t sa = smem_base + s * kStageBytes;
+        const uint32_t full = full0 + 8 * s;
+        mbar_expect_tx(full, kStageBytes);
+        const int k0 = kbeg + kb * BK;
+        if (kAMn) {
+#pragma unroll
+          for (int c = 0; c < BM / 32; ++c) {   // four 32-row chunks of the M-contiguous operand
+            tma_load_2d(sa + c * (BK * 128), &tm_a_hi, full, m0 + 32 * c, k0);
+            tma_load_2d(sa + kABytes + c * (BK * 128), &tm_a_lo, full, m0 + 32 * c, k0);
+          }
+        } else {
+          tma_load_2d(sa, &tm_a_hi, full, k0, m0);
+          tma_load_2d(sa + kABytes, &tm_a_lo, full, k0, m0);
+        }
+        tma_load_2d(sa + 2 * kABytes, &tm_b_hi, full, k0, n0);
+        tma_load_2d(sa + 2 * kABytes + kBBytes, &tm_b_lo, full, k0, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, kAMn);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_base + s * kStageBytes;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          uint64_t a_hi, a_lo;
+          if (kAMn) {   // K = 8 is two 4-deep groups (SBO = 512 B): +1024 B per step; M chunks 4096 B apart (LBO)
+            a_hi = make_desc(sa + k * 1024, BK * 128, 512, 1);
+            a_lo = make_desc(sa + kABytes + k * 1024, BK * 128, 512, 1);
+          } else {      // K-major: +32 B inside the swizzled 128 B row
+            a_hi = make_desc(sa + k * 32, 16, 1024, 2);
+            a_lo = make_desc(sa + kABytes + k * 32, 16, 1024, 2);
+          }
+          const uint64_t b_hi = make_desc(sa + 2 * kABytes + k * 32, 16, 1024, 2);
+          const uint64_t b_lo = make_desc(sa + 2 * kABytes + kBBytes + k * 32, 16, 1024, 2);
+          umma_tf32(tmem_d, a_lo, b_hi, idesc, (kb | k) != 0);
+          umma_tf32(tmem_d, a_hi, b_lo, idesc, 1);
+          umma_tf32(tmem_d, a_hi, b_hi, idesc, 1);
+        }
+        umma_commit(empty0 + 8 * s);
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    // epilogue: warp q reads TMEM lanes [32q, 32q+32) = rows m0 + 32q + lane
+    const int q = warp & 3;
+    const int m = m0 + 32 * q + lane;
+    mbar_wait(tfull, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const bool row_ok = m < M;
+    float* dz = ep.d + (long long)blockIdx.z * ep.split_stride;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
+      float old[32];
+      const int nb = n0 + 32 * c;
+      if (ep.beta != 0.f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) old[j] = (row_ok && nb + j < N) ? dz[m + (long long)(nb + j) * ep.ldd] : 0.f;
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (row_ok && nb + j < N) {
+          float r = ep.alpha * v[j];
+          if (ep.beta != 0.f) r = fmaf(ep.beta, old[j], r);
+          dz[m + (long long)(nb + j) * ep.ldd] = r;
+          if (ep.d_lo) ep.d_lo[m + (long long)(nb + j) * ep.ldd_lo] = tf32_lo(r);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN) : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map over a column-major matrix: dim0 = contiguous extent, dim1 = columns (stride ld).
+bool make_map(CUtensorMap* tm, const float* base, long long dim0, long long dim1, long long ld, int box0, int box1,
+              CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+template <int BN, bool kAMn>
+bool launch_umma(int M, int N, int K, const float* a, const float* a_lo, long long lda, const float* b, const float* b_lo,
+                 long long ldb, const Epilogue& ep, int splits, cudaStream_t s) {
+  CUtensorMap ta, tal, tb, tbl;
+  bool ok;
+  if (kAMn) ok = make_map(&ta, a, M, K, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
+                 make_map(&tal, a_lo, M, K, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  else ok = make_map(&ta, a, K, M, lda, BK, BM) && make_map(&tal, a_lo, K, M, lda, BK, BM);
+  ok = ok && make_map(&tb, b, K, N, ldb, BK, BN) && make_map(&tbl, b_lo, K, N, ldb, BK, BN);
+  if (!ok) return false;
+  constexpr int kStages = (BN == 256) ? 2 : 3;
+  constexpr size_t smem = (size_t)kStages * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024 + 256;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(umma_gemm_kernel<BN, kAMn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    attr_done = true;
+  }
+  int kper = ((K + splits - 1) / splits + BK - 1) / BK * BK;
+  if (kper < BK) kper = BK;
+  splits = (K + kper - 1) / kper;
+  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
+  ++g_launches;
+  umma_gemm_kernel<BN, kAMn><<<grid, kThreads, smem, s>>>(ta, tal, tb, tbl, ep, M, N, K, kper);
+  return true;
+}
+
+}  // namespace
+
+bool umma_available() {
+  static int state = -1;
+  if (state < 0) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    state = (get_encode() != nullptr && cudaGetDevice(&dev) == cudaSuccess &&
+             cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.major == 10)
+                ? 1 : 0;
+  }
+  return state == 1;
+}
+
+// Number of K splits the kernel will really use for a request (the reduction must agree).
+int umma_effective_splits(int K, int splits) {
+  if (splits < 1) splits = 1;
+  int kper = ((K + splits - 1) / splits + BK - 1) / BK * BK;
+  if (kper < BK) kper = BK;
+  return (K + kper - 1) / kper;
+}
+
+bool launch_gemm_tn_umma(int M, int N, int K, const float* a, const float* a_lo, long long lda, const float* b,
+                         const float* b_lo, long long ldb, float* d, long long ldd, int splits, long long d_split_stride,
+                         cudaStream_t s) {
+  if (!umma_available() || !a_lo || !b_lo) return false;
+  if (lda % 4 || ldb % 4 || !aligned16(a) || !aligned16(a_lo) || !aligned16(b) || !aligned16(b_lo)) return false;
+  if (M < 1 || N < 1 || K < 1) return false;
+  Epilogue ep{d, ldd, d_split_stride, nullptr, 0, 1.f, 0.f};
+  if (N > 128) return launch_umma<256, false>(M, N, K, a, a_lo, lda, b, b_lo, ldb, ep, splits, s);
+  return launch_umma<128, false>(M, N, K, a, a_lo, lda, b, b_lo, ldb, ep, splits, s);
+}
+
+bool launch_gemm_nn_umma(int M, int N, int K, float alpha, const float* a, const float* a_lo, long long lda, const float* b,
+                         const float* b_lo, long long ldb, float beta, float* d, long long ldd, float* d_lo,
+                         long long ldd_lo, cudaStream_t s) {
+  if (!umma_available() || !a_lo || !b_lo) return false;
+  if (lda % 4 || ldb % 4 || !aligned16(a) || !aligned16(a_lo) || !aligned16(b) || !aligned16(b_lo)) return false;
+  if (M < 1 || N < 1 || K < 1) return false;
+  Epilogue ep{d, ldd, 0, d_lo, ldd_lo, alpha, beta};
+  if (N > 128) return launch_umma<256, true>(M, N, K, a, a_lo, lda, b, b_lo, ldb, ep, 1, s);
+  return launch_umma<128, true>(M, N, K, a, a_lo, lda, b, b_lo, ldb, ep, 1, s);
+}
+
 }  // namespace cqr

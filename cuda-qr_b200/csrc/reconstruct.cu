@@ -137,7 +137,7 @@ void launch_hr_rows(const HrParams& p, cudaStream_t s) {
 //     T[0:64J, J]    = -T[0:64J,0:64J] * (G[0:64J, J] * T_JJ)
 __global__ void __launch_bounds__(256) build_t_kernel(float* g, long long ldg, const float* tau, float* t,
                                                       long long ldt, int kb, int have_diag) {
-  extern __shared__ float tmp[];   // (kb - 64) x 64, ld = rowsJ
+  extern __shared__ float tmp[];   // 64*(nb-1) x 64, ld = rowsJ
   __shared__ float Tjj[64][65];
   __shared__ float Gs[64][65];
   const int tid = threadIdx.x;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) build_t_kernel(float* g, long long ldg, c
 void launch_build_t(const float* g, long long ldg, const float* tau, float* t, long long ldt, int kb,
                     int have_diag, cudaStream_t s) {
   ++g_launches;
-  const size_t smem = (kb > 64) ? (size_t)(kb - 64) * 64 * sizeof(float) + 64 * 4 : 0;
+  const size_t smem = (kb > 64) ? (size_t)((kb - 1) / 64) * 64 * 64 * sizeof(float) + 64 * 4 : 0;   // rowsJ <= 64*(nb-1)
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(build_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 448 * 64 * 4 + 256);

@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- QR GFLOP/s (2mn^2 - 2n^3/3) of the B200-native hot path, one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload square|tsqr|batched]
+
+Workloads (BASELINE.json configs): `square` = config 2, 16384 x 16384 blocked Householder QR on one
+GPU (the default; at N > 1 every rank factors its own matrix: replicas only);
+`tsqr` = config 3, 8 388 608 x 64 row-partitioned over the N ranks with the R factors combined
+in a binary tree over NCCL point-to-point (strong scaling); `batched` = config 4, 65 536
+independent 64 x 64 matrices split across ranks.  The default run reports `square` as the
+headline line and carries the TSQR and batched numbers in the same JSON object.
+
+One JSON line is printed by rank 0.  `value` is device-resident throughput (CUDA events, max over
+ranks); `e2e` is the same metric through the reference-facing legacy call mmqr(host buffers) with
+the H2D/D2H copies inside the timed region.  `--impl reference` times the reference's own CPU
+mmqr (oracle/_ref, unmodified qr.c) on a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "QR GFLOP/s (2mn^2-2n^3/3)"
+
+
+def qr_flops(m: int, n: int) -> float:
+    return 2.0 * m * n * n - 2.0 * n ** 3 / 3.0
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (unmodified qr.c -> oracle/_ref), 1 thread
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_run(m: int, n: int, steps: int, warmup: int):
+    import oracle
+    kind = "reference" if oracle.Ref.available(4, 2) else "port"
+    A = oracle.rand_matrix(m, n, 12)
+    if kind == "reference":
+        ref = oracle.Ref(4, 2)            # qr.c as shipped: PR=4, PC=2 (qr.c:12-13)
+        run = lambda: ref.mmqr(A)
+    else:
+        port = oracle.Port()
+        run = lambda: port.mmqr(A, 4, 2)
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = (time.perf_counter() - t0) / steps
+    return kind, dt, qr_flops(m, n) / dt / 1e9
+
+
+def main_reference(args, rank: int):
+    if rank != 0:
+        return
+    m = n = args.ref_size
+    kind, dt, gf = cpu_reference_run(m, n, args.steps, args.warmup)
+    sample = f"{m}x{n} uniform[0,1) srand(12) matrix (bounded sample of the 16384x16384 workload), mmqr only, PR=4/PC=2 as shipped"
+    line = {"impl": "reference", "metric": METRIC, "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": "square 16384x16384 fp32 blocked Householder QR (config 2)",
+                                                             "sample": sample},
+            "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": 1, "kind": kind, "sample": sample},
+            "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def main_ours(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("cuda-qr_b200")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = pkg.Context(local_rank)
+    ctx.use_torch_stream()
+    pk = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_steps(step_fn, restore_fn, steps, warmup):
+        """W untimed + K timed steps; each step bracketed by CUDA events on the launching stream; inputs are
+        restored between steps outside the events (as the reference does, qr.cu:785-787)."""
+        for _ in range(warmup):
+            restore_fn(); step_fn()
+        barrier()
+        evs = []
+        wall0 = time.perf_counter()
+        for _ in range(steps):
+            restore_fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); step_fn(); e1.record()
+            evs.append((e0, e1))
+        barrier()
+        wall = time.perf_counter() - wall0
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        return max_over_ranks(ms), wall
+
+    out = {}
+    # ---------------- square 16384^2 (config 2): the headline workload --------------------------
+    m = n = args.size
+    g = torch.Generator(device=dev).manual_seed(12 + rank)
+    A0 = pkg.colmajor(m, n, device=dev)
+    A0.copy_(torch.rand((m, n), device=dev, generator=g))            # uniform[0,1), the reference's distribution
+    A = pkg.colmajor(m, n, device=dev)
+    tau = torch.zeros(n, device=dev)
+    restore = lambda: A.copy_(A0)
+    step = lambda: ctx.geqrf(A, tau)
+    restore(); step(); torch.cuda.synchronize()                       # sizes the workspace outside any timing
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    ms, wall = timed_steps(step, restore, args.steps, args.warmup)
+    launches = (ctx.launch_count() - l0) // max(1, args.steps + args.warmup) * args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    flops = qr_flops(m, n)
+    value = world * flops / (ms * 1e-3) / 1e9
+
+    # residual ||A - QR|| / ||A|| of the last timed step (outside the timed region), rank 0
+    resid = None
+    if rank == 0:
+        R = pkg.colmajor(n, n, device=dev)
+        ctx.extract_r(A, R)
+        QR = pkg.colmajor(m, n, device=dev)
+        QR.copy_(R)
+        ctx.apply_q(A, tau, QR, trans=False)
+        ctx.synchronize()
+        num = torch.zeros((), device=dev, dtype=torch.float64)
+        den = torch.zeros((), device=dev, dtype=torch.float64)
+        for c0 in range(0, n, 2048):                                   # blocked fp64 norms: bounded memory
+            d = (A0[:, c0:c0 + 2048].double() - QR[:, c0:c0 + 2048].double())
+            num += (d * d).sum(); den += (A0[:, c0:c0 + 2048].double() ** 2).sum()
+        resid = float((num / den).sqrt())
+        del R, QR
+
+    # per-kernel-class profile of one more step (CUDA events inside the library), rank 0
+    roof = None
+    if rank == 0:
+        restore(); torch.cuda.synchronize()
+        ctx.profile_begin(); step(); prof = ctx.profile_end()
+        nn = prof["gemm_nn"]
+        tot_ms = sum(v["ms"] for v in prof.values())
+        ach = nn["flops"] / (nn["ms"] * 1e-3) / 1e12 if nn["ms"] > 0 else 0.0
+        tensor_mode = ctx.get_option(pkg.OPT_GEMM) == 1
+        peak = pk["bf16_sustained"] / 2.0 / 3.0 if tensor_mode else 74.0
+        roof = {"bound": "tensor", "kernel": "umma_gemm_kernel<256,MN> (C -= V X, tcgen05 3xTF32)" if tensor_mode else "gemm_nn_simt_kernel",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_basis": (f"{pk['source']}: bf16 sustained {pk['bf16_sustained']} TF/s / 2 (tf32 rate) / 3 (hi*hi + lo*hi + hi*lo passes)"
+                               if tensor_mode else "nominal fp32 SIMT 74 TF/s"),
+                "frac_of_bf16_measured": 3.0 * ach / pk["bf16_sustained"] * 2.0 if tensor_mode else None,
+                "algorithmic_flops_per_step": nn["flops"], "launches_per_step": nn["launches"],
+                "avg_launch_ms": nn["ms"] / max(1, nn["launches"]), "share_of_step": nn["ms"] / tot_ms if tot_ms else None,
+                "hbm_GBps_algorithmic": nn["bytes"] / (nn["ms"] * 1e-3) / 1e9 if nn["ms"] > 0 else None,
+                "by_class_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
+                "by_class_launches": {k: v["launches"] for k, v in prof.items()}}
+
+    # e2e: legacy mmqr(host buffers) -- H2D, factor, D2H inside the timed region, rank-local, pinned host memory
+    e2e = None
+    if not args.no_e2e:
+        hostA = torch.empty((n, m), dtype=torch.float32, pin_memory=True)  # column-major m x n
+        hostA.copy_(A0.t())
+        hnp = hostA.numpy().T                                            # F-contiguous view
+        htau = __import__("numpy").empty(pkg.tau_size(m, n), dtype="float32")
+        pkg.mmqr(hnp, htau)                                              # warm (cudaMalloc pools, page faults)
+        ts = []
+        for _ in range(args.e2e_steps):
+            hostA.copy_(A0.t())
+            barrier()
+            t0 = time.perf_counter(); pkg.mmqr(hnp, htau); ts.append(time.perf_counter() - t0)
+        dt = max_over_ranks(sum(ts) / len(ts))
+        e2e = {"value": world * flops / dt / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": m * n * 4,
+               "d2h_bytes_per_step": m * n * 4 + n * 4, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+               "api": "mmqr(float* mat, float* tau, int m, int n) on pinned host buffers (qr.cu:475 signature)"}
+        del hostA
+    del A, A0
+    torch.cuda.empty_cache()
+
+    # ---------------- TSQR 8M x 64 (config 3), row-partitioned + NCCL R-tree --------------------
+    if not args.no_extra:
+        out["tsqr"] = bench_tsqr(args, pkg, ctx, torch, dist, dev, rank, world, timed_steps, pk)
+        out["batched"] = bench_batched(args, pkg, ctx, torch, dev, rank, world, timed_steps, pk)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        kind, dt, gf = cpu_reference_run(args.ref_size, args.ref_size, 1, 0)
+        cpu = {"value": gf, "unit": "GFLOP/s", "cores": 1, "kind": kind, "seconds": dt,
+               "sample": f"{args.ref_size}x{args.ref_size} srand(12) uniform[0,1) matrix, reference mmqr only (qr.c as shipped, PR=4/PC=2), 1 of {os.cpu_count()} host cores"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (tcgen05 3xTF32 split, fp32 accumulate)" if ctx.get_option(pkg.OPT_GEMM) == 1 else "f32",
+                "data": "synthetic",
+                "config": {"workload": f"square {m}x{n} fp32 blocked Householder QR (BASELINE config 2)" + (" x N replicas" if world > 1 else ""),
+                           "panel": 64, "outer_block": ctx.get_option(pkg.OPT_OUTER_BLOCK), "input": "uniform[0,1) Philox seed 12+rank, column-major lda=m",
+                           "l2": "input 1 GiB > 126 MB L2; restored from a pristine copy before every step"},
+                "residual": resid, "clocks": clocks, "gpu_launches": launches, "wall_s_timed_region": wall,
+                "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
+        line.update(out)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def tsqr_tree(pkg, ctx, torch, dist, dev, rank, world, A_loc, R, bufs):
+    """Local TSQR (R only) then a binary reduction tree over NCCL p2p: at level s the rank with bit s set sends
+    its 64x64 R to rank - 2^s, which stacks [R_mine; R_recv] and re-factors (cqr_stack_qr)."""
+    n = R.shape[0]
+    ctx.tsqr_r(A_loc, R)
+    s = 1
+    while s < world:
+        if rank % (2 * s) == s:
+            dist.send(R, rank - s)
+            break
+        if rank % (2 * s) == 0 and rank + s < world:
+            stack, tau = bufs
+            stack[:n].copy_(R)
+            dist.recv(bufs[2], rank + s)
+            stack[n:].copy_(bufs[2])
+            ctx.stack_qr(stack, n, tau, R)
+        s *= 2
+
+
+def bench_tsqr(args, pkg, ctx, torch, dist, dev, rank, world, timed_steps, pk):
+    m_total, n = args.tsqr_rows, 64
+    m_loc = m_total // world
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    A_loc = pkg.colmajor(m_loc, n, device=dev)
+    A_loc.copy_(torch.rand((m_loc, n), device=dev, generator=g))
+    R = pkg.colmajor(n, n, device=dev)
+    bufs = (pkg.colmajor(2 * n, n, device=dev), torch.zeros(64, device=dev), pkg.colmajor(n, n, device=dev))
+    step = lambda: tsqr_tree(pkg, ctx, torch, dist, dev, rank, world, A_loc, R, bufs)
+    step(); torch.cuda.synchronize()
+    ms, _ = timed_steps(step, lambda: None, max(args.steps, 10), args.warmup)
+    flops = qr_flops(m_total, n)
+    res = {"workload": f"tall-skinny {m_total}x{n} fp32 TSQR, R-only, row-partitioned over {world} GPU(s), NCCL p2p R-tree (config 3)",
+           "value": flops / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms, "scaling": "strong", "n_gpus": world}
+    bytes_alg = 4.0 * m_loc * n
+    ach = bytes_alg / (ms * 1e-3) / 1e9
+    res["roofline"] = {"bound": "hbm", "kernel": "tile_qr_kernel<8> (256x64 leaves, A read once)", "achieved": ach,
+                       "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                       "note": "per-GPU algorithmic bytes 4*m_loc*n over the whole step (leaves + tree + NCCL hops)"}
+    if rank == 0:
+        # Gram check of the distributed result against this rank's slab is meaningless for world > 1; check world == 1
+        if world == 1:
+            G = A_loc.t().double() @ A_loc.double()
+            Rd = torch.triu(R.double())
+            res["gram_error"] = float((Rd.t() @ Rd - G).norm() / G.norm())
+    return res
+
+
+def bench_batched(args, pkg, ctx, torch, dev, rank, world, timed_steps, pk):
+    batch_total, m, n = args.batch, 64, 64
+    batch = batch_total // world
+    g = torch.Generator(device=dev).manual_seed(200 + rank)
+    A0 = torch.rand((batch, n, m), device=dev, generator=g)
+    A = torch.empty_like(A0)
+    tau = torch.zeros((batch, n), device=dev)
+    step = lambda: ctx.geqrf_batched(A, tau)
+    restore = lambda: A.copy_(A0)
+    restore(); step(); torch.cuda.synchronize()
+    ms, _ = timed_steps(step, restore, max(args.steps, 10), args.warmup)
+    flops = batch_total * qr_flops(m, n)
+    bytes_alg = 2.0 * batch * m * n * 4
+    ach = bytes_alg / (ms * 1e-3) / 1e9
+    return {"workload": f"batched {batch_total} x ({m}x{n}) fp32 QR, one CTA per matrix, split over {world} GPU(s) (config 4)",
+            "value": flops / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms, "scaling": "strong", "n_gpus": world,
+            "roofline": {"bound": "hbm", "kernel": "tile_qr_kernel<2>", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": ach / pk["hbm_gbs"], "traffic": None}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=16384, help="square workload edge (config 2: 16384)")
+    ap.add_argument("--tsqr-rows", type=int, default=8388608)
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--ref-size", type=int, default=1536, help="edge of the bounded CPU sample")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        main_reference(args, rank)
+        return
+    main_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

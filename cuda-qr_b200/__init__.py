@@ -34,7 +34,7 @@ GEMM_SIMT, GEMM_TF32X3 = 0, 1
 EXPORTS = [
     "getPanelDims", "mmqr", "mmqr_alloc", "explicitQR", "dgemm", "identity", "printMat",
     "cqr_create", "cqr_destroy", "cqr_set_stream", "cqr_set_option", "cqr_get_option", "cqr_synchronize",
-    "cqr_error_string", "cqr_launch_count", "cqr_reserve", "cqr_geqrf", "cqr_extract_r", "cqr_form_q",
+    "cqr_error_string", "cqr_launch_count", "cqr_profile_begin", "cqr_profile_end", "cqr_reserve", "cqr_geqrf", "cqr_extract_r", "cqr_form_q",
     "cqr_apply_q", "cqr_tsqr_r", "cqr_tsqr_factor", "cqr_tsqr_form_q", "cqr_stack_qr", "cqr_stack_form_q",
     "cqr_geqrf_batched", "cqr_gemm", "cqr_gemm_tf32x3", "cqr_set_identity", "cqr_version",
 ]
@@ -78,6 +78,9 @@ def _load() -> ctypes.CDLL:
     lib.cqr_launch_count.argtypes = [_VP]
     lib.cqr_launch_count.restype = ll
     lib.cqr_reserve.argtypes = [_VP, ctypes.c_size_t]
+    lib.cqr_profile_begin.argtypes = [_VP]
+    lib.cqr_profile_end.argtypes = [_VP, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                    ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ll), i]
     lib.cqr_geqrf.argtypes = [_VP, _VP, i, i, i, _VP]
     lib.cqr_extract_r.argtypes = [_VP, _VP, i, i, i, _VP, i, i]
     lib.cqr_form_q.argtypes = [_VP, _VP, i, i, i, _VP, _VP, i, i]
@@ -261,6 +264,20 @@ class Context:
 
     def launch_count(self) -> int:
         return int(lib.cqr_launch_count(self.h))
+
+    PROF_CLASSES = ("panel", "gemm_tn", "gemm_nn", "misc")
+
+    def profile_begin(self):
+        _check(lib.cqr_profile_begin(self.h), "cqr_profile_begin")
+
+    def profile_end(self) -> dict:
+        """{class: {"ms", "flops", "bytes", "launches"}} for the launches since profile_begin()."""
+        n = len(self.PROF_CLASSES)
+        ms, fl, by = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_double * n)()
+        la = (ctypes.c_longlong * n)()
+        _check(lib.cqr_profile_end(self.h, ms, fl, by, la, n), "cqr_profile_end")
+        return {k: {"ms": ms[j], "flops": fl[j], "bytes": by[j], "launches": int(la[j])}
+                for j, k in enumerate(self.PROF_CLASSES)}
 
     def reserve(self, nbytes: int):
         _check(lib.cqr_reserve(self.h, nbytes), "cqr_reserve")

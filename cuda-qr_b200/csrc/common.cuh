@@ -17,6 +17,20 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// N independent warp all-reduces, issued stage by stage so the N shuffle chains overlap (a
+// branchy per-value loop serialises them: ~150 cycles each).
+template <int N>
+__device__ __forceinline__ void warp_sum_n(float (&s)[N]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float t[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) t[i] = __shfl_xor_sync(kFull, s[i], o);
+#pragma unroll
+    for (int i = 0; i < N; ++i) s[i] += t[i];
+  }
+}
+
 // x = hi + lo with hi carrying the top 11 significand bits (the TF32 payload, low 13 bits
 // zero) and lo the exact remainder: the operand split behind the 3xTF32 tensor-core GEMMs.
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }

@@ -58,6 +58,12 @@ struct cqr_context {
   int opt_gemm = 1, opt_outer = 256, opt_tile_rows = 256, opt_splitk = 0;
   long long launches0 = 0;
   cudaError_t last = cudaSuccess;
+  // optional per-kernel-class timing (cqr_profile_begin/end): CUDA events around each launch group
+  bool prof_on = false;
+  struct ProfRec { int cat; double flops; double bytes; long long launches; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
 };
 
 namespace {
@@ -67,6 +73,35 @@ namespace {
     cudaError_t e__ = (x);                   \
     if (e__ != cudaSuccess) return (int)e__; \
   } while (0)
+
+cudaEvent_t prof_event(cqr_context* c) {
+  if (c->ev_used == c->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->ev_pool.push_back(e);
+  }
+  return c->ev_pool[c->ev_used++];
+}
+
+// RAII scope: when profiling is on, brackets the launches made inside it with two events.
+struct ProfScope {
+  cqr_context* c; int idx = -1; long long l0 = 0;
+  ProfScope(cqr_context* ctx, int cat, double flops, double bytes) : c(ctx) {
+    if (!c->prof_on) return;
+    cqr_context::ProfRec r{cat, flops, bytes, 0, prof_event(c), prof_event(c)};
+    cudaEventRecord(r.e0, c->stream);
+    l0 = g_launches;
+    c->prof.push_back(r);
+    idx = (int)c->prof.size() - 1;
+  }
+  void finish() {
+    if (idx < 0) return;
+    c->prof[idx].launches = g_launches - l0;
+    cudaEventRecord(c->prof[idx].e1, c->stream);
+    idx = -1;
+  }
+  ~ProfScope() { finish(); }
+};
 
 int ws_ensure(cqr_context* c, size_t bytes) {
   if (bytes <= c->ws_bytes) { c->ws_off = 0; return 0; }
@@ -178,15 +213,23 @@ void gemm_tn(cqr_context* c, int M, int N, int K, Operand A, Operand B, float* p
   const long long ldp = round_up(M, 4);
   const long long stride = ldp * N;
   bool done = false;
-  if (c->opt_gemm == 1 && A.lo && B.lo)
-    done = launch_gemm_tn_umma(M, N, K, A.hi, A.lo, A.ld, B.hi, B.lo, B.ld, part, ldp, splits, stride, c->stream);
-  if (!done) launch_gemm_tn_simt(M, N, K, A.hi, A.ld, B.hi, B.ld, part, ldp, splits, stride, c->stream);
+  {
+    // algorithmic traffic: both operands read once (hi + lo on the tensor path), partials written
+    ProfScope ps(c, CQR_PROF_GEMM_TN, 2.0 * M * N * K, 4.0 * ((double)K * (M + N) * (A.lo ? 2 : 1) + (double)M * N * splits));
+    if (c->opt_gemm == 1 && A.lo && B.lo)
+      done = launch_gemm_tn_umma(M, N, K, A.hi, A.lo, A.ld, B.hi, B.lo, B.ld, part, ldp, splits, stride, c->stream);
+    if (!done) launch_gemm_tn_simt(M, N, K, A.hi, A.ld, B.hi, B.ld, part, ldp, splits, stride, c->stream);
+  }
+  ProfScope ps2(c, CQR_PROF_MISC, 0.0, 4.0 * M * N * (splits + 2));
   launch_reduce_splits(M, N, part, ldp, stride, splits, d, ldd, d_lo, ldd, c->stream);
 }
 
 void gemm_nn(cqr_context* c, int M, int N, int K, float alpha, Operand A, Operand B, float beta, float* d,
              long long ldd, float* d_lo) {
   bool done = false;
+  // algorithmic traffic: D read (beta != 0) and written once (+ its lo), A and B read once
+  ProfScope ps(c, CQR_PROF_GEMM_NN, 2.0 * M * N * K,
+               4.0 * ((double)M * N * ((beta != 0.f ? 1 : 0) + 1 + (d_lo ? 1 : 0)) + (double)K * (M + N) * (A.lo ? 2 : 1)));
   if (c->opt_gemm == 1 && A.lo && B.lo)
     done = launch_gemm_nn_umma(M, N, K, alpha, A.hi, A.lo, A.ld, B.hi, B.lo, B.ld, beta, d, ldd, d_lo, ldd, c->stream);
   if (!done) launch_gemm_nn_simt(M, N, K, alpha, A.hi, A.ld, B.hi, B.ld, beta, d, ldd, d_lo, ldd, c->stream);
@@ -275,6 +318,7 @@ int cqr_destroy(cqr_context* c) {
   cudaStreamSynchronize(c->stream);
   if (c->ws) cudaFree(c->ws);
   if (c->ts) cudaFree(c->ts);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   delete c;
   return 0;
 }
@@ -311,6 +355,28 @@ int cqr_synchronize(cqr_context* c) {
 }
 
 long long cqr_launch_count(cqr_context* c) { return c ? g_launches - c->launches0 : 0; }
+
+int cqr_profile_begin(cqr_context* c) {
+  if (!c) return CQR_EINVAL;
+  c->prof.clear();
+  c->ev_used = 0;
+  c->prof_on = true;
+  return 0;
+}
+
+int cqr_profile_end(cqr_context* c, double* ms, double* flops, double* bytes, long long* launches, int ncat) {
+  if (!c || !ms || !flops || !bytes || !launches || ncat < CQR_PROF_NCAT) return CQR_EINVAL;
+  c->prof_on = false;
+  CQR_CUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < ncat; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
+  for (auto& r : c->prof) {
+    float t = 0.f;
+    CQR_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms[r.cat] += t; flops[r.cat] += r.flops; bytes[r.cat] += r.bytes; launches[r.cat] += r.launches;
+  }
+  c->prof.clear();
+  return 0;
+}
 
 int cqr_reserve(cqr_context* c, size_t bytes) { if (!c) return CQR_EINVAL; cudaSetDevice(c->device); return ws_ensure(c, bytes); }
 
@@ -417,6 +483,8 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
       // (1) panel TSQR: R_tsqr + implicit Q   (2) explicit thin Q   (3) Householder reconstruction
       TsqrPlan pp;
       { Carver cv2(c->ws); plan_tsqr(pp, mp, b, th, cv2); }   // same carve order => same buffers, sized for mp <= m
+      // panel: 2 mp b^2 (TSQR) + 2 mp b^2 (thin Q) + mp b^2 (Y = Q U^-1) flops; panel read 2x, written 2x, Q 2x
+      ProfScope pps(c, CQR_PROF_PANEL, 5.0 * mp * b * b, 4.0 * 6.0 * mp * b);
       run_tsqr_factor(c, pp, ap, lda, true, rt, 64);
       run_tsqr_form_q(c, pp, ap, lda, nullptr, 0, b, qthin, ldv);
       HrParams hp{};
@@ -427,6 +495,7 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
       hp.mp = mp; hp.b = b;
       launch_hr_top(hp, st);
       launch_hr_rows(hp, st);
+      pps.finish();
       // (4) inner update: remaining columns of this outer block
       const int ninner = K0 + kbw - (j0 + b);
       if (ninner > 0) {
@@ -444,6 +513,7 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
       Operand V{vbuf, vlo, ldv};
       if (kbw > 64) {
         gemm_tn(c, kbw, kbw, (int)mK, V, V, gpart, gram, KB, nullptr, kMaxSplits);
+        ProfScope pbt(c, CQR_PROF_MISC, 0.0, 0.0);
         launch_build_t(gram, KB, dtau + K0, tbig, KB, kbw, 1, st);
       }
       if (tlo) launch_split_lo(kbw, kbw, tbig, KB, tlo, KB, st);
@@ -537,7 +607,10 @@ static int tsqr_common(cqr_context* c, float* dA, int lda, long long m, int n, f
       }
     }
   }
-  run_tsqr_factor(c, plan, dA, lda, keep, dR, ldr);
+  {
+    ProfScope ps(c, CQR_PROF_PANEL, 2.0 * m * n * n, 4.0 * (double)m * n * (keep ? 2 : 1));
+    run_tsqr_factor(c, plan, dA, lda, keep, dR, ldr);
+  }
   if (keep) { c->ts_plan = plan; c->ts_a = dA; c->ts_lda = lda; c->ts_valid = true; }
   return (int)cudaGetLastError();
 }

@@ -10,8 +10,9 @@
 // {l, l+32, ...}.  A column's dot products are warp-shuffle reductions (north_star: "reflectors
 // generated with warp-shuffle norm/dot reductions"); the only block-level traffic is the
 // 1 KB reflector broadcast through shared memory, one __syncthreads per column.
-// Reflector maths follow qr.c:144-167 (beta = -sign*norm, u = x0 + sign*norm, tau = sign*u/norm)
-// except that a zero tail gives tau = 0 (H = I) instead of the reference's NaN.
+// Reflector maths follow qr.c:144-167 (beta = -sign*norm, u = x0 + sign*norm, tau = sign*u/norm;
+// a length-1 reflector gets tau = 2 like the reference) except that an all-zero column gives
+// tau = 0 (H = I) instead of the reference's NaN.
 #include "common.cuh"
 
 namespace cqr {
@@ -29,7 +30,6 @@ __global__ void __launch_bounds__(256, (RI <= 4 ? 3 : 2)) tile_qr_kernel(TileQRP
   const int t = blockIdx.x;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   __shared__ float vs[2][TH];
-  __shared__ float stau[2];
 
   const int rows = tile_rows_of(p.a, t, TH);
   float* src = p.a.base + (long long)t * p.a.tile_stride;
@@ -47,60 +47,92 @@ __global__ void __launch_bounds__(256, (RI <= 4 ? 3 : 2)) tile_qr_kernel(TileQRP
     }
   }
 
+  // One __syncthreads and ONE round of warp reductions per column: the pivot column x (rows >= j,
+  // zero above) is broadcast through shared memory, every warp forms s_c = x^T a_c for its live
+  // columns together with s_j = x^T x, and derives the reflector scalars redundantly:
+  //   beta = -sign(alpha) sqrt(s_j), u = alpha - beta, tau = -u / beta      (qr.c:149-152)
+  //   v = (x - beta e_j) / u  =>  v^T a_c = (s_c - beta a_jc) / u
+  // so no second reduction (norm first, then dots) and no second barrier is needed.
 #pragma unroll
   for (int ci = 0; ci < 8; ++ci) {
     for (int wj = 0; wj < 8; ++wj) {
       const int j = 8 * ci + wj;   // pivot column; owned by warp wj, register slot ci
       if (j >= nc) break;
       const int buf = j & 1;
+      const int rj = ci >> 2;      // row j lives in lane j%32, register slot j/32 = ci/4 (static after unroll)
       if (w == wj) {
-        const int rj = ci >> 2;   // row j lives in lane j%32, register slot j/32 = ci/4 (static after unroll)
-        float ss = 0.f;
-#pragma unroll
-        for (int ri = 0; ri < RI; ++ri) {
-          const float x = a[ci][ri];
-          ss += (l + 32 * ri > j) ? x * x : 0.f;
-        }
-        ss = warp_sum(ss);
-        const float alpha = __shfl_sync(kFull, a[ci][rj], j & 31);
-        float beta = alpha, tau = 0.f, u = 1.f;
-        if (ss != 0.f) {
-          const float nrm = sqrtf(alpha * alpha + ss);
-          beta = (alpha < 0.f) ? nrm : -nrm;
-          u = alpha - beta;
-          tau = (beta - alpha) / beta;
-        }
 #pragma unroll
         for (int ri = 0; ri < RI; ++ri) {
           const int r = l + 32 * ri;
-          const float x = a[ci][ri];
-          const float vv = (r > j) ? x / u : (r == j ? 1.f : 0.f);
-          vs[buf][r] = vv;
-          if (r > j) a[ci][ri] = vv;
-          else if (r == j) a[ci][ri] = beta;
-        }
-        if (l == 0) {
-          stau[buf] = tau;
-          p.tau[(long long)t * p.tau_stride + j] = tau;
+          vs[buf][r] = (r >= j) ? a[ci][ri] : 0.f;
         }
       }
       __syncthreads();
-      const float tau = stau[buf];
-      if (tau != 0.f) {
-        float v[RI];
+      float x[RI];
 #pragma unroll
-        for (int ri = 0; ri < RI; ++ri) v[ri] = vs[buf][l + 32 * ri];
+      for (int ri = 0; ri < RI; ++ri) x[ri] = vs[buf][l + 32 * ri];
+      const float alpha = vs[buf][j];
+      // Branch-free over the (compile-time) live register slots c2 >= ci so the dot products and
+      // the shuffle chains of all columns interleave; slot ci is live only in warps w > wj and is
+      // masked out of the update below.  red[0] = x^T x, red[1 + c2 - ci] = x^T a_c2.
+      constexpr int NLIVE = 8;   // upper bound; entries below ci are never touched after unrolling
+      float red[NLIVE + 1], ajc[NLIVE];
+      red[0] = 0.f;
 #pragma unroll
-        for (int c2 = ci; c2 < 8; ++c2) {
-          if (c2 > ci || w > wj) {
-            float d = 0.f;
+      for (int ri = 0; ri < RI; ++ri) red[0] = fmaf(x[ri], x[ri], red[0]);
 #pragma unroll
-            for (int ri = 0; ri < RI; ++ri) d = fmaf(v[ri], a[c2][ri], d);
-            d = warp_sum(d) * tau;
+      for (int c2 = 0; c2 < 8; ++c2) {
+        red[1 + c2] = 0.f;
+        ajc[c2] = 0.f;
+        if (c2 >= ci) {
 #pragma unroll
-            for (int ri = 0; ri < RI; ++ri) a[c2][ri] = fmaf(-d, v[ri], a[c2][ri]);
+          for (int ri = 0; ri < RI; ++ri) red[1 + c2] = fmaf(x[ri], a[c2][ri], red[1 + c2]);
+          ajc[c2] = __shfl_sync(kFull, a[c2][rj], j & 31);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {   // stage-wise so all live chains overlap; guards fold after unrolling ci
+        float t[NLIVE + 1];
+        t[0] = __shfl_xor_sync(kFull, red[0], o);
+#pragma unroll
+        for (int c2 = 0; c2 < 8; ++c2)
+          if (c2 >= ci) t[1 + c2] = __shfl_xor_sync(kFull, red[1 + c2], o);
+        red[0] += t[0];
+#pragma unroll
+        for (int c2 = 0; c2 < 8; ++c2)
+          if (c2 >= ci) red[1 + c2] += t[1 + c2];
+      }
+      const float sj = red[0];
+      float beta = 0.f, tau = 0.f, inv_u = 0.f, u = 1.f;
+      if (sj != 0.f) {
+        const float nrm = sqrtf(sj);
+        beta = (alpha < 0.f) ? nrm : -nrm;
+        u = alpha - beta;
+        inv_u = 1.f / u;
+        tau = -u / beta;
+      }
+      // a_c -= w_c v with v = x / u except v_j = 1: fold 1/u into w_c and patch x_j := u instead
+      if ((j & 31) == l) x[rj] = u;
+      const float scale = tau * inv_u * inv_u;
+#pragma unroll
+      for (int c2 = 0; c2 < 8; ++c2) {
+        if (c2 >= ci) {
+          float wc = scale * (red[1 + c2] - beta * ajc[c2]);
+          if (c2 == ci && w <= wj) wc = 0.f;
+#pragma unroll
+          for (int ri = 0; ri < RI; ++ri) a[c2][ri] = fmaf(-wc, x[ri], a[c2][ri]);
+        }
+      }
+      if (w == wj) {
+        if (sj != 0.f) {
+#pragma unroll
+          for (int ri = 0; ri < RI; ++ri) {
+            const int r = l + 32 * ri;
+            if (r > j) a[ci][ri] = x[ri] * inv_u;
+            else if (r == j) a[ci][ri] = beta;
           }
         }
+        if (l == 0) p.tau[(long long)t * p.tau_stride + j] = tau;
       }
     }
   }
@@ -179,16 +211,21 @@ __global__ void __launch_bounds__(256, (RI <= 4 ? 3 : 2)) tile_apply_q_kernel(Ti
       const int r = l + 32 * ri;
       v[ri] = (r > j) ? sv[r + j * TH] : (r == j ? 1.f : 0.f);
     }
+    // all 8 register columns unconditionally (columns >= nc hold zeros): no branches, so the eight
+    // dot-product / shuffle chains overlap
+    float d[8];
 #pragma unroll
     for (int ci = 0; ci < 8; ++ci) {
-      if (w + 8 * ci < nc) {
-        float d = 0.f;
+      d[ci] = 0.f;
 #pragma unroll
-        for (int ri = 0; ri < RI; ++ri) d = fmaf(v[ri], y[ci][ri], d);
-        d = warp_sum(d) * tau;
+      for (int ri = 0; ri < RI; ++ri) d[ci] = fmaf(v[ri], y[ci][ri], d[ci]);
+    }
+    warp_sum_n(d);
 #pragma unroll
-        for (int ri = 0; ri < RI; ++ri) y[ci][ri] = fmaf(-d, v[ri], y[ci][ri]);
-      }
+    for (int ci = 0; ci < 8; ++ci) {
+      const float dc = d[ci] * tau;
+#pragma unroll
+      for (int ri = 0; ri < RI; ++ri) y[ci][ri] = fmaf(-dc, v[ri], y[ci][ri]);
     }
   }
 

@@ -220,7 +220,7 @@ def test_apply_q_and_qt_roundtrip(pkg, torch, ctx):
     ctx.apply_q(dA, tau, dC, trans=False)
     ctx.synchronize()
     back = host(dC)
-    assert np.linalg.norm(back - C) / np.linalg.norm(C) < 50 * metrics.EPS32
+    assert np.linalg.norm(back - C) / np.linalg.norm(C) < 10 * n * metrics.EPS32   # ||Q Q^T - I|| scale
     # Q^T A = R: apply Q^T to A itself
     dA2 = dev(pkg, torch, A)
     ctx.apply_q(dA, tau, dA2, trans=True)
@@ -372,7 +372,7 @@ def test_square_8192_properties(pkg, torch, ctx):
     assert be <= metrics.TOL_BACKWARD
     G = A0.t().double() @ A0.double()
     Rd = R.double()
-    assert float((Rd.t() @ Rd - G).norm() / G.norm()) < 1e-5
+    assert float((Rd.t() @ Rd - G).norm() / G.norm()) / (n * metrics.EPS32) <= metrics.TOL_BACKWARD
     Q = pkg.colmajor(m, 256)
     ctx.form_q(A, tau, Q)                        # first 256 columns of Q
     ctx.synchronize()

@@ -55,7 +55,11 @@ struct cqr_context {
   float* ts_a = nullptr;
   long long ts_lda = 0;
   bool ts_valid = false;
-  int opt_gemm = 1, opt_outer = 256, opt_tile_rows = 256, opt_splitk = 0;
+  // look-ahead: panel work of block K+1 runs on `side` while block K's trailing update runs on `stream`
+  cudaStream_t side = nullptr;
+  cudaStream_t cur = nullptr;      // stream the launch helpers use right now (nullptr = `stream`)
+  cudaEvent_t ev_start = nullptr, ev_a = nullptr, ev_panel[2] = {nullptr, nullptr};
+  int opt_gemm = 1, opt_outer = 256, opt_tile_rows = 256, opt_splitk = 0, opt_lookahead = 1;
   long long launches0 = 0;
   cudaError_t last = cudaSuccess;
   // optional per-kernel-class timing (cqr_profile_begin/end): CUDA events around each launch group
@@ -74,6 +78,8 @@ namespace {
     if (e__ != cudaSuccess) return (int)e__; \
   } while (0)
 
+inline cudaStream_t cur_stream(cqr_context* c) { return c->cur ? c->cur : c->stream; }
+
 cudaEvent_t prof_event(cqr_context* c) {
   if (c->ev_used == c->ev_pool.size()) {
     cudaEvent_t e;
@@ -85,11 +91,12 @@ cudaEvent_t prof_event(cqr_context* c) {
 
 // RAII scope: when profiling is on, brackets the launches made inside it with two events.
 struct ProfScope {
-  cqr_context* c; int idx = -1; long long l0 = 0;
+  cqr_context* c; int idx = -1; long long l0 = 0; cudaStream_t s0 = nullptr;
   ProfScope(cqr_context* ctx, int cat, double flops, double bytes) : c(ctx) {
     if (!c->prof_on) return;
     cqr_context::ProfRec r{cat, flops, bytes, 0, prof_event(c), prof_event(c)};
-    cudaEventRecord(r.e0, c->stream);
+    s0 = cur_stream(c);
+    cudaEventRecord(r.e0, s0);
     l0 = g_launches;
     c->prof.push_back(r);
     idx = (int)c->prof.size() - 1;
@@ -97,7 +104,7 @@ struct ProfScope {
   void finish() {
     if (idx < 0) return;
     c->prof[idx].launches = g_launches - l0;
-    cudaEventRecord(c->prof[idx].e1, c->stream);
+    cudaEventRecord(c->prof[idx].e1, s0);
     idx = -1;
   }
   ~ProfScope() { finish(); }
@@ -169,7 +176,7 @@ void run_tsqr_factor(cqr_context* c, const TsqrPlan& P, float* a, long long lda,
     p.fan = P.fan;
     if (l == L - 1) { p.r_out = r; p.r_tile_stride = 0; p.r_ld = ldr; p.r_rows = P.n; p.fan = 1; }
     else { p.r_out = P.lv[l + 1].store; p.r_tile_stride = (long long)P.th * 64; p.r_ld = P.th; p.r_rows = CQR_SLOT; }
-    launch_tile_qr(p, P.lv[l].tiles, P.th, c->stream);
+    launch_tile_qr(p, P.lv[l].tiles, P.th, cur_stream(c));
   }
 }
 
@@ -187,7 +194,7 @@ void run_tsqr_form_q(cqr_context* c, const TsqrPlan& P, const float* a, long lon
     else { p.x = P.lv[l + 1].xbuf; p.x_tile_stride = (long long)P.th * 64; p.x_ld = P.th; p.x_rows = P.n; p.fan = P.fan; }
     if (l == 0) { p.out.base = q; p.out.tile_stride = P.th; p.out.ld = ldq; p.out.rows_total = P.m; }
     else { p.out.base = P.lv[l].xbuf; p.out.tile_stride = (long long)P.th * 64; p.out.ld = P.th; p.out.rows_total = P.lv[l].rows_total; }
-    launch_tile_apply_q(p, P.lv[l].tiles, P.th, c->stream);
+    launch_tile_apply_q(p, P.lv[l].tiles, P.th, cur_stream(c));
   }
 }
 
@@ -217,11 +224,11 @@ void gemm_tn(cqr_context* c, int M, int N, int K, Operand A, Operand B, float* p
     // algorithmic traffic: both operands read once (hi + lo on the tensor path), partials written
     ProfScope ps(c, CQR_PROF_GEMM_TN, 2.0 * M * N * K, 4.0 * ((double)K * (M + N) * (A.lo ? 2 : 1) + (double)M * N * splits));
     if (c->opt_gemm == 1 && A.lo && B.lo)
-      done = launch_gemm_tn_umma(M, N, K, A.hi, A.lo, A.ld, B.hi, B.lo, B.ld, part, ldp, splits, stride, c->stream);
-    if (!done) launch_gemm_tn_simt(M, N, K, A.hi, A.ld, B.hi, B.ld, part, ldp, splits, stride, c->stream);
+      done = launch_gemm_tn_umma(M, N, K, A.hi, A.lo, A.ld, B.hi, B.lo, B.ld, part, ldp, splits, stride, cur_stream(c));
+    if (!done) launch_gemm_tn_simt(M, N, K, A.hi, A.ld, B.hi, B.ld, part, ldp, splits, stride, cur_stream(c));
   }
   ProfScope ps2(c, CQR_PROF_MISC, 0.0, 4.0 * M * N * (splits + 2));
-  launch_reduce_splits(M, N, part, ldp, stride, splits, d, ldd, d_lo, ldd, c->stream);
+  launch_reduce_splits(M, N, part, ldp, stride, splits, d, ldd, d_lo, ldd, cur_stream(c));
 }
 
 void gemm_nn(cqr_context* c, int M, int N, int K, float alpha, Operand A, Operand B, float beta, float* d,
@@ -231,8 +238,8 @@ void gemm_nn(cqr_context* c, int M, int N, int K, float alpha, Operand A, Operan
   ProfScope ps(c, CQR_PROF_GEMM_NN, 2.0 * M * N * K,
                4.0 * ((double)M * N * ((beta != 0.f ? 1 : 0) + 1 + (d_lo ? 1 : 0)) + (double)K * (M + N) * (A.lo ? 2 : 1)));
   if (c->opt_gemm == 1 && A.lo && B.lo)
-    done = launch_gemm_nn_umma(M, N, K, alpha, A.hi, A.lo, A.ld, B.hi, B.lo, B.ld, beta, d, ldd, d_lo, ldd, c->stream);
-  if (!done) launch_gemm_nn_simt(M, N, K, alpha, A.hi, A.ld, B.hi, B.ld, beta, d, ldd, d_lo, ldd, c->stream);
+    done = launch_gemm_nn_umma(M, N, K, alpha, A.hi, A.lo, A.ld, B.hi, B.lo, B.ld, beta, d, ldd, d_lo, ldd, cur_stream(c));
+  if (!done) launch_gemm_nn_simt(M, N, K, alpha, A.hi, A.ld, B.hi, B.ld, beta, d, ldd, d_lo, ldd, cur_stream(c));
 }
 
 constexpr int kMaxSplits = 32;
@@ -307,6 +314,14 @@ int cqr_create(cqr_context** out, int device) {
     return (int)cudaErrorNoKernelImageForDevice;
   }
   c->launches0 = g_launches;
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  CQR_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi));
+  CQR_CUDA(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+  CQR_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+  CQR_CUDA(cudaEventCreateWithFlags(&c->ev_panel[0], cudaEventDisableTiming));
+  CQR_CUDA(cudaEventCreateWithFlags(&c->ev_panel[1], cudaEventDisableTiming));
+  if (const char* e = getenv("CQR_LOOKAHEAD")) c->opt_lookahead = atoi(e) != 0;
   if (const char* e = getenv("CQR_GEMM")) c->opt_gemm = (strcmp(e, "simt") == 0) ? 0 : 1;   // debugging aid
   *out = c;
   return 0;
@@ -319,6 +334,8 @@ int cqr_destroy(cqr_context* c) {
   if (c->ws) cudaFree(c->ws);
   if (c->ts) cudaFree(c->ts);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+  for (cudaEvent_t e : {c->ev_start, c->ev_a, c->ev_panel[0], c->ev_panel[1]}) if (e) cudaEventDestroy(e);
   delete c;
   return 0;
 }
@@ -332,6 +349,7 @@ int cqr_set_option(cqr_context* c, int opt, int v) {
     case CQR_OPT_OUTER_BLOCK: if (v < 64 || v > 512 || v % 64) return CQR_EINVAL; c->opt_outer = v; return 0;
     case CQR_OPT_TILE_ROWS: if (v != 128 && v != 256) return CQR_EINVAL; c->opt_tile_rows = v; return 0;
     case CQR_OPT_SPLITK: if (v < 0 || v > kMaxSplits) return CQR_EINVAL; c->opt_splitk = v; return 0;
+    case CQR_OPT_LOOKAHEAD: if (v != 0 && v != 1) return CQR_EINVAL; c->opt_lookahead = v; return 0;
   }
   return CQR_EINVAL;
 }
@@ -343,6 +361,7 @@ int cqr_get_option(cqr_context* c, int opt, int* v) {
     case CQR_OPT_OUTER_BLOCK: *v = c->opt_outer; return 0;
     case CQR_OPT_TILE_ROWS: *v = c->opt_tile_rows; return 0;
     case CQR_OPT_SPLITK: *v = c->opt_splitk; return 0;
+    case CQR_OPT_LOOKAHEAD: *v = c->opt_lookahead; return 0;
   }
   return CQR_EINVAL;
 }
@@ -447,38 +466,47 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
   const int KB = c->opt_outer < n ? c->opt_outer : (int)round_up(n, 64);
   const bool tensor = tensor_ok(c, dA, lda) && m >= 128 && n > 64;
   const long long ldv = round_up(m, 4);
+  const int nblk = (n + KB - 1) / KB;
+  const bool look = c->opt_lookahead && nblk > 1;
   const int ncmax = n > 64 ? n - 64 : 1;
 
+  struct BlockBufs { float *vbuf, *vlo, *tbig, *tlo; } bb[2];
   TsqrPlan plan;
-  float *vbuf = nullptr, *vlo = nullptr, *tbig = nullptr, *tlo = nullptr, *gram = nullptr, *gpart = nullptr;
-  float *qthin = nullptr, *rt = nullptr, *uinv = nullptr, *alo = nullptr;
-  BlockWs bw{};
+  float *gram = nullptr, *gpart = nullptr, *qthin = nullptr, *rt = nullptr, *uinv = nullptr, *alo = nullptr;
+  BlockWs bw_main{}, bw_side{};
   for (int pass = 0; pass < 2; ++pass) {
     Carver cv(pass ? c->ws : nullptr);
     plan_tsqr(plan, m, n < 64 ? n : 64, th, cv);
-    vbuf = cv.take(ldv * KB);
-    vlo = tensor ? cv.take(ldv * KB) : nullptr;
-    tbig = cv.take((long long)KB * KB);
-    tlo = tensor ? cv.take((long long)KB * KB) : nullptr;
+    for (int i = 0; i < 2; ++i) {
+      bb[i].vbuf = cv.take(ldv * KB);
+      bb[i].vlo = tensor ? cv.take(ldv * KB) : nullptr;
+      bb[i].tbig = cv.take((long long)KB * KB);
+      bb[i].tlo = tensor ? cv.take((long long)KB * KB) : nullptr;
+    }
     gram = cv.take((long long)KB * KB);
     gpart = cv.take((long long)KB * KB * kMaxSplits);
     qthin = cv.take(ldv * 64);
     rt = cv.take(64 * 64);
     uinv = cv.take(64 * 64);
     alo = tensor ? cv.take((long long)lda * n) : nullptr;
-    bw = carve_block_ws(cv, KB, ncmax, tensor);
+    bw_main = carve_block_ws(cv, KB, ncmax, tensor);
+    bw_side = carve_block_ws(cv, 64, KB, tensor);   // inner updates: 64 reflectors on < KB columns
     if (!pass) { int rc = ws_ensure(c, cv.off); if (rc) return rc; }
   }
   if (tensor) launch_split_lo(m, n, dA, lda, alo, lda, st);
 
-  for (int K0 = 0; K0 < n; K0 += KB) {
+  // Panels + inner updates of the outer block starting at column K0 (runs on the current stream):
+  // fills B.vbuf/B.tbig (aggregated V and T of the block) and dtau[K0 .. K0+kbw).
+  auto do_panels = [&](int K0, BlockBufs& B) {
+    cudaStream_t s = cur_stream(c);
     const int kbw = (n - K0 < KB) ? n - K0 : KB;
     const long long mK = m - K0;
-    launch_fill_zero(vbuf, ldv, mK, kbw, st);
-    if (vlo) launch_fill_zero(vlo, ldv, mK, kbw, st);
+    launch_fill_zero(B.vbuf, ldv, mK, kbw, s);
+    if (B.vlo) launch_fill_zero(B.vlo, ldv, mK, kbw, s);
     for (int j0 = K0; j0 < K0 + kbw; j0 += 64) {
       const int b = (K0 + kbw - j0 < 64) ? K0 + kbw - j0 : 64;
       const long long mp = m - j0;
+      const int off = j0 - K0;
       float* ap = dA + j0 + (long long)j0 * lda;
       // (1) panel TSQR: R_tsqr + implicit Q   (2) explicit thin Q   (3) Householder reconstruction
       TsqrPlan pp;
@@ -489,40 +517,83 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
       run_tsqr_form_q(c, pp, ap, lda, nullptr, 0, b, qthin, ldv);
       HrParams hp{};
       hp.q = qthin; hp.ldq = ldv; hp.rt = rt; hp.ldrt = 64; hp.a = ap; hp.lda = lda; hp.tau = dtau + j0;
-      hp.t = tbig + (j0 - K0) + (long long)(j0 - K0) * KB; hp.ldt = KB; hp.uinv = uinv;
-      hp.vbuf = vbuf + (j0 - K0) + (long long)(j0 - K0) * ldv; hp.ldv = ldv;
-      hp.vlo = vlo ? vlo + (j0 - K0) + (long long)(j0 - K0) * ldv : nullptr;
+      hp.t = B.tbig + off + (long long)off * KB; hp.ldt = KB; hp.uinv = uinv;
+      hp.vbuf = B.vbuf + off + (long long)off * ldv; hp.ldv = ldv;
+      hp.vlo = B.vlo ? B.vlo + off + (long long)off * ldv : nullptr;
       hp.mp = mp; hp.b = b;
-      launch_hr_top(hp, st);
-      launch_hr_rows(hp, st);
+      launch_hr_top(hp, s);
+      launch_hr_rows(hp, s);
       pps.finish();
       // (4) inner update: remaining columns of this outer block
       const int ninner = K0 + kbw - (j0 + b);
       if (ninner > 0) {
         float* cp = dA + j0 + (long long)(j0 + b) * lda;
         float* cpl = alo ? alo + j0 + (long long)(j0 + b) * lda : nullptr;
-        if (tlo) launch_split_lo(b, b, hp.t, KB, tlo + (j0 - K0) + (long long)(j0 - K0) * KB, KB, st);
+        float* tl = B.tlo ? B.tlo + off + (long long)off * KB : nullptr;
+        if (tl) launch_split_lo(b, b, hp.t, KB, tl, KB, s);
         Operand V{hp.vbuf, hp.vlo, ldv};
-        Operand T{hp.t, tlo ? tlo + (j0 - K0) + (long long)(j0 - K0) * KB : nullptr, KB};
-        apply_block(c, mp, b, ninner, V, T, cp, cpl, lda, 1, bw);
+        Operand T{hp.t, tl, KB};
+        apply_block(c, mp, b, ninner, V, T, cp, cpl, lda, 1, bw_side);
       }
     }
-    // (5) outer update with the aggregated (V, T) of the whole block
-    const int nrest = n - (K0 + kbw);
-    if (nrest > 0) {
-      Operand V{vbuf, vlo, ldv};
+    // aggregated T of the whole block (only needed when something is left to update)
+    if (n - (K0 + kbw) > 0) {
+      Operand V{B.vbuf, B.vlo, ldv};
       if (kbw > 64) {
         gemm_tn(c, kbw, kbw, (int)mK, V, V, gpart, gram, KB, nullptr, kMaxSplits);
         ProfScope pbt(c, CQR_PROF_MISC, 0.0, 0.0);
-        launch_build_t(gram, KB, dtau + K0, tbig, KB, kbw, 1, st);
+        launch_build_t(gram, KB, dtau + K0, B.tbig, KB, kbw, 1, s);
       }
-      if (tlo) launch_split_lo(kbw, kbw, tbig, KB, tlo, KB, st);
-      Operand T{tbig, tlo, KB};
-      float* cp = dA + K0 + (long long)(K0 + kbw) * lda;
-      float* cpl = alo ? alo + K0 + (long long)(K0 + kbw) * lda : nullptr;
-      apply_block(c, mK, kbw, nrest, V, T, cp, cpl, lda, 1, bw);
+      if (B.tlo) launch_split_lo(kbw, kbw, B.tbig, KB, B.tlo, KB, s);
     }
+  };
+  // Trailing update of columns [c0, c1) with block K0's aggregated reflector (current stream).
+  auto do_update = [&](int K0, BlockBufs& B, int c0, int c1) {
+    if (c1 <= c0) return;
+    const int kbw = (n - K0 < KB) ? n - K0 : KB;
+    Operand V{B.vbuf, B.vlo, ldv};
+    Operand T{B.tbig, B.tlo, KB};
+    float* cp = dA + K0 + (long long)c0 * lda;
+    float* cpl = alo ? alo + K0 + (long long)c0 * lda : nullptr;
+    apply_block(c, m - K0, kbw, c1 - c0, V, T, cp, cpl, lda, 1, bw_main);
+  };
+
+  if (!look) {
+    for (int blk = 0; blk < nblk; ++blk) {
+      const int K0 = blk * KB;
+      const int kbw = (n - K0 < KB) ? n - K0 : KB;
+      do_panels(K0, bb[0]);
+      do_update(K0, bb[0], K0 + kbw, n);
+    }
+    return (int)cudaGetLastError();
   }
+
+  // Look-ahead: once the next block's columns are updated (ev_a) its panel work starts on the side
+  // stream while the main stream finishes the rest of the trailing update.
+  CQR_CUDA(cudaEventRecord(c->ev_start, st));
+  CQR_CUDA(cudaStreamWaitEvent(c->side, c->ev_start, 0));
+  c->cur = c->side;
+  do_panels(0, bb[0]);
+  CQR_CUDA(cudaEventRecord(c->ev_panel[0], c->side));
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int K0 = blk * KB;
+    const int kbw = (n - K0 < KB) ? n - K0 : KB;
+    const int cnext = K0 + kbw;
+    const int nrest = n - cnext;
+    c->cur = nullptr;
+    CQR_CUDA(cudaStreamWaitEvent(st, c->ev_panel[blk & 1], 0));
+    if (nrest <= 0) break;
+    const int la = nrest < KB ? nrest : KB;
+    do_update(K0, bb[blk & 1], cnext, cnext + la);
+    CQR_CUDA(cudaEventRecord(c->ev_a, st));
+    CQR_CUDA(cudaStreamWaitEvent(c->side, c->ev_a, 0));
+    c->cur = c->side;
+    do_panels(cnext, bb[(blk + 1) & 1]);
+    CQR_CUDA(cudaEventRecord(c->ev_panel[(blk + 1) & 1], c->side));
+    c->cur = nullptr;
+    do_update(K0, bb[blk & 1], cnext + la, n);
+  }
+  c->cur = nullptr;
   return (int)cudaGetLastError();
 }
 
@@ -675,13 +746,18 @@ int cqr_geqrf_batched(cqr_context* c, float* dA, int lda, long long stride, int 
 // ================================================================================================
 // Legacy entry points (host pointers, blocking, print + exit(1) on failure like qr.cu:467-471)
 // ================================================================================================
+// One context per device, created on first use for the calling thread's CURRENT device.  The
+// reference hard-wires device 0 (qr.cu:480,711), which is what the current device is in a process
+// that never calls cudaSetDevice; one-process-per-GPU launchers select their GPU before calling in.
 static cqr_context* legacy_ctx() {
-  static cqr_context* c = nullptr;
-  if (!c) {
-    int rc = cqr_create(&c, 0);   // device 0 hard-wired, qr.cu:480,711
+  static cqr_context* ctxs[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { printf("CUDA error on line %i: no device\n", __LINE__); exit(1); }
+  if (!ctxs[dev]) {
+    int rc = cqr_create(&ctxs[dev], dev);
     if (rc) { printf("CUDA error on line %i: %d\n", __LINE__, rc); exit(1); }
   }
-  return c;
+  return ctxs[dev];
 }
 
 #define LEGACY_CHECK(x)                                                          \

@@ -44,7 +44,20 @@ __global__ void __launch_bounds__(256) hr_top_kernel(HrParams p) {
     if (ti > j && ti < b) {
       const float li = M[ti][j] / pv;
       if (tk == 0) L[ti][j] = li;
-      for (int k = j + 1 + tk; k < b; k += 4) M[ti][k] = fmaf(-li, M[j][k], M[ti][k]);
+      // stage through registers: the compiler cannot prove M[ti][.] and M[j][.] do not alias and would
+      // otherwise serialise load -> fma -> store per element
+      float mi[16], mj[16];
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int k = j + 1 + tk + 4 * it;
+        mi[it] = (k < b) ? M[ti][k] : 0.f;
+        mj[it] = (k < b) ? M[j][k] : 0.f;
+      }
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int k = j + 1 + tk + 4 * it;
+        if (k < b) M[ti][k] = fmaf(-li, mj[it], mi[it]);
+      }
     }
   }
   __syncthreads();
@@ -65,11 +78,33 @@ __global__ void __launch_bounds__(256) hr_top_kernel(HrParams p) {
     if (tk < 2) {
       if (ti <= k) {
         const float tik = Tm[ti][k];
-        for (int k2 = k + 1 + tk; k2 < b; k2 += 2) Tm[ti][k2] = fmaf(-tik, L[k2][k], Tm[ti][k2]);
+        float tv[32], lv[32];
+#pragma unroll
+        for (int it = 0; it < 32; ++it) {
+          const int k2 = k + 1 + tk + 2 * it;
+          tv[it] = (k2 < b) ? Tm[ti][k2] : 0.f;
+          lv[it] = (k2 < b) ? L[k2][k] : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < 32; ++it) {
+          const int k2 = k + 1 + tk + 2 * it;
+          if (k2 < b) Tm[ti][k2] = fmaf(-tik, lv[it], tv[it]);
+        }
       }
     } else if (ti >= q && ti < b) {
       const float xq = Ui[q][ti];
-      for (int i = tk - 2; i < q; i += 2) Ui[i][ti] = fmaf(-M[i][q], xq, Ui[i][ti]);
+      float uv[32], mv[32];
+#pragma unroll
+      for (int it = 0; it < 32; ++it) {
+        const int i = tk - 2 + 2 * it;
+        uv[it] = (i < q) ? Ui[i][ti] : 0.f;
+        mv[it] = (i < q) ? M[i][q] : 0.f;
+      }
+#pragma unroll
+      for (int it = 0; it < 32; ++it) {
+        const int i = tk - 2 + 2 * it;
+        if (i < q) Ui[i][ti] = fmaf(-mv[it], xq, uv[it]);
+      }
     }
   }
   __syncthreads();

@@ -83,7 +83,6 @@ struct HrParams {
   float* t;        long long ldt;     // b x b compact-WY T (upper)
   float* uinv;                        // 64 x 64 scratch: inverse of the LU's U factor
   float* vbuf;     long long ldv;     // explicit Y (unit diagonal, zeros above), mp x b
-  float* vlo;                         // optional: Y - tf32_hi(Y) (nullptr = skip)
   long long mp; int b;
 };
 void launch_hr_top(const HrParams& p, cudaStream_t s);
@@ -98,14 +97,12 @@ void launch_build_t(const float* g, long long ldg, const float* tau, float* t, l
 // D[z](M x N) = A(:, z-th K chunk)^T * B(z-th K chunk, :) ; D[z] = d + z * d_split_stride
 void launch_gemm_tn_simt(int M, int N, int K, const float* a, long long lda, const float* b, long long ldb,
                          float* d, long long ldd, int splits, long long d_split_stride, cudaStream_t s);
-// D = alpha * A * B + beta * D ; optional d_lo = D - tf32_hi(D)
+// D = alpha * A * B + beta * D
 void launch_gemm_nn_simt(int M, int N, int K, float alpha, const float* a, long long lda, const float* b,
-                         long long ldb, float beta, float* d, long long ldd, float* d_lo, long long ldd_lo,
-                         cudaStream_t s);
-// out = sum_z part[z] (M x N, part ld = ldp, stride between parts = stride); optional lo output
+                         long long ldb, float beta, float* d, long long ldd, cudaStream_t s);
+// out = sum_z part[z] (M x N, part ld = ldp, stride between parts = stride)
 void launch_reduce_splits(int M, int N, const float* part, long long ldp, long long stride, int splits, float* out,
-                          long long ldo, float* out_lo, long long ldo_lo, cudaStream_t s);
-void launch_split_lo(int M, int N, const float* a, long long lda, float* lo, long long ldlo, cudaStream_t s);
+                          long long ldo, cudaStream_t s);
 void launch_set_identity(float* a, long long lda, int m, int n, cudaStream_t s);
 void launch_fill_zero(float* a, long long lda, long long m, int n, cudaStream_t s);
 void launch_copy_matrix(long long m, int n, const float* a, long long lda, float* b, long long ldb, cudaStream_t s);
@@ -113,20 +110,18 @@ void launch_copy_matrix(long long m, int n, const float* a, long long lda, float
 void launch_extract_r(const float* a, long long lda, int m, int n, float* r, long long ldr, int r_rows,
                       cudaStream_t s);
 // V extraction from LAPACK-format storage: v(i,j) = i<j ? 0 : i==j ? 1 : a(i,j), for a panel whose
-// diagonal starts at local row d0 of the mp x b block; optional lo copy
+// diagonal starts at local row d0 of the mp x b block
 void launch_extract_v(const float* a, long long lda, long long mp, int b, int d0, float* v, long long ldv,
-                      float* vlo, cudaStream_t s);
+                      cudaStream_t s);
 
 // ---- tcgen05 3xTF32 GEMMs: gemm_umma.cu -------------------------------------------------------
 // Both return false (nothing launched) when shape/alignment rules out the TMA path.
 bool umma_available();
 int umma_effective_splits(int K, int splits);   // K splits the tensor kernel really uses for a request
-bool launch_gemm_tn_umma(int M, int N, int K, const float* a, const float* a_lo, long long lda, const float* b,
-                         const float* b_lo, long long ldb, float* d, long long ldd, int splits,
-                         long long d_split_stride, cudaStream_t s);
-bool launch_gemm_nn_umma(int M, int N, int K, float alpha, const float* a, const float* a_lo, long long lda,
-                         const float* b, const float* b_lo, long long ldb, float beta, float* d, long long ldd,
-                         float* d_lo, long long ldd_lo, cudaStream_t s);
+bool launch_gemm_tn_umma(int M, int N, int K, const float* a, long long lda, const float* b, long long ldb, float* d,
+                         long long ldd, int splits, long long d_split_stride, cudaStream_t s);
+bool launch_gemm_nn_umma(int M, int N, int K, float alpha, const float* a, long long lda, const float* b, long long ldb,
+                         float beta, float* d, long long ldd, cudaStream_t s);
 
 // global launch counter (gpu_launches evidence)
 extern long long g_launches;

@@ -209,11 +209,11 @@ int pick_splits(cqr_context* c, int M, int N, int K, int tile_m, int tile_n) {
   return s < 1 ? 1 : (int)s;
 }
 
-struct Operand { const float* hi; const float* lo; long long ld; };
+struct Operand { const float* p; long long ld; };
 
-// d(M x N) = A^T B through a split-K partial buffer + reduction (also emits d_lo when asked)
+// d(M x N) = A^T B through a split-K partial buffer + reduction
 void gemm_tn(cqr_context* c, int M, int N, int K, Operand A, Operand B, float* part, float* d, long long ldd,
-             float* d_lo, int max_splits) {
+             int max_splits, bool tensor) {
   int splits = pick_splits(c, M, N, K, 128, 128);
   if (splits > max_splits) splits = max_splits;
   splits = umma_effective_splits(K, splits);   // no empty K ranges; the reduction below must agree
@@ -221,57 +221,55 @@ void gemm_tn(cqr_context* c, int M, int N, int K, Operand A, Operand B, float* p
   const long long stride = ldp * N;
   bool done = false;
   {
-    // algorithmic traffic: both operands read once (hi + lo on the tensor path), partials written
-    ProfScope ps(c, CQR_PROF_GEMM_TN, 2.0 * M * N * K, 4.0 * ((double)K * (M + N) * (A.lo ? 2 : 1) + (double)M * N * splits));
-    if (c->opt_gemm == 1 && A.lo && B.lo)
-      done = launch_gemm_tn_umma(M, N, K, A.hi, A.lo, A.ld, B.hi, B.lo, B.ld, part, ldp, splits, stride, cur_stream(c));
-    if (!done) launch_gemm_tn_simt(M, N, K, A.hi, A.ld, B.hi, B.ld, part, ldp, splits, stride, cur_stream(c));
+    // algorithmic traffic: both operands read once, partials written
+    ProfScope ps(c, CQR_PROF_GEMM_TN, 2.0 * M * N * K, 4.0 * ((double)K * (M + N) + (double)M * N * splits));
+    if (tensor && c->opt_gemm == 1)
+      done = launch_gemm_tn_umma(M, N, K, A.p, A.ld, B.p, B.ld, part, ldp, splits, stride, cur_stream(c));
+    if (!done) launch_gemm_tn_simt(M, N, K, A.p, A.ld, B.p, B.ld, part, ldp, splits, stride, cur_stream(c));
   }
-  ProfScope ps2(c, CQR_PROF_MISC, 0.0, 4.0 * M * N * (splits + 2));
-  launch_reduce_splits(M, N, part, ldp, stride, splits, d, ldd, d_lo, ldd, cur_stream(c));
+  ProfScope ps2(c, CQR_PROF_MISC, 0.0, 4.0 * M * N * (splits + 1));
+  launch_reduce_splits(M, N, part, ldp, stride, splits, d, ldd, cur_stream(c));
 }
 
 void gemm_nn(cqr_context* c, int M, int N, int K, float alpha, Operand A, Operand B, float beta, float* d,
-             long long ldd, float* d_lo) {
+             long long ldd, bool tensor) {
   bool done = false;
-  // algorithmic traffic: D read (beta != 0) and written once (+ its lo), A and B read once
+  // algorithmic traffic: D read (beta != 0) and written once, A and B read once
   ProfScope ps(c, CQR_PROF_GEMM_NN, 2.0 * M * N * K,
-               4.0 * ((double)M * N * ((beta != 0.f ? 1 : 0) + 1 + (d_lo ? 1 : 0)) + (double)K * (M + N) * (A.lo ? 2 : 1)));
-  if (c->opt_gemm == 1 && A.lo && B.lo)
-    done = launch_gemm_nn_umma(M, N, K, alpha, A.hi, A.lo, A.ld, B.hi, B.lo, B.ld, beta, d, ldd, d_lo, ldd, cur_stream(c));
-  if (!done) launch_gemm_nn_simt(M, N, K, alpha, A.hi, A.ld, B.hi, B.ld, beta, d, ldd, d_lo, ldd, cur_stream(c));
+               4.0 * ((double)M * N * ((beta != 0.f ? 1 : 0) + 1) + (double)K * (M + N)));
+  if (tensor && c->opt_gemm == 1)
+    done = launch_gemm_nn_umma(M, N, K, alpha, A.p, A.ld, B.p, B.ld, beta, d, ldd, cur_stream(c));
+  if (!done) launch_gemm_nn_simt(M, N, K, alpha, A.p, A.ld, B.p, B.ld, beta, d, ldd, cur_stream(c));
 }
 
 constexpr int kMaxSplits = 32;
 
 struct BlockWs {   // scratch of one block-reflector application with kb reflectors on nc columns
-  float *part, *w, *w_lo, *x, *x_lo;
+  float *part, *w, *x;
   long long ldw;
 };
 
-BlockWs carve_block_ws(Carver& cv, int kb, int nc, bool lo) {
+BlockWs carve_block_ws(Carver& cv, int kb, int nc) {
   BlockWs b{};
   b.ldw = round_up(kb, 4);
   b.part = cv.take(b.ldw * (long long)nc * kMaxSplits);
   b.w = cv.take(b.ldw * nc);
   b.x = cv.take(b.ldw * nc);
-  b.w_lo = lo ? cv.take(b.ldw * nc) : nullptr;
-  b.x_lo = lo ? cv.take(b.ldw * nc) : nullptr;
   return b;
 }
 
 // C <- (I - V op(T) V^T) C.   trans_t = 1: op(T) = T^T (this is Q^T C), 0: op(T) = T (Q C).
 // Replaces trailingUpdateKernel (qr.cu:335-465) and the CPU loop qr.c:255-293.
-void apply_block(cqr_context* c, long long mk, int kb, int nc, Operand V, Operand T, float* C, float* C_lo,
-                 long long ldc, int trans_t, BlockWs& ws) {
+void apply_block(cqr_context* c, long long mk, int kb, int nc, Operand V, Operand T, float* C, long long ldc,
+                 int trans_t, BlockWs& ws, bool tensor) {
   if (nc <= 0 || kb <= 0) return;
-  Operand Cop{C, C_lo, ldc};
-  gemm_tn(c, kb, nc, (int)mk, V, Cop, ws.part, ws.w, ws.ldw, ws.w_lo, kMaxSplits);        // W = V^T C
-  Operand W{ws.w, ws.w_lo, ws.ldw};
-  if (trans_t) gemm_tn(c, kb, nc, kb, T, W, ws.part, ws.x, ws.ldw, ws.x_lo, 1);             // X = T^T W
-  else gemm_nn(c, kb, nc, kb, 1.f, T, W, 0.f, ws.x, ws.ldw, ws.x_lo);                       // X = T W
-  Operand X{ws.x, ws.x_lo, ws.ldw};
-  gemm_nn(c, (int)mk, nc, kb, -1.f, V, X, 1.f, C, ldc, C_lo);                               // C -= V X
+  Operand Cop{C, ldc};
+  gemm_tn(c, kb, nc, (int)mk, V, Cop, ws.part, ws.w, ws.ldw, kMaxSplits, tensor);           // W = V^T C
+  Operand W{ws.w, ws.ldw};
+  if (trans_t) gemm_tn(c, kb, nc, kb, T, W, ws.part, ws.x, ws.ldw, 1, tensor);              // X = T^T W
+  else gemm_nn(c, kb, nc, kb, 1.f, T, W, 0.f, ws.x, ws.ldw, tensor);                        // X = T W
+  Operand X{ws.x, ws.ldw};
+  gemm_nn(c, (int)mk, nc, kb, -1.f, V, X, 1.f, C, ldc, tensor);                             // C -= V X
 }
 
 bool tensor_ok(cqr_context* c, const void* a, long long lda) {
@@ -417,7 +415,7 @@ int cqr_gemm(cqr_context* c, int transA, int M, int N, int K, float alpha, const
   if (transA ? lda < K : lda < M) return CQR_EINVAL;
   cudaSetDevice(c->device);
   if (!transA) {
-    launch_gemm_nn_simt(M, N, K, alpha, dA, lda, dB, ldb, beta, dD, ldd, nullptr, 0, c->stream);
+    launch_gemm_nn_simt(M, N, K, alpha, dA, lda, dB, ldb, beta, dD, ldd, c->stream);
   } else {
     if (alpha != 1.f || beta != 0.f) return CQR_EUNSUPPORTED;
     launch_gemm_tn_simt(M, N, K, dA, lda, dB, ldb, dD, ldd, 1, 0, c->stream);
@@ -425,7 +423,7 @@ int cqr_gemm(cqr_context* c, int transA, int M, int N, int K, float alpha, const
   return (int)cudaGetLastError();
 }
 
-// D = op(A) B on the tcgen05 3xTF32 kernels (operands split into hi/lo in workspace).  Returns
+// D = op(A) B on the tcgen05 3xTF32 kernels (operands are split into hi/lo inside the kernel).  Returns
 // CQR_EUNSUPPORTED when the shape/alignment rules out the TMA path (no silent fallback here).
 int cqr_gemm_tf32x3(cqr_context* c, int transA, int M, int N, int K, const float* dA, int lda, const float* dB, int ldb,
                     float* dD, int ldd) {
@@ -433,25 +431,20 @@ int cqr_gemm_tf32x3(cqr_context* c, int transA, int M, int N, int K, const float
   if (transA ? lda < K : lda < M) return CQR_EINVAL;
   cudaSetDevice(c->device);
   if (!umma_available()) return CQR_EUNSUPPORTED;
-  const int arows = transA ? K : M, acols = transA ? M : K;
-  float *alo = nullptr, *blo = nullptr, *part = nullptr;
+  float* part = nullptr;
   int splits = transA ? umma_effective_splits(K, pick_splits(c, M, N, K, 128, 128)) : 1;
   const long long ldp = round_up(M, 4);
   for (int pass = 0; pass < 2; ++pass) {
     Carver cv(pass ? c->ws : nullptr);
-    alo = cv.take((long long)lda * acols);
-    blo = cv.take((long long)ldb * N);
     part = cv.take(ldp * N * splits);
     if (!pass) { int rc = ws_ensure(c, cv.off); if (rc) return rc; }
   }
-  launch_split_lo(arows, acols, dA, lda, alo, lda, c->stream);
-  launch_split_lo(K, N, dB, ldb, blo, ldb, c->stream);
   bool ok;
   if (transA) {
-    ok = launch_gemm_tn_umma(M, N, K, dA, alo, lda, dB, blo, ldb, part, ldp, splits, ldp * N, c->stream);
-    if (ok) launch_reduce_splits(M, N, part, ldp, ldp * N, splits, dD, ldd, nullptr, 0, c->stream);
+    ok = launch_gemm_tn_umma(M, N, K, dA, lda, dB, ldb, part, ldp, splits, ldp * N, c->stream);
+    if (ok) launch_reduce_splits(M, N, part, ldp, ldp * N, splits, dD, ldd, c->stream);
   } else {
-    ok = launch_gemm_nn_umma(M, N, K, 1.f, dA, alo, lda, dB, blo, ldb, 0.f, dD, ldd, nullptr, 0, c->stream);
+    ok = launch_gemm_nn_umma(M, N, K, 1.f, dA, lda, dB, ldb, 0.f, dD, ldd, c->stream);
   }
   if (!ok) return CQR_EUNSUPPORTED;
   return (int)cudaGetLastError();
@@ -470,30 +463,26 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
   const bool look = c->opt_lookahead && nblk > 1;
   const int ncmax = n > 64 ? n - 64 : 1;
 
-  struct BlockBufs { float *vbuf, *vlo, *tbig, *tlo; } bb[2];
+  struct BlockBufs { float *vbuf, *tbig; } bb[2];
   TsqrPlan plan;
-  float *gram = nullptr, *gpart = nullptr, *qthin = nullptr, *rt = nullptr, *uinv = nullptr, *alo = nullptr;
+  float *gram = nullptr, *gpart = nullptr, *qthin = nullptr, *rt = nullptr, *uinv = nullptr;
   BlockWs bw_main{}, bw_side{};
   for (int pass = 0; pass < 2; ++pass) {
     Carver cv(pass ? c->ws : nullptr);
     plan_tsqr(plan, m, n < 64 ? n : 64, th, cv);
     for (int i = 0; i < 2; ++i) {
       bb[i].vbuf = cv.take(ldv * KB);
-      bb[i].vlo = tensor ? cv.take(ldv * KB) : nullptr;
       bb[i].tbig = cv.take((long long)KB * KB);
-      bb[i].tlo = tensor ? cv.take((long long)KB * KB) : nullptr;
     }
     gram = cv.take((long long)KB * KB);
     gpart = cv.take((long long)KB * KB * kMaxSplits);
     qthin = cv.take(ldv * 64);
     rt = cv.take(64 * 64);
     uinv = cv.take(64 * 64);
-    alo = tensor ? cv.take((long long)lda * n) : nullptr;
-    bw_main = carve_block_ws(cv, KB, ncmax, tensor);
-    bw_side = carve_block_ws(cv, 64, KB, tensor);   // inner updates: 64 reflectors on < KB columns
+    bw_main = carve_block_ws(cv, KB, ncmax);
+    bw_side = carve_block_ws(cv, 64, KB);   // inner updates: 64 reflectors on < KB columns
     if (!pass) { int rc = ws_ensure(c, cv.off); if (rc) return rc; }
   }
-  if (tensor) launch_split_lo(m, n, dA, lda, alo, lda, st);
 
   // Panels + inner updates of the outer block starting at column K0 (runs on the current stream):
   // fills B.vbuf/B.tbig (aggregated V and T of the block) and dtau[K0 .. K0+kbw).
@@ -502,7 +491,6 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
     const int kbw = (n - K0 < KB) ? n - K0 : KB;
     const long long mK = m - K0;
     launch_fill_zero(B.vbuf, ldv, mK, kbw, s);
-    if (B.vlo) launch_fill_zero(B.vlo, ldv, mK, kbw, s);
     for (int j0 = K0; j0 < K0 + kbw; j0 += 64) {
       const int b = (K0 + kbw - j0 < 64) ? K0 + kbw - j0 : 64;
       const long long mp = m - j0;
@@ -519,7 +507,6 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
       hp.q = qthin; hp.ldq = ldv; hp.rt = rt; hp.ldrt = 64; hp.a = ap; hp.lda = lda; hp.tau = dtau + j0;
       hp.t = B.tbig + off + (long long)off * KB; hp.ldt = KB; hp.uinv = uinv;
       hp.vbuf = B.vbuf + off + (long long)off * ldv; hp.ldv = ldv;
-      hp.vlo = B.vlo ? B.vlo + off + (long long)off * ldv : nullptr;
       hp.mp = mp; hp.b = b;
       launch_hr_top(hp, s);
       launch_hr_rows(hp, s);
@@ -528,34 +515,29 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
       const int ninner = K0 + kbw - (j0 + b);
       if (ninner > 0) {
         float* cp = dA + j0 + (long long)(j0 + b) * lda;
-        float* cpl = alo ? alo + j0 + (long long)(j0 + b) * lda : nullptr;
-        float* tl = B.tlo ? B.tlo + off + (long long)off * KB : nullptr;
-        if (tl) launch_split_lo(b, b, hp.t, KB, tl, KB, s);
-        Operand V{hp.vbuf, hp.vlo, ldv};
-        Operand T{hp.t, tl, KB};
-        apply_block(c, mp, b, ninner, V, T, cp, cpl, lda, 1, bw_side);
+        Operand V{hp.vbuf, ldv};
+        Operand T{hp.t, KB};
+        apply_block(c, mp, b, ninner, V, T, cp, lda, 1, bw_side, tensor);
       }
     }
     // aggregated T of the whole block (only needed when something is left to update)
     if (n - (K0 + kbw) > 0) {
-      Operand V{B.vbuf, B.vlo, ldv};
+      Operand V{B.vbuf, ldv};
       if (kbw > 64) {
-        gemm_tn(c, kbw, kbw, (int)mK, V, V, gpart, gram, KB, nullptr, kMaxSplits);
+        gemm_tn(c, kbw, kbw, (int)mK, V, V, gpart, gram, KB, kMaxSplits, tensor);
         ProfScope pbt(c, CQR_PROF_MISC, 0.0, 0.0);
         launch_build_t(gram, KB, dtau + K0, B.tbig, KB, kbw, 1, s);
       }
-      if (B.tlo) launch_split_lo(kbw, kbw, B.tbig, KB, B.tlo, KB, s);
     }
   };
   // Trailing update of columns [c0, c1) with block K0's aggregated reflector (current stream).
   auto do_update = [&](int K0, BlockBufs& B, int c0, int c1) {
     if (c1 <= c0) return;
     const int kbw = (n - K0 < KB) ? n - K0 : KB;
-    Operand V{B.vbuf, B.vlo, ldv};
-    Operand T{B.tbig, B.tlo, KB};
+    Operand V{B.vbuf, ldv};
+    Operand T{B.tbig, KB};
     float* cp = dA + K0 + (long long)c0 * lda;
-    float* cpl = alo ? alo + K0 + (long long)c0 * lda : nullptr;
-    apply_block(c, m - K0, kbw, c1 - c0, V, T, cp, cpl, lda, 1, bw_main);
+    apply_block(c, m - K0, kbw, c1 - c0, V, T, cp, lda, 1, bw_main, tensor);
   };
 
   if (!look) {
@@ -605,38 +587,32 @@ static int apply_q_impl(cqr_context* c, int trans, const float* dA, int lda, int
   const int KB = c->opt_outer < n ? c->opt_outer : (int)round_up(n, 64);
   const bool tensor = tensor_ok(c, dC, ldc) && m >= 128 && nc >= 64 && n >= 64;
   const long long ldv = round_up(m, 4);
-  float *vbuf = nullptr, *vlo = nullptr, *tbig = nullptr, *tlo = nullptr, *gram = nullptr, *gpart = nullptr, *clo = nullptr;
+  float *vbuf = nullptr, *tbig = nullptr, *gram = nullptr, *gpart = nullptr;
   BlockWs bw{};
   for (int pass = 0; pass < 2; ++pass) {
     Carver cv(pass ? c->ws : nullptr);
     vbuf = cv.take(ldv * KB);
-    vlo = tensor ? cv.take(ldv * KB) : nullptr;
     tbig = cv.take((long long)KB * KB);
-    tlo = tensor ? cv.take((long long)KB * KB) : nullptr;
     gram = cv.take((long long)KB * KB);
     gpart = cv.take((long long)KB * KB * kMaxSplits);
-    clo = tensor ? cv.take((long long)ldc * nc) : nullptr;
-    bw = carve_block_ws(cv, KB, nc, tensor);
+    bw = carve_block_ws(cv, KB, nc);
     if (!pass) { int rc = ws_ensure(c, cv.off); if (rc) return rc; }
   }
-  if (tensor) launch_split_lo(m, nc, dC, ldc, clo, ldc, st);
   const int nblk = (n + KB - 1) / KB;
   for (int bi = 0; bi < nblk; ++bi) {
     const int K0 = (trans ? bi : nblk - 1 - bi) * KB;
     const int kbw = (n - K0 < KB) ? n - K0 : KB;
     const long long mK = m - K0;
-    launch_extract_v(dA + K0 + (long long)K0 * lda, lda, mK, kbw, 0, vbuf, ldv, vlo, st);
-    Operand V{vbuf, vlo, ldv};
-    gemm_tn(c, kbw, kbw, (int)mK, V, V, gpart, gram, KB, nullptr, kMaxSplits);
+    launch_extract_v(dA + K0 + (long long)K0 * lda, lda, mK, kbw, 0, vbuf, ldv, st);
+    Operand V{vbuf, ldv};
+    gemm_tn(c, kbw, kbw, (int)mK, V, V, gpart, gram, KB, kMaxSplits, tensor);
     launch_build_t(gram, KB, dtau + K0, tbig, KB, kbw, 0, st);
-    if (tlo) launch_split_lo(kbw, kbw, tbig, KB, tlo, KB, st);
-    Operand T{tbig, tlo, KB};
+    Operand T{tbig, KB};
     // Q = H_0..H_{n-1} applied to [I; 0]: block K0 only touches rows >= K0, and (backward
     // accumulation from the identity) only columns >= K0 are non-zero there.
     const int cskip = (c_is_identity_start && !trans) ? (K0 < nc ? K0 : nc) : 0;
     float* cp = dC + K0 + (long long)cskip * ldc;
-    float* cpl = clo ? clo + K0 + (long long)cskip * ldc : nullptr;
-    apply_block(c, mK, kbw, nc - cskip, V, T, cp, cpl, ldc, trans ? 1 : 0, bw);
+    apply_block(c, mK, kbw, nc - cskip, V, T, cp, ldc, trans ? 1 : 0, bw, tensor);
   }
   return (int)cudaGetLastError();
 }

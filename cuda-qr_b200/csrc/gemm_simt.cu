@@ -63,8 +63,7 @@ __global__ void __launch_bounds__(256) gemm_tn_simt_kernel(int M, int N, int K, 
 __global__ void __launch_bounds__(256) gemm_nn_simt_kernel(int M, int N, int K, float alpha,
                                                            const float* __restrict__ a, long long lda,
                                                            const float* __restrict__ b, long long ldb, float beta,
-                                                           float* __restrict__ d, long long ldd,
-                                                           float* __restrict__ d_lo, long long ldd_lo) {
+                                                           float* __restrict__ d, long long ldd) {
   __shared__ float As[BK][BT + 4];
   __shared__ float Bs[BK][BT + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -107,41 +106,36 @@ __global__ void __launch_bounds__(256) gemm_nn_simt_kernel(int M, int N, int K, 
         float v = alpha * acc[i][j];
         if (beta != 0.f) v = fmaf(beta, *dp, v);
         *dp = v;
-        if (d_lo) d_lo[m + (long long)n * ldd_lo] = tf32_lo(v);
       }
     }
 }
 
 __global__ void reduce_splits_kernel(int M, int N, const float* __restrict__ part, long long ldp, long long stride,
-                                     int splits, float* __restrict__ out, long long ldo, float* __restrict__ out_lo,
-                                     long long ldo_lo) {
+                                     int splits, float* __restrict__ out, long long ldo) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   for (int n = blockIdx.y; n < N; n += gridDim.y) {
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += part[m + (long long)n * ldp + (long long)z * stride];
     out[m + (long long)n * ldo] = s;
-    if (out_lo) out_lo[m + (long long)n * ldo_lo] = tf32_lo(s);
   }
 }
 
-// mode 0: lo = tf32_lo(a); 1: identity; 2: zero; 3: copy; 4: extract R; 5: extract V (+lo)
+// mode 1: identity; 2: zero; 3: copy; 4: extract R; 5: extract V
 template <int MODE>
 __global__ void elementwise_kernel(long long m, int n, const float* __restrict__ a, long long lda, float* __restrict__ b,
-                                   long long ldb, float* __restrict__ b2, int aux) {
+                                   long long ldb, int aux) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   for (int j = blockIdx.y; j < n; j += gridDim.y) {
     float v;
-    if (MODE == 0) v = tf32_lo(a[i + j * lda]);
-    else if (MODE == 1) v = (i == j) ? 1.f : 0.f;
+    if (MODE == 1) v = (i == j) ? 1.f : 0.f;
     else if (MODE == 2) v = 0.f;
     else if (MODE == 3) v = a[i + j * lda];
     else if (MODE == 4) v = (i <= j && i < aux) ? a[i + j * lda] : 0.f;   // aux = rows of A
     else {                                                                 // aux = d0: diagonal offset
       const long long dj = (long long)aux + j;
       v = (i < dj) ? 0.f : (i == dj ? 1.f : a[i + j * lda]);
-      if (b2) b2[i + j * ldb] = tf32_lo(v);
     }
     b[i + j * ldb] = v;
   }
@@ -163,57 +157,50 @@ void launch_gemm_tn_simt(int M, int N, int K, const float* a, long long lda, con
 }
 
 void launch_gemm_nn_simt(int M, int N, int K, float alpha, const float* a, long long lda, const float* b,
-                         long long ldb, float beta, float* d, long long ldd, float* d_lo, long long ldd_lo,
-                         cudaStream_t s) {
+                         long long ldb, float beta, float* d, long long ldd, cudaStream_t s) {
   if (M <= 0 || N <= 0) return;
   ++g_launches;
   dim3 grid((M + BT - 1) / BT, (N + BT - 1) / BT, 1);
-  gemm_nn_simt_kernel<<<grid, 256, 0, s>>>(M, N, K, alpha, a, lda, b, ldb, beta, d, ldd, d_lo, ldd_lo);
+  gemm_nn_simt_kernel<<<grid, 256, 0, s>>>(M, N, K, alpha, a, lda, b, ldb, beta, d, ldd);
 }
 
 void launch_reduce_splits(int M, int N, const float* part, long long ldp, long long stride, int splits, float* out,
-                          long long ldo, float* out_lo, long long ldo_lo, cudaStream_t s) {
+                          long long ldo, cudaStream_t s) {
   if (M <= 0 || N <= 0) return;
   ++g_launches;
-  reduce_splits_kernel<<<ew_grid(M, N), 256, 0, s>>>(M, N, part, ldp, stride, splits, out, ldo, out_lo, ldo_lo);
-}
-
-void launch_split_lo(int M, int N, const float* a, long long lda, float* lo, long long ldlo, cudaStream_t s) {
-  if (M <= 0 || N <= 0) return;
-  ++g_launches;
-  elementwise_kernel<0><<<ew_grid(M, N), 256, 0, s>>>(M, N, a, lda, lo, ldlo, nullptr, 0);
+  reduce_splits_kernel<<<ew_grid(M, N), 256, 0, s>>>(M, N, part, ldp, stride, splits, out, ldo);
 }
 
 void launch_set_identity(float* a, long long lda, int m, int n, cudaStream_t s) {
   if (m <= 0 || n <= 0) return;
   ++g_launches;
-  elementwise_kernel<1><<<ew_grid(m, n), 256, 0, s>>>(m, n, nullptr, 0, a, lda, nullptr, 0);
+  elementwise_kernel<1><<<ew_grid(m, n), 256, 0, s>>>(m, n, nullptr, 0, a, lda, 0);
 }
 
 void launch_fill_zero(float* a, long long lda, long long m, int n, cudaStream_t s) {
   if (m <= 0 || n <= 0) return;
   ++g_launches;
-  elementwise_kernel<2><<<ew_grid(m, n), 256, 0, s>>>(m, n, nullptr, 0, a, lda, nullptr, 0);
+  elementwise_kernel<2><<<ew_grid(m, n), 256, 0, s>>>(m, n, nullptr, 0, a, lda, 0);
 }
 
 void launch_copy_matrix(long long m, int n, const float* a, long long lda, float* b, long long ldb, cudaStream_t s) {
   if (m <= 0 || n <= 0) return;
   ++g_launches;
-  elementwise_kernel<3><<<ew_grid(m, n), 256, 0, s>>>(m, n, a, lda, b, ldb, nullptr, 0);
+  elementwise_kernel<3><<<ew_grid(m, n), 256, 0, s>>>(m, n, a, lda, b, ldb, 0);
 }
 
 void launch_extract_r(const float* a, long long lda, int m, int n, float* r, long long ldr, int r_rows,
                       cudaStream_t s) {
   if (r_rows <= 0 || n <= 0) return;
   ++g_launches;
-  elementwise_kernel<4><<<ew_grid(r_rows, n), 256, 0, s>>>(r_rows, n, a, lda, r, ldr, nullptr, m);
+  elementwise_kernel<4><<<ew_grid(r_rows, n), 256, 0, s>>>(r_rows, n, a, lda, r, ldr, m);
 }
 
-void launch_extract_v(const float* a, long long lda, long long mp, int b, int d0, float* v, long long ldv, float* vlo,
+void launch_extract_v(const float* a, long long lda, long long mp, int b, int d0, float* v, long long ldv,
                       cudaStream_t s) {
   if (mp <= 0 || b <= 0) return;
   ++g_launches;
-  elementwise_kernel<5><<<ew_grid(mp, b), 256, 0, s>>>(mp, b, a, lda, v, ldv, vlo, d0);
+  elementwise_kernel<5><<<ew_grid(mp, b), 256, 0, s>>>(mp, b, a, lda, v, ldv, d0);
 }
 
 }  // namespace cqr

@@ -4,11 +4,14 @@
 // fp32 fidelity on a tensor pipe that has no fp32 MMA comes from the 3xTF32 split: every
 // operand is held as hi + lo (hi = top 11 significand bits, lo = exact remainder, see
 // common.cuh) and each K step issues  A_hi B_hi + A_lo B_hi + A_hi B_lo  into the same TMEM
-// accumulator (the dropped lo*lo term is 2^-22 relative).  Operands are pre-split in global
-// memory by their producers, so the kernel is a plain TMA -> smem -> tcgen05.mma pipeline:
+// accumulator (the dropped lo*lo term is 2^-22 relative).  The split happens INSIDE the kernel:
+// TMA lands the raw fp32 tile (which the tensor core reads as `hi` -- it ignores the low 13 bits),
+// four converter warps write lo = x - trunc(x) to a sibling buffer at the same swizzled offsets,
+// fence.proxy.async, and hand the stage to the MMA warp.  HBM/L2 see every operand exactly once.
 //   warp 0   : TMA producer (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx)
+//   warps 2-5: converters during the main loop (ld.shared.v4 -> lo -> st.shared.v4), then the
+//              epilogue (tcgen05.ld 32x32b -> registers -> coalesced column-major stores)
 //   warp 1   : MMA issuer   (one elected lane, tcgen05.mma kind::tf32, M=128, N=BN, K=8)
-//   warps 2-5: epilogue     (tcgen05.ld 32x32b -> registers -> coalesced column-major stores)
 // A is K-major for TN (columns of V are contiguous along K) and MN-major for NN (V itself);
 // B is always K-major.  Ragged M/N/K edges rely on TMA zero fill plus masked stores.
 #include <cuda.h>
@@ -99,26 +102,25 @@ struct Epilogue {
   float* d;
   long long ldd;
   long long split_stride;   // TN: partial z at d + z*split_stride
-  float* d_lo;              // NN: optional tf32 remainder of the result
-  long long ldd_lo;
   float alpha, beta;
 };
 
 template <int BN, bool kAMn>
 __global__ void __launch_bounds__(kThreads, 1)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, Epilogue ep,
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, Epilogue ep,
                  int M, int N, int K, int kper) {
   constexpr int kStages = (BN == 256) ? 2 : 3;
-  constexpr uint32_t kABytes = BM * BK * 4;            // 16 KB per hi or lo tile
+  constexpr uint32_t kABytes = BM * BK * 4;            // 16 KB
   constexpr uint32_t kBBytes = BN * BK * 4;
-  constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;
+  constexpr uint32_t kRawBytes = kABytes + kBBytes;    // what TMA loads per stage: [A raw][B raw]
+  constexpr uint32_t kStageBytes = 2 * kRawBytes;      // followed by [A lo][B lo] at +kRawBytes
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kStages, tfull = full0 + 16 * kStages;
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kStages, conv0 = full0 + 16 * kStages,
+                 tfull = full0 + 24 * kStages;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -127,7 +129,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   const int nkb = (kend - kbeg + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+      mbar_init(conv0 + 8 * s, 128);   // every converter thread arrives
+    }
     mbar_init(tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -148,20 +154,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         mbar_wait(empty0 + 8 * s, ph ^ 1);
         const uint32_t sa = smem_base + s * kStageBytes;
         const uint32_t full = full0 + 8 * s;
-        mbar_expect_tx(full, kStageBytes);
+        mbar_expect_tx(full, kRawBytes);
         const int k0 = kbeg + kb * BK;
         if (kAMn) {
 #pragma unroll
-          for (int c = 0; c < BM / 32; ++c) {   // four 32-row chunks of the M-contiguous operand
-            tma_load_2d(sa + c * (BK * 128), &tm_a_hi, full, m0 + 32 * c, k0);
-            tma_load_2d(sa + kABytes + c * (BK * 128), &tm_a_lo, full, m0 + 32 * c, k0);
-          }
+          for (int c = 0; c < BM / 32; ++c)   // four 32-row chunks of the M-contiguous operand
+            tma_load_2d(sa + c * (BK * 128), &tm_a, full, m0 + 32 * c, k0);
         } else {
-          tma_load_2d(sa, &tm_a_hi, full, k0, m0);
-          tma_load_2d(sa + kABytes, &tm_a_lo, full, k0, m0);
+          tma_load_2d(sa, &tm_a, full, k0, m0);
         }
-        tma_load_2d(sa + 2 * kABytes, &tm_b_hi, full, k0, n0);
-        tma_load_2d(sa + 2 * kABytes + kBBytes, &tm_b_lo, full, k0, n0);
+        tma_load_2d(sa + kABytes, &tm_b, full, k0, n0);
       }
     }
   } else if (warp == 1) {
@@ -170,7 +172,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(full0 + 8 * s, ph);
+        mbar_wait(conv0 + 8 * s, ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_base + s * kStageBytes;
 #pragma unroll
@@ -178,13 +180,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           uint64_t a_hi, a_lo;
           if (kAMn) {   // K = 8 is two 4-deep groups (SBO = 512 B): +1024 B per step; M chunks 4096 B apart (LBO)
             a_hi = make_desc(sa + k * 1024, BK * 128, 512, 1);
-            a_lo = make_desc(sa + kABytes + k * 1024, BK * 128, 512, 1);
+            a_lo = make_desc(sa + kRawBytes + k * 1024, BK * 128, 512, 1);
           } else {      // K-major: +32 B inside the swizzled 128 B row
             a_hi = make_desc(sa + k * 32, 16, 1024, 2);
-            a_lo = make_desc(sa + kABytes + k * 32, 16, 1024, 2);
+            a_lo = make_desc(sa + kRawBytes + k * 32, 16, 1024, 2);
           }
-          const uint64_t b_hi = make_desc(sa + 2 * kABytes + k * 32, 16, 1024, 2);
-          const uint64_t b_lo = make_desc(sa + 2 * kABytes + kBBytes + k * 32, 16, 1024, 2);
+          const uint64_t b_hi = make_desc(sa + kABytes + k * 32, 16, 1024, 2);
+          const uint64_t b_lo = make_desc(sa + kRawBytes + kABytes + k * 32, 16, 1024, 2);
           umma_tf32(tmem_d, a_lo, b_hi, idesc, (kb | k) != 0);
           umma_tf32(tmem_d, a_hi, b_lo, idesc, 1);
           umma_tf32(tmem_d, a_hi, b_hi, idesc, 1);
@@ -194,6 +196,25 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       umma_commit(tfull);
     }
   } else {
+    // converters: lo = x - trunc(x) for the freshly landed stage, same (swizzled) offsets, +kRawBytes
+    {
+      const int ct = threadIdx.x - 64;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        const uint32_t sa = smem_base + s * kStageBytes;
+#pragma unroll 4
+        for (uint32_t off = ct * 16; off < kRawBytes; off += 128 * 16) {
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sa + off));
+          v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + kRawBytes + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05.mma
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(conv0 + 8 * s) : "memory");
+      }
+    }
     // epilogue: warp q reads TMEM lanes [32q, 32q+32) = rows m0 + 32q + lane
     const int q = warp & 3;
     const int m = m0 + 32 * q + lane;
@@ -218,7 +239,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           float r = ep.alpha * v[j];
           if (ep.beta != 0.f) r = fmaf(ep.beta, old[j], r);
           dz[m + (long long)(nb + j) * ep.ldd] = r;
-          if (ep.d_lo) ep.d_lo[m + (long long)(nb + j) * ep.ldd_lo] = tf32_lo(r);
         }
       }
     }
@@ -267,14 +287,13 @@ bool make_map(CUtensorMap* tm, const float* base, long long dim0, long long dim1
 bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 template <int BN, bool kAMn>
-bool launch_umma(int M, int N, int K, const float* a, const float* a_lo, long long lda, const float* b, const float* b_lo,
-                 long long ldb, const Epilogue& ep, int splits, cudaStream_t s) {
-  CUtensorMap ta, tal, tb, tbl;
+bool launch_umma(int M, int N, int K, const float* a, long long lda, const float* b, long long ldb, const Epilogue& ep,
+                 int splits, cudaStream_t s) {
+  CUtensorMap ta, tb;
   bool ok;
-  if (kAMn) ok = make_map(&ta, a, M, K, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
-                 make_map(&tal, a_lo, M, K, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-  else ok = make_map(&ta, a, K, M, lda, BK, BM) && make_map(&tal, a_lo, K, M, lda, BK, BM);
-  ok = ok && make_map(&tb, b, K, N, ldb, BK, BN) && make_map(&tbl, b_lo, K, N, ldb, BK, BN);
+  if (kAMn) ok = make_map(&ta, a, M, K, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  else ok = make_map(&ta, a, K, M, lda, BK, BM);
+  ok = ok && make_map(&tb, b, K, N, ldb, BK, BN);
   if (!ok) return false;
   constexpr int kStages = (BN == 256) ? 2 : 3;
   constexpr size_t smem = (size_t)kStages * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024 + 256;
@@ -291,7 +310,7 @@ bool launch_umma(int M, int N, int K, const float* a, const float* a_lo, long lo
   splits = (K + kper - 1) / kper;
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
   ++g_launches;
-  umma_gemm_kernel<BN, kAMn><<<grid, kThreads, smem, s>>>(ta, tal, tb, tbl, ep, M, N, K, kper);
+  umma_gemm_kernel<BN, kAMn><<<grid, kThreads, smem, s>>>(ta, tb, ep, M, N, K, kper);
   return true;
 }
 
@@ -317,26 +336,24 @@ int umma_effective_splits(int K, int splits) {
   return (K + kper - 1) / kper;
 }
 
-bool launch_gemm_tn_umma(int M, int N, int K, const float* a, const float* a_lo, long long lda, const float* b,
-                         const float* b_lo, long long ldb, float* d, long long ldd, int splits, long long d_split_stride,
-                         cudaStream_t s) {
-  if (!umma_available() || !a_lo || !b_lo) return false;
-  if (lda % 4 || ldb % 4 || !aligned16(a) || !aligned16(a_lo) || !aligned16(b) || !aligned16(b_lo)) return false;
+bool launch_gemm_tn_umma(int M, int N, int K, const float* a, long long lda, const float* b, long long ldb, float* d,
+                         long long ldd, int splits, long long d_split_stride, cudaStream_t s) {
+  if (!umma_available()) return false;
+  if (lda % 4 || ldb % 4 || !aligned16(a) || !aligned16(b)) return false;
   if (M < 1 || N < 1 || K < 1) return false;
-  Epilogue ep{d, ldd, d_split_stride, nullptr, 0, 1.f, 0.f};
-  if (N > 128) return launch_umma<256, false>(M, N, K, a, a_lo, lda, b, b_lo, ldb, ep, splits, s);
-  return launch_umma<128, false>(M, N, K, a, a_lo, lda, b, b_lo, ldb, ep, splits, s);
+  Epilogue ep{d, ldd, d_split_stride, 1.f, 0.f};
+  if (N > 128) return launch_umma<256, false>(M, N, K, a, lda, b, ldb, ep, splits, s);
+  return launch_umma<128, false>(M, N, K, a, lda, b, ldb, ep, splits, s);
 }
 
-bool launch_gemm_nn_umma(int M, int N, int K, float alpha, const float* a, const float* a_lo, long long lda, const float* b,
-                         const float* b_lo, long long ldb, float beta, float* d, long long ldd, float* d_lo,
-                         long long ldd_lo, cudaStream_t s) {
-  if (!umma_available() || !a_lo || !b_lo) return false;
-  if (lda % 4 || ldb % 4 || !aligned16(a) || !aligned16(a_lo) || !aligned16(b) || !aligned16(b_lo)) return false;
+bool launch_gemm_nn_umma(int M, int N, int K, float alpha, const float* a, long long lda, const float* b, long long ldb,
+                         float beta, float* d, long long ldd, cudaStream_t s) {
+  if (!umma_available()) return false;
+  if (lda % 4 || ldb % 4 || !aligned16(a) || !aligned16(b)) return false;
   if (M < 1 || N < 1 || K < 1) return false;
-  Epilogue ep{d, ldd, 0, d_lo, ldd_lo, alpha, beta};
-  if (N > 128) return launch_umma<256, true>(M, N, K, a, a_lo, lda, b, b_lo, ldb, ep, 1, s);
-  return launch_umma<128, true>(M, N, K, a, a_lo, lda, b, b_lo, ldb, ep, 1, s);
+  Epilogue ep{d, ldd, 0, alpha, beta};
+  if (N > 128) return launch_umma<256, true>(M, N, K, a, lda, b, ldb, ep, 1, s);
+  return launch_umma<128, true>(M, N, K, a, lda, b, ldb, ep, 1, s);
 }
 
 }  // namespace cqr

@@ -117,7 +117,6 @@ __global__ void __launch_bounds__(256) hr_top_kernel(HrParams p) {
       if (i < p.mp) {
         p.a[i + j * p.lda] = (i > j) ? L[i][j] : sgn[i] * p.rt[i + j * p.ldrt];
         p.vbuf[i + j * p.ldv] = y;
-        if (p.vlo) p.vlo[i + j * p.ldv] = tf32_lo(y);
       }
     }
   }
@@ -149,7 +148,6 @@ __global__ void __launch_bounds__(256) hr_rows_kernel(HrParams p) {
     if (j < b) {
       p.a[r + j * p.lda] = acc[jj];
       p.vbuf[r + j * p.ldv] = acc[jj];
-      if (p.vlo) p.vlo[r + j * p.ldv] = tf32_lo(acc[jj]);
     }
   }
 }

@@ -24,7 +24,6 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 32;               // fp32 elements per 128-byte swizzle row
-constexpr int kThreads = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -105,148 +104,206 @@ struct Epilogue {
   float alpha, beta;
 };
 
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent, warp-specialised: grid = min(tiles, #SMs); tile t -> (m-tile fastest, then n-tile, then K split).
+//   warp 0       TMA producer: raw fp32 A/B k-blocks into a 2-stage ring (48 KB raw + 48 KB lo per stage at BN = 256)
+//   warps 2-9    converters: lo = x - trunc(x) of the landed k-block into the stage's lo half (overlaps the
+//                MMAs of the previous k-block)
+//   warp 1       MMA issuer: 12 tcgen05.mma per k-block into one of two TMEM accumulators
+//   warps 10-13  epilogue: drains the other accumulator (tcgen05.ld) while the next tile's MMAs run
+// Barriers: full[s] (TMA landed), conv[s] (lo written, 256 arrivals), empty[s] (MMAs done with the stage),
+// tfull[a]/tempty[a] per accumulator.  All roles walk the same (tile, k-block) sequence, so phases are
+// derived from two running counters: g = k-blocks so far, i = tiles so far on this CTA.
+constexpr int kRing = 2;
+constexpr int kConvThreads = 256;
+constexpr int kThreadsP = 64 + kConvThreads + 128;
+
 template <int BN, bool kAMn>
-__global__ void __launch_bounds__(kThreads, 1)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, Epilogue ep,
-                 int M, int N, int K, int kper) {
-  constexpr int kStages = (BN == 256) ? 2 : 3;
+__global__ void __launch_bounds__(kThreadsP, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const __grid_constant__ CUtensorMap tm_d, Epilogue ep, int M, int N, int K, int kper, int tiles_m,
+                 int tiles_n, int splits) {
   constexpr uint32_t kABytes = BM * BK * 4;            // 16 KB
   constexpr uint32_t kBBytes = BN * BK * 4;
-  constexpr uint32_t kRawBytes = kABytes + kBBytes;    // what TMA loads per stage: [A raw][B raw]
-  constexpr uint32_t kStageBytes = 2 * kRawBytes;      // followed by [A lo][B lo] at +kRawBytes
+  constexpr uint32_t kRawBytes = kABytes + kBBytes;    // one k-block: [A raw][B raw]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+  constexpr uint32_t kStageBytes = 2 * kRawBytes;    // [A raw][B raw][A lo][B lo]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRing * kStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kRing + 4);
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kStages, conv0 = full0 + 16 * kStages,
-                 tfull = full0 + 24 * kStages;
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kRing, conv0 = full0 + 16 * kRing,
+                 tfull0 = full0 + 24 * kRing, tempty0 = tfull0 + 16;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int kbeg = blockIdx.z * kper;
-  const int kend = min(K, kbeg + kper);
-  const int nkb = (kend - kbeg + BK - 1) / BK;
+  const int total = tiles_m * tiles_n * splits;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
-      mbar_init(conv0 + 8 * s, 128);   // every converter thread arrives
+    for (int r = 0; r < kRing; ++r) {
+      mbar_init(full0 + 8 * r, 1);
+      mbar_init(empty0 + 8 * r, 1);
+      mbar_init(conv0 + 8 * r, kConvThreads);
     }
-    mbar_init(tfull, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile decomposition shared by all roles
+  auto tile_coords = [&](int t, int& m0, int& n0, int& z, int& kbeg, int& nkb) {
+    const int mt = t % tiles_m;
+    const int rest = t / tiles_m;
+    const int nt = rest % tiles_n;
+    z = rest / tiles_n;
+    m0 = mt * BM; n0 = nt * BN;
+    kbeg = z * kper;
+    const int kend = min(K, kbeg + kper);
+    nkb = (kend - kbeg + BK - 1) / BK;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(empty0 + 8 * s, ph ^ 1);
-        const uint32_t sa = smem_base + s * kStageBytes;
-        const uint32_t full = full0 + 8 * s;
-        mbar_expect_tx(full, kRawBytes);
-        const int k0 = kbeg + kb * BK;
-        if (kAMn) {
+      uint32_t g = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        int m0, n0, z, kbeg, nkb;
+        tile_coords(t, m0, n0, z, kbeg, nkb);
+        if (ep.beta != 0.f) {   // pull the C tile into L2 now; the epilogue reads it ~10 us later
 #pragma unroll
-          for (int c = 0; c < BM / 32; ++c)   // four 32-row chunks of the M-contiguous operand
-            tma_load_2d(sa + c * (BK * 128), &tm_a, full, m0 + 32 * c, k0);
-        } else {
-          tma_load_2d(sa, &tm_a, full, k0, m0);
+          for (int c = 0; c < BN; c += 64) tma_prefetch_2d(&tm_d, m0, n0 + c);
         }
-        tma_load_2d(sa + kABytes, &tm_b, full, k0, n0);
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const uint32_t r = g % kRing, ph = (g / kRing) & 1;
+          mbar_wait(empty0 + 8 * r, ph ^ 1);
+          const uint32_t sa = smem_base + r * kStageBytes;
+          const uint32_t full = full0 + 8 * r;
+          mbar_expect_tx(full, kRawBytes);
+          const int k0 = kbeg + kb * BK;
+          if (kAMn) {
+#pragma unroll
+            for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + c * (BK * 128), &tm_a, full, m0 + 32 * c, k0);
+          } else {
+            tma_load_2d(sa, &tm_a, full, k0, m0);
+          }
+          tma_load_2d(sa + kABytes, &tm_b, full, k0, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN, kAMn);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(conv0 + 8 * s, ph);
+      uint32_t g = 0, i = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+        int m0, n0, z, kbeg, nkb;
+        tile_coords(t, m0, n0, z, kbeg, nkb);
+        const uint32_t a = i & 1;
+        mbar_wait(tempty0 + 8 * a, ((i >> 1) & 1) ^ 1);          // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_base + s * kStageBytes;
+        const uint32_t tmem_d = tmem_base + a * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const uint32_t r = g % kRing, ph = (g / kRing) & 1;
+          mbar_wait(conv0 + 8 * r, ph);                            // raw landed AND lo written
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_base + r * kStageBytes;
+          const uint32_t lo_base = sa + kRawBytes;
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {
-          uint64_t a_hi, a_lo;
-          if (kAMn) {   // K = 8 is two 4-deep groups (SBO = 512 B): +1024 B per step; M chunks 4096 B apart (LBO)
-            a_hi = make_desc(sa + k * 1024, BK * 128, 512, 1);
-            a_lo = make_desc(sa + kRawBytes + k * 1024, BK * 128, 512, 1);
-          } else {      // K-major: +32 B inside the swizzled 128 B row
-            a_hi = make_desc(sa + k * 32, 16, 1024, 2);
-            a_lo = make_desc(sa + kRawBytes + k * 32, 16, 1024, 2);
+          for (int k = 0; k < BK / 8; ++k) {
+            uint64_t a_hi, a_lo;
+            if (kAMn) {   // K = 8 is two 4-deep groups (SBO = 512 B): +1024 B per step; M chunks 4096 B apart (LBO)
+              a_hi = make_desc(sa + k * 1024, BK * 128, 512, 1);
+              a_lo = make_desc(lo_base + k * 1024, BK * 128, 512, 1);
+            } else {      // K-major: +32 B inside the swizzled 128 B row
+              a_hi = make_desc(sa + k * 32, 16, 1024, 2);
+              a_lo = make_desc(lo_base + k * 32, 16, 1024, 2);
+            }
+            const uint64_t b_hi = make_desc(sa + kABytes + k * 32, 16, 1024, 2);
+            const uint64_t b_lo = make_desc(lo_base + kABytes + k * 32, 16, 1024, 2);
+            umma_tf32(tmem_d, a_lo, b_hi, idesc, (kb | k) != 0);
+            umma_tf32(tmem_d, a_hi, b_lo, idesc, 1);
+            umma_tf32(tmem_d, a_hi, b_hi, idesc, 1);
           }
-          const uint64_t b_hi = make_desc(sa + kABytes + k * 32, 16, 1024, 2);
-          const uint64_t b_lo = make_desc(sa + kRawBytes + kABytes + k * 32, 16, 1024, 2);
-          umma_tf32(tmem_d, a_lo, b_hi, idesc, (kb | k) != 0);
-          umma_tf32(tmem_d, a_hi, b_lo, idesc, 1);
-          umma_tf32(tmem_d, a_hi, b_hi, idesc, 1);
+          umma_commit(empty0 + 8 * r);   // stage (raw + lo) may be refilled
         }
-        umma_commit(empty0 + 8 * s);
+        umma_commit(tfull0 + 8 * a);
       }
-      umma_commit(tfull);
     }
-  } else {
-    // converters: lo = x - trunc(x) for the freshly landed stage, same (swizzled) offsets, +kRawBytes
-    {
-      const int ct = threadIdx.x - 64;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(full0 + 8 * s, ph);
-        const uint32_t sa = smem_base + s * kStageBytes;
+  } else if (warp < 2 + kConvThreads / 32) {
+    // converters: lo = x - trunc(x), same (swizzled) offsets
+    const int ct = threadIdx.x - 64;
+    uint32_t g = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      int m0, n0, z, kbeg, nkb;
+      tile_coords(t, m0, n0, z, kbeg, nkb);
+      for (int kb = 0; kb < nkb; ++kb, ++g) {
+        const uint32_t r = g % kRing, ph = (g / kRing) & 1;
+        mbar_wait(full0 + 8 * r, ph);     // implies the stage's previous MMAs are done (producer waited on empty)
+        const uint32_t sa = smem_base + r * kStageBytes;
+        const uint32_t lo_base = sa + kRawBytes;
 #pragma unroll 4
-        for (uint32_t off = ct * 16; off < kRawBytes; off += 128 * 16) {
+        for (uint32_t off = ct * 16; off < kRawBytes; off += kConvThreads * 16) {
           float4 v;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sa + off));
           v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + kRawBytes + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_base + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05.mma
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(conv0 + 8 * s) : "memory");
+        mbar_arrive(conv0 + 8 * r);
       }
     }
+  } else {
     // epilogue: warp q reads TMEM lanes [32q, 32q+32) = rows m0 + 32q + lane
     const int q = warp & 3;
-    const int m = m0 + 32 * q + lane;
-    mbar_wait(tfull, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const bool row_ok = m < M;
-    float* dz = ep.d + (long long)blockIdx.z * ep.split_stride;
+    uint32_t i = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+      int m0, n0, z, kbeg, nkb;
+      tile_coords(t, m0, n0, z, kbeg, nkb);
+      const uint32_t a = i & 1;
+      const int m = m0 + 32 * q + lane;
+      const bool row_ok = m < M;
+      float* dz = ep.d + (long long)z * ep.split_stride;
+      mbar_wait(tfull0 + 8 * a, (i >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_base + a * BN;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      float v[32];
-      tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
-      float old[32];
-      const int nb = n0 + 32 * c;
-      if (ep.beta != 0.f) {
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
+        float old[32];
+        const int nb = n0 + 32 * c;
+        if (ep.beta != 0.f) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) old[j] = (row_ok && nb + j < N) ? dz[m + (long long)(nb + j) * ep.ldd] : 0.f;
-      }
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          for (int j = 0; j < 32; ++j) old[j] = (row_ok && nb + j < N) ? dz[m + (long long)(nb + j) * ep.ldd] : 0.f;
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (row_ok && nb + j < N) {
-          float r = ep.alpha * v[j];
-          if (ep.beta != 0.f) r = fmaf(ep.beta, old[j], r);
-          dz[m + (long long)(nb + j) * ep.ldd] = r;
+        for (int j = 0; j < 32; ++j) {
+          if (row_ok && nb + j < N) {
+            float r = ep.alpha * v[j];
+            if (ep.beta != 0.f) r = fmaf(ep.beta, old[j], r);
+            dz[m + (long long)(nb + j) * ep.ldd] = r;
+          }
         }
       }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(tempty0 + 8 * a);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
   }
 }
 
@@ -286,17 +343,31 @@ bool make_map(CUtensorMap* tm, const float* base, long long dim0, long long dim1
 
 bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int BN, bool kAMn>
 bool launch_umma(int M, int N, int K, const float* a, long long lda, const float* b, long long ldb, const Epilogue& ep,
                  int splits, cudaStream_t s) {
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, td;
   bool ok;
   if (kAMn) ok = make_map(&ta, a, M, K, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   else ok = make_map(&ta, a, K, M, lda, BK, BM);
   ok = ok && make_map(&tb, b, K, N, ldb, BK, BN);
+  // D is only touched by TMA for the L2 prefetch of the C tile (beta != 0); plain (unswizzled) 128 x 64 boxes
+  if (ep.beta != 0.f && ep.ldd % 4 == 0 && aligned16(ep.d)) ok = ok && make_map(&td, ep.d, M, N, ep.ldd, BM, 64, CU_TENSOR_MAP_SWIZZLE_NONE);
+  else td = tb;
   if (!ok) return false;
-  constexpr int kStages = (BN == 256) ? 2 : 3;
-  constexpr size_t smem = (size_t)kStages * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024 + 256;
+  Epilogue e2 = ep;
+  constexpr size_t smem = (size_t)kRing * 2 * (BM * BK * 4 + BN * BK * 4) + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(umma_gemm_kernel<BN, kAMn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -308,9 +379,11 @@ bool launch_umma(int M, int N, int K, const float* a, long long lda, const float
   int kper = ((K + splits - 1) / splits + BK - 1) / BK * BK;
   if (kper < BK) kper = BK;
   splits = (K + kper - 1) / kper;
-  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  const long long total = (long long)tiles_m * tiles_n * splits;
+  const int grid = (int)(total < sm_count() ? total : sm_count());
   ++g_launches;
-  umma_gemm_kernel<BN, kAMn><<<grid, kThreads, smem, s>>>(ta, tb, ep, M, N, K, kper);
+  umma_gemm_kernel<BN, kAMn><<<grid, kThreadsP, smem, s>>>(ta, tb, td, e2, M, N, K, kper, tiles_m, tiles_n, splits);
   return true;
 }
 

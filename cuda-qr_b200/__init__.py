@@ -92,7 +92,7 @@ def _load() -> ctypes.CDLL:
     lib.cqr_stack_form_q.argtypes = [_VP, _VP, i, i, i, _VP, _VP, i, _VP, i]
     lib.cqr_geqrf_batched.argtypes = [_VP, _VP, i, ll, i, i, i, _VP]
     lib.cqr_gemm.argtypes = [_VP, i, i, i, i, f, _VP, i, _VP, i, f, _VP, i]
-    lib.cqr_gemm_tf32x3.argtypes = [_VP, i, i, i, i, _VP, i, _VP, i, _VP, i]
+    lib.cqr_gemm_tf32x3.argtypes = [_VP, i, i, i, i, f, _VP, i, _VP, i, f, _VP, i]
     lib.cqr_set_identity.argtypes = [_VP, _VP, i, i, i]
     lib.cqr_version.restype = ctypes.c_char_p
     return lib
@@ -336,12 +336,12 @@ class Context:
         _check(lib.cqr_gemm(self.h, 1 if trans_a else 0, M, N, K, alpha, _dptr(A), _ld(A), _dptr(B), _ld(B), beta,
                             _dptr(D), _ld(D)), "cqr_gemm")
 
-    def gemm_tf32x3(self, A, B, D, trans_a: bool = False):
+    def gemm_tf32x3(self, A, B, D, trans_a: bool = False, alpha: float = 1.0, beta: float = 0.0):
         """D = op(A) B on the tcgen05 3xTF32 kernels; raises if the shape cannot take the TMA path."""
         M, N = D.shape
         K = A.shape[0] if trans_a else A.shape[1]
-        _check(lib.cqr_gemm_tf32x3(self.h, 1 if trans_a else 0, M, N, K, _dptr(A), _ld(A), _dptr(B), _ld(B),
-                                   _dptr(D), _ld(D)), "cqr_gemm_tf32x3")
+        _check(lib.cqr_gemm_tf32x3(self.h, 1 if trans_a else 0, M, N, K, alpha, _dptr(A), _ld(A), _dptr(B), _ld(B),
+                                   beta, _dptr(D), _ld(D)), "cqr_gemm_tf32x3")
 
     def set_identity(self, A):
         _check(lib.cqr_set_identity(self.h, _dptr(A), _ld(A), A.shape[0], A.shape[1]), "cqr_set_identity")

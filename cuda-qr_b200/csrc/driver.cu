@@ -425,10 +425,11 @@ int cqr_gemm(cqr_context* c, int transA, int M, int N, int K, float alpha, const
 
 // D = op(A) B on the tcgen05 3xTF32 kernels (operands are split into hi/lo inside the kernel).  Returns
 // CQR_EUNSUPPORTED when the shape/alignment rules out the TMA path (no silent fallback here).
-int cqr_gemm_tf32x3(cqr_context* c, int transA, int M, int N, int K, const float* dA, int lda, const float* dB, int ldb,
-                    float* dD, int ldd) {
+int cqr_gemm_tf32x3(cqr_context* c, int transA, int M, int N, int K, float alpha, const float* dA, int lda,
+                    const float* dB, int ldb, float beta, float* dD, int ldd) {
   if (!c || !dA || !dB || !dD || M < 1 || N < 1 || K < 1 || ldd < M || ldb < K) return CQR_EINVAL;
   if (transA ? lda < K : lda < M) return CQR_EINVAL;
+  if (transA && (alpha != 1.f || beta != 0.f)) return CQR_EUNSUPPORTED;
   cudaSetDevice(c->device);
   if (!umma_available()) return CQR_EUNSUPPORTED;
   float* part = nullptr;
@@ -444,7 +445,7 @@ int cqr_gemm_tf32x3(cqr_context* c, int transA, int M, int N, int K, const float
     ok = launch_gemm_tn_umma(M, N, K, dA, lda, dB, ldb, part, ldp, splits, ldp * N, c->stream);
     if (ok) launch_reduce_splits(M, N, part, ldp, ldp * N, splits, dD, ldd, c->stream);
   } else {
-    ok = launch_gemm_nn_umma(M, N, K, 1.f, dA, lda, dB, ldb, 0.f, dD, ldd, c->stream);
+    ok = launch_gemm_nn_umma(M, N, K, alpha, dA, lda, dB, ldb, beta, dD, ldd, c->stream);
   }
   if (!ok) return CQR_EUNSUPPORTED;
   return (int)cudaGetLastError();
@@ -748,6 +749,25 @@ void getPanelDims(int m, int n, int* rowPanels, int* colPanels) {
   if (m > kLegacyPR) *rowPanels += (m - kLegacyPR) / (kLegacyPR - kLegacyPC) + ((m - kLegacyPR) % (kLegacyPR - kLegacyPC) != 0);
 }
 
+// Device staging buffers of the legacy entry points: grow-only, one set per device, so that a caller
+// looping over mmqr (the reference's trials loop, qr.cu:777-788) does not pay a multi-GiB
+// cudaMalloc/cudaFree per call the way qr.cu:492-497,550-552 does.
+struct LegacyBufs { float* p[4] = {nullptr, nullptr, nullptr, nullptr}; size_t bytes[4] = {0, 0, 0, 0}; };
+static float* legacy_buf(int slot, size_t bytes) {
+  static LegacyBufs bufs[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  LegacyBufs& b = bufs[dev];
+  if (bytes > b.bytes[slot]) {
+    if (b.p[slot]) cudaFree(b.p[slot]);
+    b.p[slot] = nullptr; b.bytes[slot] = 0;
+    cudaError_t e = cudaMalloc((void**)&b.p[slot], bytes);
+    if (e != cudaSuccess) { printf("CUDA error on line %i: %d\n", __LINE__, (int)e); exit(1); }
+    b.bytes[slot] = bytes;
+  }
+  return b.p[slot];
+}
+
 void mmqr(float* mat, float* tau, int m, int n) {
   if (!(m && n && m >= n)) { printf("mmqr: need m >= n >= 1 (got %d x %d)\n", m, n); exit(1); }   // qr.cu:736
   cqr_context* c = legacy_ctx();
@@ -755,9 +775,8 @@ void mmqr(float* mat, float* tau, int m, int n) {
   getPanelDims(m, n, &rp, &cp);
   const size_t tau_count = (size_t)rp * cp * kLegacyPC;
   const long long lda = round_up(m, 4);
-  float *dA = nullptr, *dtau = nullptr;
-  LEGACY_CHECK(cudaMalloc((void**)&dA, (size_t)lda * n * sizeof(float)));
-  LEGACY_CHECK(cudaMalloc((void**)&dtau, (size_t)n * sizeof(float)));
+  float* dA = legacy_buf(0, (size_t)lda * n * sizeof(float));
+  float* dtau = legacy_buf(1, (size_t)n * sizeof(float));
   LEGACY_CHECK(cudaMemcpy2D(dA, lda * sizeof(float), mat, (size_t)m * sizeof(float), (size_t)m * sizeof(float), n,
                             cudaMemcpyHostToDevice));
   LEGACY_CHECK(cqr_geqrf(c, dA, (int)lda, m, n, dtau));
@@ -765,8 +784,6 @@ void mmqr(float* mat, float* tau, int m, int n) {
                             cudaMemcpyDeviceToHost));
   memset(tau, 0, tau_count * sizeof(float));   // unused slots zero, qr.c:62
   LEGACY_CHECK(cudaMemcpy(tau, dtau, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
-  cudaFree(dA);
-  cudaFree(dtau);
 }
 
 void mmqr_alloc(float* mat, float** tau, int m, int n) {
@@ -781,11 +798,10 @@ void explicitQR(float* A, float* tau, float* Q, float* R, int m, int n) {
   if (!(m && n && m >= n)) { printf("explicitQR: need m >= n >= 1 (got %d x %d)\n", m, n); exit(1); }
   cqr_context* c = legacy_ctx();
   const long long ld = round_up(m, 4);
-  float *dA = nullptr, *dtau = nullptr, *dQ = nullptr, *dR = nullptr;
-  LEGACY_CHECK(cudaMalloc((void**)&dA, (size_t)ld * n * sizeof(float)));
-  LEGACY_CHECK(cudaMalloc((void**)&dR, (size_t)ld * n * sizeof(float)));
-  LEGACY_CHECK(cudaMalloc((void**)&dQ, (size_t)ld * m * sizeof(float)));
-  LEGACY_CHECK(cudaMalloc((void**)&dtau, (size_t)n * sizeof(float)));
+  float* dA = legacy_buf(0, (size_t)ld * n * sizeof(float));
+  float* dtau = legacy_buf(1, (size_t)n * sizeof(float));
+  float* dR = legacy_buf(2, (size_t)ld * n * sizeof(float));
+  float* dQ = legacy_buf(3, (size_t)ld * m * sizeof(float));
   LEGACY_CHECK(cudaMemcpy2D(dA, ld * sizeof(float), A, (size_t)m * sizeof(float), (size_t)m * sizeof(float), n,
                             cudaMemcpyHostToDevice));
   LEGACY_CHECK(cudaMemcpy(dtau, tau, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
@@ -795,7 +811,6 @@ void explicitQR(float* A, float* tau, float* Q, float* R, int m, int n) {
                             cudaMemcpyDeviceToHost));
   LEGACY_CHECK(cudaMemcpy2D(Q, (size_t)m * sizeof(float), dQ, ld * sizeof(float), (size_t)m * sizeof(float), m,
                             cudaMemcpyDeviceToHost));
-  cudaFree(dA); cudaFree(dR); cudaFree(dQ); cudaFree(dtau);
 }
 
 void dgemm(float* A, float* B, float* C, int k, int m, int n) {

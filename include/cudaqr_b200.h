@@ -133,10 +133,11 @@ int cqr_geqrf_batched(cqr_context* ctx, float* dA, int lda, long long stride, in
 int cqr_gemm(cqr_context* ctx, int transA, int M, int N, int K, float alpha, const float* dA, int lda,
              const float* dB, int ldb, float beta, float* dD, int ldd);
 
-/* D = op(A) * B on the tcgen05 tensor cores with the 3xTF32 operand split (fp32-faithful to ~2^-21).
+/* D = alpha * op(A) * B + beta * D on the tcgen05 tensor cores with the 3xTF32 operand split
+ * (fp32-faithful to ~2^-21).  transA = 1 supports alpha = 1, beta = 0 only (split-K partials).
  * CQR_EUNSUPPORTED if pointers are not 16-byte aligned or leading dimensions not multiples of 4. */
-int cqr_gemm_tf32x3(cqr_context* ctx, int transA, int M, int N, int K, const float* dA, int lda, const float* dB,
-                    int ldb, float* dD, int ldd);
+int cqr_gemm_tf32x3(cqr_context* ctx, int transA, int M, int N, int K, float alpha, const float* dA, int lda,
+                    const float* dB, int ldb, float beta, float* dD, int ldd);
 
 int cqr_set_identity(cqr_context* ctx, float* dA, int lda, int m, int n);
 

@@ -93,6 +93,28 @@ void launch_hr_rows(const HrParams& p, cudaStream_t s);
 void launch_build_t(const float* g, long long ldg, const float* tau, float* t, long long ldt, int kb,
                     int have_diag, cudaStream_t s);
 
+// ---- multi-CTA Householder panel: panel_hh.cu -------------------------------------------------
+constexpr int kPanelHHMaxCtas = 128;   // slab partials exchanged per step (slots: 2 x 128 x 64 + 2 x 64 uint2)
+struct PanelHHParams {
+  float* a; long long lda;      // panel (m_p x b), overwritten with R / v (LAPACK geqrf storage)
+  long long mp; int b;
+  float* tau;                   // b
+  float* vbuf; long long ldv;   // explicit V (unit diagonal, zeros above), m_p x b
+  float* t; long long ldt;      // b x b compact-WY T (upper, zero below); nullptr = not wanted
+  uint2* slots; int pmax;       // exchange area {value bits, tag}
+  unsigned epoch;               // unique per launch: tags of earlier launches never match
+  int* err;                     // set to 1 if a spin timed out (grid was not co-resident)
+};
+inline size_t panel_hh_slot_bytes() { return (size_t)(2 * kPanelHHMaxCtas * 64 + 2 * 64) * sizeof(uint2); }
+bool panel_hh_plan(long long mp, int max_ctas, int* ri, int* ctas);
+void launch_panel_hh(const PanelHHParams& p, int ri, int ctas, cudaStream_t s);
+// one-cluster variant (DSMEM exchange), m_p <= 8192: rows per thread rr, cluster size cs; false if the launch failed
+bool panel_hh_cluster_plan(long long mp, int* rr, int* cs);
+bool launch_panel_hh_cluster(const PanelHHParams& p, int rr, int cs, cudaStream_t s);
+#ifdef CQR_HH_TRACE
+void panel_hh_read_trace(long long* out);
+#endif
+
 // ---- fp32 SIMT GEMMs and element-wise utilities: gemm_simt.cu -------------------------------
 // D[z](M x N) = A(:, z-th K chunk)^T * B(z-th K chunk, :) ; D[z] = d + z * d_split_stride
 void launch_gemm_tn_simt(int M, int N, int K, const float* a, long long lda, const float* b, long long ldb,

@@ -59,7 +59,11 @@ struct cqr_context {
   cudaStream_t side = nullptr;
   cudaStream_t cur = nullptr;      // stream the launch helpers use right now (nullptr = `stream`)
   cudaEvent_t ev_start = nullptr, ev_a = nullptr, ev_panel[2] = {nullptr, nullptr};
-  int opt_gemm = 1, opt_outer = 256, opt_tile_rows = 256, opt_splitk = 0, opt_lookahead = 1;
+  int opt_gemm = 1, opt_outer = 256, opt_tile_rows = 256, opt_splitk = 0, opt_lookahead = 1, opt_panel = 1, opt_cluster = 1;
+  // multi-CTA panel kernel (panel_hh.cu): cross-CTA exchange slots, launch epoch, spin-timeout flag
+  uint2* hh_slots = nullptr;
+  int* hh_err = nullptr;
+  unsigned hh_epoch = 0;
   long long launches0 = 0;
   cudaError_t last = cudaSuccess;
   // optional per-kernel-class timing (cqr_profile_begin/end): CUDA events around each launch group
@@ -283,6 +287,10 @@ bool tensor_ok(cqr_context* c, const void* a, long long lda) {
 // ================================================================================================
 extern "C" {
 
+#ifdef CQR_HH_TRACE
+__attribute__((visibility("default"))) void cqr_debug_hh_trace(long long* out) { cqr::panel_hh_read_trace(out); }
+#endif
+
 const char* cqr_version(void) { return "cudaqr_b200 0.1;sm_100a;tsqr+hr+wy;tcgen05-3xtf32"; }
 
 const char* cqr_error_string(int status) {
@@ -319,7 +327,12 @@ int cqr_create(cqr_context** out, int device) {
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_panel[0], cudaEventDisableTiming));
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_panel[1], cudaEventDisableTiming));
+  CQR_CUDA(cudaMalloc((void**)&c->hh_slots, panel_hh_slot_bytes() + 256));
+  CQR_CUDA(cudaMemset(c->hh_slots, 0, panel_hh_slot_bytes() + 256));
+  c->hh_err = reinterpret_cast<int*>(reinterpret_cast<char*>(c->hh_slots) + panel_hh_slot_bytes());
   if (const char* e = getenv("CQR_LOOKAHEAD")) c->opt_lookahead = atoi(e) != 0;
+  if (const char* e = getenv("CQR_PANEL")) c->opt_panel = atoi(e) != 0;
+  if (const char* e = getenv("CQR_CLUSTER")) c->opt_cluster = atoi(e) != 0;   // debugging aid: 0 = global-flag exchange only
   if (const char* e = getenv("CQR_GEMM")) c->opt_gemm = (strcmp(e, "simt") == 0) ? 0 : 1;   // debugging aid
   *out = c;
   return 0;
@@ -331,6 +344,7 @@ int cqr_destroy(cqr_context* c) {
   cudaStreamSynchronize(c->stream);
   if (c->ws) cudaFree(c->ws);
   if (c->ts) cudaFree(c->ts);
+  if (c->hh_slots) cudaFree(c->hh_slots);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
   for (cudaEvent_t e : {c->ev_start, c->ev_a, c->ev_panel[0], c->ev_panel[1]}) if (e) cudaEventDestroy(e);
@@ -348,6 +362,7 @@ int cqr_set_option(cqr_context* c, int opt, int v) {
     case CQR_OPT_TILE_ROWS: if (v != 128 && v != 256) return CQR_EINVAL; c->opt_tile_rows = v; return 0;
     case CQR_OPT_SPLITK: if (v < 0 || v > kMaxSplits) return CQR_EINVAL; c->opt_splitk = v; return 0;
     case CQR_OPT_LOOKAHEAD: if (v != 0 && v != 1) return CQR_EINVAL; c->opt_lookahead = v; return 0;
+    case CQR_OPT_PANEL: if (v != 0 && v != 1) return CQR_EINVAL; c->opt_panel = v; return 0;
   }
   return CQR_EINVAL;
 }
@@ -360,6 +375,7 @@ int cqr_get_option(cqr_context* c, int opt, int* v) {
     case CQR_OPT_TILE_ROWS: *v = c->opt_tile_rows; return 0;
     case CQR_OPT_SPLITK: *v = c->opt_splitk; return 0;
     case CQR_OPT_LOOKAHEAD: *v = c->opt_lookahead; return 0;
+    case CQR_OPT_PANEL: *v = c->opt_panel; return 0;
   }
   return CQR_EINVAL;
 }
@@ -368,6 +384,9 @@ int cqr_synchronize(cqr_context* c) {
   if (!c) return CQR_EINVAL;
   CQR_CUDA(cudaStreamSynchronize(c->stream));
   CQR_CUDA(cudaGetLastError());
+  int hh_err = 0;   // a panel_hh spin timed out: its CTAs were never co-resident, results are invalid
+  CQR_CUDA(cudaMemcpy(&hh_err, c->hh_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (hh_err) { cudaMemset(c->hh_err, 0, sizeof(int)); return CQR_ESTATE; }
   return 0;
 }
 
@@ -466,7 +485,7 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
 
   struct BlockBufs { float *vbuf, *tbig; } bb[2];
   TsqrPlan plan;
-  float *gram = nullptr, *gpart = nullptr, *qthin = nullptr, *rt = nullptr, *uinv = nullptr;
+  float *gram = nullptr, *gpart = nullptr, *qthin = nullptr, *rt = nullptr, *uinv = nullptr, *gsmall = nullptr;
   BlockWs bw_main{}, bw_side{};
   for (int pass = 0; pass < 2; ++pass) {
     Carver cv(pass ? c->ws : nullptr);
@@ -480,6 +499,7 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
     qthin = cv.take(ldv * 64);
     rt = cv.take(64 * 64);
     uinv = cv.take(64 * 64);
+    gsmall = cv.take(64 * 64);
     bw_main = carve_block_ws(cv, KB, ncmax);
     bw_side = carve_block_ws(cv, 64, KB);   // inner updates: 64 reflectors on < KB columns
     if (!pass) { int rc = ws_ensure(c, cv.off); if (rc) return rc; }
@@ -497,6 +517,22 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
       const long long mp = m - j0;
       const int off = j0 - K0;
       float* ap = dA + j0 + (long long)j0 * lda;
+      float* tj = B.tbig + off + (long long)off * KB;
+      float* vj = B.vbuf + off + (long long)off * ldv;
+      int hh_ri = 0, hh_ctas = 0;
+      if (c->opt_panel == 1 && panel_hh_plan(mp, c->sm_count, &hh_ri, &hh_ctas)) {
+        // one launch: P co-resident CTAs factor the panel in registers (LAPACK storage + explicit V + V^T V),
+        // including the panel's compact-WY T.  2 mp b^2 (Householder) + mp b^2 (V^T V) flops; panel read once,
+        // panel and V written once.
+        ProfScope pps(c, CQR_PROF_PANEL, 3.0 * mp * b * b, 4.0 * 3.0 * mp * b);
+        PanelHHParams hp{};
+        hp.a = ap; hp.lda = lda; hp.mp = mp; hp.b = b; hp.tau = dtau + j0;
+        hp.vbuf = vj; hp.ldv = ldv; hp.t = tj; hp.ldt = KB;
+        hp.slots = c->hh_slots; hp.pmax = kPanelHHMaxCtas; hp.epoch = ++c->hh_epoch; hp.err = c->hh_err;
+        int rr = 0, cs = 0;
+        if (!(c->opt_cluster && panel_hh_cluster_plan(mp, &rr, &cs) && launch_panel_hh_cluster(hp, rr, cs, s)))
+          launch_panel_hh(hp, hh_ri, hh_ctas, s);
+      } else {
       // (1) panel TSQR: R_tsqr + implicit Q   (2) explicit thin Q   (3) Householder reconstruction
       TsqrPlan pp;
       { Carver cv2(c->ws); plan_tsqr(pp, mp, b, th, cv2); }   // same carve order => same buffers, sized for mp <= m
@@ -506,18 +542,19 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
       run_tsqr_form_q(c, pp, ap, lda, nullptr, 0, b, qthin, ldv);
       HrParams hp{};
       hp.q = qthin; hp.ldq = ldv; hp.rt = rt; hp.ldrt = 64; hp.a = ap; hp.lda = lda; hp.tau = dtau + j0;
-      hp.t = B.tbig + off + (long long)off * KB; hp.ldt = KB; hp.uinv = uinv;
-      hp.vbuf = B.vbuf + off + (long long)off * ldv; hp.ldv = ldv;
+      hp.t = tj; hp.ldt = KB; hp.uinv = uinv;
+      hp.vbuf = vj; hp.ldv = ldv;
       hp.mp = mp; hp.b = b;
       launch_hr_top(hp, s);
       launch_hr_rows(hp, s);
       pps.finish();
+      }
       // (4) inner update: remaining columns of this outer block
       const int ninner = K0 + kbw - (j0 + b);
       if (ninner > 0) {
         float* cp = dA + j0 + (long long)(j0 + b) * lda;
-        Operand V{hp.vbuf, ldv};
-        Operand T{hp.t, KB};
+        Operand V{vj, ldv};
+        Operand T{tj, KB};
         apply_block(c, mp, b, ninner, V, T, cp, lda, 1, bw_side, tensor);
       }
     }

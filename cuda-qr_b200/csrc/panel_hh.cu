@@ -1,0 +1,586 @@
+// panel_hh.cu -- multi-CTA Householder factorisation of one m_p x b panel (b <= 64) in ONE launch.
+//
+// Replaces, for the blocked square/rectangular path, the reference's serial window sweep over a
+// column block (qr.cu:505-546: one 1-CTA panelHouseholderKernel launch per 64 x 4 window) and this
+// library's own first-generation panel (TSQR tree -> explicit thin Q -> Householder reconstruction,
+// ~10 launches and ~0.5 ms per panel at m_p = 16384).  Here the panel is distributed by row slabs over
+// P co-resident CTAs that hold their slab in REGISTERS for the whole factorisation; a column step is
+//   1. owner warp broadcasts the pivot column x (rows >= j) through shared memory,
+//   2. every warp forms the slab-local dots x^T a_c for its 4 columns with warp-shuffle reductions
+//      (north_star item 1; reflector maths as qr.c:144-167: beta = -sign*norm, u = x0 - beta, tau = -u/beta),
+//   3. the P slab partials are exchanged through a flag-tagged slot array in global memory (8-byte
+//      {value, tag} stores, readers poll the tag -- no fence, no atomics, no separate counter), lane i
+//      of every warp fetching CTA i's partial so the cross-CTA sum is one more shuffle reduction
+//      (fixed order => bitwise reproducible),
+//   4. every CTA derives beta/u/tau redundantly and updates its rows: a_c -= tau v (v^T a_c).
+// The same dots taken against the already finished columns c < j give G(c, j) = v_c^T v_j, i.e. the
+// strict upper triangle of V^T V, from which build_t_kernel forms the panel's compact-WY T (qr.c:170-213's
+// W/Y accumulation in LAPACK larft form) -- no separate Gram GEMM.  Output is directly LAPACK geqrf
+// storage (R on/above the diagonal, v below, tau) plus the explicit unit-lower V the tensor-core update
+// reads, so no tree, no thin Q and no reconstruction are needed.
+//
+// Layout: 512 threads = 16 warps.  Warp w owns columns {w, w+16, w+32, w+48}; lane l owns slab rows
+// {l, l+32, ...} (RI of them).  CTAs spin on each other: the grid must be co-resident (P <= #SMs, one
+// CTA per SM); spins are bounded by a clock64 timeout that raises an error flag instead of hanging.
+#include "common.cuh"
+
+namespace cqr {
+
+namespace {
+
+__device__ __forceinline__ void st_flag(uint2* p, float v, unsigned tag) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_flag(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+  return r;
+}
+
+constexpr long long kSpinTimeout = 6000000000LL;   // ~3 s of SM clocks: co-residency never arrived
+
+}  // namespace
+
+// Optional phase trace (debug builds only: -DCQR_HH_TRACE): clock64 of lane 0 of every warp of CTA 0 and the
+// last CTA at six points of each column step -> g_hh_trace[cta01][warp][step][6].
+#ifdef CQR_HH_TRACE
+__device__ long long g_hh_trace[2][16][64][6];
+#define HH_TRACE(k)                                                                         \
+  do {                                                                                      \
+    if (l == 0 && (cta == 0 || cta == P - 1)) g_hh_trace[cta == 0 ? 0 : 1][w][j][k] = clock64(); \
+  } while (0)
+#else
+#define HH_TRACE(k) do { } while (0)
+#endif
+
+template <int RI>
+__global__ void __launch_bounds__(512, 1) panel_hh_kernel(PanelHHParams p) {
+  constexpr int TH = 32 * RI;
+  __shared__ float xs[2][TH];
+  __shared__ float sc[2][4];            // {beta, 1/u, tau, u} of the current step, written by the owner warp
+  __shared__ float gs[64][65];          // CTA 0: G(c, j) = v_c^T v_j (c < j), then reused for T
+  __shared__ float ts[64][65];
+  __shared__ float staus[64];
+  const int P = gridDim.x, cta = blockIdx.x;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const long long row0 = (long long)cta * TH;
+  const long long rem = p.mp - row0;
+  const int rows = rem >= TH ? TH : (int)rem;
+  const int b = p.b;
+  float* __restrict__ A = p.a + row0;
+  uint2* slots = p.slots;                                   // [2][pmax][64]
+  uint2* prow = p.slots + 2 * (size_t)p.pmax * 64;          // [2][64]  row j of the panel, published by CTA 0
+
+  float a[4][RI];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = w + 16 * k;
+#pragma unroll
+    for (int ri = 0; ri < RI; ++ri) {
+      const int r = l + 32 * ri;
+      a[k][ri] = (c < b && r < rows) ? A[r + (long long)c * p.lda] : 0.f;
+    }
+  }
+
+#pragma unroll
+  for (int sj = 0; sj < 4; ++sj) {
+    for (int wj = 0; wj < 16; ++wj) {
+      const int j = 16 * sj + wj;          // pivot column: warp wj, register slot sj
+      if (j >= b) break;
+      const int buf = j & 1;
+      const int rj = sj >> 1;              // panel row j lives in CTA 0, lane j % 32, register slot j / 32
+      const unsigned tag = p.epoch * 64u + (unsigned)j + 1u;
+      if (w == wj) {
+#pragma unroll
+        for (int ri = 0; ri < RI; ++ri) {
+          const int r = l + 32 * ri;
+          xs[buf][r] = (row0 + r >= j) ? a[sj][ri] : 0.f;
+        }
+      }
+      __syncthreads();
+      HH_TRACE(0);
+      float x[RI];
+#pragma unroll
+      for (int ri = 0; ri < RI; ++ri) x[ri] = xs[buf][l + 32 * ri];
+      // slab-local dots of x with all four owned columns (finished ones feed G, live ones the update; the
+      // owner's own column gives x^T x)
+      float tot[4], ajc[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        tot[k] = 0.f;
+#pragma unroll
+        for (int ri = 0; ri < RI; ++ri) tot[k] = fmaf(x[ri], a[k][ri], tot[k]);
+      }
+      warp_sum_n(tot);
+      HH_TRACE(1);
+      if (P > 1) {
+        uint2* myslot = slots + ((size_t)buf * p.pmax + cta) * 64;
+        if (l < 4) {
+          const float v = l == 0 ? tot[0] : (l == 1 ? tot[1] : (l == 2 ? tot[2] : tot[3]));
+          st_flag(myslot + w + 16 * l, v, tag);
+        }
+        if (cta == 0 && l == (j & 31)) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) st_flag(prow + buf * 64 + w + 16 * k, a[k][rj], tag);
+        }
+        // gather: lane i sums the partials of CTAs i, i+32, ... for this warp's four columns, and every lane
+        // fetches the warp's four pivot-row entries.  All eight slots are polled TOGETHER (one L2 round trip
+        // per attempt).  Each slot is read by one warp per CTA only: no hot addresses.
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tot[k] = 0.f;
+        const uint2* pr = prow + buf * 64;
+        uint2 q[4];
+        for (int i0 = 0; i0 < P; i0 += 32) {
+          const int i = i0 + l;
+          const bool have = i < P;
+          const uint2* src = slots + ((size_t)buf * p.pmax + (have ? i : 0)) * 64;
+          uint2 r[4];
+          long long t0 = 0;
+          for (;;) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r[k] = ld_flag(src + w + 16 * k);
+            bool ok = true;
+            if (i0 == 0) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) q[k] = ld_flag(pr + w + 16 * k);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ok = ok && (q[k].y == tag);
+            }
+            if (have) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ok = ok && (r[k].y == tag);
+            }
+            if (__all_sync(kFull, ok)) break;
+            if (t0 == 0) t0 = clock64();
+            if (*(volatile int*)p.err != 0) break;
+            if (clock64() - t0 > kSpinTimeout) { atomicExch(p.err, 1); break; }
+          }
+          if (have) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tot[k] += __uint_as_float(r[k].x);
+          }
+        }
+        warp_sum_n(tot);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ajc[k] = __uint_as_float(q[k].x);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ajc[k] = __shfl_sync(kFull, a[k][rj], j & 31);
+      }
+      HH_TRACE(2);
+      // the owner warp turns (x^T x, alpha) into the reflector scalars once and hands them to the other
+      // fifteen warps through shared memory (no redundant sqrt / divisions on the issue slots)
+      if (w == wj) {
+        const float sjt = tot[sj], alpha = ajc[sj];
+        float beta = 0.f, tau = 0.f, inv_u = 0.f, u = 1.f;
+        if (sjt != 0.f) {
+          const float nrm = sqrtf(sjt);
+          beta = (alpha < 0.f) ? nrm : -nrm;
+          u = alpha - beta;
+          inv_u = 1.f / u;
+          tau = -u / beta;
+        }
+        if (l == 0) { sc[buf][0] = beta; sc[buf][1] = inv_u; sc[buf][2] = tau; sc[buf][3] = u; }
+      }
+      HH_TRACE(3);
+      __syncthreads();
+      HH_TRACE(4);
+      const float beta = sc[buf][0], inv_u = sc[buf][1], tau = sc[buf][2], u = sc[buf][3];
+      const bool nz = inv_u != 0.f;
+      if (RI >= 16) {   // big slabs: do not carry x across the exchange (register pressure), re-read it
+#pragma unroll
+        for (int ri = 0; ri < RI; ++ri) x[ri] = xs[buf][l + 32 * ri];
+      }
+      // v = x / u with v_j = 1: fold 1/u into the column scalars and patch x_j := u
+      if (cta == 0 && l == (j & 31)) x[rj] = u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = w + 16 * k;
+        const float d = nz ? (tot[k] - beta * ajc[k]) * inv_u : ajc[k];   // v^T a_c (zero column: v = e_j)
+        const bool live = (k > sj) || (k == sj && w > wj);
+        if (live) {
+          const float wc = tau * d * inv_u;
+#pragma unroll
+          for (int ri = 0; ri < RI; ++ri) a[k][ri] = fmaf(-wc, x[ri], a[k][ri]);
+        } else if (c < j && cta == 0 && l == 0) {
+          gs[c][j] = d;   // G(c, j) = v_c^T v_j
+        }
+      }
+      if (w == wj) {
+        if (nz) {
+#pragma unroll
+          for (int ri = 0; ri < RI; ++ri) {
+            const long long gr = row0 + l + 32 * ri;
+            if (gr > j) a[sj][ri] = x[ri] * inv_u;
+            else if (gr == j) a[sj][ri] = beta;
+          }
+        }
+        if (cta == 0 && l == 0) { p.tau[j] = tau; staus[j] = tau; }
+      }
+      HH_TRACE(5);
+    }
+  }
+
+  float* __restrict__ V = p.vbuf + row0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = w + 16 * k;
+#pragma unroll
+    for (int ri = 0; ri < RI; ++ri) {
+      const int r = l + 32 * ri;
+      if (c < b && r < rows) {
+        const long long gr = row0 + r;
+        A[r + (long long)c * p.lda] = a[k][ri];
+        V[r + (long long)c * p.ldv] = gr > c ? a[k][ri] : (gr == c ? 1.f : 0.f);
+      }
+    }
+  }
+
+  // Compact-WY T of the panel (replaces qr.c:170-213's W accumulation), CTA 0 only.  With G = striu(V^T V):
+  //   T(c, c) = tau_c,   T(i, c) = -tau_i * sum_{k = i+1..c} G(i, k) T(k, c)     (i = c-1 .. 0)
+  // i.e. T = (striu(G) + diag(1/tau))^-1 by back substitution, tau_i = 0 giving a zero row/column (H_i = I).
+  // Column c is handled by 8 lanes of one warp (dot over k split 8 ways) and only ever reads its own column
+  // of T, so the 64 columns run without any block-level synchronisation.
+  if (cta == 0 && p.t != nullptr) {
+    __syncthreads();
+    const int c = threadIdx.x >> 3, q8 = threadIdx.x & 7;     // 64 columns x 8 lanes; a warp holds columns 4w .. 4w+3
+    if (q8 == 0 && c < b) ts[c][c] = staus[c];
+    __syncwarp();
+    for (int i = 4 * w + 2; i >= 0; --i) {                    // warp-uniform trip count: shuffles stay convergent
+      const bool act = i < c && c < b;
+      float acc = 0.f;
+      if (act)
+        for (int k = i + 1 + q8; k <= c; k += 8) acc = fmaf(gs[i][k], ts[k][c], acc);
+      acc += __shfl_xor_sync(kFull, acc, 1);
+      acc += __shfl_xor_sync(kFull, acc, 2);
+      acc += __shfl_xor_sync(kFull, acc, 4);
+      if (act && q8 == 0) ts[i][c] = -staus[i] * acc;
+      __syncwarp();
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < b * b; idx += 512) {
+      const int i = idx % b, cc = idx / b;
+      p.t[i + (long long)cc * p.ldt] = (i <= cc) ? ts[i][cc] : 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cluster variant: the P <= 16 slab CTAs form ONE thread-block cluster and exchange their partial dots
+// through distributed shared memory (st local -> barrier.cluster -> ld.shared::cluster from every peer):
+// ~0.5 us per column step instead of the ~2-3 us an L2 round trip costs on B200 (measured, tools/hh_trace.py).
+// Thread layout differs from the kernel above: a thread owns ONE column (c = tid / 8) and the rows
+// {4 (g + 8 ch) + e} of its slab (g = tid % 8, RR rows in chunks of 4), so a dot product needs only a
+// 3-stage shuffle reduction over the 8 row groups and four columns reduce at once in one warp.
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem(const float* local, unsigned rank) {
+  unsigned la = (unsigned)__cvta_generic_to_shared(local), ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+// One-sided push into a peer CTA's shared memory that also credits `bytes` on the peer's mbarrier (the
+// receiver just waits on its own barrier: no cluster-wide barrier, no fence).
+__device__ __forceinline__ void st_async_f32(float* local_dst, unsigned long long* local_bar, unsigned rank, float v) {
+  unsigned la = (unsigned)__cvta_generic_to_shared(local_dst), lb = (unsigned)__cvta_generic_to_shared(local_bar), ra, rb;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(lb), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(ra), "r"(__float_as_uint(v)), "r"(rb)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init_local(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_local(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_local(unsigned long long* bar, unsigned parity) {
+  unsigned ok, a = (unsigned)__cvta_generic_to_shared(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ float sel4(float v0, float v1, float v2, float v3, int e) {
+  return e == 0 ? v0 : (e == 1 ? v1 : (e == 2 ? v2 : v3));
+}
+
+template <int RR>
+__global__ void __launch_bounds__(512, 1) panel_hh_cluster_kernel(PanelHHParams p) {
+  constexpr int TH = 8 * RR, NCH = RR / 4;
+  __shared__ __align__(16) float xs[2][TH];
+  __shared__ float inbox[2][16][64];    // slab-local dots pushed here by every CTA of the cluster (st.async)
+  __shared__ float prow[2][64];         // row j of the panel, pushed by CTA 0
+  __shared__ unsigned long long mbar[2];
+  __shared__ float sc[2][4];            // {beta, 1/u, tau, u}
+  __shared__ float gs[64][65];          // CTA 0: G(c, j) = v_c^T v_j (c < j)
+  __shared__ float ts[64][65];
+  __shared__ float staus[64];
+  const unsigned cta = cluster_ctarank(), CS = cluster_nctarank();
+  const unsigned P = CS; (void)P;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int c = threadIdx.x >> 3, g = l & 7;       // my column, my row group
+  const long long row0 = (long long)cta * TH;
+  const long long rem = p.mp - row0;
+  const int rows = rem >= TH ? TH : (rem > 0 ? (int)rem : 0);
+  const int b = p.b;
+  float* __restrict__ Ac = p.a + row0 + (long long)c * p.lda;
+  float* __restrict__ Vc = p.vbuf + row0 + (long long)c * p.ldv;
+  const bool vec_ok = (p.lda % 4 == 0) && (p.ldv % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.a) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p.vbuf) & 15) == 0);
+
+  float a[RR];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int r0 = 4 * (g + 8 * ch);
+    if (c < b && vec_ok && r0 + 3 < rows) {
+      const float4 v = *reinterpret_cast<const float4*>(Ac + r0);
+      a[4 * ch] = v.x; a[4 * ch + 1] = v.y; a[4 * ch + 2] = v.z; a[4 * ch + 3] = v.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[4 * ch + e] = (c < b && r0 + e < rows) ? Ac[r0 + e] : 0.f;
+    }
+  }
+  float4 (*xs4)[TH / 4] = reinterpret_cast<float4 (*)[TH / 4]>(xs);
+  if (CS > 1) {
+    if (threadIdx.x == 0) {
+      mbar_init_local(&mbar[0], 1);
+      mbar_init_local(&mbar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster_sync_all();   // every peer's barriers exist before anyone pushes
+  }
+
+#pragma unroll
+  for (int sj = 0; sj < 4; ++sj) {
+    for (int wj = 0; wj < 16; ++wj) {
+      const int j = 16 * sj + wj;
+      if (j >= b) break;
+      const int buf = j & 1;
+      const int chj = sj >> 1;                 // row j: chunk j / 32 (static after unrolling), group (j / 4) % 8, element j % 4
+      const int gj = (j >> 2) & 7, ej = j & 3;
+      const bool owner = (c == j);
+      const int jrel = j - (int)row0;          // pivot row in slab-local numbering (negative below slab 0)
+      if (owner) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int r0 = 4 * (g + 8 * ch);
+          float4 v;
+          v.x = (r0 + 0 >= jrel) ? a[4 * ch + 0] : 0.f;
+          v.y = (r0 + 1 >= jrel) ? a[4 * ch + 1] : 0.f;
+          v.z = (r0 + 2 >= jrel) ? a[4 * ch + 2] : 0.f;
+          v.w = (r0 + 3 >= jrel) ? a[4 * ch + 3] : 0.f;
+          xs4[buf][g + 8 * ch] = v;
+        }
+      }
+      __syncthreads();
+      HH_TRACE(0);
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const float4 xv = xs4[buf][g + 8 * ch];
+        acc0 = fmaf(xv.x, a[4 * ch + 0], acc0);
+        acc1 = fmaf(xv.y, a[4 * ch + 1], acc1);
+        acc2 = fmaf(xv.z, a[4 * ch + 2], acc2);
+        acc3 = fmaf(xv.w, a[4 * ch + 3], acc3);
+        if (RR > 16 && (ch & 3) == 3) asm volatile("" ::: "memory");   // keep the LDS look-ahead (register pressure) bounded
+      }
+      float s = (acc0 + acc1) + (acc2 + acc3);
+      s += __shfl_xor_sync(kFull, s, 1);
+      s += __shfl_xor_sync(kFull, s, 2);
+      s += __shfl_xor_sync(kFull, s, 4);
+      const float mine = sel4(a[4 * chj], a[4 * chj + 1], a[4 * chj + 2], a[4 * chj + 3], ej);   // a(j, c) if g == gj on CTA 0
+      float ajc;
+      HH_TRACE(1);
+      if (CS > 1) {
+        // push my column's slab-local dot to peers g and g + 8 (all 8 lanes of the column group hold s); CTA 0
+        // pushes the pivot-row entry the same way; then wait for the CS x 64 (+64) floats addressed to me
+        if (threadIdx.x == 0) mbar_expect_tx_local(&mbar[buf], (CS * 64 + 64) * 4);
+        const float pj = __shfl_sync(kFull, mine, (l & 24) | gj);
+        for (unsigned i = g; i < CS; i += 8) {
+          st_async_f32(&inbox[buf][cta][c], &mbar[buf], i, s);
+          if (cta == 0) st_async_f32(&prow[buf][c], &mbar[buf], i, pj);
+        }
+        mbar_wait_local(&mbar[buf], (j >> 1) & 1);
+        float t = 0.f;
+        for (unsigned i = g; i < CS; i += 8) t += inbox[buf][i][c];
+        ajc = prow[buf][c];
+        t += __shfl_xor_sync(kFull, t, 1);
+        t += __shfl_xor_sync(kFull, t, 2);
+        t += __shfl_xor_sync(kFull, t, 4);
+        s = t;
+      } else {
+        ajc = __shfl_sync(kFull, mine, (l & 24) | gj);
+      }
+      HH_TRACE(2);
+      if (owner && g == 0) {   // reflector scalars once per CTA (qr.c:144-152), handed over through shared memory
+        const float sjt = s, alpha = ajc;
+        float beta = 0.f, tau = 0.f, inv_u = 0.f, u = 1.f;
+        if (sjt != 0.f) {
+          const float nrm = sqrtf(sjt);
+          beta = (alpha < 0.f) ? nrm : -nrm;
+          u = alpha - beta;
+          inv_u = 1.f / u;
+          tau = -u / beta;
+        }
+        sc[buf][0] = beta; sc[buf][1] = inv_u; sc[buf][2] = tau; sc[buf][3] = u;
+        if (cta == 0) { p.tau[j] = tau; staus[j] = tau; }
+      }
+      HH_TRACE(3);
+      __syncthreads();
+      HH_TRACE(4);
+      const float beta = sc[buf][0], inv_u = sc[buf][1], tau = sc[buf][2], u = sc[buf][3];
+      const bool nz = inv_u != 0.f;
+      const float d = nz ? (s - beta * ajc) * inv_u : ajc;   // v^T a_c (zero column: v = e_j)
+      if (c > j) {
+        const float wc = tau * d * inv_u;   // a_c -= tau (v^T a_c) v with v = x / u, v_j = 1 (x_j patched to u)
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          float4 xv = xs4[buf][g + 8 * ch];
+          if (ch == chj && cta == 0 && g == gj) {
+            if (ej == 0) xv.x = u; else if (ej == 1) xv.y = u; else if (ej == 2) xv.z = u; else xv.w = u;
+          }
+          a[4 * ch + 0] = fmaf(-wc, xv.x, a[4 * ch + 0]);
+          a[4 * ch + 1] = fmaf(-wc, xv.y, a[4 * ch + 1]);
+          a[4 * ch + 2] = fmaf(-wc, xv.z, a[4 * ch + 2]);
+          a[4 * ch + 3] = fmaf(-wc, xv.w, a[4 * ch + 3]);
+          if (RR > 16 && (ch & 3) == 3) asm volatile("" ::: "memory");
+        }
+      } else if (c < j) {
+        if (cta == 0 && g == 0) gs[c][j] = d;   // G(c, j) = v_c^T v_j
+      } else if (nz) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const float4 xv = xs4[buf][g + 8 * ch];
+          const int r0 = 4 * (g + 8 * ch);
+          const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (r0 + e > jrel) a[4 * ch + e] = xe[e] * inv_u;
+            else if (r0 + e == jrel) a[4 * ch + e] = beta;
+          }
+        }
+      }
+      HH_TRACE(5);
+    }
+  }
+
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int r0 = 4 * (g + 8 * ch);
+    const long long gr0 = row0 + r0;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = gr0 + e > c ? a[4 * ch + e] : (gr0 + e == c ? 1.f : 0.f);
+    if (c < b && vec_ok && r0 + 3 < rows) {
+      *reinterpret_cast<float4*>(Ac + r0) = make_float4(a[4 * ch], a[4 * ch + 1], a[4 * ch + 2], a[4 * ch + 3]);
+      *reinterpret_cast<float4*>(Vc + r0) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (c < b && r0 + e < rows) { Ac[r0 + e] = a[4 * ch + e]; Vc[r0 + e] = v[e]; }
+    }
+  }
+
+  // compact-WY T by back substitution (see panel_hh_kernel), CTA 0 only
+  if (cta == 0 && p.t != nullptr) {
+    __syncthreads();
+    if (g == 0 && c < b) ts[c][c] = staus[c];
+    __syncwarp();
+    for (int i = 4 * w + 2; i >= 0; --i) {
+      const bool act = i < c && c < b;
+      float acc = 0.f;
+      if (act)
+        for (int k = i + 1 + g; k <= c; k += 8) acc = fmaf(gs[i][k], ts[k][c], acc);
+      acc += __shfl_xor_sync(kFull, acc, 1);
+      acc += __shfl_xor_sync(kFull, acc, 2);
+      acc += __shfl_xor_sync(kFull, acc, 4);
+      if (act && g == 0) ts[i][c] = -staus[i] * acc;
+      __syncwarp();
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < b * b; idx += 512) {
+      const int i = idx % b, cc = idx / b;
+      p.t[i + (long long)cc * p.ldt] = (i <= cc) ? ts[i][cc] : 0.f;
+    }
+  }
+  if (CS > 1) cluster_sync_all();   // no CTA leaves while pushes addressed to it (or by it) are in flight
+}
+
+// Rows-per-thread and cluster size for an m_p-row panel on the cluster kernel (m_p <= 16 * 512).
+bool panel_hh_cluster_plan(long long mp, int* rr, int* cs) {
+  if (mp > 16 * 512) return false;
+  int r = 8;
+  while ((mp + 8 * r - 1) / (8 * r) > 16) r *= 2;
+  const int P = (int)((mp + 8 * r - 1) / (8 * r));
+  int c = 1;
+  while (c < P) c *= 2;
+  *rr = r; *cs = c;
+  return true;
+}
+
+template <int RR>
+static cudaError_t launch_cluster_t(const PanelHHParams& p, int cs, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(panel_hh_cluster_kernel<RR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cs, 1, 1);
+  cfg.blockDim = dim3(512, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, panel_hh_cluster_kernel<RR>, p);
+}
+
+bool launch_panel_hh_cluster(const PanelHHParams& p, int rr, int cs, cudaStream_t s) {
+  ++g_launches;
+  cudaError_t e;
+  if (rr == 8) e = launch_cluster_t<8>(p, cs, s);
+  else if (rr == 16) e = launch_cluster_t<16>(p, cs, s);
+  else if (rr == 32) e = launch_cluster_t<32>(p, cs, s);
+  else e = launch_cluster_t<64>(p, cs, s);
+  if (e != cudaSuccess) { cudaGetLastError(); --g_launches; return false; }
+  return true;
+}
+
+// Slab height and CTA count for an m_p-row panel; false if it does not fit the co-residency budget.
+bool panel_hh_plan(long long mp, int max_ctas, int* ri, int* ctas) {
+  int r = 2;
+  if (mp > 4096) r = 16;
+  else if (mp > 2048) r = 8;
+  else if (mp > 1024) r = 4;
+  const long long P = (mp + 32 * r - 1) / (32 * r);
+  if (P > max_ctas || P > kPanelHHMaxCtas) return false;
+  *ri = r; *ctas = (int)P;
+  return true;
+}
+
+#ifdef CQR_HH_TRACE
+void panel_hh_read_trace(long long* out) { cudaMemcpyFromSymbol(out, g_hh_trace, sizeof(g_hh_trace)); }
+#endif
+
+void launch_panel_hh(const PanelHHParams& p, int ri, int ctas, cudaStream_t s) {
+  ++g_launches;
+  if (ri == 2) panel_hh_kernel<2><<<ctas, 512, 0, s>>>(p);
+  else if (ri == 4) panel_hh_kernel<4><<<ctas, 512, 0, s>>>(p);
+  else if (ri == 8) panel_hh_kernel<8><<<ctas, 512, 0, s>>>(p);
+  else panel_hh_kernel<16><<<ctas, 512, 0, s>>>(p);
+}
+
+}  // namespace cqr

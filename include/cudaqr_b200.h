@@ -73,7 +73,8 @@ enum {
   CQR_OPT_OUTER_BLOCK = 2,  /* aggregated block width for the trailing update: 64..512 (default 256) */
   CQR_OPT_TILE_ROWS = 3,    /* TSQR leaf height: 128 or 256 (default 256)                            */
   CQR_OPT_SPLITK = 4,       /* 0 = automatic                                                        */
-  CQR_OPT_LOOKAHEAD = 5     /* 1 (default): next block's panels overlap the trailing update on a side stream */
+  CQR_OPT_LOOKAHEAD = 5,    /* 1 (default): next block's panels overlap the trailing update on a side stream */
+  CQR_OPT_PANEL = 6         /* 1 (default): one-launch multi-CTA Householder panel; 0: TSQR tree + Householder reconstruction */
 };
 
 int cqr_create(cqr_context** ctx, int device);

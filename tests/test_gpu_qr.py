@@ -206,6 +206,91 @@ def test_geqrf_outer_block_widths_agree(pkg, torch, ctx, outer):
     ctx.set_option(pkg.OPT_OUTER_BLOCK, 256)
 
 
+@pytest.mark.parametrize("panel_mode", [0, 1])
+@pytest.mark.parametrize("m,n", [(1536, 1100), (20000, 64), (5000, 200), (3000, 37), (70000, 64), (40000, 128)])
+def test_geqrf_panel_modes(pkg, torch, ctx, panel_mode, m, n):
+    """CQR_OPT_PANEL 1 = one-launch multi-CTA Householder panel (1, <=32, >32 and >128 slabs -> fallback),
+    0 = TSQR tree + Householder reconstruction; both must meet the north_star tolerances."""
+    ctx.set_option(pkg.OPT_PANEL, panel_mode)
+    A = oracle.rand_matrix(m, n, 7)
+    dA = dev(pkg, torch, A)
+    tau = torch.zeros(n, device="cuda")
+    ctx.geqrf(dA, tau)
+    Q = pkg.colmajor(m, n)
+    ctx.form_q(dA, tau, Q)
+    R = pkg.colmajor(n, n)
+    ctx.extract_r(dA, R)
+    ctx.synchronize()
+    check_factorisation(A, host(Q), host(R), np.linalg.qr(A.astype(np.float64), mode="r"))
+    ctx.set_option(pkg.OPT_PANEL, 1)
+
+
+def test_geqrf_panel_hh_matches_lapack_storage(pkg, torch, ctx):
+    """The multi-CTA panel writes LAPACK geqrf storage directly: v below the diagonal and tau must reproduce
+    the fp64 Householder vectors of the same sign convention (beta = -sign(alpha) norm, qr.c:149-152), and the
+    run must be bitwise reproducible (fixed-order cross-CTA reduction)."""
+    m, n = 9000, 64
+    rng = np.random.default_rng(3)
+    A = np.asfortranarray(rng.standard_normal((m, n)).astype(np.float32))
+    outs = []
+    for _ in range(2):
+        dA = dev(pkg, torch, A)
+        tau = torch.zeros(n, device="cuda")
+        ctx.geqrf(dA, tau)
+        ctx.synchronize()
+        outs.append((host(dA), tau.cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    # fp64 unblocked Householder with the reference's sign convention
+    W = A.astype(np.float64)
+    taus = np.zeros(n)
+    for j in range(n):
+        x = W[j:, j].copy()
+        nrm = np.linalg.norm(x)
+        beta = nrm if x[0] < 0 else -nrm
+        u = x[0] - beta
+        v = x / u
+        v[0] = 1.0
+        taus[j] = -u / beta
+        W[j:, j:] -= taus[j] * np.outer(v, v @ W[j:, j:])
+        W[j + 1:, j] = v[1:]
+    got, gtau = outs[0]
+    assert np.linalg.norm(gtau - taus) / np.linalg.norm(taus) < 1e-5
+    assert np.linalg.norm(np.triu(got[:n]) - np.triu(W[:n])) / np.linalg.norm(np.triu(W[:n])) < 1e-5
+    assert np.linalg.norm(np.tril(got, -1) - np.tril(W, -1)) / np.linalg.norm(np.tril(W, -1)) < 1e-4
+
+
+def test_geqrf_panel_hh_edge_cases(pkg, torch, ctx):
+    """Zero column (tau = 0, no NaN: SURVEY App. B5), duplicated columns (rank deficiency) and a length-1 last
+    reflector (square matrix: tau = 2 sign flip like the reference)."""
+    rng = np.random.default_rng(11)
+    A = np.asfortranarray(rng.standard_normal((2500, 96)).astype(np.float32))
+    A[:, 5] = 0.0
+    A[:, 70] = A[:, 3]
+    dA = dev(pkg, torch, A)
+    tau = torch.zeros(96, device="cuda")
+    ctx.geqrf(dA, tau)
+    Q = pkg.colmajor(2500, 96)
+    ctx.form_q(dA, tau, Q)
+    R = pkg.colmajor(96, 96)
+    ctx.extract_r(dA, R)
+    ctx.synchronize()
+    assert np.isfinite(host(dA)).all() and np.isfinite(tau.cpu().numpy()).all()
+    assert float(tau[5]) == 0.0
+    check_factorisation(A, host(Q), host(R))
+    S = np.asfortranarray(rng.standard_normal((192, 192)).astype(np.float32))
+    dS = dev(pkg, torch, S)
+    tau = torch.zeros(192, device="cuda")
+    ctx.geqrf(dS, tau)
+    ctx.synchronize()
+    assert float(tau[191]) == 2.0
+    Q = pkg.colmajor(192, 192)
+    ctx.form_q(dS, tau, Q)
+    R = pkg.colmajor(192, 192)
+    ctx.extract_r(dS, R)
+    ctx.synchronize()
+    check_factorisation(S, host(Q), host(R), np.linalg.qr(S.astype(np.float64), mode="r"))
+
+
 def test_apply_q_and_qt_roundtrip(pkg, torch, ctx):
     m, n, nc = 1500, 300, 77
     rng = np.random.default_rng(1)

@@ -108,9 +108,10 @@ struct PanelHHParams {
 inline size_t panel_hh_slot_bytes() { return (size_t)(2 * kPanelHHMaxCtas * 64 + 2 * 64) * sizeof(uint2); }
 bool panel_hh_plan(long long mp, int max_ctas, int* ri, int* ctas);
 void launch_panel_hh(const PanelHHParams& p, int ri, int ctas, cudaStream_t s);
-// one-cluster variant (DSMEM exchange), m_p <= 8192: rows per thread rr, cluster size cs; false if the launch failed
-bool panel_hh_cluster_plan(long long mp, int* rr, int* cs);
-bool launch_panel_hh_cluster(const PanelHHParams& p, int rr, int cs, cudaStream_t s);
+// cluster variant (DSMEM exchange): one cluster for m_p <= 8192, two for m_p <= 16384; rows per thread rr, cluster
+// size cs, cluster count ncl; launch returns false if the launch failed
+bool panel_hh_cluster_plan(long long mp, int* rr, int* cs, int* ncl);
+bool launch_panel_hh_cluster(const PanelHHParams& p, int rr, int cs, int ncl, cudaStream_t s);
 #ifdef CQR_HH_TRACE
 void panel_hh_read_trace(long long* out);
 #endif
@@ -140,10 +141,11 @@ void launch_extract_v(const float* a, long long lda, long long mp, int b, int d0
 // Both return false (nothing launched) when shape/alignment rules out the TMA path.
 bool umma_available();
 int umma_effective_splits(int K, int splits);   // K splits the tensor kernel really uses for a request
+// max_ctas: SMs available to the launching stream (persistent grid = min(tiles, max_ctas)).
 bool launch_gemm_tn_umma(int M, int N, int K, const float* a, long long lda, const float* b, long long ldb, float* d,
-                         long long ldd, int splits, long long d_split_stride, cudaStream_t s);
+                         long long ldd, int splits, long long d_split_stride, int max_ctas, cudaStream_t s);
 bool launch_gemm_nn_umma(int M, int N, int K, float alpha, const float* a, long long lda, const float* b, long long ldb,
-                         float beta, float* d, long long ldd, cudaStream_t s);
+                         float beta, float* d, long long ldd, int max_ctas, cudaStream_t s);
 
 // global launch counter (gpu_launches evidence)
 extern long long g_launches;

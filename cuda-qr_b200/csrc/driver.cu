@@ -5,6 +5,7 @@
 // 64 x 4 window (70 516 launches for 4084^2), a panel is one TSQR tree (a handful of launches
 // over all row tiles at once), reconstructed to a single (Y, T), and the trailing matrix is
 // updated once per aggregated block of panels by GEMMs.
+#include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -41,6 +42,16 @@ struct TsqrPlan {
 
 }  // namespace
 
+// Spatial partition of the GPU for look-ahead (CUDA green contexts): the panel chain (latency-bound, a 16-CTA
+// cluster or two) owns `sm_p` SMs, the trailing-update GEMMs the remaining `sm_g`; the two streams are bound to
+// disjoint SM sets, so the persistent GEMM kernels can never hold the SMs a co-resident panel cluster needs.
+struct SmPartition {
+  CUgreenCtx gp = nullptr, gg = nullptr;
+  cudaStream_t sp = nullptr, sg = nullptr;
+  int sm_p = 0, sm_g = 0;
+  bool ok = false;
+};
+
 struct cqr_context {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -56,9 +67,12 @@ struct cqr_context {
   long long ts_lda = 0;
   bool ts_valid = false;
   // look-ahead: panel work of block K+1 runs on `side` while block K's trailing update runs on `stream`
-  cudaStream_t side = nullptr;
+  cudaStream_t side = nullptr, work = nullptr;
   cudaStream_t cur = nullptr;      // stream the launch helpers use right now (nullptr = `stream`)
-  cudaEvent_t ev_start = nullptr, ev_a = nullptr, ev_panel[2] = {nullptr, nullptr};
+  int cur_ctas = 0;                // SMs behind `cur` (0 = the whole device): caps persistent grids and split-K choices
+  SmPartition part[3];             // [0] unpartitioned (side/work streams), [1] 16 + 132 SMs, [2] 2 x 16 + 116 SMs
+  int opt_partition = 1;
+  cudaEvent_t ev_start = nullptr, ev_a = nullptr, ev_g = nullptr, ev_panel[2] = {nullptr, nullptr};
   int opt_gemm = 1, opt_outer = 256, opt_tile_rows = 256, opt_splitk = 0, opt_lookahead = 1, opt_panel = 1, opt_cluster = 1;
   // multi-CTA panel kernel (panel_hh.cu): cross-CTA exchange slots, launch epoch, spin-timeout flag
   uint2* hh_slots = nullptr;
@@ -83,6 +97,79 @@ namespace {
   } while (0)
 
 inline cudaStream_t cur_stream(cqr_context* c) { return c->cur ? c->cur : c->stream; }
+inline int cur_ctas(cqr_context* c) { return (c->cur && c->cur_ctas > 0) ? c->cur_ctas : c->sm_count; }
+
+// ---- green contexts (driver API through cudaGetDriverEntryPoint: the library does not link libcuda) -------
+struct DrvApi {
+  CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
+  CUresult (*DeviceGetDevResource)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+  CUresult (*DevSmResourceSplitByCount)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int,
+                                        unsigned int) = nullptr;
+  CUresult (*DevResourceGenerateDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+  CUresult (*GreenCtxCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+  CUresult (*GreenCtxStreamCreate)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+  CUresult (*GreenCtxDestroy)(CUgreenCtx) = nullptr;
+  bool ok = false;
+};
+
+template <typename F>
+bool drv_sym(const char* name, F& fn) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+    cudaGetLastError();
+    return false;
+  }
+  fn = reinterpret_cast<F>(p);
+  return true;
+}
+
+DrvApi& drv_api() {
+  static DrvApi a;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    a.ok = drv_sym("cuDeviceGet", a.DeviceGet) && drv_sym("cuDeviceGetDevResource", a.DeviceGetDevResource) &&
+           drv_sym("cuDevSmResourceSplitByCount", a.DevSmResourceSplitByCount) &&
+           drv_sym("cuDevResourceGenerateDesc", a.DevResourceGenerateDesc) && drv_sym("cuGreenCtxCreate", a.GreenCtxCreate) &&
+           drv_sym("cuGreenCtxStreamCreate", a.GreenCtxStreamCreate) && drv_sym("cuGreenCtxDestroy", a.GreenCtxDestroy);
+  }
+  return a;
+}
+
+// `groups` groups of 16 SMs (cluster-capable: CU_DEV_SM_RESOURCE_SPLIT_MAX_POTENTIAL_CLUSTER_SIZE) for the panel
+// stream, everything else for the GEMM stream.
+bool make_partition(int device, int groups, int prio_hi, SmPartition& out) {
+  DrvApi& d = drv_api();
+  if (!d.ok) return false;
+  CUdevice dev;
+  CUdevResource all, res[2], rem;
+  if (d.DeviceGet(&dev, device) != CUDA_SUCCESS) return false;
+  if (d.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+  unsigned int n = (unsigned)groups;
+  if (d.DevSmResourceSplitByCount(res, &n, &all, &rem, CU_DEV_SM_RESOURCE_SPLIT_MAX_POTENTIAL_CLUSTER_SIZE, 16) != CUDA_SUCCESS ||
+      n != (unsigned)groups)
+    return false;
+  for (int i = 0; i < groups; ++i) if (res[i].sm.smCount != 16) return false;
+  if (rem.sm.smCount < 64) return false;
+  CUdevResourceDesc dp, dg;
+  if (d.DevResourceGenerateDesc(&dp, res, (unsigned)groups) != CUDA_SUCCESS) return false;
+  if (d.DevResourceGenerateDesc(&dg, &rem, 1) != CUDA_SUCCESS) return false;
+  if (d.GreenCtxCreate(&out.gp, dp, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+  if (d.GreenCtxCreate(&out.gg, dg, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { d.GreenCtxDestroy(out.gp); out.gp = nullptr; return false; }
+  CUstream sp = nullptr, sg = nullptr;
+  if (d.GreenCtxStreamCreate(&sp, out.gp, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS ||
+      d.GreenCtxStreamCreate(&sg, out.gg, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
+    if (sp) cudaStreamDestroy((cudaStream_t)sp);
+    d.GreenCtxDestroy(out.gp); d.GreenCtxDestroy(out.gg);
+    out.gp = out.gg = nullptr;
+    return false;
+  }
+  out.sp = (cudaStream_t)sp; out.sg = (cudaStream_t)sg;
+  out.sm_p = 16 * groups; out.sm_g = (int)rem.sm.smCount;
+  out.ok = true;
+  return true;
+}
 
 cudaEvent_t prof_event(cqr_context* c) {
   if (c->ev_used == c->ev_pool.size()) {
@@ -206,7 +293,7 @@ void run_tsqr_form_q(cqr_context* c, const TsqrPlan& P, const float* a, long lon
 int pick_splits(cqr_context* c, int M, int N, int K, int tile_m, int tile_n) {
   if (c->opt_splitk > 0) return c->opt_splitk;
   const long long tiles = (long long)((M + tile_m - 1) / tile_m) * ((N + tile_n - 1) / tile_n);
-  long long s = (2LL * c->sm_count + tiles - 1) / tiles;
+  long long s = (2LL * cur_ctas(c) + tiles - 1) / tiles;
   const long long kmax = K / 512 > 0 ? K / 512 : 1;
   if (s > kmax) s = kmax;
   if (s > 32) s = 32;
@@ -228,7 +315,7 @@ void gemm_tn(cqr_context* c, int M, int N, int K, Operand A, Operand B, float* p
     // algorithmic traffic: both operands read once, partials written
     ProfScope ps(c, CQR_PROF_GEMM_TN, 2.0 * M * N * K, 4.0 * ((double)K * (M + N) + (double)M * N * splits));
     if (tensor && c->opt_gemm == 1)
-      done = launch_gemm_tn_umma(M, N, K, A.p, A.ld, B.p, B.ld, part, ldp, splits, stride, cur_stream(c));
+      done = launch_gemm_tn_umma(M, N, K, A.p, A.ld, B.p, B.ld, part, ldp, splits, stride, cur_ctas(c), cur_stream(c));
     if (!done) launch_gemm_tn_simt(M, N, K, A.p, A.ld, B.p, B.ld, part, ldp, splits, stride, cur_stream(c));
   }
   ProfScope ps2(c, CQR_PROF_MISC, 0.0, 4.0 * M * N * (splits + 1));
@@ -242,7 +329,7 @@ void gemm_nn(cqr_context* c, int M, int N, int K, float alpha, Operand A, Operan
   ProfScope ps(c, CQR_PROF_GEMM_NN, 2.0 * M * N * K,
                4.0 * ((double)M * N * ((beta != 0.f ? 1 : 0) + 1) + (double)K * (M + N)));
   if (tensor && c->opt_gemm == 1)
-    done = launch_gemm_nn_umma(M, N, K, alpha, A.p, A.ld, B.p, B.ld, beta, d, ldd, cur_stream(c));
+    done = launch_gemm_nn_umma(M, N, K, alpha, A.p, A.ld, B.p, B.ld, beta, d, ldd, cur_ctas(c), cur_stream(c));
   if (!done) launch_gemm_nn_simt(M, N, K, alpha, A.p, A.ld, B.p, B.ld, beta, d, ldd, cur_stream(c));
 }
 
@@ -323,13 +410,21 @@ int cqr_create(cqr_context** out, int device) {
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   CQR_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi));
+  CQR_CUDA(cudaStreamCreateWithFlags(&c->work, cudaStreamNonBlocking));
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+  CQR_CUDA(cudaEventCreateWithFlags(&c->ev_g, cudaEventDisableTiming));
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_panel[0], cudaEventDisableTiming));
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_panel[1], cudaEventDisableTiming));
   CQR_CUDA(cudaMalloc((void**)&c->hh_slots, panel_hh_slot_bytes() + 256));
   CQR_CUDA(cudaMemset(c->hh_slots, 0, panel_hh_slot_bytes() + 256));
   c->hh_err = reinterpret_cast<int*>(reinterpret_cast<char*>(c->hh_slots) + panel_hh_slot_bytes());
+  if (const char* e = getenv("CQR_PARTITION")) c->opt_partition = atoi(e) != 0;   // debugging aid: 0 = no green contexts
+  c->part[0].sp = c->side; c->part[0].sg = c->work; c->part[0].sm_p = c->part[0].sm_g = c->sm_count; c->part[0].ok = true;
+  if (c->opt_partition) {
+    CQR_CUDA(cudaFree(0));   // the primary context must exist before green contexts are carved out of it
+    if (!make_partition(device, 1, prio_hi, c->part[1]) || !make_partition(device, 2, prio_hi, c->part[2])) c->opt_partition = 0;
+  }
   if (const char* e = getenv("CQR_LOOKAHEAD")) c->opt_lookahead = atoi(e) != 0;
   if (const char* e = getenv("CQR_PANEL")) c->opt_panel = atoi(e) != 0;
   if (const char* e = getenv("CQR_CLUSTER")) c->opt_cluster = atoi(e) != 0;   // debugging aid: 0 = global-flag exchange only
@@ -347,7 +442,15 @@ int cqr_destroy(cqr_context* c) {
   if (c->hh_slots) cudaFree(c->hh_slots);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
-  for (cudaEvent_t e : {c->ev_start, c->ev_a, c->ev_panel[0], c->ev_panel[1]}) if (e) cudaEventDestroy(e);
+  if (c->work) { cudaStreamSynchronize(c->work); cudaStreamDestroy(c->work); }
+  for (int i = 1; i < 3; ++i) {
+    SmPartition& pt = c->part[i];
+    if (pt.sp) { cudaStreamSynchronize(pt.sp); cudaStreamDestroy(pt.sp); }
+    if (pt.sg) { cudaStreamSynchronize(pt.sg); cudaStreamDestroy(pt.sg); }
+    if (pt.gp) drv_api().GreenCtxDestroy(pt.gp);
+    if (pt.gg) drv_api().GreenCtxDestroy(pt.gg);
+  }
+  for (cudaEvent_t e : {c->ev_start, c->ev_a, c->ev_g, c->ev_panel[0], c->ev_panel[1]}) if (e) cudaEventDestroy(e);
   delete c;
   return 0;
 }
@@ -461,10 +564,10 @@ int cqr_gemm_tf32x3(cqr_context* c, int transA, int M, int N, int K, float alpha
   }
   bool ok;
   if (transA) {
-    ok = launch_gemm_tn_umma(M, N, K, dA, lda, dB, ldb, part, ldp, splits, ldp * N, c->stream);
+    ok = launch_gemm_tn_umma(M, N, K, dA, lda, dB, ldb, part, ldp, splits, ldp * N, c->sm_count, c->stream);
     if (ok) launch_reduce_splits(M, N, part, ldp, ldp * N, splits, dD, ldd, c->stream);
   } else {
-    ok = launch_gemm_nn_umma(M, N, K, alpha, dA, lda, dB, ldb, beta, dD, ldd, c->stream);
+    ok = launch_gemm_nn_umma(M, N, K, alpha, dA, lda, dB, ldb, beta, dD, ldd, c->sm_count, c->stream);
   }
   if (!ok) return CQR_EUNSUPPORTED;
   return (int)cudaGetLastError();
@@ -529,8 +632,8 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
         hp.a = ap; hp.lda = lda; hp.mp = mp; hp.b = b; hp.tau = dtau + j0;
         hp.vbuf = vj; hp.ldv = ldv; hp.t = tj; hp.ldt = KB;
         hp.slots = c->hh_slots; hp.pmax = kPanelHHMaxCtas; hp.epoch = ++c->hh_epoch; hp.err = c->hh_err;
-        int rr = 0, cs = 0;
-        if (!(c->opt_cluster && panel_hh_cluster_plan(mp, &rr, &cs) && launch_panel_hh_cluster(hp, rr, cs, s)))
+        int rr = 0, cs = 0, ncl = 0;
+        if (!(c->opt_cluster && panel_hh_cluster_plan(mp, &rr, &cs, &ncl) && launch_panel_hh_cluster(hp, rr, cs, ncl, s)))
           launch_panel_hh(hp, hh_ri, hh_ctas, s);
       } else {
       // (1) panel TSQR: R_tsqr + implicit Q   (2) explicit thin Q   (3) Householder reconstruction
@@ -558,14 +661,16 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
         apply_block(c, mp, b, ninner, V, T, cp, lda, 1, bw_side, tensor);
       }
     }
-    // aggregated T of the whole block (only needed when something is left to update)
-    if (n - (K0 + kbw) > 0) {
+  };
+  // Aggregated T of the whole block from the Gram matrix V^T V (only needed when something is left to update).
+  // Runs on the stream that applies the block: it is off the panel chain.
+  auto do_block_t = [&](int K0, BlockBufs& B) {
+    const int kbw = (n - K0 < KB) ? n - K0 : KB;
+    if (n - (K0 + kbw) > 0 && kbw > 64) {
       Operand V{B.vbuf, ldv};
-      if (kbw > 64) {
-        gemm_tn(c, kbw, kbw, (int)mK, V, V, gpart, gram, KB, kMaxSplits, tensor);
-        ProfScope pbt(c, CQR_PROF_MISC, 0.0, 0.0);
-        launch_build_t(gram, KB, dtau + K0, B.tbig, KB, kbw, 1, s);
-      }
+      gemm_tn(c, kbw, kbw, (int)(m - K0), V, V, gpart, gram, KB, kMaxSplits, tensor);
+      ProfScope pbt(c, CQR_PROF_MISC, 0.0, 0.0);
+      launch_build_t(gram, KB, dtau + K0, B.tbig, KB, kbw, 1, cur_stream(c));
     }
   };
   // Trailing update of columns [c0, c1) with block K0's aggregated reflector (current stream).
@@ -583,37 +688,61 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
       const int K0 = blk * KB;
       const int kbw = (n - K0 < KB) ? n - K0 : KB;
       do_panels(K0, bb[0]);
+      do_block_t(K0, bb[0]);
       do_update(K0, bb[0], K0 + kbw, n);
     }
     return (int)cudaGetLastError();
   }
 
-  // Look-ahead: once the next block's columns are updated (ev_a) its panel work starts on the side
-  // stream while the main stream finishes the rest of the trailing update.
+  // Look-ahead: once the next block's columns are updated (ev_a) its panel chain starts on the panel stream while
+  // the GEMM stream finishes the rest of the trailing update.  With green contexts the two streams own disjoint
+  // SM sets (16 or 2 x 16 SMs for the panel clusters, the rest for the GEMMs), chosen per block by panel height.
+  auto pair_for = [&](long long mp) -> SmPartition& {
+    if (!c->opt_partition || c->opt_panel != 1 || !c->opt_cluster || mp > 16384) return c->part[0];
+    return mp > 8192 ? c->part[2] : c->part[1];
+  };
+  auto use = [&](cudaStream_t s, int ctas) { c->cur = s; c->cur_ctas = ctas; };
   CQR_CUDA(cudaEventRecord(c->ev_start, st));
-  CQR_CUDA(cudaStreamWaitEvent(c->side, c->ev_start, 0));
-  c->cur = c->side;
+  SmPartition* pp = &pair_for(m);
+  cudaStream_t prev_p = pp->sp, prev_g = nullptr;
+  CQR_CUDA(cudaStreamWaitEvent(prev_p, c->ev_start, 0));
+  use(prev_p, pp->sm_p);
   do_panels(0, bb[0]);
-  CQR_CUDA(cudaEventRecord(c->ev_panel[0], c->side));
+  CQR_CUDA(cudaEventRecord(c->ev_panel[0], prev_p));
   for (int blk = 0; blk < nblk; ++blk) {
     const int K0 = blk * KB;
     const int kbw = (n - K0 < KB) ? n - K0 : KB;
     const int cnext = K0 + kbw;
     const int nrest = n - cnext;
-    c->cur = nullptr;
-    CQR_CUDA(cudaStreamWaitEvent(st, c->ev_panel[blk & 1], 0));
     if (nrest <= 0) break;
+    SmPartition& pr = pair_for(m - cnext);
+    cudaStream_t G = pr.sg, P = pr.sp;
+    if (prev_g && prev_g != G) {   // partition changed: chain the new GEMM stream behind the old one
+      CQR_CUDA(cudaEventRecord(c->ev_g, prev_g));
+      CQR_CUDA(cudaStreamWaitEvent(G, c->ev_g, 0));
+    }
+    CQR_CUDA(cudaStreamWaitEvent(G, c->ev_panel[blk & 1], 0));
+    use(G, pr.sm_g);
+    do_block_t(K0, bb[blk & 1]);
     const int la = nrest < KB ? nrest : KB;
     do_update(K0, bb[blk & 1], cnext, cnext + la);
-    CQR_CUDA(cudaEventRecord(c->ev_a, st));
-    CQR_CUDA(cudaStreamWaitEvent(c->side, c->ev_a, 0));
-    c->cur = c->side;
+    CQR_CUDA(cudaEventRecord(c->ev_a, G));
+    if (prev_p != P) CQR_CUDA(cudaStreamWaitEvent(P, c->ev_panel[blk & 1], 0));
+    CQR_CUDA(cudaStreamWaitEvent(P, c->ev_a, 0));
+    use(P, pr.sm_p);
     do_panels(cnext, bb[(blk + 1) & 1]);
-    CQR_CUDA(cudaEventRecord(c->ev_panel[(blk + 1) & 1], c->side));
-    c->cur = nullptr;
+    CQR_CUDA(cudaEventRecord(c->ev_panel[(blk + 1) & 1], P));
+    use(G, pr.sm_g);
     do_update(K0, bb[blk & 1], cnext + la, n);
+    prev_g = G; prev_p = P;
   }
-  c->cur = nullptr;
+  use(nullptr, 0);
+  // hand the result back to the caller's stream: last panel chain and last trailing update
+  CQR_CUDA(cudaStreamWaitEvent(st, c->ev_panel[(nblk - 1) & 1], 0));
+  if (prev_g) {
+    CQR_CUDA(cudaEventRecord(c->ev_g, prev_g));
+    CQR_CUDA(cudaStreamWaitEvent(st, c->ev_g, 0));
+  }
   return (int)cudaGetLastError();
 }
 

@@ -356,7 +356,7 @@ int sm_count() {
 
 template <int BN, bool kAMn>
 bool launch_umma(int M, int N, int K, const float* a, long long lda, const float* b, long long ldb, const Epilogue& ep,
-                 int splits, cudaStream_t s) {
+                 int splits, int max_ctas, cudaStream_t s) {
   CUtensorMap ta, tb, td;
   bool ok;
   if (kAMn) ok = make_map(&ta, a, M, K, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
@@ -381,7 +381,8 @@ bool launch_umma(int M, int N, int K, const float* a, long long lda, const float
   splits = (K + kper - 1) / kper;
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   const long long total = (long long)tiles_m * tiles_n * splits;
-  const int grid = (int)(total < sm_count() ? total : sm_count());
+  if (max_ctas < 1 || max_ctas > sm_count()) max_ctas = sm_count();
+  const int grid = (int)(total < max_ctas ? total : max_ctas);
   ++g_launches;
   umma_gemm_kernel<BN, kAMn><<<grid, kThreadsP, smem, s>>>(ta, tb, td, e2, M, N, K, kper, tiles_m, tiles_n, splits);
   return true;
@@ -410,23 +411,23 @@ int umma_effective_splits(int K, int splits) {
 }
 
 bool launch_gemm_tn_umma(int M, int N, int K, const float* a, long long lda, const float* b, long long ldb, float* d,
-                         long long ldd, int splits, long long d_split_stride, cudaStream_t s) {
+                         long long ldd, int splits, long long d_split_stride, int max_ctas, cudaStream_t s) {
   if (!umma_available()) return false;
   if (lda % 4 || ldb % 4 || !aligned16(a) || !aligned16(b)) return false;
   if (M < 1 || N < 1 || K < 1) return false;
   Epilogue ep{d, ldd, d_split_stride, 1.f, 0.f};
-  if (N > 128) return launch_umma<256, false>(M, N, K, a, lda, b, ldb, ep, splits, s);
-  return launch_umma<128, false>(M, N, K, a, lda, b, ldb, ep, splits, s);
+  if (N > 128) return launch_umma<256, false>(M, N, K, a, lda, b, ldb, ep, splits, max_ctas, s);
+  return launch_umma<128, false>(M, N, K, a, lda, b, ldb, ep, splits, max_ctas, s);
 }
 
 bool launch_gemm_nn_umma(int M, int N, int K, float alpha, const float* a, long long lda, const float* b, long long ldb,
-                         float beta, float* d, long long ldd, cudaStream_t s) {
+                         float beta, float* d, long long ldd, int max_ctas, cudaStream_t s) {
   if (!umma_available()) return false;
   if (lda % 4 || ldb % 4 || !aligned16(a) || !aligned16(b)) return false;
   if (M < 1 || N < 1 || K < 1) return false;
   Epilogue ep{d, ldd, 0, alpha, beta};
-  if (N > 128) return launch_umma<256, true>(M, N, K, a, lda, b, ldb, ep, 1, s);
-  return launch_umma<128, true>(M, N, K, a, lda, b, ldb, ep, 1, s);
+  if (N > 128) return launch_umma<256, true>(M, N, K, a, lda, b, ldb, ep, 1, max_ctas, s);
+  return launch_umma<128, true>(M, N, K, a, lda, b, ldb, ep, 1, max_ctas, s);
 }
 
 }  // namespace cqr

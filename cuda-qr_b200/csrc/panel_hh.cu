@@ -266,31 +266,30 @@ __global__ void __launch_bounds__(512, 1) panel_hh_kernel(PanelHHParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Cluster variant: the P <= 16 slab CTAs form ONE thread-block cluster and exchange their partial dots
-// through distributed shared memory (st local -> barrier.cluster -> ld.shared::cluster from every peer):
-// ~0.5 us per column step instead of the ~2-3 us an L2 round trip costs on B200 (measured, tools/hh_trace.py).
-// Thread layout differs from the kernel above: a thread owns ONE column (c = tid / 8) and the rows
-// {4 (g + 8 ch) + e} of its slab (g = tid % 8, RR rows in chunks of 4), so a dot product needs only a
-// 3-stage shuffle reduction over the 8 row groups and four columns reduce at once in one warp.
+// Cluster variant: the slab CTAs form one (m_p <= 8192) or two (m_p <= 16384) thread-block clusters of up to 16
+// CTAs.  Inside a cluster the slab-local dots are all-gathered through distributed shared memory with one-sided
+// 16-byte st.async pushes that credit the receiver's mbarrier (16 x 16 transactions per CTA and step; the first
+// version pushed single floats and was bound by DSMEM transaction rate: ~1400 cycles per step, tools/hh_trace.py).
+// Two clusters exchange their 64 cluster sums (and the pivot row) through flag-tagged 8-byte slots in global
+// memory: one L2 round trip between exactly two parties.  All CTAs add the partials in the same order, so every CTA
+// derives bitwise identical reflector scalars.
+// Thread layout: a thread owns ONE column (c = tid / 8) and the rows {4 (g + 8 ch) + e} of its slab (g = tid % 8,
+// RR rows in chunks of 4) held as packed f32x2 register pairs, so the dot and the rank-1 update run on FFMA2
+// (two fp32 FMAs per issue slot: the 3-operand scalar FFMA issues at half rate on sm_100) and a dot product needs
+// only a 3-stage shuffle reduction over the 8 row groups.
 __device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ float ld_dsmem(const float* local, unsigned rank) {
-  unsigned la = (unsigned)__cvta_generic_to_shared(local), ra;
-  float v;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
-  return v;
-}
-// One-sided push into a peer CTA's shared memory that also credits `bytes` on the peer's mbarrier (the
+// One-sided 16-byte push into a peer CTA's shared memory that also credits 16 bytes on the peer's mbarrier (the
 // receiver just waits on its own barrier: no cluster-wide barrier, no fence).
-__device__ __forceinline__ void st_async_f32(float* local_dst, unsigned long long* local_bar, unsigned rank, float v) {
+__device__ __forceinline__ void st_async_v4(float* local_dst, unsigned long long* local_bar, unsigned rank, float4 v) {
   unsigned la = (unsigned)__cvta_generic_to_shared(local_dst), lb = (unsigned)__cvta_generic_to_shared(local_bar), ra, rb;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(lb), "r"(rank));
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(ra), "r"(__float_as_uint(v)), "r"(rb)
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(ra),
+               "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)), "r"(rb)
                : "memory");
 }
 __device__ __forceinline__ void mbar_init_local(unsigned long long* bar, unsigned count) {
@@ -311,23 +310,29 @@ __device__ __forceinline__ void mbar_wait_local(unsigned long long* bar, unsigne
         : "memory");
   } while (!ok);
 }
-__device__ __forceinline__ float sel4(float v0, float v1, float v2, float v3, int e) {
-  return e == 0 ? v0 : (e == 1 ? v1 : (e == 2 ? v2 : v3));
-}
+// packed fp32 pairs (FFMA2)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
 template <int RR>
 __global__ void __launch_bounds__(512, 1) panel_hh_cluster_kernel(PanelHHParams p) {
   constexpr int TH = 8 * RR, NCH = RR / 4;
   __shared__ __align__(16) float xs[2][TH];
-  __shared__ float inbox[2][16][64];    // slab-local dots pushed here by every CTA of the cluster (st.async)
-  __shared__ float prow[2][64];         // row j of the panel, pushed by CTA 0
+  __shared__ __align__(16) float inbox[2][16][64];   // slab-local dots pushed here by every CTA of the cluster (st.async)
+  __shared__ __align__(16) float prow[2][64];        // row j of the panel, pushed by CTA 0 (cluster 0 only)
   __shared__ unsigned long long mbar[2];
   __shared__ float sc[2][4];            // {beta, 1/u, tau, u}
   __shared__ float gs[64][65];          // CTA 0: G(c, j) = v_c^T v_j (c < j)
   __shared__ float ts[64][65];
   __shared__ float staus[64];
-  const unsigned cta = cluster_ctarank(), CS = cluster_nctarank();
-  const unsigned P = CS; (void)P;
+  const unsigned rank = cluster_ctarank(), CS = cluster_nctarank();
+  const unsigned cta = blockIdx.x;                 // slab index over the whole grid
+  const unsigned cl = cta / CS;                    // cluster index (0 or 1)
+  const unsigned ncl = gridDim.x / CS;
+  const int P = (int)gridDim.x; (void)P;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   const int c = threadIdx.x >> 3, g = l & 7;       // my column, my row group
   const long long row0 = (long long)cta * TH;
@@ -338,20 +343,24 @@ __global__ void __launch_bounds__(512, 1) panel_hh_cluster_kernel(PanelHHParams 
   float* __restrict__ Vc = p.vbuf + row0 + (long long)c * p.ldv;
   const bool vec_ok = (p.lda % 4 == 0) && (p.ldv % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.a) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(p.vbuf) & 15) == 0);
+  uint2* xslot = p.slots;                          // [2 buffers][3: cluster 0 sums, cluster 1 sums, pivot row][64]
 
-  float a[RR];
+  f32x2 a[RR / 2];                                 // a[2 ch] = rows 4(g+8ch)+{0,1}, a[2 ch + 1] = rows +{2,3}
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     const int r0 = 4 * (g + 8 * ch);
+    float4 v;
     if (c < b && vec_ok && r0 + 3 < rows) {
-      const float4 v = *reinterpret_cast<const float4*>(Ac + r0);
-      a[4 * ch] = v.x; a[4 * ch + 1] = v.y; a[4 * ch + 2] = v.z; a[4 * ch + 3] = v.w;
+      v = *reinterpret_cast<const float4*>(Ac + r0);
     } else {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) a[4 * ch + e] = (c < b && r0 + e < rows) ? Ac[r0 + e] : 0.f;
+      v.x = (c < b && r0 + 0 < rows) ? Ac[r0 + 0] : 0.f;
+      v.y = (c < b && r0 + 1 < rows) ? Ac[r0 + 1] : 0.f;
+      v.z = (c < b && r0 + 2 < rows) ? Ac[r0 + 2] : 0.f;
+      v.w = (c < b && r0 + 3 < rows) ? Ac[r0 + 3] : 0.f;
     }
+    a[2 * ch] = pack2(v.x, v.y);
+    a[2 * ch + 1] = pack2(v.z, v.w);
   }
-  float4 (*xs4)[TH / 4] = reinterpret_cast<float4 (*)[TH / 4]>(xs);
   if (CS > 1) {
     if (threadIdx.x == 0) {
       mbar_init_local(&mbar[0], 1);
@@ -360,6 +369,7 @@ __global__ void __launch_bounds__(512, 1) panel_hh_cluster_kernel(PanelHHParams 
     }
     cluster_sync_all();   // every peer's barriers exist before anyone pushes
   }
+  const unsigned expect_bytes = (CS * 64 + (cl == 0 ? 64 : 0)) * 4;
 
 #pragma unroll
   for (int sj = 0; sj < 4; ++sj) {
@@ -370,57 +380,99 @@ __global__ void __launch_bounds__(512, 1) panel_hh_cluster_kernel(PanelHHParams 
       const int chj = sj >> 1;                 // row j: chunk j / 32 (static after unrolling), group (j / 4) % 8, element j % 4
       const int gj = (j >> 2) & 7, ej = j & 3;
       const bool owner = (c == j);
-      const int jrel = j - (int)row0;          // pivot row in slab-local numbering (negative below slab 0)
+      const int jrel = j - (int)row0;          // pivot row in slab-local numbering (negative below slab 0); row0 < 2^31 here
+      const unsigned tag = p.epoch * 64u + (unsigned)j + 1u;
       if (owner) {
+        // x = column j below (and including) the diagonal.  Only slab 0 holds rows above it, all inside chunks 0 and 1.
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
-          const int r0 = 4 * (g + 8 * ch);
           float4 v;
-          v.x = (r0 + 0 >= jrel) ? a[4 * ch + 0] : 0.f;
-          v.y = (r0 + 1 >= jrel) ? a[4 * ch + 1] : 0.f;
-          v.z = (r0 + 2 >= jrel) ? a[4 * ch + 2] : 0.f;
-          v.w = (r0 + 3 >= jrel) ? a[4 * ch + 3] : 0.f;
-          xs4[buf][g + 8 * ch] = v;
+          unpack2(a[2 * ch], v.x, v.y);
+          unpack2(a[2 * ch + 1], v.z, v.w);
+          if (ch < 2 && cta == 0) {
+            const int r0 = 4 * (g + 8 * ch);
+            v.x = (r0 + 0 >= jrel) ? v.x : 0.f;
+            v.y = (r0 + 1 >= jrel) ? v.y : 0.f;
+            v.z = (r0 + 2 >= jrel) ? v.z : 0.f;
+            v.w = (r0 + 3 >= jrel) ? v.w : 0.f;
+          }
+          *reinterpret_cast<float4*>(&xs[buf][4 * (g + 8 * ch)]) = v;
         }
       }
       __syncthreads();
       HH_TRACE(0);
-      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      f32x2 acc0 = 0ull, acc1 = 0ull;
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
-        const float4 xv = xs4[buf][g + 8 * ch];
-        acc0 = fmaf(xv.x, a[4 * ch + 0], acc0);
-        acc1 = fmaf(xv.y, a[4 * ch + 1], acc1);
-        acc2 = fmaf(xv.z, a[4 * ch + 2], acc2);
-        acc3 = fmaf(xv.w, a[4 * ch + 3], acc3);
-        if (RR > 16 && (ch & 3) == 3) asm volatile("" ::: "memory");   // keep the LDS look-ahead (register pressure) bounded
+        const ulonglong2 xv = *reinterpret_cast<const ulonglong2*>(&xs[buf][4 * (g + 8 * ch)]);
+        acc0 = fma2(xv.x, a[2 * ch], acc0);
+        acc1 = fma2(xv.y, a[2 * ch + 1], acc1);
       }
-      float s = (acc0 + acc1) + (acc2 + acc3);
+      float s;
+      {
+        float s0, s1, s2, s3;
+        unpack2(acc0, s0, s1);
+        unpack2(acc1, s2, s3);
+        s = (s0 + s1) + (s2 + s3);
+      }
       s += __shfl_xor_sync(kFull, s, 1);
       s += __shfl_xor_sync(kFull, s, 2);
       s += __shfl_xor_sync(kFull, s, 4);
-      const float mine = sel4(a[4 * chj], a[4 * chj + 1], a[4 * chj + 2], a[4 * chj + 3], ej);   // a(j, c) if g == gj on CTA 0
-      float ajc;
+      float mine;   // a(j, c) if this thread holds row j (slab 0, g == gj)
+      {
+        float m0, m1, m2, m3;
+        unpack2(a[2 * chj], m0, m1);
+        unpack2(a[2 * chj + 1], m2, m3);
+        mine = ej == 0 ? m0 : (ej == 1 ? m1 : (ej == 2 ? m2 : m3));
+      }
+      float ajc = __shfl_sync(kFull, mine, (l & 24) | gj);   // valid on slab 0
       HH_TRACE(1);
       if (CS > 1) {
-        // push my column's slab-local dot to peers g and g + 8 (all 8 lanes of the column group hold s); CTA 0
-        // pushes the pivot-row entry the same way; then wait for the CS x 64 (+64) floats addressed to me
-        if (threadIdx.x == 0) mbar_expect_tx_local(&mbar[buf], (CS * 64 + 64) * 4);
-        const float pj = __shfl_sync(kFull, mine, (l & 24) | gj);
-        for (unsigned i = g; i < CS; i += 8) {
-          st_async_f32(&inbox[buf][cta][c], &mbar[buf], i, s);
-          if (cta == 0) st_async_f32(&prow[buf][c], &mbar[buf], i, pj);
-        }
+        // all-gather inside the cluster: lane i < CS of warp w pushes the warp's four column sums to peer i; on
+        // slab 0 lanes 16 .. 16+CS push the pivot-row entries the same way
+        if (threadIdx.x == 0) mbar_expect_tx_local(&mbar[buf], expect_bytes);
+        float4 sv, pv;
+        sv.x = __shfl_sync(kFull, s, 0); sv.y = __shfl_sync(kFull, s, 8); sv.z = __shfl_sync(kFull, s, 16); sv.w = __shfl_sync(kFull, s, 24);
+        pv.x = __shfl_sync(kFull, ajc, 0); pv.y = __shfl_sync(kFull, ajc, 8); pv.z = __shfl_sync(kFull, ajc, 16); pv.w = __shfl_sync(kFull, ajc, 24);
+        if ((unsigned)l < CS) st_async_v4(&inbox[buf][rank][4 * w], &mbar[buf], (unsigned)l, sv);
+        else if (cta == 0 && l >= 16 && (unsigned)(l - 16) < CS) st_async_v4(&prow[buf][4 * w], &mbar[buf], (unsigned)(l - 16), pv);
         mbar_wait_local(&mbar[buf], (j >> 1) & 1);
         float t = 0.f;
         for (unsigned i = g; i < CS; i += 8) t += inbox[buf][i][c];
-        ajc = prow[buf][c];
         t += __shfl_xor_sync(kFull, t, 1);
         t += __shfl_xor_sync(kFull, t, 2);
         t += __shfl_xor_sync(kFull, t, 4);
         s = t;
-      } else {
-        ajc = __shfl_sync(kFull, mine, (l & 24) | gj);
+        if (cl == 0) ajc = prow[buf][c];
+      }
+      if (ncl > 1) {
+        // two clusters: the cluster leaders publish their 64 cluster sums (cluster 0 also the pivot row) as
+        // {value, tag} pairs; every CTA polls the other cluster's slots for its own columns
+        uint2* mys = xslot + ((size_t)buf * 3 + cl) * 64;
+        const uint2* oth = xslot + ((size_t)buf * 3 + (cl ^ 1u)) * 64;
+        uint2* piv = xslot + ((size_t)buf * 3 + 2) * 64;
+        if (rank == 0 && g == 0) {
+          st_flag(mys + c, s, tag);
+          if (cl == 0) st_flag(piv + c, ajc, tag);
+        }
+        float so = 0.f, po = 0.f;
+        if (g == 0) {
+          long long t0 = 0;
+          for (;;) {
+            const uint2 r = ld_flag(oth + c);
+            uint2 q; q.x = 0u; q.y = tag;
+            if (cl != 0) q = ld_flag(piv + c);
+            so = __uint_as_float(r.x); po = __uint_as_float(q.x);
+            if (r.y == tag && q.y == tag) break;
+            if (t0 == 0) t0 = clock64();
+            if (*(volatile int*)p.err != 0) break;
+            if (clock64() - t0 > kSpinTimeout) { atomicExch(p.err, 1); break; }
+          }
+        }
+        so = __shfl_sync(kFull, so, l & 24);
+        po = __shfl_sync(kFull, po, l & 24);
+        s = (cl == 0) ? (s + so) : (so + s);   // same order on both sides: cluster 0 + cluster 1
+        if (cl != 0) ajc = po;
       }
       HH_TRACE(2);
       if (owner && g == 0) {   // reflector scalars once per CTA (qr.c:144-152), handed over through shared memory
@@ -443,31 +495,42 @@ __global__ void __launch_bounds__(512, 1) panel_hh_cluster_kernel(PanelHHParams 
       const bool nz = inv_u != 0.f;
       const float d = nz ? (s - beta * ajc) * inv_u : ajc;   // v^T a_c (zero column: v = e_j)
       if (c > j) {
-        const float wc = tau * d * inv_u;   // a_c -= tau (v^T a_c) v with v = x / u, v_j = 1 (x_j patched to u)
+        // a_c -= tau (v^T a_c) v with v = x / u and v_j = 1: 1/u is folded into the column scalar and x_j patched to u
+        const float nwc = -(tau * d * inv_u);
+        const f32x2 nw2 = pack2(nwc, nwc);
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
-          float4 xv = xs4[buf][g + 8 * ch];
+          ulonglong2 xv = *reinterpret_cast<const ulonglong2*>(&xs[buf][4 * (g + 8 * ch)]);
           if (ch == chj && cta == 0 && g == gj) {
-            if (ej == 0) xv.x = u; else if (ej == 1) xv.y = u; else if (ej == 2) xv.z = u; else xv.w = u;
+            float x0, x1, x2, x3;
+            unpack2(xv.x, x0, x1); unpack2(xv.y, x2, x3);
+            if (ej == 0) x0 = u; else if (ej == 1) x1 = u; else if (ej == 2) x2 = u; else x3 = u;
+            xv.x = pack2(x0, x1); xv.y = pack2(x2, x3);
           }
-          a[4 * ch + 0] = fmaf(-wc, xv.x, a[4 * ch + 0]);
-          a[4 * ch + 1] = fmaf(-wc, xv.y, a[4 * ch + 1]);
-          a[4 * ch + 2] = fmaf(-wc, xv.z, a[4 * ch + 2]);
-          a[4 * ch + 3] = fmaf(-wc, xv.w, a[4 * ch + 3]);
-          if (RR > 16 && (ch & 3) == 3) asm volatile("" ::: "memory");
+          a[2 * ch] = fma2(xv.x, nw2, a[2 * ch]);
+          a[2 * ch + 1] = fma2(xv.y, nw2, a[2 * ch + 1]);
         }
       } else if (c < j) {
         if (cta == 0 && g == 0) gs[c][j] = d;   // G(c, j) = v_c^T v_j
       } else if (nz) {
+        const f32x2 iu2 = pack2(inv_u, inv_u);
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
-          const float4 xv = xs4[buf][g + 8 * ch];
-          const int r0 = 4 * (g + 8 * ch);
-          const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+          const ulonglong2 xv = *reinterpret_cast<const ulonglong2*>(&xs[buf][4 * (g + 8 * ch)]);
+          if (ch < 2 && cta == 0) {
+            const int r0 = 4 * (g + 8 * ch);
+            float xe[4], ae[4];
+            unpack2(xv.x, xe[0], xe[1]); unpack2(xv.y, xe[2], xe[3]);
+            unpack2(a[2 * ch], ae[0], ae[1]); unpack2(a[2 * ch + 1], ae[2], ae[3]);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (r0 + e > jrel) a[4 * ch + e] = xe[e] * inv_u;
-            else if (r0 + e == jrel) a[4 * ch + e] = beta;
+            for (int e = 0; e < 4; ++e) {
+              if (r0 + e > jrel) ae[e] = xe[e] * inv_u;
+              else if (r0 + e == jrel) ae[e] = beta;
+            }
+            a[2 * ch] = pack2(ae[0], ae[1]); a[2 * ch + 1] = pack2(ae[2], ae[3]);
+          } else {
+            a[2 * ch] = mul2(xv.x, iu2);
+            a[2 * ch + 1] = mul2(xv.y, iu2);
           }
         }
       }
@@ -479,16 +542,18 @@ __global__ void __launch_bounds__(512, 1) panel_hh_cluster_kernel(PanelHHParams 
   for (int ch = 0; ch < NCH; ++ch) {
     const int r0 = 4 * (g + 8 * ch);
     const long long gr0 = row0 + r0;
-    float v[4];
+    float av[4], v[4];
+    unpack2(a[2 * ch], av[0], av[1]);
+    unpack2(a[2 * ch + 1], av[2], av[3]);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] = gr0 + e > c ? a[4 * ch + e] : (gr0 + e == c ? 1.f : 0.f);
+    for (int e = 0; e < 4; ++e) v[e] = gr0 + e > c ? av[e] : (gr0 + e == c ? 1.f : 0.f);
     if (c < b && vec_ok && r0 + 3 < rows) {
-      *reinterpret_cast<float4*>(Ac + r0) = make_float4(a[4 * ch], a[4 * ch + 1], a[4 * ch + 2], a[4 * ch + 3]);
+      *reinterpret_cast<float4*>(Ac + r0) = make_float4(av[0], av[1], av[2], av[3]);
       *reinterpret_cast<float4*>(Vc + r0) = make_float4(v[0], v[1], v[2], v[3]);
     } else {
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        if (c < b && r0 + e < rows) { Ac[r0 + e] = a[4 * ch + e]; Vc[r0 + e] = v[e]; }
+        if (c < b && r0 + e < rows) { Ac[r0 + e] = av[e]; Vc[r0 + e] = v[e]; }
     }
   }
 
@@ -517,27 +582,28 @@ __global__ void __launch_bounds__(512, 1) panel_hh_cluster_kernel(PanelHHParams 
   if (CS > 1) cluster_sync_all();   // no CTA leaves while pushes addressed to it (or by it) are in flight
 }
 
-// Rows-per-thread and cluster size for an m_p-row panel on the cluster kernel (m_p <= 16 * 512).
-bool panel_hh_cluster_plan(long long mp, int* rr, int* cs) {
-  if (mp > 16 * 512) return false;
+// Rows-per-thread, cluster size and cluster count for an m_p-row panel on the cluster kernel (m_p <= 2 * 16 * 512).
+bool panel_hh_cluster_plan(long long mp, int* rr, int* cs, int* ncl) {
+  if (mp > 2 * 16 * 512) return false;
+  if (mp > 16 * 512) { *rr = 64; *cs = 16; *ncl = 2; return true; }
   int r = 8;
   while ((mp + 8 * r - 1) / (8 * r) > 16) r *= 2;
   const int P = (int)((mp + 8 * r - 1) / (8 * r));
   int c = 1;
   while (c < P) c *= 2;
-  *rr = r; *cs = c;
+  *rr = r; *cs = c; *ncl = 1;
   return true;
 }
 
 template <int RR>
-static cudaError_t launch_cluster_t(const PanelHHParams& p, int cs, cudaStream_t s) {
+static cudaError_t launch_cluster_t(const PanelHHParams& p, int cs, int ncl, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(panel_hh_cluster_kernel<RR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     attr_done = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cs, 1, 1);
+  cfg.gridDim = dim3(cs * ncl, 1, 1);
   cfg.blockDim = dim3(512, 1, 1);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = s;
@@ -548,13 +614,13 @@ static cudaError_t launch_cluster_t(const PanelHHParams& p, int cs, cudaStream_t
   return cudaLaunchKernelEx(&cfg, panel_hh_cluster_kernel<RR>, p);
 }
 
-bool launch_panel_hh_cluster(const PanelHHParams& p, int rr, int cs, cudaStream_t s) {
+bool launch_panel_hh_cluster(const PanelHHParams& p, int rr, int cs, int ncl, cudaStream_t s) {
   ++g_launches;
   cudaError_t e;
-  if (rr == 8) e = launch_cluster_t<8>(p, cs, s);
-  else if (rr == 16) e = launch_cluster_t<16>(p, cs, s);
-  else if (rr == 32) e = launch_cluster_t<32>(p, cs, s);
-  else e = launch_cluster_t<64>(p, cs, s);
+  if (rr == 8) e = launch_cluster_t<8>(p, cs, ncl, s);
+  else if (rr == 16) e = launch_cluster_t<16>(p, cs, ncl, s);
+  else if (rr == 32) e = launch_cluster_t<32>(p, cs, ncl, s);
+  else e = launch_cluster_t<64>(p, cs, ncl, s);
   if (e != cudaSuccess) { cudaGetLastError(); --g_launches; return false; }
   return true;
 }

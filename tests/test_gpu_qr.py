@@ -225,11 +225,13 @@ def test_geqrf_panel_modes(pkg, torch, ctx, panel_mode, m, n):
     ctx.set_option(pkg.OPT_PANEL, 1)
 
 
-def test_geqrf_panel_hh_matches_lapack_storage(pkg, torch, ctx):
+@pytest.mark.parametrize("m", [300, 2500, 6000, 9000, 16384, 20000])
+def test_geqrf_panel_hh_matches_lapack_storage(pkg, torch, ctx, m):
     """The multi-CTA panel writes LAPACK geqrf storage directly: v below the diagonal and tau must reproduce
     the fp64 Householder vectors of the same sign convention (beta = -sign(alpha) norm, qr.c:149-152), and the
-    run must be bitwise reproducible (fixed-order cross-CTA reduction)."""
-    m, n = 9000, 64
+    run must be bitwise reproducible (fixed-order cross-CTA reduction).  Sizes cover one cluster (DSMEM exchange,
+    8 .. 64 rows per thread), two clusters (global-flag exchange between them, m > 8192) and the flag-only kernel."""
+    n = 64
     rng = np.random.default_rng(3)
     A = np.asfortranarray(rng.standard_normal((m, n)).astype(np.float32))
     outs = []

@@ -265,7 +265,7 @@ class Context:
     def launch_count(self) -> int:
         return int(lib.cqr_launch_count(self.h))
 
-    PROF_CLASSES = ("panel", "gemm_tn", "gemm_nn", "misc")
+    PROF_CLASSES = ("panel", "gemm_tn", "gemm_nn", "misc", "chain_tn", "chain_nn", "chain_misc")
 
     def profile_begin(self):
         _check(lib.cqr_profile_begin(self.h), "cqr_profile_begin")

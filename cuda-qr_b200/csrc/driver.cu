@@ -69,6 +69,7 @@ struct cqr_context {
   // look-ahead: panel work of block K+1 runs on `side` while block K's trailing update runs on `stream`
   cudaStream_t side = nullptr, work = nullptr;
   cudaStream_t cur = nullptr;      // stream the launch helpers use right now (nullptr = `stream`)
+  bool cur_chain = false;          // `cur` is the panel-chain stream (profiling classes CQR_PROF_CHAIN_*)
   int cur_ctas = 0;                // SMs behind `cur` (0 = the whole device): caps persistent grids and split-K choices
   SmPartition part[3];             // [0] unpartitioned (side/work streams), [1] 16 + 132 SMs, [2] 2 x 16 + 116 SMs
   int opt_partition = 1;
@@ -185,6 +186,7 @@ struct ProfScope {
   cqr_context* c; int idx = -1; long long l0 = 0; cudaStream_t s0 = nullptr;
   ProfScope(cqr_context* ctx, int cat, double flops, double bytes) : c(ctx) {
     if (!c->prof_on) return;
+    if (c->cur_chain && cat >= CQR_PROF_GEMM_TN && cat <= CQR_PROF_MISC) cat += 3;
     cqr_context::ProfRec r{cat, flops, bytes, 0, prof_event(c), prof_event(c)};
     s0 = cur_stream(c);
     cudaEventRecord(r.e0, s0);
@@ -290,14 +292,26 @@ void run_tsqr_form_q(cqr_context* c, const TsqrPlan& P, const float* a, long lon
 }
 
 // ---- GEMM dispatch (tcgen05 3xTF32 when the shape allows, else fp32 SIMT) ---------------------
+// K splits of a TN product: the persistent kernel walks tiles x splits work items on `ctas` CTAs, so pick the split
+// count whose last wave is fullest (a 2.16-wave launch runs as long as a 3-wave one), preferring fewer splits
+// (less partial traffic) among near-equal choices.  Every split keeps at least 256 rows of K.
 int pick_splits(cqr_context* c, int M, int N, int K, int tile_m, int tile_n) {
   if (c->opt_splitk > 0) return c->opt_splitk;
   const long long tiles = (long long)((M + tile_m - 1) / tile_m) * ((N + tile_n - 1) / tile_n);
-  long long s = (2LL * cur_ctas(c) + tiles - 1) / tiles;
-  const long long kmax = K / 512 > 0 ? K / 512 : 1;
-  if (s > kmax) s = kmax;
-  if (s > 32) s = 32;
-  return s < 1 ? 1 : (int)s;
+  const int ctas = cur_ctas(c);
+  int smax = K / 256;
+  if (smax > 32) smax = 32;
+  if (smax < 1) smax = 1;
+  int best = 1;
+  double best_t = 1e300;
+  for (int s = 1; s <= smax; ++s) {
+    const long long items = tiles * s;
+    const long long waves = (items + ctas - 1) / ctas;
+    // time ~ waves x (K / s per item) + a per-item cost (epilogue + partial traffic) worth ~64 rows of K
+    const double t = (double)waves * ((double)K / s + 64.0);
+    if (t < best_t * 0.97) { best_t = t; best = s; }
+  }
+  return best;
 }
 
 struct Operand { const float* p; long long ld; };
@@ -701,12 +715,12 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
     if (!c->opt_partition || c->opt_panel != 1 || !c->opt_cluster || mp > 16384) return c->part[0];
     return mp > 8192 ? c->part[2] : c->part[1];
   };
-  auto use = [&](cudaStream_t s, int ctas) { c->cur = s; c->cur_ctas = ctas; };
+  auto use = [&](cudaStream_t s, int ctas, bool chain) { c->cur = s; c->cur_ctas = ctas; c->cur_chain = chain; };
   CQR_CUDA(cudaEventRecord(c->ev_start, st));
   SmPartition* pp = &pair_for(m);
   cudaStream_t prev_p = pp->sp, prev_g = nullptr;
   CQR_CUDA(cudaStreamWaitEvent(prev_p, c->ev_start, 0));
-  use(prev_p, pp->sm_p);
+  use(prev_p, pp->sm_p, true);
   do_panels(0, bb[0]);
   CQR_CUDA(cudaEventRecord(c->ev_panel[0], prev_p));
   for (int blk = 0; blk < nblk; ++blk) {
@@ -722,21 +736,21 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
       CQR_CUDA(cudaStreamWaitEvent(G, c->ev_g, 0));
     }
     CQR_CUDA(cudaStreamWaitEvent(G, c->ev_panel[blk & 1], 0));
-    use(G, pr.sm_g);
+    use(G, pr.sm_g, false);
     do_block_t(K0, bb[blk & 1]);
     const int la = nrest < KB ? nrest : KB;
     do_update(K0, bb[blk & 1], cnext, cnext + la);
     CQR_CUDA(cudaEventRecord(c->ev_a, G));
     if (prev_p != P) CQR_CUDA(cudaStreamWaitEvent(P, c->ev_panel[blk & 1], 0));
     CQR_CUDA(cudaStreamWaitEvent(P, c->ev_a, 0));
-    use(P, pr.sm_p);
+    use(P, pr.sm_p, true);
     do_panels(cnext, bb[(blk + 1) & 1]);
     CQR_CUDA(cudaEventRecord(c->ev_panel[(blk + 1) & 1], P));
-    use(G, pr.sm_g);
+    use(G, pr.sm_g, false);
     do_update(K0, bb[blk & 1], cnext + la, n);
     prev_g = G; prev_p = P;
   }
-  use(nullptr, 0);
+  use(nullptr, 0, false);
   // hand the result back to the caller's stream: last panel chain and last trailing update
   CQR_CUDA(cudaStreamWaitEvent(st, c->ev_panel[(nblk - 1) & 1], 0));
   if (prev_g) {

@@ -76,6 +76,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 // Shared-memory matrix descriptor, 128B swizzle, Blackwell version bit set.
 //   K-major : rows of 128 B, 8-row atoms 1024 B apart (SBO); LBO unused (1)
 //   MN-major: 32-element chunks along M at LBO, 8-deep K groups at SBO = 1024
@@ -116,13 +127,18 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 //   warps 2-9    converters: lo = x - trunc(x) of the landed k-block into the stage's lo half (overlaps the
 //                MMAs of the previous k-block)
 //   warp 1       MMA issuer: 12 tcgen05.mma per k-block into one of two TMEM accumulators
-//   warps 10-13  epilogue: drains the other accumulator (tcgen05.ld) while the next tile's MMAs run
+//   warps 10-17  epilogue: drain the other accumulator (tcgen05.ld) while the next tile's MMAs run.  A warp may only
+//                touch TMEM lanes 32 (warp % 4) .. +31, so two warps share a lane quarter and split the columns; each
+//                walks its half in 16-column chunks with the C values of the NEXT chunk already in flight (the
+//                C -= V X update reads 128 KB of C per tile: with 4 warps and no prefetch the epilogue, not the
+//                tensor pipe, set the pace: 122 vs 190 TF/s at K = 256)
 // Barriers: full[s] (TMA landed), conv[s] (lo written, 256 arrivals), empty[s] (MMAs done with the stage),
 // tfull[a]/tempty[a] per accumulator.  All roles walk the same (tile, k-block) sequence, so phases are
 // derived from two running counters: g = k-blocks so far, i = tiles so far on this CTA.
 constexpr int kRing = 2;
 constexpr int kConvThreads = 256;
-constexpr int kThreadsP = 64 + kConvThreads + 128;
+constexpr int kEpiThreads = 256;
+constexpr int kThreadsP = 64 + kConvThreads + kEpiThreads;
 
 template <int BN, bool kAMn>
 __global__ void __launch_bounds__(kThreadsP, 1)
@@ -150,7 +166,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       mbar_init(empty0 + 8 * r, 1);
       mbar_init(conv0 + 8 * r, kConvThreads);
     }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, kEpiThreads); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -263,8 +279,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
     }
   } else {
-    // epilogue: warp q reads TMEM lanes [32q, 32q+32) = rows m0 + 32q + lane
-    const int q = warp & 3;
+    // epilogue: warp reads TMEM lanes [32q, 32q+32) = rows m0 + 32q + lane, columns [h BN/2, (h+1) BN/2)
+    const int q = warp & 3, h = (warp - (2 + kConvThreads / 32)) >> 2;
+    constexpr int CH = 16, NCHUNK = (BN / 2) / CH;
+    const bool has_c = ep.beta != 0.f;
     uint32_t i = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
       int m0, n0, z, kbeg, nkb;
@@ -272,28 +290,37 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const uint32_t a = i & 1;
       const int m = m0 + 32 * q + lane;
       const bool row_ok = m < M;
-      float* dz = ep.d + (long long)z * ep.split_stride;
+      float* dz = ep.d + (long long)z * ep.split_stride + m;
+      const int nbase = n0 + h * (BN / 2);
+      float old[CH], nxt[CH];
+      if (has_c) {   // first chunk of C: issued before the accumulator is even complete
+#pragma unroll
+        for (int j = 0; j < CH; ++j) old[j] = (row_ok && nbase + j < N) ? __ldcg(dz + (long long)(nbase + j) * ep.ldd) : 0.f;
+      }
       mbar_wait(tfull0 + 8 * a, (i >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tmem_d = tmem_base + a * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        float v[32];
-        tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), v);
-        float old[32];
-        const int nb = n0 + 32 * c;
-        if (ep.beta != 0.f) {
+      const uint32_t tmem_d = tmem_base + a * BN + ((uint32_t)(32 * q) << 16) + (uint32_t)(h * (BN / 2));
 #pragma unroll
-          for (int j = 0; j < 32; ++j) old[j] = (row_ok && nb + j < N) ? dz[m + (long long)(nb + j) * ep.ldd] : 0.f;
+      for (int c = 0; c < NCHUNK; ++c) {
+        float v[CH];
+        tmem_ld16(tmem_d + (uint32_t)(CH * c), v);
+        const int nb = nbase + CH * c;
+        if (has_c && c + 1 < NCHUNK) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) nxt[j] = (row_ok && nb + CH + j < N) ? __ldcg(dz + (long long)(nb + CH + j) * ep.ldd) : 0.f;
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < CH; ++j) {
           if (row_ok && nb + j < N) {
             float r = ep.alpha * v[j];
-            if (ep.beta != 0.f) r = fmaf(ep.beta, old[j], r);
-            dz[m + (long long)(nb + j) * ep.ldd] = r;
+            if (has_c) r = fmaf(ep.beta, old[j], r);
+            dz[(long long)(nb + j) * ep.ldd] = r;
           }
+        }
+        if (has_c) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) old[j] = nxt[j];
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

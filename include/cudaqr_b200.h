@@ -89,7 +89,9 @@ long long cqr_launch_count(cqr_context* ctx);
 /* Per-kernel-class timing for roofline reports: between begin and end every launch group is
  * bracketed by CUDA events on the context's stream; end synchronises and returns, per class,
  * the summed device milliseconds, algorithmic flops, algorithmic bytes and launch counts. */
-enum { CQR_PROF_PANEL = 0, CQR_PROF_GEMM_TN = 1, CQR_PROF_GEMM_NN = 2, CQR_PROF_MISC = 3, CQR_PROF_NCAT = 4 };
+enum { CQR_PROF_PANEL = 0, CQR_PROF_GEMM_TN = 1, CQR_PROF_GEMM_NN = 2, CQR_PROF_MISC = 3,
+       /* the same three classes when launched on the panel-chain stream (inner updates of a block) */
+       CQR_PROF_CHAIN_TN = 4, CQR_PROF_CHAIN_NN = 5, CQR_PROF_CHAIN_MISC = 6, CQR_PROF_NCAT = 7 };
 int cqr_profile_begin(cqr_context* ctx);
 int cqr_profile_end(cqr_context* ctx, double* ms, double* flops, double* bytes, long long* launches, int ncat);
 /* Pre-size the internal workspace (bytes) so no allocation happens in a timed region. */

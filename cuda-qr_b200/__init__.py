@@ -34,7 +34,7 @@ GEMM_SIMT, GEMM_TF32X3 = 0, 1
 EXPORTS = [
     "getPanelDims", "mmqr", "mmqr_alloc", "explicitQR", "dgemm", "identity", "printMat",
     "cqr_create", "cqr_destroy", "cqr_set_stream", "cqr_set_option", "cqr_get_option", "cqr_synchronize",
-    "cqr_error_string", "cqr_launch_count", "cqr_profile_begin", "cqr_profile_end", "cqr_reserve", "cqr_geqrf", "cqr_extract_r", "cqr_form_q",
+    "cqr_error_string", "cqr_launch_count", "cqr_profile_begin", "cqr_profile_end", "cqr_profile_timeline", "cqr_reserve", "cqr_geqrf", "cqr_extract_r", "cqr_form_q",
     "cqr_apply_q", "cqr_tsqr_r", "cqr_tsqr_factor", "cqr_tsqr_form_q", "cqr_stack_qr", "cqr_stack_form_q",
     "cqr_geqrf_batched", "cqr_gemm", "cqr_gemm_tf32x3", "cqr_set_identity", "cqr_version",
 ]
@@ -81,6 +81,8 @@ def _load() -> ctypes.CDLL:
     lib.cqr_profile_begin.argtypes = [_VP]
     lib.cqr_profile_end.argtypes = [_VP, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                     ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ll), i]
+    lib.cqr_profile_timeline.argtypes = [_VP, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                         ctypes.POINTER(ctypes.c_int), i]
     lib.cqr_geqrf.argtypes = [_VP, _VP, i, i, i, _VP]
     lib.cqr_extract_r.argtypes = [_VP, _VP, i, i, i, _VP, i, i]
     lib.cqr_form_q.argtypes = [_VP, _VP, i, i, i, _VP, _VP, i, i]
@@ -278,6 +280,14 @@ class Context:
         _check(lib.cqr_profile_end(self.h, ms, fl, by, la, n), "cqr_profile_end")
         return {k: {"ms": ms[j], "flops": fl[j], "bytes": by[j], "launches": int(la[j])}
                 for j, k in enumerate(self.PROF_CLASSES)}
+
+    def profile_timeline(self, cap: int = 1 << 16):
+        """[(start_ms, end_ms, class)] of every bracketed launch group since profile_begin(); call before profile_end()."""
+        t0, t1, cl = (ctypes.c_double * cap)(), (ctypes.c_double * cap)(), (ctypes.c_int * cap)()
+        n = lib.cqr_profile_timeline(self.h, t0, t1, cl, cap)
+        if n < 0:
+            raise RuntimeError("cqr_profile_timeline failed")
+        return [(t0[i], t1[i], self.PROF_CLASSES[cl[i]]) for i in range(n)]
 
     def reserve(self, nbytes: int):
         _check(lib.cqr_reserve(self.h, nbytes), "cqr_reserve")

@@ -126,6 +126,10 @@ void launch_gemm_nn_simt(int M, int N, int K, float alpha, const float* a, long 
 // out = sum_z part[z] (M x N, part ld = ldp, stride between parts = stride)
 void launch_reduce_splits(int M, int N, const float* part, long long ldp, long long stride, int splits, float* out,
                           long long ldo, cudaStream_t s);
+// x(kb x nc) = op(T) * sum_z part[z]: split-K reduction fused with the multiplication by the kb x kb upper-triangular
+// T (kb <= 256); trans != 0 -> T^T
+void launch_tw_fused(int kb, int nc, const float* part, long long ldp, long long stride, int splits, const float* t,
+                     long long ldt, int trans, float* x, long long ldx, cudaStream_t s);
 void launch_set_identity(float* a, long long lda, int m, int n, cudaStream_t s);
 void launch_fill_zero(float* a, long long lda, long long m, int n, cudaStream_t s);
 void launch_copy_matrix(long long m, int n, const float* a, long long lda, float* b, long long ldb, cudaStream_t s);

@@ -316,22 +316,36 @@ int pick_splits(cqr_context* c, int M, int N, int K, int tile_m, int tile_n) {
 
 struct Operand { const float* p; long long ld; };
 
-// d(M x N) = A^T B through a split-K partial buffer + reduction
-void gemm_tn(cqr_context* c, int M, int N, int K, Operand A, Operand B, float* part, float* d, long long ldd,
-             int max_splits, bool tensor) {
+// Split-K partials of A^T B: part[z] (M x N, ld *ldp, *stride apart), z < *splits
+void gemm_tn_part(cqr_context* c, int M, int N, int K, Operand A, Operand B, float* part, int max_splits, bool tensor,
+                  int* splits_out, long long* ldp_out, long long* stride_out) {
   int splits = pick_splits(c, M, N, K, 128, 128);
   if (splits > max_splits) splits = max_splits;
-  splits = umma_effective_splits(K, splits);   // no empty K ranges; the reduction below must agree
+  splits = umma_effective_splits(K, splits);   // no empty K ranges; the reduction must agree
   const long long ldp = round_up(M, 4);
   const long long stride = ldp * N;
   bool done = false;
-  {
-    // algorithmic traffic: both operands read once, partials written
-    ProfScope ps(c, CQR_PROF_GEMM_TN, 2.0 * M * N * K, 4.0 * ((double)K * (M + N) + (double)M * N * splits));
+  // algorithmic traffic: both operands read once, partials written
+  ProfScope ps(c, CQR_PROF_GEMM_TN, 2.0 * M * N * K, 4.0 * ((double)K * (M + N) + (double)M * N * splits));
+  if (tensor && c->opt_gemm == 1)
+    done = launch_gemm_tn_umma(M, N, K, A.p, A.ld, B.p, B.ld, part, ldp, splits, stride, cur_ctas(c), cur_stream(c));
+  if (!done) launch_gemm_tn_simt(M, N, K, A.p, A.ld, B.p, B.ld, part, ldp, splits, stride, cur_stream(c));
+  *splits_out = splits; *ldp_out = ldp; *stride_out = stride;
+}
+
+// d(M x N) = A^T B through a split-K partial buffer + reduction
+void gemm_tn(cqr_context* c, int M, int N, int K, Operand A, Operand B, float* part, float* d, long long ldd,
+             int max_splits, bool tensor) {
+  int splits; long long ldp, stride;
+  if (max_splits == 1 && ldd % 4 == 0) {   // single K range: the product lands in d directly, no partial buffer, no copy
+    ProfScope ps(c, CQR_PROF_GEMM_TN, 2.0 * M * N * K, 4.0 * ((double)K * (M + N) + (double)M * N));
+    bool done = false;
     if (tensor && c->opt_gemm == 1)
-      done = launch_gemm_tn_umma(M, N, K, A.p, A.ld, B.p, B.ld, part, ldp, splits, stride, cur_ctas(c), cur_stream(c));
-    if (!done) launch_gemm_tn_simt(M, N, K, A.p, A.ld, B.p, B.ld, part, ldp, splits, stride, cur_stream(c));
+      done = launch_gemm_tn_umma(M, N, K, A.p, A.ld, B.p, B.ld, d, ldd, 1, 0, cur_ctas(c), cur_stream(c));
+    if (!done) launch_gemm_tn_simt(M, N, K, A.p, A.ld, B.p, B.ld, d, ldd, 1, 0, cur_stream(c));
+    return;
   }
+  gemm_tn_part(c, M, N, K, A, B, part, max_splits, tensor, &splits, &ldp, &stride);
   ProfScope ps2(c, CQR_PROF_MISC, 0.0, 4.0 * M * N * (splits + 1));
   launch_reduce_splits(M, N, part, ldp, stride, splits, d, ldd, cur_stream(c));
 }
@@ -369,10 +383,18 @@ void apply_block(cqr_context* c, long long mk, int kb, int nc, Operand V, Operan
                  int trans_t, BlockWs& ws, bool tensor) {
   if (nc <= 0 || kb <= 0) return;
   Operand Cop{C, ldc};
-  gemm_tn(c, kb, nc, (int)mk, V, Cop, ws.part, ws.w, ws.ldw, kMaxSplits, tensor);           // W = V^T C
-  Operand W{ws.w, ws.ldw};
-  if (trans_t) gemm_tn(c, kb, nc, kb, T, W, ws.part, ws.x, ws.ldw, 1, tensor);              // X = T^T W
-  else gemm_nn(c, kb, nc, kb, 1.f, T, W, 0.f, ws.x, ws.ldw, tensor);                        // X = T W
+  if (nc <= 512 && kb <= 256) {
+    // narrow (latency-critical) update: W partials, then reduction and T multiply fused in one SIMT kernel
+    int splits; long long ldp, stride;
+    gemm_tn_part(c, kb, nc, (int)mk, V, Cop, ws.part, kMaxSplits, tensor, &splits, &ldp, &stride);   // W = V^T C
+    ProfScope ps(c, CQR_PROF_MISC, 1.0 * kb * kb * nc, 4.0 * kb * nc * (splits + 1));
+    launch_tw_fused(kb, nc, ws.part, ldp, stride, splits, T.p, T.ld, trans_t, ws.x, ws.ldw, cur_stream(c));   // X = op(T) W
+  } else {
+    gemm_tn(c, kb, nc, (int)mk, V, Cop, ws.part, ws.w, ws.ldw, kMaxSplits, tensor);           // W = V^T C
+    Operand W{ws.w, ws.ldw};
+    if (trans_t) gemm_tn(c, kb, nc, kb, T, W, ws.part, ws.x, ws.ldw, 1, tensor);              // X = T^T W
+    else gemm_nn(c, kb, nc, kb, 1.f, T, W, 0.f, ws.x, ws.ldw, tensor);                        // X = T W
+  }
   Operand X{ws.x, ws.ldw};
   gemm_nn(c, (int)mk, nc, kb, -1.f, V, X, 1.f, C, ldc, tensor);                             // C -= V X
 }
@@ -529,6 +551,21 @@ int cqr_profile_end(cqr_context* c, double* ms, double* flops, double* bytes, lo
   }
   c->prof.clear();
   return 0;
+}
+
+int cqr_profile_timeline(cqr_context* c, double* t0_ms, double* t1_ms, int* cls, int cap) {
+  if (!c || !t0_ms || !t1_ms || !cls || cap < 0) return -CQR_EINVAL;
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -CQR_ESTATE;
+  int n = 0;
+  for (auto& r : c->prof) {
+    if (n >= cap) break;
+    float a = 0.f, b = 0.f;
+    if (cudaEventElapsedTime(&a, c->prof[0].e0, r.e0) != cudaSuccess) return -CQR_ESTATE;
+    if (cudaEventElapsedTime(&b, c->prof[0].e0, r.e1) != cudaSuccess) return -CQR_ESTATE;
+    t0_ms[n] = a; t1_ms[n] = b; cls[n] = r.cat;
+    ++n;
+  }
+  return n;
 }
 
 int cqr_reserve(cqr_context* c, size_t bytes) { if (!c) return CQR_EINVAL; cudaSetDevice(c->device); return ws_ensure(c, bytes); }
@@ -720,8 +757,13 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
   SmPartition* pp = &pair_for(m);
   cudaStream_t prev_p = pp->sp, prev_g = nullptr;
   CQR_CUDA(cudaStreamWaitEvent(prev_p, c->ev_start, 0));
+  // While the remaining matrix is tall the GEMM stream is the busy one (it also owns fewer SMs then), so the block's
+  // aggregated T is built on the panel stream right after its last panel; later the panel chain is the critical
+  // path and the GEMM stream builds T.
+  auto t_on_chain = [&](int K0) { return c->opt_partition && (m - K0) > 8192; };
   use(prev_p, pp->sm_p, true);
   do_panels(0, bb[0]);
+  if (t_on_chain(0)) do_block_t(0, bb[0]);
   CQR_CUDA(cudaEventRecord(c->ev_panel[0], prev_p));
   for (int blk = 0; blk < nblk; ++blk) {
     const int K0 = blk * KB;
@@ -737,7 +779,7 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
     }
     CQR_CUDA(cudaStreamWaitEvent(G, c->ev_panel[blk & 1], 0));
     use(G, pr.sm_g, false);
-    do_block_t(K0, bb[blk & 1]);
+    if (!t_on_chain(K0)) do_block_t(K0, bb[blk & 1]);
     const int la = nrest < KB ? nrest : KB;
     do_update(K0, bb[blk & 1], cnext, cnext + la);
     CQR_CUDA(cudaEventRecord(c->ev_a, G));
@@ -745,6 +787,7 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
     CQR_CUDA(cudaStreamWaitEvent(P, c->ev_a, 0));
     use(P, pr.sm_p, true);
     do_panels(cnext, bb[(blk + 1) & 1]);
+    if (t_on_chain(cnext)) do_block_t(cnext, bb[(blk + 1) & 1]);
     CQR_CUDA(cudaEventRecord(c->ev_panel[(blk + 1) & 1], P));
     use(G, pr.sm_g, false);
     do_update(K0, bb[blk & 1], cnext + la, n);

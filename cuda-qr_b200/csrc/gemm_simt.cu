@@ -121,6 +121,68 @@ __global__ void reduce_splits_kernel(int M, int N, const float* __restrict__ par
   }
 }
 
+// X(kb x nc) = op(T) * (sum_z part_z), op(T) = T^T (trans != 0) or T, with T kb x kb upper triangular (zeros below):
+// the split-K reduction of W = V^T C fused with the multiplication by the compact-WY T.  Replaces three launches
+// (reduce, tensor GEMM with K = kb, copy) on the latency-critical narrow updates (inner block updates, look-ahead
+// slice).  One CTA per 8 columns; thread i owns row i of X.
+__global__ void __launch_bounds__(256) tw_fused_kernel(int kb, int nc, const float* __restrict__ part, long long ldp,
+                                                       long long stride, int splits, const float* __restrict__ t,
+                                                       long long ldt, int trans, float* __restrict__ x, long long ldx) {
+  __shared__ __align__(16) float Ws[256][8];
+  __shared__ float Ts[32][257];
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * 8;
+  const int kb32 = (kb + 31) & ~31;   // rows kb .. kb32 are read by the last k chunk (against zeros of T): keep them finite
+  for (int idx = tid; idx < kb32 * 8; idx += 256) {
+    const int k = idx % kb32, cc = idx / kb32;
+    const int n = n0 + cc;
+    float s = 0.f;
+    if (n < nc && k < kb)
+      for (int z = 0; z < splits; ++z) s += part[k + (long long)n * ldp + (long long)z * stride];
+    Ws[k][cc] = s;
+  }
+  float acc[8];
+#pragma unroll
+  for (int cc = 0; cc < 8; ++cc) acc[cc] = 0.f;
+  const int i = tid;
+  const int wlo = tid & ~31, whi = tid | 31;   // rows of this warp
+  for (int k0 = 0; k0 < kb; k0 += 32) {
+    __syncthreads();
+    const int kn = min(32, kb - k0);
+    if (trans) {   // op(T)[i][k] = T[k][i]
+      for (int idx = tid; idx < 32 * kb; idx += 256) {
+        const int kk = idx & 31, ii = idx >> 5;
+        Ts[kk][ii] = (kk < kn) ? t[(k0 + kk) + (long long)ii * ldt] : 0.f;
+      }
+    } else {       // op(T)[i][k] = T[i][k]
+      for (int idx = tid; idx < 32 * kb; idx += 256) {
+        const int ii = idx % kb, kk = idx / kb;
+        Ts[kk][ii] = (kk < kn) ? t[ii + (long long)(k0 + kk) * ldt] : 0.f;
+      }
+    }
+    __syncthreads();
+    // triangular structure: T^T couples row i with k <= i, T with k >= i (warp-uniform skip)
+    const bool need = trans ? (k0 <= whi) : (k0 + 31 >= wlo);
+    if (i < kb && need) {
+#pragma unroll 8
+      for (int kk = 0; kk < 32; ++kk) {
+        const float tv = Ts[kk][i];
+        const float4 w0 = *reinterpret_cast<const float4*>(&Ws[k0 + kk][0]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&Ws[k0 + kk][4]);
+        acc[0] = fmaf(tv, w0.x, acc[0]); acc[1] = fmaf(tv, w0.y, acc[1]);
+        acc[2] = fmaf(tv, w0.z, acc[2]); acc[3] = fmaf(tv, w0.w, acc[3]);
+        acc[4] = fmaf(tv, w1.x, acc[4]); acc[5] = fmaf(tv, w1.y, acc[5]);
+        acc[6] = fmaf(tv, w1.z, acc[6]); acc[7] = fmaf(tv, w1.w, acc[7]);
+      }
+    }
+  }
+  if (i < kb) {
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc)
+      if (n0 + cc < nc) x[i + (long long)(n0 + cc) * ldx] = acc[cc];
+  }
+}
+
 // mode 1: identity; 2: zero; 3: copy; 4: extract R; 5: extract V
 template <int MODE>
 __global__ void elementwise_kernel(long long m, int n, const float* __restrict__ a, long long lda, float* __restrict__ b,
@@ -169,6 +231,12 @@ void launch_reduce_splits(int M, int N, const float* part, long long ldp, long l
   if (M <= 0 || N <= 0) return;
   ++g_launches;
   reduce_splits_kernel<<<ew_grid(M, N), 256, 0, s>>>(M, N, part, ldp, stride, splits, out, ldo);
+}
+
+void launch_tw_fused(int kb, int nc, const float* part, long long ldp, long long stride, int splits, const float* t,
+                     long long ldt, int trans, float* x, long long ldx, cudaStream_t s) {
+  ++g_launches;
+  tw_fused_kernel<<<(nc + 7) / 8, 256, 0, s>>>(kb, nc, part, ldp, stride, splits, t, ldt, trans, x, ldx);
 }
 
 void launch_set_identity(float* a, long long lda, int m, int n, cudaStream_t s) {

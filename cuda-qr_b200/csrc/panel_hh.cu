@@ -321,9 +321,11 @@ template <int RR>
 __global__ void __launch_bounds__(512, 1) panel_hh_cluster_kernel(PanelHHParams p) {
   constexpr int TH = 8 * RR, NCH = RR / 4;
   __shared__ __align__(16) float xs[2][TH];
-  __shared__ __align__(16) float inbox[2][16][64];   // slab-local dots pushed here by every CTA of the cluster (st.async)
-  __shared__ __align__(16) float prow[2][64];        // row j of the panel, pushed by CTA 0 (cluster 0 only)
-  __shared__ unsigned long long mbar[2];
+  __shared__ __align__(16) float rs_in[2][16][4];    // phase 1 inbox of the column owner: [source CTA x slot][4 columns]
+  __shared__ __align__(16) float prs_in[2][16][4];   // phase 1: pivot-row entries of my columns (from slab 0)
+  __shared__ __align__(16) float tot_in[2][64];      // phase 2: cluster totals of all 64 columns
+  __shared__ __align__(16) float prow[2][64];        // phase 2: row j of the panel (cluster 0 only)
+  __shared__ unsigned long long mbar1[2], mbar2[2];
   __shared__ float sc[2][4];            // {beta, 1/u, tau, u}
   __shared__ float gs[64][65];          // CTA 0: G(c, j) = v_c^T v_j (c < j)
   __shared__ float ts[64][65];
@@ -363,13 +365,14 @@ __global__ void __launch_bounds__(512, 1) panel_hh_cluster_kernel(PanelHHParams 
   }
   if (CS > 1) {
     if (threadIdx.x == 0) {
-      mbar_init_local(&mbar[0], 1);
-      mbar_init_local(&mbar[1], 1);
+      mbar_init_local(&mbar1[0], 1);
+      mbar_init_local(&mbar1[1], 1);
+      mbar_init_local(&mbar2[0], 1);
+      mbar_init_local(&mbar2[1], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     cluster_sync_all();   // every peer's barriers exist before anyone pushes
   }
-  const unsigned expect_bytes = (CS * 64 + (cl == 0 ? 64 : 0)) * 4;
 
 #pragma unroll
   for (int sj = 0; sj < 4; ++sj) {
@@ -401,19 +404,28 @@ __global__ void __launch_bounds__(512, 1) panel_hh_cluster_kernel(PanelHHParams 
       }
       __syncthreads();
       HH_TRACE(0);
-      f32x2 acc0 = 0ull, acc1 = 0ull;
+      // dot in batches of up to four chunks: the LDS of a batch are issued together so their latency overlaps
+      f32x2 acc[4] = {0ull, 0ull, 0ull, 0ull};
+      constexpr int BAT = NCH < 4 ? NCH : 4;
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        const ulonglong2 xv = *reinterpret_cast<const ulonglong2*>(&xs[buf][4 * (g + 8 * ch)]);
-        acc0 = fma2(xv.x, a[2 * ch], acc0);
-        acc1 = fma2(xv.y, a[2 * ch + 1], acc1);
+      for (int ch0 = 0; ch0 < NCH; ch0 += BAT) {
+        ulonglong2 xv[BAT];
+#pragma unroll
+        for (int k = 0; k < BAT; ++k) xv[k] = *reinterpret_cast<const ulonglong2*>(&xs[buf][4 * (g + 8 * (ch0 + k))]);
+#pragma unroll
+        for (int k = 0; k < BAT; ++k) {
+          acc[(2 * k) & 3] = fma2(xv[k].x, a[2 * (ch0 + k)], acc[(2 * k) & 3]);
+          acc[(2 * k + 1) & 3] = fma2(xv[k].y, a[2 * (ch0 + k) + 1], acc[(2 * k + 1) & 3]);
+        }
       }
       float s;
       {
-        float s0, s1, s2, s3;
-        unpack2(acc0, s0, s1);
-        unpack2(acc1, s2, s3);
-        s = (s0 + s1) + (s2 + s3);
+        float s0, s1, s2, s3, s4, s5, s6, s7;
+        unpack2(acc[0], s0, s1);
+        unpack2(acc[1], s2, s3);
+        unpack2(acc[2], s4, s5);
+        unpack2(acc[3], s6, s7);
+        s = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
       }
       s += __shfl_xor_sync(kFull, s, 1);
       s += __shfl_xor_sync(kFull, s, 2);
@@ -428,21 +440,48 @@ __global__ void __launch_bounds__(512, 1) panel_hh_cluster_kernel(PanelHHParams 
       float ajc = __shfl_sync(kFull, mine, (l & 24) | gj);   // valid on slab 0
       HH_TRACE(1);
       if (CS > 1) {
-        // all-gather inside the cluster: lane i < CS of warp w pushes the warp's four column sums to peer i; on
-        // slab 0 lanes 16 .. 16+CS push the pivot-row entries the same way
-        if (threadIdx.x == 0) mbar_expect_tx_local(&mbar[buf], expect_bytes);
+        // All-reduce inside the cluster in two one-sided phases (st.async, 16 B, crediting the receiver's mbarrier):
+        //   1. reduce-scatter: warp w sends its four column sums to the CTA that owns those columns
+        //      (owner = w CS / 16; slab 0 also sends the four pivot-row entries),
+        //   2. the owner's warp 0 adds the CS contributions per column (shuffle tree, fixed order) and sends the
+        //      totals (and the pivot-row entries) to every peer.
+        // 16 + 16 incoming messages per CTA and step instead of the 256 of a direct all-gather: DSMEM delivers
+        // ~1 message per 4 cycles per CTA, so the all-gather cost ~1550 cycles per step against ~950 for this
+        // (tools/probes/dsmem_probe.cu).
+        const unsigned wpo = 16u / CS;                  // warps (groups of four columns) per owner CTA
+        const unsigned par = (j >> 1) & 1;
+        if (threadIdx.x == 0) {
+          mbar_expect_tx_local(&mbar1[buf], (16 + (cl == 0 ? wpo : 0)) * 16);
+          mbar_expect_tx_local(&mbar2[buf], (16 + (cl == 0 ? 16 : 0)) * 16);
+        }
+        const unsigned owner = ((unsigned)w * CS) >> 4, wl = (unsigned)w - owner * wpo;
         float4 sv, pv;
         sv.x = __shfl_sync(kFull, s, 0); sv.y = __shfl_sync(kFull, s, 8); sv.z = __shfl_sync(kFull, s, 16); sv.w = __shfl_sync(kFull, s, 24);
-        pv.x = __shfl_sync(kFull, ajc, 0); pv.y = __shfl_sync(kFull, ajc, 8); pv.z = __shfl_sync(kFull, ajc, 16); pv.w = __shfl_sync(kFull, ajc, 24);
-        if ((unsigned)l < CS) st_async_v4(&inbox[buf][rank][4 * w], &mbar[buf], (unsigned)l, sv);
-        else if (cta == 0 && l >= 16 && (unsigned)(l - 16) < CS) st_async_v4(&prow[buf][4 * w], &mbar[buf], (unsigned)(l - 16), pv);
-        mbar_wait_local(&mbar[buf], (j >> 1) & 1);
-        float t = 0.f;
-        for (unsigned i = g; i < CS; i += 8) t += inbox[buf][i][c];
-        t += __shfl_xor_sync(kFull, t, 1);
-        t += __shfl_xor_sync(kFull, t, 2);
-        t += __shfl_xor_sync(kFull, t, 4);
-        s = t;
+        if (l == 0) st_async_v4(&rs_in[buf][rank * wpo + wl][0], &mbar1[buf], owner, sv);
+        if (cta == 0) {
+          pv.x = __shfl_sync(kFull, ajc, 0); pv.y = __shfl_sync(kFull, ajc, 8); pv.z = __shfl_sync(kFull, ajc, 16); pv.w = __shfl_sync(kFull, ajc, 24);
+          if (l == 1) st_async_v4(&prs_in[buf][wl][0], &mbar1[buf], owner, pv);
+        }
+        if (w == 0) {
+          mbar_wait_local(&mbar1[buf], par);
+          // lane i < 16 holds contribution i = src * wpo + slot: add over src (bits >= log2 wpo of the lane index)
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (l < 16) t = *reinterpret_cast<const float4*>(&rs_in[buf][l][0]);
+          for (unsigned o = 8; o >= wpo; o >>= 1) {
+            t.x += __shfl_xor_sync(kFull, t.x, o); t.y += __shfl_xor_sync(kFull, t.y, o);
+            t.z += __shfl_xor_sync(kFull, t.z, o); t.w += __shfl_xor_sync(kFull, t.w, o);
+          }
+          // lane L < 16: totals of slot L % wpo to peer L / wpo; lane 16 + L: the pivot entries of that slot
+          const unsigned L = (unsigned)l & 15u, slot = L % wpo, peer = L / wpo;
+          float4 tv;
+          tv.x = __shfl_sync(kFull, t.x, slot); tv.y = __shfl_sync(kFull, t.y, slot);
+          tv.z = __shfl_sync(kFull, t.z, slot); tv.w = __shfl_sync(kFull, t.w, slot);
+          const unsigned col4 = 4u * (rank * wpo + slot);
+          if (l < 16) st_async_v4(&tot_in[buf][col4], &mbar2[buf], peer, tv);
+          else if (cl == 0) st_async_v4(&prow[buf][col4], &mbar2[buf], peer, *reinterpret_cast<const float4*>(&prs_in[buf][slot][0]));
+        }
+        mbar_wait_local(&mbar2[buf], par);
+        s = tot_in[buf][c];
         if (cl == 0) ajc = prow[buf][c];
       }
       if (ncl > 1) {
@@ -498,17 +537,24 @@ __global__ void __launch_bounds__(512, 1) panel_hh_cluster_kernel(PanelHHParams 
         // a_c -= tau (v^T a_c) v with v = x / u and v_j = 1: 1/u is folded into the column scalar and x_j patched to u
         const float nwc = -(tau * d * inv_u);
         const f32x2 nw2 = pack2(nwc, nwc);
+        constexpr int BATU = NCH < 4 ? NCH : 4;
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-          ulonglong2 xv = *reinterpret_cast<const ulonglong2*>(&xs[buf][4 * (g + 8 * ch)]);
-          if (ch == chj && cta == 0 && g == gj) {
-            float x0, x1, x2, x3;
-            unpack2(xv.x, x0, x1); unpack2(xv.y, x2, x3);
-            if (ej == 0) x0 = u; else if (ej == 1) x1 = u; else if (ej == 2) x2 = u; else x3 = u;
-            xv.x = pack2(x0, x1); xv.y = pack2(x2, x3);
+        for (int ch0 = 0; ch0 < NCH; ch0 += BATU) {
+          ulonglong2 xv[BATU];
+#pragma unroll
+          for (int k = 0; k < BATU; ++k) xv[k] = *reinterpret_cast<const ulonglong2*>(&xs[buf][4 * (g + 8 * (ch0 + k))]);
+#pragma unroll
+          for (int k = 0; k < BATU; ++k) {
+            const int ch = ch0 + k;
+            if (ch == chj && cta == 0 && g == gj) {
+              float x0, x1, x2, x3;
+              unpack2(xv[k].x, x0, x1); unpack2(xv[k].y, x2, x3);
+              if (ej == 0) x0 = u; else if (ej == 1) x1 = u; else if (ej == 2) x2 = u; else x3 = u;
+              xv[k].x = pack2(x0, x1); xv[k].y = pack2(x2, x3);
+            }
+            a[2 * ch] = fma2(xv[k].x, nw2, a[2 * ch]);
+            a[2 * ch + 1] = fma2(xv[k].y, nw2, a[2 * ch + 1]);
           }
-          a[2 * ch] = fma2(xv.x, nw2, a[2 * ch]);
-          a[2 * ch + 1] = fma2(xv.y, nw2, a[2 * ch + 1]);
         }
       } else if (c < j) {
         if (cta == 0 && g == 0) gs[c][j] = d;   // G(c, j) = v_c^T v_j

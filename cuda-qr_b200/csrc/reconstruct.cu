@@ -170,115 +170,120 @@ void launch_hr_rows(const HrParams& p, cudaStream_t s) {
   hr_rows_kernel<<<(unsigned)((rest + 63) / 64), 256, 0, s>>>(p);
 }
 
-// One CTA, 256 threads as a 16 x 16 grid of 4 x 4 register tiles over 64 x 64 blocks.
-// G (kb x kb Gram matrix, upper part read), tau (kb), T (kb x kb upper, zero below).  Block column J:
-//     T_JJ        : larft column recurrence  T[0:i,i] = -tau_i T[0:i,0:i] G[0:i,i]   (unless have_diag)
-//     tmp[rb]     = G[rb, J] T_JJ                              rb < J
-//     T[rb, J]    = -sum_{kb = rb}^{J-1} T[rb, kb] tmp[kb]
-__device__ __forceinline__ void block_mm_acc(float (&acc)[4][4], const float (*As)[65], const float (*Bs)[65], int tx,
-                                             int ty) {
-#pragma unroll 8
-  for (int k = 0; k < 64; ++k) {
-    float av[4], bv[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { av[i] = As[tx + 16 * i][k]; bv[i] = Bs[k][ty + 16 * i]; }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(av[i], bv[jj], acc[i][jj]);
+// Compact-WY T of kb aggregated reflectors from the Gram matrix G = V^T V (upper part read) and tau.
+//   diagonal 64 x 64 blocks: larft column recurrence  T[0:i,i] = -tau_i T[0:i,0:i] G[0:i,i]  (build_t_diag_kernel,
+//                            one CTA per block; skipped when the panel kernels already wrote them: have_diag)
+//   block column J > 0     : T[0:c0, J] = -T[0:c0, 0:c0] (G[0:c0, J] T_JJ),  c0 = 64 J     (build_t_offdiag_kernel)
+// The off-diagonal kernel is ONE cluster of 8 CTAs; CTA r owns columns 8r .. 8r+7 of every block column, thread i
+// owns row i.  Block columns are sequential (column J needs T[0:c0, 0:c0]) and separated by a cluster barrier.
+// An earlier single-CTA version spent ~80 us per outer block here, FMA-issue bound on one SM and on the critical path
+// of every block (panel chain -> T -> look-ahead slice).
+__global__ void __launch_bounds__(64) build_t_diag_kernel(const float* __restrict__ g, long long ldg,
+                                                          const float* __restrict__ tau, float* __restrict__ t,
+                                                          long long ldt, int kb) {
+  __shared__ float Tjj[64][65], Gjj[64][65];
+  const int tid = threadIdx.x, c0 = 64 * blockIdx.x, bj = min(64, kb - c0);
+  for (int j = 0; j < 64; ++j) {
+    const bool in = tid < bj && j < bj;
+    Gjj[tid][j] = in ? g[(c0 + tid) + (long long)(c0 + j) * ldg] : 0.f;
+    Tjj[tid][j] = 0.f;
   }
+  __syncthreads();
+  for (int i = 0; i < bj; ++i) {
+    const float ti = tau[c0 + i];
+    if (tid < i) {
+      float acc = 0.f;
+      for (int k = tid; k < i; ++k) acc = fmaf(Tjj[tid][k], Gjj[k][i], acc);
+      Tjj[tid][i] = -ti * acc;
+    } else if (tid == i) {
+      Tjj[i][i] = ti;
+    }
+    __syncthreads();
+  }
+  if (tid < bj)
+    for (int j = 0; j < bj; ++j) t[(c0 + tid) + (long long)(c0 + j) * ldt] = (tid <= j) ? Tjj[tid][j] : 0.f;
 }
 
-__global__ void __launch_bounds__(256) build_t_kernel(float* g, long long ldg, const float* tau, float* t,
-                                                      long long ldt, int kb, int have_diag) {
-  extern __shared__ float bt_smem[];
-  float (*Tjj)[65] = reinterpret_cast<float (*)[65]>(bt_smem);
-  float (*As)[65] = reinterpret_cast<float (*)[65]>(bt_smem + 64 * 65);
-  float (*Bs)[65] = reinterpret_cast<float (*)[65]>(bt_smem + 2 * 64 * 65);
-  float* tmp = bt_smem + 3 * 64 * 65;   // (nb-1) blocks of 64 x 64 (row-major within a block, ld 64)
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+__global__ void __launch_bounds__(512) build_t_offdiag_kernel(const float* __restrict__ g, long long ldg, float* t,
+                                                              long long ldt, int kb) {
+  __shared__ float Tj8[64][8];       // T_JJ[:, my 8 columns]
+  __shared__ __align__(16) float tmp8[512][8];   // (G[0:c0, J] T_JJ)[:, my 8 columns]
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  const int i = threadIdx.x;
   const int nb = (kb + 63) / 64;
   for (int J = 0; J < nb; ++J) {
-    const int c0 = 64 * J;
-    const int bj = min(64, kb - c0);
-    for (int idx = tid; idx < 64 * 64; idx += 256) {
-      const int i = idx & 63, j = idx >> 6;
-      const bool in = (i < bj && j < bj);
-      As[i][j] = in ? g[(c0 + i) + (long long)(c0 + j) * ldg] : 0.f;   // G_JJ for the recurrence
-      Tjj[i][j] = (in && have_diag && i <= j) ? t[(c0 + i) + (long long)(c0 + j) * ldt] : 0.f;
+    const int c0 = 64 * J, bj = min(64, kb - c0);
+    const int col0 = c0 + 8 * (int)r;                       // my columns: col0 .. col0+7 (those < kb)
+    // zero everything below the diagonal block in my columns (T is applied as a dense kb x kb operand)
+    for (int idx = i; idx < (kb - c0 - bj) * 8; idx += 512) {
+      const int row = c0 + bj + idx % (kb - c0 - bj), cc = idx / (kb - c0 - bj);
+      if (col0 + cc < kb) t[row + (long long)(col0 + cc) * ldt] = 0.f;
     }
-    __syncthreads();
-    if (!have_diag) {
-      for (int i = 0; i < bj; ++i) {
-        const float ti = tau[c0 + i];
-        if (tid < i) {
-          float acc = 0.f;
-          for (int k = tid; k < i; ++k) acc = fmaf(Tjj[tid][k], As[k][i], acc);
-          Tjj[tid][i] = -ti * acc;
-        } else if (tid == i) {
-          Tjj[i][i] = ti;
-        }
-        __syncthreads();
-      }
-    }
-    for (int idx = tid; idx < 64 * 64; idx += 256) {
-      const int i = idx & 63, j = idx >> 6;
-      if (i < bj && j < bj) t[(c0 + i) + (long long)(c0 + j) * ldt] = (i <= j) ? Tjj[i][j] : 0.f;
-    }
-    for (int idx = tid; idx < (kb - c0 - bj) * bj; idx += 256) {   // zero below the diagonal block
-      const int i = c0 + bj + idx % (kb - c0 - bj), j = c0 + idx / (kb - c0 - bj);
-      t[i + (long long)j * ldt] = 0.f;
-    }
-    // tmp[rb] = G[rb, J] * T_JJ
-    for (int rb = 0; rb < J; ++rb) {
-      __syncthreads();
-      for (int idx = tid; idx < 64 * 64; idx += 256) {
-        const int i = idx & 63, j = idx >> 6;
-        As[i][j] = (j < bj) ? g[(64 * rb + i) + (long long)(c0 + j) * ldg] : 0.f;
+    if (J > 0) {
+      for (int idx = i; idx < 64 * 8; idx += 512) {
+        const int k = idx & 63, cc = idx >> 6;
+        Tj8[k][cc] = (k < bj && col0 + cc < kb) ? __ldcg(t + (c0 + k) + (long long)(col0 + cc) * ldt) : 0.f;
       }
       __syncthreads();
-      float acc[4][4] = {};
-      block_mm_acc(acc, As, Tjj, tx, ty);
+      float acc[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int cc = 0; cc < 8; ++cc) acc[cc] = 0.f;
+      if (i < c0) {
+#pragma unroll 8
+        for (int k = 0; k < 64; ++k) {
+          const float gv = (k < bj) ? g[i + (long long)(c0 + k) * ldg] : 0.f;
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) tmp[rb * 4096 + (tx + 16 * i) * 64 + ty + 16 * jj] = acc[i][jj];
-    }
-    // T[rb, J] = -sum_kb T[rb, kb] tmp[kb]
-    for (int rb = 0; rb < J; ++rb) {
-      float acc[4][4] = {};
-      for (int kbk = rb; kbk < J; ++kbk) {
-        __syncthreads();
-        for (int idx = tid; idx < 64 * 64; idx += 256) {
-          const int i = idx & 63, j = idx >> 6;
-          As[i][j] = t[(64 * rb + i) + (long long)(64 * kbk + j) * ldt];
-          Bs[i][j] = tmp[kbk * 4096 + i * 64 + j];
+          for (int cc = 0; cc < 8; ++cc) acc[cc] = fmaf(gv, Tj8[k][cc], acc[cc]);
         }
-        __syncthreads();
-        block_mm_acc(acc, As, Bs, tx, ty);
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) tmp8[i][cc] = acc[cc];
       }
+      __syncthreads();
+      if (i < c0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int col = ty + 16 * jj;
-          if (col < bj) t[(64 * rb + tx + 16 * i) + (long long)(c0 + col) * ldt] = -acc[i][jj];
+        for (int cc = 0; cc < 8; ++cc) acc[cc] = 0.f;
+        // T[0:c0, 0:c0] is upper triangular: row i couples with k >= i; warp-uniform start keeps loads coalesced
+        const int kstart = i & ~31;
+#pragma unroll 4
+        for (int k = kstart; k < c0; ++k) {
+          const float tv = __ldcg(t + i + (long long)k * ldt);   // zero below the diagonal
+          const float4 w0 = *reinterpret_cast<const float4*>(&tmp8[k][0]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&tmp8[k][4]);
+          acc[0] = fmaf(tv, w0.x, acc[0]); acc[1] = fmaf(tv, w0.y, acc[1]);
+          acc[2] = fmaf(tv, w0.z, acc[2]); acc[3] = fmaf(tv, w0.w, acc[3]);
+          acc[4] = fmaf(tv, w1.x, acc[4]); acc[5] = fmaf(tv, w1.y, acc[5]);
+          acc[6] = fmaf(tv, w1.z, acc[6]); acc[7] = fmaf(tv, w1.w, acc[7]);
         }
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc)
+          if (col0 + cc < kb) t[i + (long long)(col0 + cc) * ldt] = -acc[cc];
+      }
     }
-    __syncthreads();
+    // block column J complete on every CTA before anyone reads it as part of T[0:c0', 0:c0']
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
 }
 
 void launch_build_t(const float* g, long long ldg, const float* tau, float* t, long long ldt, int kb,
                     int have_diag, cudaStream_t s) {
-  ++g_launches;
-  const size_t smem = (size_t)(3 * 64 * 65 + ((kb - 1) / 64) * 4096) * sizeof(float);   // Tjj, As, Bs + (nb-1) tmp blocks
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(build_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (3 * 64 * 65 + 7 * 4096) * 4);
-    attr_done = true;
+  const int nb = (kb + 63) / 64;
+  if (!have_diag) {
+    ++g_launches;
+    build_t_diag_kernel<<<nb, 64, 0, s>>>(g, ldg, tau, t, ldt, kb);
   }
-  build_t_kernel<<<1, 256, smem, s>>>(const_cast<float*>(g), ldg, tau, t, ldt, kb, have_diag);
+  ++g_launches;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(8, 1, 1);
+  cfg.blockDim = dim3(512, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, build_t_offdiag_kernel, g, ldg, t, ldt, kb);
 }
 
 }  // namespace cqr

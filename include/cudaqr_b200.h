@@ -94,6 +94,9 @@ enum { CQR_PROF_PANEL = 0, CQR_PROF_GEMM_TN = 1, CQR_PROF_GEMM_NN = 2, CQR_PROF_
        CQR_PROF_CHAIN_TN = 4, CQR_PROF_CHAIN_NN = 5, CQR_PROF_CHAIN_MISC = 6, CQR_PROF_NCAT = 7 };
 int cqr_profile_begin(cqr_context* ctx);
 int cqr_profile_end(cqr_context* ctx, double* ms, double* flops, double* bytes, long long* launches, int ncat);
+/* Timeline of the bracketed launch groups since cqr_profile_begin (call BEFORE cqr_profile_end): start/end in ms
+ * relative to the first bracket, class per bracket.  Returns the number of brackets (<= cap written), < 0 on error. */
+int cqr_profile_timeline(cqr_context* ctx, double* t0_ms, double* t1_ms, int* cls, int cap);
 /* Pre-size the internal workspace (bytes) so no allocation happens in a timed region. */
 int cqr_reserve(cqr_context* ctx, size_t bytes);
 

@@ -73,6 +73,10 @@ struct cqr_context {
   int cur_ctas = 0;                // SMs behind `cur` (0 = the whole device): caps persistent grids and split-K choices
   SmPartition part[3];             // [0] unpartitioned (side/work streams), [1] 16 + 132 SMs, [2] 2 x 16 + 116 SMs
   int opt_partition = 1;
+  // legacy mmqr: finished column blocks are copied back to the caller's host matrix (column-major, ld = m) on
+  // `copy` while later blocks are still being factored
+  float* host_out = nullptr;
+  cudaStream_t copy = nullptr;
   cudaEvent_t ev_start = nullptr, ev_a = nullptr, ev_g = nullptr, ev_panel[2] = {nullptr, nullptr};
   int opt_gemm = 1, opt_outer = 256, opt_tile_rows = 256, opt_splitk = 0, opt_lookahead = 1, opt_panel = 1, opt_cluster = 1;
   // multi-CTA panel kernel (panel_hh.cu): cross-CTA exchange slots, launch epoch, spin-timeout flag
@@ -447,6 +451,7 @@ int cqr_create(cqr_context** out, int device) {
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   CQR_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi));
   CQR_CUDA(cudaStreamCreateWithFlags(&c->work, cudaStreamNonBlocking));
+  CQR_CUDA(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_g, cudaEventDisableTiming));
@@ -479,6 +484,7 @@ int cqr_destroy(cqr_context* c) {
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
   if (c->work) { cudaStreamSynchronize(c->work); cudaStreamDestroy(c->work); }
+  if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
   for (int i = 1; i < 3; ++i) {
     SmPartition& pt = c->part[i];
     if (pt.sp) { cudaStreamSynchronize(pt.sp); cudaStreamDestroy(pt.sp); }
@@ -724,6 +730,14 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
       launch_build_t(gram, KB, dtau + K0, B.tbig, KB, kbw, 1, cur_stream(c));
     }
   };
+  // Columns [K0, K0 + kbw) are final once the block's panel chain is done (event ev): R above, V below.
+  auto ship = [&](int K0, cudaEvent_t ev) {
+    if (!c->host_out) return;
+    const int kbw = (n - K0 < KB) ? n - K0 : KB;
+    cudaStreamWaitEvent(c->copy, ev, 0);
+    cudaMemcpy2DAsync(c->host_out + (size_t)K0 * m, (size_t)m * sizeof(float), dA + (size_t)K0 * lda, (size_t)lda * sizeof(float),
+                      (size_t)m * sizeof(float), kbw, cudaMemcpyDeviceToHost, c->copy);
+  };
   // Trailing update of columns [c0, c1) with block K0's aggregated reflector (current stream).
   auto do_update = [&](int K0, BlockBufs& B, int c0, int c1) {
     if (c1 <= c0) return;
@@ -739,6 +753,7 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
       const int K0 = blk * KB;
       const int kbw = (n - K0 < KB) ? n - K0 : KB;
       do_panels(K0, bb[0]);
+      if (c->host_out) { CQR_CUDA(cudaEventRecord(c->ev_panel[0], st)); ship(K0, c->ev_panel[0]); }
       do_block_t(K0, bb[0]);
       do_update(K0, bb[0], K0 + kbw, n);
     }
@@ -763,8 +778,9 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
   auto t_on_chain = [&](int K0) { return c->opt_partition && (m - K0) > 8192; };
   use(prev_p, pp->sm_p, true);
   do_panels(0, bb[0]);
-  if (t_on_chain(0)) do_block_t(0, bb[0]);
   CQR_CUDA(cudaEventRecord(c->ev_panel[0], prev_p));
+  ship(0, c->ev_panel[0]);
+  if (t_on_chain(0)) { do_block_t(0, bb[0]); CQR_CUDA(cudaEventRecord(c->ev_panel[0], prev_p)); }
   for (int blk = 0; blk < nblk; ++blk) {
     const int K0 = blk * KB;
     const int kbw = (n - K0 < KB) ? n - K0 : KB;
@@ -787,8 +803,9 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
     CQR_CUDA(cudaStreamWaitEvent(P, c->ev_a, 0));
     use(P, pr.sm_p, true);
     do_panels(cnext, bb[(blk + 1) & 1]);
-    if (t_on_chain(cnext)) do_block_t(cnext, bb[(blk + 1) & 1]);
     CQR_CUDA(cudaEventRecord(c->ev_panel[(blk + 1) & 1], P));
+    ship(cnext, c->ev_panel[(blk + 1) & 1]);
+    if (t_on_chain(cnext)) { do_block_t(cnext, bb[(blk + 1) & 1]); CQR_CUDA(cudaEventRecord(c->ev_panel[(blk + 1) & 1], P)); }
     use(G, pr.sm_g, false);
     do_update(K0, bb[blk & 1], cnext + la, n);
     prev_g = G; prev_p = P;
@@ -1002,9 +1019,11 @@ void mmqr(float* mat, float* tau, int m, int n) {
   float* dtau = legacy_buf(1, (size_t)n * sizeof(float));
   LEGACY_CHECK(cudaMemcpy2D(dA, lda * sizeof(float), mat, (size_t)m * sizeof(float), (size_t)m * sizeof(float), n,
                             cudaMemcpyHostToDevice));
-  LEGACY_CHECK(cqr_geqrf(c, dA, (int)lda, m, n, dtau));
-  LEGACY_CHECK(cudaMemcpy2D(mat, (size_t)m * sizeof(float), dA, lda * sizeof(float), (size_t)m * sizeof(float), n,
-                            cudaMemcpyDeviceToHost));
+  c->host_out = mat;   // finished column blocks stream back while the rest is still being factored
+  const int rc = cqr_geqrf(c, dA, (int)lda, m, n, dtau);
+  c->host_out = nullptr;
+  LEGACY_CHECK(rc);
+  LEGACY_CHECK(cudaStreamSynchronize(c->copy));
   memset(tau, 0, tau_count * sizeof(float));   // unused slots zero, qr.c:62
   LEGACY_CHECK(cudaMemcpy(tau, dtau, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
 }

@@ -231,6 +231,16 @@ def main_ours(args, rank: int, world: int, local_rank: int):
                 "hbm_GBps_algorithmic": nn["bytes"] / (nn["ms"] * 1e-3) / 1e9 if nn["ms"] > 0 else None,
                 "by_class_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
                 "by_class_launches": {k: v["launches"] for k, v in prof.items()}}
+        # measured DRAM traffic of the dominant kernel from the committed ncu --set full capture (one launch at the
+        # first-block shape; `achieved` above averages all launches of the step, whose shapes shrink)
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["gemm_nn"]
+            roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            roof["traffic_detail"] = {"shape": tr["shape"], "algorithmic_bytes": tr["algorithmic_bytes"],
+                                      "ratio": (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["algorithmic_bytes"],
+                                      "source": tr["source"]}
+        except Exception:
+            pass
 
     # e2e: legacy mmqr(host buffers) -- H2D, factor, D2H inside the timed region, rank-local, pinned host memory
     e2e = None
@@ -257,6 +267,8 @@ def main_ours(args, rank: int, world: int, local_rank: int):
     if not args.no_extra:
         out["tsqr"] = bench_tsqr(args, pkg, ctx, torch, dist, dev, rank, world, timed_steps, pk)
         out["batched"] = bench_batched(args, pkg, ctx, torch, dev, rank, world, timed_steps, pk)
+        if world > 1:
+            out["caqr"] = bench_caqr(args, pkg, ctx, torch, dist, dev, rank, world, timed_steps, pk)
 
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -312,6 +324,38 @@ def bench_tsqr(args, pkg, ctx, torch, dist, dev, rank, world, timed_steps, pk):
     return res
 
 
+def bench_caqr(args, pkg, ctx, torch, dist, dev, rank, world, timed_steps, pk):
+    """BASELINE config 5: row-partitioned CAQR, 16384 x 4096 per rank (131072 x 4096 at 8 GPUs), R-only timing."""
+    dc = importlib.import_module("cuda-qr_b200.dist_caqr")
+    m_loc, n = args.caqr_rows_per_gpu, args.caqr_cols
+    g = torch.Generator(device=dev).manual_seed(300 + rank)
+    A0 = pkg.colmajor(m_loc, n, device=dev)
+    A0.copy_(torch.rand((m_loc, n), device=dev, generator=g))
+    A = pkg.colmajor(m_loc, n, device=dev)
+    cq = dc.DistCAQR(pkg, ctx, m_loc, n, rank, world, dev)
+    step = lambda: cq.factor(A)
+    restore = lambda: A.copy_(A0)
+    restore(); step(); torch.cuda.synchronize()
+    ms, _ = timed_steps(step, restore, max(min(args.steps, 5), 3), args.warmup)
+    m_total = m_loc * world
+    flops = qr_flops(m_total, n)
+    res = {"workload": f"rectangular {m_total}x{n} fp32 CAQR, {m_loc} rows per GPU over {world} GPU(s): local blocked Householder + "
+                       f"tcgen05 trailing update, R / top-row all_gather per 256-column block (config 5)",
+           "value": flops / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms, "scaling": "weak", "n_gpus": world,
+           "nvlink_bytes_per_rank_per_step": None}
+    cq.bytes_exchanged = 0
+    restore(); step(); torch.cuda.synchronize()
+    res["nvlink_bytes_per_rank_per_step"] = int(cq.bytes_exchanged)
+    G = A0.t().double() @ A0.double()
+    dist.all_reduce(G)
+    if rank == 0:
+        R = pkg.colmajor(n, n, device=dev)
+        cq.extract_r(A, R)
+        Rd = torch.triu(R.double())
+        res["gram_error"] = float((Rd.t() @ Rd - G).norm() / G.norm())
+    return res
+
+
 def bench_batched(args, pkg, ctx, torch, dev, rank, world, timed_steps, pk):
     batch_total, m, n = args.batch, 64, 64
     batch = batch_total // world
@@ -340,6 +384,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=16384, help="square workload edge (config 2: 16384)")
     ap.add_argument("--tsqr-rows", type=int, default=8388608)
+    ap.add_argument("--caqr-rows-per-gpu", type=int, default=16384)
+    ap.add_argument("--caqr-cols", type=int, default=4096)
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--ref-size", type=int, default=1536, help="edge of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=2)

@@ -15,6 +15,7 @@
 // A is K-major for TN (columns of V are contiguous along K) and MN-major for NN (V itself);
 // B is always K-major.  Ragged M/N/K edges rely on TMA zero fill plus masked stores.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -113,6 +114,7 @@ struct Epilogue {
   long long ldd;
   long long split_stride;   // TN: partial z at d + z*split_stride
   float alpha, beta;
+  int prefetch_kb;          // k-block (counted from the END of the tile's K loop) at which the C tile is pulled into L2; < 0: never
 };
 
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
@@ -196,11 +198,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         int m0, n0, z, kbeg, nkb;
         tile_coords(t, m0, n0, z, kbeg, nkb);
-        if (ep.beta != 0.f) {   // pull the C tile into L2 now; the epilogue reads it ~10 us later
-#pragma unroll
-          for (int c = 0; c < BN; c += 64) tma_prefetch_2d(&tm_d, m0, n0 + c);
-        }
+        // pull the C tile into L2 shortly before the epilogue reads it: issued too early (at the start of the tile)
+        // the lines are evicted again by the ~100 MB the other CTAs stream through L2 in the meantime
+        const int pf_at = (ep.beta != 0.f && ep.prefetch_kb >= 0) ? max(0, nkb - 1 - ep.prefetch_kb) : -1;
         for (int kb = 0; kb < nkb; ++kb, ++g) {
+          if (kb == pf_at) {
+#pragma unroll
+            for (int c = 0; c < BN; c += 64) tma_prefetch_2d(&tm_d, m0, n0 + c);
+          }
           const uint32_t r = g % kRing, ph = (g / kRing) & 1;
           mbar_wait(empty0 + 8 * r, ph ^ 1);
           const uint32_t sa = smem_base + r * kStageBytes;
@@ -442,7 +447,7 @@ bool launch_gemm_tn_umma(int M, int N, int K, const float* a, long long lda, con
   if (!umma_available()) return false;
   if (lda % 4 || ldb % 4 || !aligned16(a) || !aligned16(b)) return false;
   if (M < 1 || N < 1 || K < 1) return false;
-  Epilogue ep{d, ldd, d_split_stride, 1.f, 0.f};
+  Epilogue ep{d, ldd, d_split_stride, 1.f, 0.f, -1};
   if (N > 128) return launch_umma<256, false>(M, N, K, a, lda, b, ldb, ep, splits, max_ctas, s);
   return launch_umma<128, false>(M, N, K, a, lda, b, ldb, ep, splits, max_ctas, s);
 }
@@ -452,7 +457,9 @@ bool launch_gemm_nn_umma(int M, int N, int K, float alpha, const float* a, long 
   if (!umma_available()) return false;
   if (lda % 4 || ldb % 4 || !aligned16(a) || !aligned16(b)) return false;
   if (M < 1 || N < 1 || K < 1) return false;
-  Epilogue ep{d, ldd, 0, alpha, beta};
+  static int pf = -2;
+  if (pf == -2) { const char* e = getenv("CQR_CPREFETCH"); pf = e ? atoi(e) : 1000; }   // default: at the start of the tile
+  Epilogue ep{d, ldd, 0, alpha, beta, pf};
   if (N > 128) return launch_umma<256, true>(M, N, K, a, lda, b, ldb, ep, 1, max_ctas, s);
   return launch_umma<128, true>(M, N, K, a, lda, b, ldb, ep, 1, max_ctas, s);
 }

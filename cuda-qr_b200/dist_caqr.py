@@ -1,0 +1,138 @@
+"""Row-partitioned CAQR of a tall rectangular matrix across the GPUs of one box (BASELINE config 5).
+
+Each rank owns a contiguous block of rows of A (column-major local slab).  The factorisation walks outer blocks of
+`kb` columns (default 256, the library's aggregated block width).  For block K
+
+  1. every rank factors its local rows of the block with the single-GPU blocked Householder path (``cqr_geqrf``:
+     multi-CTA register-resident panels, compact-WY T) -> local R_i (kb x kb) on top of its active rows, local V_i below;
+  2. every rank applies its local Q_i^T to its rows of the trailing columns (``cqr_apply_q``: tcgen05 3xTF32 GEMMs);
+  3. the kb x kb R_i and the top kb rows of each rank's trailing block are exchanged (``all_gather`` over NCCL /
+     NVLink: kb x (kb + n_trail) floats per rank, the only communication of the block) and every rank redundantly
+     factors the stacked [R_0; ...; R_{P-1}] (flat reduction tree at the node level, Demmel et al. CAQR) and applies
+     that Q_tree^T to the stacked top rows, keeping its own kb rows.
+
+After step 3 rank 0's top rows hold the final R rows of the block (its active row range shrinks by kb), the other
+ranks' top blocks hold their slice of the tree reflectors in the upper triangle (the stacked-triangle structure is
+preserved exactly by Householder), and their rows of the trailing columns stay active.  Q is kept implicitly:
+(V_i, tau_i) per rank and block in the local slab, (V_tree, tau_tree) per block replicated on every rank.
+
+The reference has no multi-GPU code (qr.cu:737); parity is judged against the fp64 / single-device R of the same
+matrix.  The schedule below is free of CUDA calls: the gloo CPU tests drive it with numpy stand-ins.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Tuple
+
+
+def block_plan(m_loc: int, n: int, kb: int, rank: int) -> List[Tuple[int, int, int]]:
+    """[(K0, width, r0)] per outer block: columns [K0, K0 + width), first active local row r0 (rank 0 gives one row
+    per finished column to R; the other ranks keep all their rows active)."""
+    plan = []
+    for k0 in range(0, n, kb):
+        w = min(kb, n - k0)
+        plan.append((k0, w, k0 if rank == 0 else 0))
+    return plan
+
+
+def check_shape(m_loc: int, n: int, kb: int, world: int) -> None:
+    if kb % 4:
+        raise ValueError("kb must be a multiple of 4 (16-byte aligned sub-blocks)")
+    if m_loc < n:
+        raise ValueError(f"every rank needs at least n = {n} local rows (got {m_loc}): all of R lives on rank 0")
+
+
+def caqr_generic(rank: int, world: int, m_loc: int, n: int, kb: int, local_qr: Callable, local_apply: Callable,
+                 gather: Callable, tree_qr: Callable, tree_apply: Callable, put_back: Callable) -> None:
+    """The CAQR schedule with injected steps (shared by the GPU driver and the CPU tests):
+    local_qr(K0, w, r0); local_apply(K0, w, r0); (Rs, Cs) = gather(K0, w, r0); tree_qr(K0, w, Rs);
+    tree_apply(K0, w, Rs, Cs); put_back(K0, w, r0, Rs, Cs)."""
+    check_shape(m_loc, n, kb, world)
+    for (k0, w, r0) in block_plan(m_loc, n, kb, rank):
+        local_qr(k0, w, r0)
+        if k0 + w < n:
+            local_apply(k0, w, r0)
+        if world == 1:
+            continue
+        rs, cs = gather(k0, w, r0)
+        tree_qr(k0, w, rs)
+        if cs is not None:
+            tree_apply(k0, w, rs, cs)
+        put_back(k0, w, r0, rs, cs)
+
+
+class DistCAQR:
+    """CAQR of a row-partitioned m x n matrix (n <= local rows); one instance per rank (one process per GPU)."""
+
+    def __init__(self, pkg, ctx, m_loc: int, n: int, rank: int, world: int, device, kb: int = 256):
+        import torch
+        self.torch, self.pkg, self.ctx = torch, pkg, ctx
+        self.m_loc, self.n, self.rank, self.world, self.device, self.kb = m_loc, n, rank, world, device, kb
+        check_shape(m_loc, n, kb, world)
+        nblk = (n + kb - 1) // kb
+        self.tau_loc = torch.zeros(n, device=device)                       # local reflectors, LAPACK tau per column
+        self.tau_tree = torch.zeros((nblk, kb), device=device)             # tree reflectors per block (replicated)
+        if world > 1:
+            # exchange buffers: [R_i | top rows of the trailing block] packed per rank as one (kb x (kb + n)) slab, ld = kb
+            self.send = torch.empty((kb + n, kb), dtype=torch.float32, device=device)            # storage (cols, ld)
+            self.recv = torch.empty(world * (kb + n) * kb, dtype=torch.float32, device=device)
+            self.stackR = pkg.colmajor(world * kb, kb, device=device)
+            self.stackC = pkg.colmajor(world * kb, n, device=device)
+        self.bytes_exchanged = 0
+
+    # -- steps -----------------------------------------------------------------------------------------------
+    def _blk(self, A, k0, w, r0):
+        return A[r0:, k0:k0 + w]
+
+    def factor(self, A_loc):
+        """In-place CAQR of the local slab A_loc (m_loc x n column-major device tensor).  Afterwards rank 0 holds R
+        in the upper triangle of its first n rows."""
+        t, kb, n, P = self.torch, self.kb, self.n, self.world
+        import torch.distributed as dist
+
+        def local_qr(k0, w, r0):
+            self.ctx.geqrf(self._blk(A_loc, k0, w, r0), self.tau_loc[k0:k0 + w])
+
+        def local_apply(k0, w, r0):
+            self.ctx.apply_q(self._blk(A_loc, k0, w, r0), self.tau_loc[k0:k0 + w], A_loc[r0:, k0 + w:], trans=True)
+
+        def gather(k0, w, r0):
+            nt = n - (k0 + w)
+            # pack [triu(R_i) | C_top] into the send slab (column-major, ld = kb; only the first w rows are meaningful)
+            s = self.send[:w + nt].t()                         # (kb, w + nt) view, element (i, j) at i + j*kb
+            s[:w, :w].copy_(t.triu(A_loc[r0:r0 + w, k0:k0 + w]))
+            if nt:
+                s[:w, w:].copy_(A_loc[r0:r0 + w, k0 + w:])
+            chunk = self.send[:w + nt]                         # contiguous prefix of the slab storage
+            out = self.recv[:P * (w + nt) * kb].view(P, w + nt, kb)
+            dist.all_gather_into_tensor(out, chunk)
+            self.bytes_exchanged += chunk.numel() * 4 * (P - 1)
+            rs = self.stackR[:P * w, :w]
+            cs = self.stackC[:P * w, :nt] if nt else None
+            for p in range(P):
+                blk = out[p].t()                               # (kb, w + nt)
+                rs[p * w:(p + 1) * w].copy_(blk[:w, :w])
+                if nt:
+                    cs[p * w:(p + 1) * w].copy_(blk[:w, w:])
+            return rs, cs
+
+        def tree_qr(k0, w, rs):
+            self.ctx.geqrf(rs, self.tau_tree[k0 // kb, :w])
+
+        def tree_apply(k0, w, rs, cs):
+            self.ctx.apply_q(rs, self.tau_tree[k0 // kb, :w], cs, trans=True)
+
+        def put_back(k0, w, r0, rs, cs):
+            me = self.rank
+            top = A_loc[r0:r0 + w, k0:k0 + w]
+            keep = t.tril(top, -1)                              # local reflectors stay below the diagonal
+            top.copy_(keep + t.triu(rs[me * w:(me + 1) * w]))   # rank 0: final R; others: their slice of V_tree
+            if cs is not None:
+                A_loc[r0:r0 + w, k0 + w:].copy_(cs[me * w:(me + 1) * w])
+
+        caqr_generic(self.rank, self.world, self.m_loc, n, kb, local_qr, local_apply, gather, tree_qr, tree_apply, put_back)
+        return A_loc
+
+    def extract_r(self, A_loc, R):
+        """R (n x n) from rank 0's slab (valid on rank 0)."""
+        self.ctx.extract_r(A_loc[:self.n], R)
+        return R

@@ -372,7 +372,7 @@ def bench_batched(args, pkg, ctx, torch, dev, rank, world, timed_steps, pk):
     ach = bytes_alg / (ms * 1e-3) / 1e9
     return {"workload": f"batched {batch_total} x ({m}x{n}) fp32 QR, one CTA per matrix, split over {world} GPU(s) (config 4)",
             "value": flops / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms, "scaling": "strong", "n_gpus": world,
-            "roofline": {"bound": "hbm", "kernel": "tile_qr_kernel<2>", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "batched_qr_col_kernel (two threads per column)", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": ach / pk["hbm_gbs"], "traffic": None}}
 
 

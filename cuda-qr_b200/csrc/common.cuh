@@ -73,6 +73,9 @@ struct TileApplyParams {
 
 void launch_tile_qr(const TileQRParams& p, int tiles, int tile_rows, cudaStream_t s);
 void launch_tile_apply_q(const TileApplyParams& p, int tiles, int tile_rows, cudaStream_t s);
+// batched QR of m x n matrices with m, n <= 64: one 64-thread CTA per matrix, one thread per column (LAPACK storage
+// in place, tau[b * n + j])
+void launch_batched_qr_col(float* base, long long stride, long long lda, int m, int n, int batch, float* tau, cudaStream_t s);
 
 // ---- Householder reconstruction + T builder: reconstruct.cu ---------------------------------
 struct HrParams {

@@ -242,6 +242,151 @@ __global__ void __launch_bounds__(256, (RI <= 4 ? 3 : 2)) tile_apply_q_kernel(Ti
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Batched small QR (BASELINE config 4: independent 64 x 64 matrices, one CTA per matrix): a column lives in the
+// registers of ONE thread pair, so a Householder step needs a single shuffle instead of a warp-wide reduction:
+// the owner thread of column j forms norm / beta / tau / v from its own registers (qr.c:144-167), publishes v through
+// shared memory (double-buffered: one barrier per step), and every thread to its right applies the reflector to its own
+// column with a private dot product.  The step loop is fully unrolled so every register index is static and each step
+// only touches rows >= j.  The tile kernel above spends its issue slots on 5-stage shuffle reductions for 16 elements
+// per thread (6.9 ms for 65 536 matrices, 4.8 % of the HBM roof); here a matrix costs ~13 K warp-instructions.
+// Two threads per column (h = tid & 1; thread h owns the 4-row chunks 8 i + 4 h .. +3, i = 0..7): 32 registers of
+// matrix per thread instead of 64 doubles the resident warps (the per-step critical path is the owner's serial
+// norm -> sqrt -> divide chain, hidden only by other matrices), and a column's dot needs one shuffle.
+template <int J>
+__device__ __forceinline__ void qr_col_step(float (&a)[32], const int c, const int h, const int n, float (*vs)[64], float* stau,
+                                            float* __restrict__ tau_row) {
+  constexpr int buf = J & 1, iJ = J / 8, hJ = (J / 4) & 1, eJ = J & 3;
+  const int lane = threadIdx.x & 31;
+  // row(i, e) = 8 i + 4 h + e > J  <=>  i > iJ, or i == iJ and 4 h + e > 4 hJ + eJ
+  const int bnd = 4 * hJ + eJ - 4 * h;   // in chunk iJ: element e is below the diagonal iff e > bnd
+  const unsigned pair_mask = 3u << (lane & ~1);                       // the two threads of my column
+  const unsigned live_mask = __ballot_sync(kFull, c > J && c < n);    // threads that update in this step (whole pairs)
+  if (c == J) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s[e] = (e > bnd) ? a[4 * iJ + e] * a[4 * iJ + e] : 0.f;
+#pragma unroll
+    for (int i = iJ + 1; i < 8; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[e] = fmaf(a[4 * i + e], a[4 * i + e], s[e]);
+    float sig = (s[0] + s[1]) + (s[2] + s[3]);
+    sig += __shfl_xor_sync(pair_mask, sig, 1);
+    const float alpha = __shfl_sync(pair_mask, a[4 * iJ + eJ], (lane & ~1) | hJ);
+    const float sj = fmaf(alpha, alpha, sig);
+    float tau = 0.f;
+    if (sj != 0.f) {
+      const float nrm = sqrtf(sj);
+      const float beta = (alpha < 0.f) ? nrm : -nrm;
+      const float u = alpha - beta;
+      const float inv_u = 1.f / u;
+      tau = -u / beta;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (e > bnd) a[4 * iJ + e] *= inv_u;
+      if (h == hJ) a[4 * iJ + eJ] = beta;
+#pragma unroll
+      for (int i = iJ + 1; i < 8; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) a[4 * i + e] *= inv_u;
+    }
+    // publish v (rows > J are meaningful; v_J = 1 implicit) and tau
+#pragma unroll
+    for (int i = iJ; i < 8; ++i)
+      *reinterpret_cast<float4*>(&vs[buf][8 * i + 4 * h]) = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+    if (h == 0) { stau[buf] = tau; tau_row[J] = tau; }
+  }
+  __syncthreads();
+  if (c > J && c < n) {   // both threads of a column take the same branch (shuffle below is pair-convergent)
+    const float tau = stau[buf];
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+      const float4 t = *reinterpret_cast<const float4*>(&vs[buf][8 * iJ + 4 * h]);
+      const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) d[e] = (e > bnd) ? tv[e] * a[4 * iJ + e] : 0.f;
+      if (h == hJ) d[eJ] = a[4 * iJ + eJ];   // v_J = 1
+    }
+#pragma unroll
+    for (int i = iJ + 1; i < 8; ++i) {
+      const float4 t = *reinterpret_cast<const float4*>(&vs[buf][8 * i + 4 * h]);
+      d[0] = fmaf(t.x, a[4 * i], d[0]); d[1] = fmaf(t.y, a[4 * i + 1], d[1]);
+      d[2] = fmaf(t.z, a[4 * i + 2], d[2]); d[3] = fmaf(t.w, a[4 * i + 3], d[3]);
+    }
+    float dot = (d[0] + d[1]) + (d[2] + d[3]);
+    dot += __shfl_xor_sync(live_mask, dot, 1);
+    const float w = tau * dot;
+    if (w != 0.f) {
+      const float4 t = *reinterpret_cast<const float4*>(&vs[buf][8 * iJ + 4 * h]);
+      const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (e > bnd) a[4 * iJ + e] = fmaf(-w, tv[e], a[4 * iJ + e]);
+      if (h == hJ) a[4 * iJ + eJ] -= w;
+#pragma unroll
+      for (int i = iJ + 1; i < 8; ++i) {
+        const float4 t2 = *reinterpret_cast<const float4*>(&vs[buf][8 * i + 4 * h]);
+        a[4 * i] = fmaf(-w, t2.x, a[4 * i]); a[4 * i + 1] = fmaf(-w, t2.y, a[4 * i + 1]);
+        a[4 * i + 2] = fmaf(-w, t2.z, a[4 * i + 2]); a[4 * i + 3] = fmaf(-w, t2.w, a[4 * i + 3]);
+      }
+    }
+  }
+}
+
+template <int J>
+struct QrColSteps {
+  static __device__ __forceinline__ void run(float (&a)[32], int c, int h, int n, float (*vs)[64], float* stau, float* tau_row) {
+    if (J < n) {   // uniform
+      qr_col_step<J>(a, c, h, n, vs, stau, tau_row);
+      QrColSteps<J + 1>::run(a, c, h, n, vs, stau, tau_row);
+    }
+  }
+};
+template <>
+struct QrColSteps<64> {
+  static __device__ __forceinline__ void run(float (&)[32], int, int, int, float (*)[64], float*, float*) {}
+};
+
+__global__ void __launch_bounds__(128) batched_qr_col_kernel(float* __restrict__ base, long long stride, long long lda, int m, int n,
+                                                             float* __restrict__ tau_out) {
+  __shared__ __align__(16) float vs[2][64];
+  __shared__ float stau[2];
+  const int c = threadIdx.x >> 1, h = threadIdx.x & 1;
+  float* A = base + (long long)blockIdx.x * stride + (long long)c * lda + 4 * h;
+  float a[32];
+  const bool vec = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && (stride % 4 == 0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r0 = 8 * i + 4 * h;
+    if (c < n && vec && r0 + 3 < m) {
+      const float4 v = *reinterpret_cast<const float4*>(A + 8 * i);
+      a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[4 * i + e] = (c < n && r0 + e < m) ? A[8 * i + e] : 0.f;
+    }
+  }
+  QrColSteps<0>::run(a, c, h, n, vs, stau, tau_out + (long long)blockIdx.x * n);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r0 = 8 * i + 4 * h;
+    if (c < n && vec && r0 + 3 < m) {
+      *reinterpret_cast<float4*>(A + 8 * i) = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (c < n && r0 + e < m) A[8 * i + e] = a[4 * i + e];
+    }
+  }
+}
+
+void launch_batched_qr_col(float* base, long long stride, long long lda, int m, int n, int batch, float* tau, cudaStream_t s) {
+  if (batch <= 0) return;
+  ++g_launches;
+  batched_qr_col_kernel<<<batch, 128, 0, s>>>(base, stride, lda, m, n, tau);
+}
+
 void launch_tile_qr(const TileQRParams& p, int tiles, int tile_rows, cudaStream_t s) {
   if (tiles <= 0) return;
   ++g_launches;

@@ -77,6 +77,19 @@ void launch_tile_apply_q(const TileApplyParams& p, int tiles, int tile_rows, cud
 // in place, tau[b * n + j])
 void launch_batched_qr_col(float* base, long long stride, long long lda, int m, int n, int batch, float* tau, cudaStream_t s);
 
+// ---- warp-resident flat-tree TSQR leaf (R only): tsqr_flat.cu -------------------------------
+struct FlatTsqrParams {
+  const float* a; long long lda;   // m x n source, never written
+  long long m; int n;
+  long long rows_per_chain;        // multiple of 64; chain k factors rows [k * rows_per_chain, ...)
+  int chains;
+  float* r_out;                    // chain k's 64 x 64 R -> r_out + (k / fan) * r_tile_stride + (k % fan) * 64, ld r_ld
+  long long r_tile_stride, r_ld;
+  int fan;
+};
+int flat_tsqr_max_chains(int sm_count);   // chains resident in one wave
+void launch_tsqr_flat_r(const FlatTsqrParams& p, cudaStream_t s);
+
 // ---- Householder reconstruction + T builder: reconstruct.cu ---------------------------------
 struct HrParams {
   const float* q;  long long ldq;     // thin Q of the panel (mp x b)

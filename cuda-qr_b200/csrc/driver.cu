@@ -36,6 +36,9 @@ struct TsqrLevel {
 struct TsqrPlan {
   long long m = 0;
   int n = 0, th = 256, fan = 4;
+  // flat leaf (R-only, tsqr_flat.cu): level 0 is `lv[0].tiles` warp chains of flat_rows rows each, no tau kept
+  bool flat = false;
+  long long flat_rows = 0;
   std::vector<TsqrLevel> lv;
   size_t bytes = 0;
 };
@@ -78,7 +81,7 @@ struct cqr_context {
   float* host_out = nullptr;
   cudaStream_t copy = nullptr;
   cudaEvent_t ev_start = nullptr, ev_a = nullptr, ev_g = nullptr, ev_panel[2] = {nullptr, nullptr};
-  int opt_gemm = 1, opt_outer = 256, opt_tile_rows = 256, opt_splitk = 0, opt_lookahead = 1, opt_panel = 1, opt_cluster = 1;
+  int opt_gemm = 1, opt_outer = 256, opt_tile_rows = 256, opt_splitk = 0, opt_lookahead = 1, opt_panel = 1, opt_cluster = 1, opt_flat = 1;
   // multi-CTA panel kernel (panel_hh.cu): cross-CTA exchange slots, launch epoch, spin-timeout flag
   uint2* hh_slots = nullptr;
   int* hh_err = nullptr;
@@ -231,13 +234,26 @@ struct Carver {   // size pass (base == nullptr) and carve pass share one code p
 };
 
 // ---- TSQR plan ---------------------------------------------------------------------------
-void plan_tsqr(TsqrPlan& P, long long m, int n, int th, Carver& cv) {
+// flat_chains > 0: the leaf level is the warp-resident flat tree (R only) with at most that many chains in flight;
+// each chain gets at least 8 blocks of 64 rows so the leaf level shrinks the problem at least 8x.
+void plan_tsqr(TsqrPlan& P, long long m, int n, int th, Carver& cv, int flat_chains = 0) {
   P.m = m; P.n = n; P.th = th; P.fan = th / CQR_SLOT;
   P.lv.clear();
   TsqrLevel l0;
-  l0.tiles = (int)((m + th - 1) / th);
-  l0.rows_total = m;
-  l0.tau = cv.take((long long)l0.tiles * 64);
+  P.flat = false; P.flat_rows = 0;
+  const long long blocks = (m + 63) / 64;
+  if (flat_chains > 0 && blocks >= 16) {
+    long long bpc = (blocks + flat_chains - 1) / flat_chains;
+    if (bpc < 8) bpc = 8;
+    P.flat = true;
+    P.flat_rows = bpc * 64;
+    l0.tiles = (int)((blocks + bpc - 1) / bpc);
+    l0.rows_total = m;
+  } else {
+    l0.tiles = (int)((m + th - 1) / th);
+    l0.rows_total = m;
+    l0.tau = cv.take((long long)l0.tiles * 64);
+  }
   P.lv.push_back(l0);
   while (P.lv.back().tiles > 1) {
     const int prev = P.lv.back().tiles;
@@ -264,6 +280,13 @@ void run_tsqr_factor(cqr_context* c, const TsqrPlan& P, float* a, long long lda,
                      long long ldr) {
   const int L = (int)P.lv.size();
   for (int l = 0; l < L; ++l) {
+    if (l == 0 && P.flat) {   // >= 2 chains by construction, so a tree level follows
+      FlatTsqrParams f{};
+      f.a = a; f.lda = lda; f.m = P.m; f.n = P.n; f.rows_per_chain = P.flat_rows; f.chains = P.lv[0].tiles;
+      f.r_out = P.lv[1].store; f.r_tile_stride = (long long)P.th * 64; f.r_ld = P.th; f.fan = P.fan;
+      launch_tsqr_flat_r(f, cur_stream(c));
+      continue;
+    }
     TileQRParams p{};
     p.a = level_src(P, l, a, lda);
     p.ncols = P.n;
@@ -508,6 +531,7 @@ int cqr_set_option(cqr_context* c, int opt, int v) {
     case CQR_OPT_SPLITK: if (v < 0 || v > kMaxSplits) return CQR_EINVAL; c->opt_splitk = v; return 0;
     case CQR_OPT_LOOKAHEAD: if (v != 0 && v != 1) return CQR_EINVAL; c->opt_lookahead = v; return 0;
     case CQR_OPT_PANEL: if (v != 0 && v != 1) return CQR_EINVAL; c->opt_panel = v; return 0;
+    case CQR_OPT_FLAT_TSQR: if (v != 0 && v != 1) return CQR_EINVAL; c->opt_flat = v; return 0;
   }
   return CQR_EINVAL;
 }
@@ -521,6 +545,7 @@ int cqr_get_option(cqr_context* c, int opt, int* v) {
     case CQR_OPT_SPLITK: *v = c->opt_splitk; return 0;
     case CQR_OPT_LOOKAHEAD: *v = c->opt_lookahead; return 0;
     case CQR_OPT_PANEL: *v = c->opt_panel; return 0;
+    case CQR_OPT_FLAT_TSQR: *v = c->opt_flat; return 0;
   }
   return CQR_EINVAL;
 }
@@ -880,7 +905,7 @@ static int tsqr_common(cqr_context* c, float* dA, int lda, long long m, int n, f
   TsqrPlan plan;
   for (int pass = 0; pass < 2; ++pass) {
     Carver cv(pass ? (keep ? c->ts : c->ws) : nullptr);
-    plan_tsqr(plan, m, n, th, cv);
+    plan_tsqr(plan, m, n, th, cv, (!keep && c->opt_flat && m >= 16384) ? flat_tsqr_max_chains(c->sm_count) : 0);
     if (!pass) {
       if (keep) {
         if (cv.off > c->ts_bytes) {

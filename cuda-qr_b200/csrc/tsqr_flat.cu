@@ -1,0 +1,237 @@
+// tsqr_flat.cu -- R-only leaf of the tall-skinny QR (BASELINE config 3): warp-resident flat-tree Householder.
+//
+// The reference factors a tall panel by sweeping a PR x PC window bottom-to-top, carrying the running R in the
+// rows of overlap (qr.c:68-73, 109-141: "triangle on top of a square" -- the reflector of column `col` spans the
+// fresh rows plus one diagonal entry of the carried R).  This kernel is that same flat tree, re-cut for a B200:
+// every WARP owns one contiguous chain of 64-row blocks and one running 64 x 64 R, thousands of chains run at once,
+// and the chains' R factors feed the existing binary/4-ary tile tree (tile_qr.cu).
+//
+// Per block B (64 x 64) and pivot column j the structured reflector is v = [e_j ; x / u] with x = B(:, j):
+//   sigma = x^T x, alpha = R(j,j), beta = -sign(alpha) sqrt(alpha^2 + sigma), u = alpha - beta, tau = -u / beta  (qr.c:144-152)
+//   for c > j:  s = R(j,c) + (x^T B(:,c)) / u ;  R(j,c) -= tau s ;  B(:,c) -= (tau s / u) x
+// Only row j of R and the block change, so the flop count is the Householder minimum 2 m n^2 -- no stacked-R overhead.
+//
+// Lane layout (lane = 8 h + q): column group q in 0..7 owns columns {q, q+8, .., q+56} (register slot i = c / 8),
+// row part h in 0..3 owns rows 16 h .. 16 h + 15 of the block.  A lane holds 8 slots x 16 rows as 64 packed f32x2
+// pairs, so every dot product and rank-1 update is FFMA2; a column's dot needs two shuffle stages (over h) instead of
+// the five of a lane-per-row layout, and x reaches the lanes as four broadcast LDS.128.  Slots die as the pivot moves
+// right (slot i is skipped once 8 i + 7 <= j): the step body exists in eight statically specialised versions
+// (template I0 = j / 8) and loops dynamically over j % 8, which keeps every register index static while the whole
+// sweep stays ~2 K instructions (a fully unrolled 64-step body would not fit the instruction cache).
+// R lives in shared memory (row-major, 16 KB per warp): a step touches only row j, one conflict-free word per slot.
+// There is no block-level barrier anywhere: warps are independent, __syncwarp orders the x broadcast.
+#include "common.cuh"
+#include <stdlib.h>
+
+namespace cqr {
+
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 fpack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void funpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ float fsum2(f32x2 v) { float lo, hi; funpack2(v, lo, hi); return lo + hi; }
+
+__device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_newton(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.f), r);
+}
+
+constexpr int kFlatWarpFloats = 64 * 64 + 2 * 64;   // R (row-major) + double-buffered x
+
+// Steps j = 8 I0 .. 8 I0 + 7 of one block: slots < I0 are finished columns and are not touched.
+template <int I0>
+__device__ __forceinline__ void flat_steps(f32x2 (&b)[8][8], float* __restrict__ Rs, float* __restrict__ xs, const int q,
+                                           const int h, const int n) {
+#pragma unroll 1
+  for (int jj = 0; jj < 8; ++jj) {
+    const int j = 8 * I0 + jj;
+    if (j >= n) break;                       // warp-uniform
+    float* xb = xs + (jj & 1) * 64;
+    float* Rj = Rs + j * 64;
+    // row j of R (last written one block ago) is read before the warp barrier and written after it
+    float r[8];
+#pragma unroll
+    for (int i = I0; i < 8; ++i) r[i] = Rj[q + 8 * i];
+    const float alpha = Rj[j];
+    if (q == jj) {                           // the four lanes holding column j publish x = B(:, j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ulonglong2 v; v.x = b[I0][2 * k]; v.y = b[I0][2 * k + 1];
+        *reinterpret_cast<ulonglong2*>(xb + 16 * h + 4 * k) = v;
+      }
+    }
+    __syncwarp();
+    f32x2 x[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xb + 16 * h + 4 * k);
+      x[2 * k] = v.x; x[2 * k + 1] = v.y;
+    }
+    // partial sums over this lane's 16 rows: sigma and the live columns' dots; then two butterfly stages over h.
+    // Every lane ends with bit-identical totals (commutative pairings), so the scalars below are warp-uniform.
+    float d[8];
+    f32x2 s2 = 0ull;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s2 = ffma2(x[k], x[k], s2);
+    float sig = fsum2(s2);
+#pragma unroll
+    for (int i = I0; i < 8; ++i) {
+      f32x2 d2 = 0ull;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d2 = ffma2(x[k], b[i][k], d2);
+      d[i] = fsum2(d2);
+    }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      const float ts = __shfl_xor_sync(kFull, sig, o);
+      float t[8];
+#pragma unroll
+      for (int i = I0; i < 8; ++i) t[i] = __shfl_xor_sync(kFull, d[i], o);
+      sig += ts;
+#pragma unroll
+      for (int i = I0; i < 8; ++i) d[i] += t[i];
+    }
+    // Reflector scalars on the MUFU approximations plus one Newton step each (~1 ulp, no slow-path calls): the IEEE
+    // sqrt / divide sequences cost 55 instructions per step.  Columns whose norm underflows fp32 count as zero.
+    float tau = 0.f, inv_u = 0.f, beta = alpha;
+    const float sj = fmaf(alpha, alpha, sig);
+    if (sig != 0.f && sj >= 1.2e-38f) {      // x == 0: H = I (LAPACK convention; the reference would flip a sign or NaN)
+      const float rs = rsqrt_approx(sj);
+      float nrm = sj * rs;
+      nrm = fmaf(fmaf(-nrm, nrm, sj), 0.5f * rs, nrm);
+      beta = (alpha < 0.f) ? nrm : -nrm;
+      const float u = alpha - beta;
+      inv_u = rcp_newton(u);
+      tau = -u * rcp_newton(beta);
+    }
+#pragma unroll
+    for (int i = I0; i < 8; ++i) {
+      const bool act = (i > I0) || (q > jj);           // column q + 8 i is to the right of the pivot
+      const float s = fmaf(d[i], inv_u, r[i]);
+      const float wv = act ? tau * s : 0.f;
+      if (act && h == 0) Rj[q + 8 * i] = r[i] - wv;
+      const float nwu = -(wv * inv_u);
+      const f32x2 nw2 = fpack2(nwu, nwu);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) b[i][k] = ffma2(nw2, x[k], b[i][k]);
+    }
+    if (q == jj && h == 0) Rj[j] = beta;
+  }
+}
+
+template <int I0>
+struct FlatGroups {
+  static __device__ __forceinline__ void run(f32x2 (&b)[8][8], float* Rs, float* xs, int q, int h, int n) {
+    flat_steps<I0>(b, Rs, xs, q, h, n);
+    FlatGroups<I0 + 1>::run(b, Rs, xs, q, h, n);
+  }
+};
+template <>
+struct FlatGroups<8> {
+  static __device__ __forceinline__ void run(f32x2 (&)[8][8], float*, float*, int, int, int) {}
+};
+
+template <int WPC, int MINB>
+__global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_r_kernel(FlatTsqrParams p) {
+  extern __shared__ __align__(16) float flat_smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane & 7, h = lane >> 3;
+  const long long chain = (long long)blockIdx.x * WPC + w;
+  if (chain >= p.chains) return;             // warps never meet at a block barrier
+  float* Rs = flat_smem + w * kFlatWarpFloats;
+  float* xs = Rs + 64 * 64;
+  for (int i = lane; i < 64 * 64 / 4; i += 32) reinterpret_cast<float4*>(Rs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+
+  const int n = p.n;
+  const long long row0 = chain * p.rows_per_chain;
+  const long long row1 = (row0 + p.rows_per_chain < p.m) ? row0 + p.rows_per_chain : p.m;
+  const bool aligned = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.a) & 15) == 0);
+  for (long long rb = row0; rb < row1; rb += 64) {
+    f32x2 b[8][8];
+    const float* src = p.a + rb + 16 * h;
+    if (aligned && rb + 64 <= row1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = q + 8 * i;
+        if (c < n) {
+          const ulonglong2* s4 = reinterpret_cast<const ulonglong2*>(src + (long long)c * p.lda);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const ulonglong2 v = __ldcs(s4 + k);
+            b[i][2 * k] = v.x; b[i][2 * k + 1] = v.y;
+          }
+          if (rb + 128 <= row1) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (long long)c * p.lda + 64));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) b[i][k] = 0ull;
+        }
+      }
+    } else {                                 // ragged last block or unaligned source: guarded scalar loads, zero fill
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = q + 8 * i;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const long long r = rb + 16 * h + 2 * k;
+          const float lo = (c < n && r < row1) ? src[(long long)c * p.lda + 2 * k] : 0.f;
+          const float hi = (c < n && r + 1 < row1) ? src[(long long)c * p.lda + 2 * k + 1] : 0.f;
+          b[i][k] = fpack2(lo, hi);
+        }
+      }
+    }
+    FlatGroups<0>::run(b, Rs, xs, q, h, n);
+  }
+  __syncwarp();
+  // chain k's R goes to slot (k % fan) of parent tile (k / fan); a full 64 x 64 slot is written (zeros below the diagonal
+  // and in columns >= n) so the tree above never sees stale workspace
+  float* dst = p.r_out + (chain / p.fan) * p.r_tile_stride + (chain % p.fan) * CQR_SLOT;
+  for (int c = 0; c < 64; ++c) {
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int r = lane + 32 * rr;
+      dst[r + (long long)c * p.r_ld] = (r <= c && c < n) ? Rs[r * 64 + c] : 0.f;
+    }
+  }
+}
+
+// Two register budgets are built: 3 CTAs of 4 warps per SM (168 registers, a few spills) and 2 CTAs per SM (236
+// registers, none).  CQR_FLAT_MINB=2|3 picks one (default 3).
+static constexpr int kFlatWpc = 4;
+static constexpr size_t kFlatSmem = (size_t)kFlatWpc * kFlatWarpFloats * sizeof(float);
+
+static int flat_minb() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CQR_FLAT_MINB");
+    v = (e && e[0] == '2') ? 2 : 3;
+    cudaFuncSetAttribute(tsqr_flat_r_kernel<kFlatWpc, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFlatSmem);
+    cudaFuncSetAttribute(tsqr_flat_r_kernel<kFlatWpc, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFlatSmem);
+  }
+  return v;
+}
+
+// Chains the device keeps resident at once (one wave): SMs x resident CTAs x warps per CTA.
+int flat_tsqr_max_chains(int sm_count) {
+  static int per_sm = -1;
+  if (per_sm < 0) {
+    int nb = 0;
+    cudaError_t e = flat_minb() == 2
+        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tsqr_flat_r_kernel<kFlatWpc, 2>, 32 * kFlatWpc, kFlatSmem)
+        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tsqr_flat_r_kernel<kFlatWpc, 3>, 32 * kFlatWpc, kFlatSmem);
+    if (e != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 1; }
+    per_sm = nb * kFlatWpc;
+  }
+  return sm_count * per_sm;
+}
+
+void launch_tsqr_flat_r(const FlatTsqrParams& p, cudaStream_t s) {
+  if (p.chains <= 0) return;
+  ++g_launches;
+  const int ctas = (p.chains + kFlatWpc - 1) / kFlatWpc;
+  if (flat_minb() == 2) tsqr_flat_r_kernel<kFlatWpc, 2><<<ctas, 32 * kFlatWpc, kFlatSmem, s>>>(p);
+  else tsqr_flat_r_kernel<kFlatWpc, 3><<<ctas, 32 * kFlatWpc, kFlatSmem, s>>>(p);
+}
+
+}  // namespace cqr

@@ -74,7 +74,8 @@ enum {
   CQR_OPT_TILE_ROWS = 3,    /* TSQR leaf height: 128 or 256 (default 256)                            */
   CQR_OPT_SPLITK = 4,       /* 0 = automatic                                                        */
   CQR_OPT_LOOKAHEAD = 5,    /* 1 (default): next block's panels overlap the trailing update on a side stream */
-  CQR_OPT_PANEL = 6         /* 1 (default): one-launch multi-CTA Householder panel; 0: TSQR tree + Householder reconstruction */
+  CQR_OPT_PANEL = 6,        /* 1 (default): one-launch multi-CTA Householder panel; 0: TSQR tree + Householder reconstruction */
+  CQR_OPT_FLAT_TSQR = 7     /* 1 (default): cqr_tsqr_r on >= 16384 rows uses the warp-resident flat-tree leaf; 0: 256-row tile leaves */
 };
 
 int cqr_create(cqr_context** ctx, int device);

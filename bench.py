@@ -310,10 +310,10 @@ def bench_tsqr(args, pkg, ctx, torch, dist, dev, rank, world, timed_steps, pk):
            "value": flops / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms, "scaling": "strong", "n_gpus": world}
     bytes_alg = 4.0 * m_loc * n
     ach = bytes_alg / (ms * 1e-3) / 1e9
-    res["roofline"] = {"bound": "hbm", "kernel": "tile_qr_kernel<8> (256x64 leaves, A read once)", "achieved": ach,
+    res["roofline"] = {"bound": "hbm", "kernel": "tsqr_flat_r_kernel (warp-resident flat-tree Householder leaf, A read once) + tile_qr_kernel<8> tree", "achieved": ach,
                        "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
                        "note": "per-GPU algorithmic bytes 4*m_loc*n over the whole step (leaves + tree + NCCL hops); "
-                               "SIMT Householder is FMA-issue bound at this shape (32 flop/B), see DESIGN.md"}
+                               "SIMT Householder is FMA-issue bound at this shape (32 flop/B): the fp32 FMA floor is 2mn^2 / (148 SMs x 128 lanes x 2 x clock) ~ 1.0 ms = 33 % of the HBM roof, see DESIGN.md"}
     # Gram check of the combined R against the distributed A: A^T A = sum over ranks of A_loc^T A_loc
     G = A_loc.t().double() @ A_loc.double()
     if world > 1:

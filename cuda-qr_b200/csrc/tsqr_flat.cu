@@ -39,6 +39,7 @@ __device__ __forceinline__ float rcp_newton(float x) {
 }
 
 constexpr int kFlatWarpFloats = 64 * 64 + 2 * 64;   // R (row-major) + double-buffered x
+constexpr int kFlatDefaultCfg = 2;
 
 // Steps j = 8 I0 .. 8 I0 + 7 of one block: slots < I0 are finished columns and are not touched.
 template <int I0>
@@ -133,7 +134,118 @@ struct FlatGroups<8> {
   static __device__ __forceinline__ void run(f32x2 (&)[8][8], float*, float*, int, int, int) {}
 };
 
-template <int WPC, int MINB>
+// ---- software-pipelined step body ---------------------------------------------------------------------------------
+// The step's serial chain is sigma -> two shuffles -> sqrt / reciprocals -> per-column scalars; only the rank-1 update
+// depends on it.  Here the update of reflector j-1 is deferred into step j: the pivot column's slot is updated first
+// (so x_j can be published), then sigma_j's chain is started and the remaining updates of reflector j-1 (independent
+// FFMA2 work) and the dots of step j are issued under its latency.  State carried between steps: x_{j-1} (registers)
+// and nw[i] = -(tau s_i / u) per slot (0 = nothing pending).  Iteration (I0, jj) touches slots >= I0 only: the pending
+// reflector of the group's first iteration has its pivot in slot I0-1's last column, whose remaining active columns all
+// lie in slots >= I0.
+template <int I0>
+__device__ __forceinline__ void flat_steps_pipe(f32x2 (&b)[8][8], f32x2 (&xp)[8], float (&nw)[8], float* __restrict__ Rs,
+                                                float* __restrict__ xs, const int q, const int h, const int n) {
+#pragma unroll 1
+  for (int jj = 0; jj < 8; ++jj) {
+    const int j = 8 * I0 + jj;
+    if (j >= n) break;                       // warp-uniform; what is still pending only touches zero columns
+    float* xb = xs + (jj & 1) * 64;
+    float* Rj = Rs + j * 64;
+    {                                        // pending reflector on the pivot's slot
+      const f32x2 c2 = fpack2(nw[I0], nw[I0]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) b[I0][k] = ffma2(c2, xp[k], b[I0][k]);
+    }
+    float r[8];
+#pragma unroll
+    for (int i = I0; i < 8; ++i) r[i] = Rj[q + 8 * i];
+    const float alpha = Rj[j];
+    if (q == jj) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ulonglong2 v; v.x = b[I0][2 * k]; v.y = b[I0][2 * k + 1];
+        *reinterpret_cast<ulonglong2*>(xb + 16 * h + 4 * k) = v;
+      }
+    }
+    __syncwarp();
+    f32x2 x[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xb + 16 * h + 4 * k);
+      x[2 * k] = v.x; x[2 * k + 1] = v.y;
+    }
+    f32x2 s2a = 0ull, s2b = 0ull;            // two chains: sigma heads the critical path
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s2a = ffma2(x[2 * k], x[2 * k], s2a); s2b = ffma2(x[2 * k + 1], x[2 * k + 1], s2b); }
+    float sig = fsum2(s2a) + fsum2(s2b);
+    sig += __shfl_xor_sync(kFull, sig, 8);
+    sig += __shfl_xor_sync(kFull, sig, 16);
+#pragma unroll
+    for (int i = I0 + 1; i < 8; ++i) {       // pending reflector on the other live slots
+      const f32x2 c2 = fpack2(nw[i], nw[i]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) b[i][k] = ffma2(c2, xp[k], b[i][k]);
+    }
+    // k outer / slot inner: consecutive FFMA2s share x[k] (operand reuse; an FFMA2 with three fresh 64-bit sources
+    // issues every 3 cycles on sm_100, one with two every 2 -- tools/probes/ffma2_probe.cu)
+    float d[8];
+    {
+      f32x2 d2[8];
+#pragma unroll
+      for (int i = I0; i < 8; ++i) d2[i] = 0ull;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int i = I0; i < 8; ++i) d2[i] = ffma2(x[k], b[i][k], d2[i]);
+#pragma unroll
+      for (int i = I0; i < 8; ++i) d[i] = fsum2(d2[i]);
+    }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      float t[8];
+#pragma unroll
+      for (int i = I0; i < 8; ++i) t[i] = __shfl_xor_sync(kFull, d[i], o);
+#pragma unroll
+      for (int i = I0; i < 8; ++i) d[i] += t[i];
+    }
+    // branch-free scalars (see flat_steps): a zero or underflowing column gives tau = 0, H = I
+    const float sj = fmaf(alpha, alpha, sig);
+    const bool ok = (sig != 0.f) && (sj >= 1.2e-38f);
+    const float sjs = ok ? sj : 1.f;
+    const float rs = rsqrt_approx(sjs);
+    float nrm = sjs * rs;
+    nrm = fmaf(fmaf(-nrm, nrm, sjs), 0.5f * rs, nrm);
+    const float bc = (alpha < 0.f) ? nrm : -nrm;
+    const float u = alpha - bc;
+    const float inv_u = ok ? rcp_newton(u) : 0.f;
+    const float tau = ok ? -u * rcp_newton(bc) : 0.f;
+    const float c2s = -tau * inv_u;
+    if (q == jj && h == 0) Rj[j] = ok ? bc : alpha;
+#pragma unroll
+    for (int i = I0; i < 8; ++i) {
+      const bool act = (i > I0) || (q > jj);
+      const float s = fmaf(d[i], inv_u, r[i]);
+      nw[i] = act ? c2s * s : 0.f;
+      if (act && h == 0) Rj[q + 8 * i] = fmaf(-tau, s, r[i]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) xp[k] = x[k];
+  }
+}
+
+template <int I0>
+struct FlatGroupsPipe {
+  static __device__ __forceinline__ void run(f32x2 (&b)[8][8], f32x2 (&xp)[8], float (&nw)[8], float* Rs, float* xs, int q, int h, int n) {
+    flat_steps_pipe<I0>(b, xp, nw, Rs, xs, q, h, n);
+    FlatGroupsPipe<I0 + 1>::run(b, xp, nw, Rs, xs, q, h, n);
+  }
+};
+template <>
+struct FlatGroupsPipe<8> {
+  static __device__ __forceinline__ void run(f32x2 (&)[8][8], f32x2 (&)[8], float (&)[8], float*, float*, int, int, int) {}
+};
+
+template <int WPC, int MINB, bool PIPE>
 __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_r_kernel(FlatTsqrParams p) {
   extern __shared__ __align__(16) float flat_smem[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane & 7, h = lane >> 3;
@@ -144,6 +256,10 @@ __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_r_kernel(FlatTsqrPar
   for (int i = lane; i < 64 * 64 / 4; i += 32) reinterpret_cast<float4*>(Rs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
 
+  f32x2 xp[8];
+  float nw[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) xp[k] = 0ull;
   const int n = p.n;
   const long long row0 = chain * p.rows_per_chain;
   const long long row1 = (row0 + p.rows_per_chain < p.m) ? row0 + p.rows_per_chain : p.m;
@@ -181,7 +297,13 @@ __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_r_kernel(FlatTsqrPar
         }
       }
     }
-    FlatGroups<0>::run(b, Rs, xs, q, h, n);
+    if (PIPE) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) nw[i] = 0.f;       // nothing pending at the top of a block
+      FlatGroupsPipe<0>::run(b, xp, nw, Rs, xs, q, h, n);
+    } else {
+      FlatGroups<0>::run(b, Rs, xs, q, h, n);
+    }
   }
   __syncwarp();
   // chain k's R goes to slot (k % fan) of parent tile (k / fan); a full 64 x 64 slot is written (zeros below the diagonal
@@ -196,42 +318,54 @@ __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_r_kernel(FlatTsqrPar
   }
 }
 
-// Two register budgets are built: 3 CTAs of 4 warps per SM (168 registers, a few spills) and 2 CTAs per SM (236
-// registers, none).  CQR_FLAT_MINB=2|3 picks one (default 3).
-static constexpr int kFlatWpc = 4;
-static constexpr size_t kFlatSmem = (size_t)kFlatWpc * kFlatWarpFloats * sizeof(float);
-
-static int flat_minb() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CQR_FLAT_MINB");
-    v = (e && e[0] == '2') ? 2 : 3;
-    cudaFuncSetAttribute(tsqr_flat_r_kernel<kFlatWpc, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFlatSmem);
-    cudaFuncSetAttribute(tsqr_flat_r_kernel<kFlatWpc, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFlatSmem);
+// Variants: CQR_FLAT_CFG = 0: plain step body, 3 CTAs x 4 warps per SM (168 registers);  1: plain, 2 x 4 (236 registers);
+// 2: software-pipelined, 2 x 4;  3: software-pipelined, 2 x 5.
+template <int WPC, int MINB, bool PIPE>
+struct FlatCfg {
+  static constexpr size_t smem = (size_t)WPC * kFlatWarpFloats * sizeof(float);
+  static int per_sm() {
+    cudaFuncSetAttribute(tsqr_flat_r_kernel<WPC, MINB, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tsqr_flat_r_kernel<WPC, MINB, PIPE>, 32 * WPC, smem) != cudaSuccess || nb < 1) {
+      cudaGetLastError();
+      nb = 1;
+    }
+    return nb * WPC;
   }
-  return v;
+  static void launch(const FlatTsqrParams& p, cudaStream_t s) {
+    tsqr_flat_r_kernel<WPC, MINB, PIPE><<<(p.chains + WPC - 1) / WPC, 32 * WPC, smem, s>>>(p);
+  }
+};
+
+static int g_flat_cfg = -1, g_flat_per_sm = 0;
+static void flat_init() {
+  if (g_flat_cfg >= 0) return;
+  const char* e = getenv("CQR_FLAT_CFG");
+  g_flat_cfg = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : kFlatDefaultCfg;
+  switch (g_flat_cfg) {
+    case 0: g_flat_per_sm = FlatCfg<4, 3, false>::per_sm(); break;
+    case 1: g_flat_per_sm = FlatCfg<4, 2, false>::per_sm(); break;
+    case 2: g_flat_per_sm = FlatCfg<4, 2, true>::per_sm(); break;
+    default: g_flat_per_sm = FlatCfg<5, 2, true>::per_sm(); break;
+  }
 }
 
 // Chains the device keeps resident at once (one wave): SMs x resident CTAs x warps per CTA.
 int flat_tsqr_max_chains(int sm_count) {
-  static int per_sm = -1;
-  if (per_sm < 0) {
-    int nb = 0;
-    cudaError_t e = flat_minb() == 2
-        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tsqr_flat_r_kernel<kFlatWpc, 2>, 32 * kFlatWpc, kFlatSmem)
-        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tsqr_flat_r_kernel<kFlatWpc, 3>, 32 * kFlatWpc, kFlatSmem);
-    if (e != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 1; }
-    per_sm = nb * kFlatWpc;
-  }
-  return sm_count * per_sm;
+  flat_init();
+  return sm_count * g_flat_per_sm;
 }
 
 void launch_tsqr_flat_r(const FlatTsqrParams& p, cudaStream_t s) {
   if (p.chains <= 0) return;
+  flat_init();
   ++g_launches;
-  const int ctas = (p.chains + kFlatWpc - 1) / kFlatWpc;
-  if (flat_minb() == 2) tsqr_flat_r_kernel<kFlatWpc, 2><<<ctas, 32 * kFlatWpc, kFlatSmem, s>>>(p);
-  else tsqr_flat_r_kernel<kFlatWpc, 3><<<ctas, 32 * kFlatWpc, kFlatSmem, s>>>(p);
+  switch (g_flat_cfg) {
+    case 0: FlatCfg<4, 3, false>::launch(p, s); break;
+    case 1: FlatCfg<4, 2, false>::launch(p, s); break;
+    case 2: FlatCfg<4, 2, true>::launch(p, s); break;
+    default: FlatCfg<5, 2, true>::launch(p, s); break;
+  }
 }
 
 }  // namespace cqr

@@ -975,8 +975,10 @@ int cqr_stack_form_q(cqr_context* c, const float* dRs, int ldrs, int nblk, int n
 int cqr_geqrf_batched(cqr_context* c, float* dA, int lda, long long stride, int m, int n, int batch, float* dtau) {
   if (!c || !dA || !dtau || n < 1 || n > 64 || m < n || m > 256 || lda < m || batch < 1) return CQR_EINVAL;
   cudaSetDevice(c->device);
-  if (m <= 64) {   // one thread per column, no cross-thread reductions (tile_qr.cu)
-    launch_batched_qr_col(dA, stride, lda, m, n, batch, dtau, c->stream);
+  if (m <= 64) {   // one warp per matrix (tsqr_flat.cu); CQR_BATCHED_CTA=1 selects the older two-threads-per-column CTA kernel
+    static const bool cta_kernel = getenv("CQR_BATCHED_CTA") != nullptr;
+    if (cta_kernel) launch_batched_qr_col(dA, stride, lda, m, n, batch, dtau, c->stream);
+    else launch_batched_qr_warp(dA, stride, lda, m, n, batch, dtau, c->stream);
     return (int)cudaGetLastError();
   }
   const int th = m <= 64 ? 64 : (m <= 128 ? 128 : 256);

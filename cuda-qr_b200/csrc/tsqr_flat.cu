@@ -368,4 +368,189 @@ void launch_tsqr_flat_r(const FlatTsqrParams& p, cudaStream_t s) {
   }
 }
 
+// ================================================================================================================
+// Batched small QR (BASELINE config 4: 65 536 independent 64 x 64 matrices), one WARP per matrix.
+//
+// Same machinery as the flat leaf above -- a dense Householder step is the flat step with "row j of R" being the
+// matrix's own row j -- with three differences:
+//   * rows are dealt to the four row parts in pairs (lane part h holds rows 8 k + 2 h + {0, 1}, k = 0..7), so the rows
+//     above pivot group I0 are the register pairs k < I0 of EVERY lane and are skipped statically (rows shrink);
+//   * the pivot-row entries a(j, c) come from a shuffle (they live in part h = (j % 8) / 2, pair I0) instead of shared
+//     memory, and are written back by the rank-1 update itself: x's pivot entry is patched to u, so v_j = 1;
+//   * the reflector is stored: column j below the diagonal becomes x / u, the diagonal beta, tau goes to tau[b n + j]
+//     (LAPACK geqrf storage, qr.c:144-167 scalars; an all-zero tail gives tau = 0 where the reference gives 2 or NaN).
+// 65 536 matrices: 3.5 ms with the two-threads-per-column CTA kernel (tile_qr.cu), see DESIGN.md for this one.
+template <int I0>
+__device__ __forceinline__ void dense_steps(f32x2 (&b)[8][8], float* __restrict__ xs, float* __restrict__ staus, const int q,
+                                            const int h, const int n) {
+#pragma unroll 1
+  for (int jj = 0; jj < 8; ++jj) {
+    const int j = 8 * I0 + jj;
+    if (j >= n) break;                       // warp-uniform
+    float* xb = xs + (jj & 1) * 72;
+    const int hj = jj >> 1;                  // row part holding row j (pair I0)
+    const bool hi_half = (jj & 1) != 0;      // ... in the high half of the pair
+    if (q == jj) {                           // publish x = column j strictly below the diagonal (zeros on and above it)
+      float lo, hi;
+      funpack2(b[I0][I0], lo, hi);
+      if (h == hj) xb[64] = hi_half ? hi : lo;                       // alpha = a(j, j)
+      const float zlo = (2 * h > jj) ? lo : 0.f, zhi = (2 * h + 1 > jj) ? hi : 0.f;
+      *reinterpret_cast<float2*>(xb + 8 * I0 + 2 * h) = make_float2(zlo, zhi);
+#pragma unroll
+      for (int k = I0 + 1; k < 8; ++k) *reinterpret_cast<f32x2*>(xb + 8 * k + 2 * h) = b[I0][k];
+    }
+    // pivot-row entries of my columns: from the lane of my column group in part hj
+    float r[8];
+#pragma unroll
+    for (int i = I0; i < 8; ++i) {
+      float lo, hi;
+      funpack2(b[i][I0], lo, hi);
+      r[i] = __shfl_sync(kFull, hi_half ? hi : lo, q + 8 * hj);
+    }
+    __syncwarp();
+    f32x2 x[8];
+#pragma unroll
+    for (int k = I0; k < 8; ++k) x[k] = *reinterpret_cast<const f32x2*>(xb + 8 * k + 2 * h);
+    const float alpha = xb[64];
+    f32x2 s2 = 0ull;
+#pragma unroll
+    for (int k = I0; k < 8; ++k) s2 = ffma2(x[k], x[k], s2);
+    float sig = fsum2(s2);
+    float d[8];
+    {
+      f32x2 d2[8];
+#pragma unroll
+      for (int i = I0; i < 8; ++i) d2[i] = 0ull;
+#pragma unroll
+      for (int k = I0; k < 8; ++k)
+#pragma unroll
+        for (int i = I0; i < 8; ++i) d2[i] = ffma2(x[k], b[i][k], d2[i]);
+#pragma unroll
+      for (int i = I0; i < 8; ++i) d[i] = fsum2(d2[i]);
+    }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      const float ts = __shfl_xor_sync(kFull, sig, o);
+      float t[8];
+#pragma unroll
+      for (int i = I0; i < 8; ++i) t[i] = __shfl_xor_sync(kFull, d[i], o);
+      sig += ts;
+#pragma unroll
+      for (int i = I0; i < 8; ++i) d[i] += t[i];
+    }
+    const float sj = fmaf(alpha, alpha, sig);
+    const bool ok = (sig != 0.f) && (sj >= 1.2e-38f);
+    const float sjs = ok ? sj : 1.f;
+    const float rs = rsqrt_approx(sjs);
+    float nrm = sjs * rs;
+    nrm = fmaf(fmaf(-nrm, nrm, sjs), 0.5f * rs, nrm);
+    const float bc = (alpha < 0.f) ? nrm : -nrm;
+    const float u = alpha - bc;
+    const float inv_u = ok ? rcp_newton(u) : 0.f;
+    const float tau = ok ? -u * rcp_newton(bc) : 0.f;
+    const float c2s = -tau * inv_u;
+    if (q == 0 && h == 0) staus[j] = tau;
+    // v = x / u below the diagonal and v_j = 1: patch x's pivot entry to u so the update also writes a(j, c) -= tau s
+    if (h == hj) {
+      float lo, hi;
+      funpack2(x[I0], lo, hi);
+      x[I0] = hi_half ? fpack2(lo, u) : fpack2(u, hi);
+    }
+#pragma unroll
+    for (int i = I0; i < 8; ++i) {
+      const bool act = (i > I0) || (q > jj);
+      const float s = fmaf(d[i], inv_u, r[i]);
+      const float nwv = act ? c2s * s : 0.f;
+      const f32x2 nw2 = fpack2(nwv, nwv);
+#pragma unroll
+      for (int k = I0; k < 8; ++k) b[i][k] = ffma2(nw2, x[k], b[i][k]);
+    }
+    if (q == jj && ok) {                     // store the reflector: beta on the diagonal, x / u below, R above untouched
+      float lo, hi, xlo, xhi;
+      funpack2(b[I0][I0], lo, hi);
+      funpack2(x[I0], xlo, xhi);             // the patched entry is never selected below (row == j takes beta)
+      const int r0 = 2 * h, r1 = 2 * h + 1;
+      lo = (r0 > jj) ? xlo * inv_u : (r0 == jj ? bc : lo);
+      hi = (r1 > jj) ? xhi * inv_u : (r1 == jj ? bc : hi);
+      b[I0][I0] = fpack2(lo, hi);
+      const f32x2 iu2 = fpack2(inv_u, inv_u);
+#pragma unroll
+      for (int k = I0 + 1; k < 8; ++k) asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(b[I0][k]) : "l"(b[I0][k]), "l"(iu2));
+    }
+  }
+}
+
+template <int I0>
+struct DenseGroups {
+  static __device__ __forceinline__ void run(f32x2 (&b)[8][8], float* xs, float* staus, int q, int h, int n) {
+    dense_steps<I0>(b, xs, staus, q, h, n);
+    DenseGroups<I0 + 1>::run(b, xs, staus, q, h, n);
+  }
+};
+template <>
+struct DenseGroups<8> {
+  static __device__ __forceinline__ void run(f32x2 (&)[8][8], float*, float*, int, int, int) {}
+};
+
+constexpr int kDenseWarpFloats = 2 * 72 + 64;   // double-buffered x (+ alpha) and the taus
+
+template <int WPC, int MINB>
+__global__ void __launch_bounds__(32 * WPC, MINB) batched_qr_warp_kernel(float* __restrict__ base, long long stride, long long lda,
+                                                                         int m, int n, int batch, float* __restrict__ tau_out) {
+  __shared__ __align__(16) float dsm[WPC * kDenseWarpFloats];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane & 7, h = lane >> 3;
+  const long long mat = (long long)blockIdx.x * WPC + w;
+  if (mat >= batch) return;
+  float* xs = dsm + w * kDenseWarpFloats;
+  float* staus = xs + 2 * 72;
+  float* A = base + mat * stride;
+  const bool vec = (lda % 2 == 0) && (stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(base) & 7) == 0);
+  f32x2 b[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = q + 8 * i;
+    const float* col = A + (long long)c * lda + 2 * h;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r0 = 8 * k + 2 * h;
+      if (c < n && vec && r0 + 1 < m) {
+        b[i][k] = *reinterpret_cast<const f32x2*>(col + 8 * k);
+      } else {
+        const float lo = (c < n && r0 < m) ? col[8 * k] : 0.f;
+        const float hi = (c < n && r0 + 1 < m) ? col[8 * k + 1] : 0.f;
+        b[i][k] = fpack2(lo, hi);
+      }
+    }
+  }
+  staus[lane] = 0.f; staus[lane + 32] = 0.f;
+  __syncwarp();
+  DenseGroups<0>::run(b, xs, staus, q, h, n);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = q + 8 * i;
+    float* col = A + (long long)c * lda + 2 * h;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r0 = 8 * k + 2 * h;
+      if (c < n && vec && r0 + 1 < m) {
+        *reinterpret_cast<f32x2*>(col + 8 * k) = b[i][k];
+      } else {
+        float lo, hi;
+        funpack2(b[i][k], lo, hi);
+        if (c < n && r0 < m) col[8 * k] = lo;
+        if (c < n && r0 + 1 < m) col[8 * k + 1] = hi;
+      }
+    }
+  }
+  for (int j = lane; j < n; j += 32) tau_out[mat * n + j] = staus[j];
+}
+
+void launch_batched_qr_warp(float* base, long long stride, long long lda, int m, int n, int batch, float* tau, cudaStream_t s) {
+  if (batch <= 0) return;
+  ++g_launches;
+  constexpr int WPC = 4;
+  batched_qr_warp_kernel<WPC, 2><<<(batch + WPC - 1) / WPC, 32 * WPC, 0, s>>>(base, stride, lda, m, n, batch, tau);
+}
+
 }  // namespace cqr

@@ -30,6 +30,18 @@ __device__ __forceinline__ f32x2 fpack2(float lo, float hi) { f32x2 r; asm("mov.
 __device__ __forceinline__ void funpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ float fsum2(f32x2 v) { float lo, hi; funpack2(v, lo, hi); return lo + hi; }
+#ifdef CQR_DOT_SCALAR
+// dot-product accumulate on two scalar FFMAs (experiment: an FFMA2 with three fresh 64-bit sources issues every 3 cycles)
+__device__ __forceinline__ f32x2 dfma2(f32x2 a, f32x2 b, f32x2 c) {
+  float al, ah, bl, bh, cl, ch;
+  funpack2(a, al, ah); funpack2(b, bl, bh); funpack2(c, cl, ch);
+  asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(cl) : "f"(al), "f"(bl));
+  asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(ch) : "f"(ah), "f"(bh));
+  return fpack2(cl, ch);
+}
+#else
+__device__ __forceinline__ f32x2 dfma2(f32x2 a, f32x2 b, f32x2 c) { return ffma2(a, b, c); }
+#endif
 
 __device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rcp_newton(float x) {
@@ -180,35 +192,8 @@ __device__ __forceinline__ void flat_steps_pipe(f32x2 (&b)[8][8], f32x2 (&xp)[8]
     float sig = fsum2(s2a) + fsum2(s2b);
     sig += __shfl_xor_sync(kFull, sig, 8);
     sig += __shfl_xor_sync(kFull, sig, 16);
-#pragma unroll
-    for (int i = I0 + 1; i < 8; ++i) {       // pending reflector on the other live slots
-      const f32x2 c2 = fpack2(nw[i], nw[i]);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) b[i][k] = ffma2(c2, xp[k], b[i][k]);
-    }
-    // k outer / slot inner: consecutive FFMA2s share x[k] (operand reuse; an FFMA2 with three fresh 64-bit sources
-    // issues every 3 cycles on sm_100, one with two every 2 -- tools/probes/ffma2_probe.cu)
-    float d[8];
-    {
-      f32x2 d2[8];
-#pragma unroll
-      for (int i = I0; i < 8; ++i) d2[i] = 0ull;
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-#pragma unroll
-        for (int i = I0; i < 8; ++i) d2[i] = ffma2(x[k], b[i][k], d2[i]);
-#pragma unroll
-      for (int i = I0; i < 8; ++i) d[i] = fsum2(d2[i]);
-    }
-#pragma unroll
-    for (int o = 8; o <= 16; o <<= 1) {
-      float t[8];
-#pragma unroll
-      for (int i = I0; i < 8; ++i) t[i] = __shfl_xor_sync(kFull, d[i], o);
-#pragma unroll
-      for (int i = I0; i < 8; ++i) d[i] += t[i];
-    }
-    // branch-free scalars (see flat_steps): a zero or underflowing column gives tau = 0, H = I
+    // branch-free scalars (see flat_steps): a zero or underflowing column gives tau = 0, H = I.  Written here, ahead of
+    // the FFMA2 streams below, so the MUFU chain runs under them (a warp issues in order).
     const float sj = fmaf(alpha, alpha, sig);
     const bool ok = (sig != 0.f) && (sj >= 1.2e-38f);
     const float sjs = ok ? sj : 1.f;
@@ -220,6 +205,44 @@ __device__ __forceinline__ void flat_steps_pipe(f32x2 (&b)[8][8], f32x2 (&xp)[8]
     const float inv_u = ok ? rcp_newton(u) : 0.f;
     const float tau = ok ? -u * rcp_newton(bc) : 0.f;
     const float c2s = -tau * inv_u;
+#pragma unroll
+    for (int i = I0 + 1; i < 8; ++i) {       // pending reflector on the other live slots
+      const f32x2 c2 = fpack2(nw[i], nw[i]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) b[i][k] = ffma2(c2, xp[k], b[i][k]);
+    }
+    // dots in two halves of the live slots: the second half's FFMA2s cover the first half's shuffle latency
+    // (k outer / slot inner so consecutive FFMA2s share x[k]: an FFMA2 with three fresh 64-bit sources issues every
+    // 3 cycles on sm_100, one with two every 2 -- tools/probes/ffma2_probe.cu)
+    float d[8];
+    constexpr int IM = (I0 + 8 + 1) / 2;     // first half: slots I0 .. IM-1
+    {
+      f32x2 d2[8];
+#pragma unroll
+      for (int i = I0; i < IM; ++i) d2[i] = 0ull;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int i = I0; i < IM; ++i) d2[i] = dfma2(x[k], b[i][k], d2[i]);
+#pragma unroll
+      for (int i = I0; i < IM; ++i) d[i] = fsum2(d2[i]);
+#pragma unroll
+      for (int i = I0; i < IM; ++i) d[i] += __shfl_xor_sync(kFull, d[i], 8);
+#pragma unroll
+      for (int i = IM; i < 8; ++i) d2[i] = 0ull;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int i = IM; i < 8; ++i) d2[i] = dfma2(x[k], b[i][k], d2[i]);
+#pragma unroll
+      for (int i = I0; i < IM; ++i) d[i] += __shfl_xor_sync(kFull, d[i], 16);
+#pragma unroll
+      for (int i = IM; i < 8; ++i) d[i] = fsum2(d2[i]);
+#pragma unroll
+      for (int i = IM; i < 8; ++i) d[i] += __shfl_xor_sync(kFull, d[i], 8);
+#pragma unroll
+      for (int i = IM; i < 8; ++i) d[i] += __shfl_xor_sync(kFull, d[i], 16);
+    }
     if (q == jj && h == 0) Rj[j] = ok ? bc : alpha;
 #pragma unroll
     for (int i = I0; i < 8; ++i) {
@@ -424,7 +447,7 @@ __device__ __forceinline__ void dense_steps(f32x2 (&b)[8][8], float* __restrict_
 #pragma unroll
       for (int k = I0; k < 8; ++k)
 #pragma unroll
-        for (int i = I0; i < 8; ++i) d2[i] = ffma2(x[k], b[i][k], d2[i]);
+        for (int i = I0; i < 8; ++i) d2[i] = dfma2(x[k], b[i][k], d2[i]);
 #pragma unroll
       for (int i = I0; i < 8; ++i) d[i] = fsum2(d2[i]);
     }

@@ -33,6 +33,20 @@ for m_loc, n in [(1000, 64), (65536, 64), (5000, 48)]:
         dr = metrics.r_rel_diff(R, np.linalg.qr(Af.astype(np.float64), mode="r"))
         print(f"world {world} m_loc {m_loc} n {n}: backward {be:.3f} orth {orth:.3f} dR {dr:.2e}")
         ok = ok and be <= 10 and orth <= 10 and dr <= 1e-4
+# R-only path (flat-tree warp leaf on every rank) at a size where it is active: Gram check against all ranks' rows
+for m_loc, n in [(262144, 64), (100003, 40)]:
+    g = torch.Generator(device=dev).manual_seed(50 + rank)
+    A = pkg.colmajor(m_loc, n, device=dev); A.copy_(torch.rand((m_loc, n), device=dev, generator=g))
+    ts = dt.DistTSQR(pkg, ctx, n, rank, world, dev)
+    ts.factor(A, keep_q=False)
+    G = A.t().double() @ A.double()
+    dist.all_reduce(G)
+    torch.cuda.synchronize()
+    if rank == 0:
+        Rd = torch.triu(ts.R.double())
+        ge = float((Rd.t() @ Rd - G).norm() / G.norm())
+        print(f"world {world} m_loc {m_loc} n {n}: R-only gram error {ge:.2e}")
+        ok = ok and ge < 1e-5
 dist.barrier(); dist.destroy_process_group()
 if rank == 0:
     print("DIST_TSQR_OK" if ok else "DIST_TSQR_FAIL")

@@ -35,7 +35,7 @@ EXPORTS = [
     "getPanelDims", "mmqr", "mmqr_alloc", "explicitQR", "dgemm", "identity", "printMat",
     "cqr_create", "cqr_destroy", "cqr_set_stream", "cqr_set_option", "cqr_get_option", "cqr_synchronize",
     "cqr_error_string", "cqr_launch_count", "cqr_profile_begin", "cqr_profile_end", "cqr_profile_timeline", "cqr_reserve", "cqr_geqrf", "cqr_extract_r", "cqr_form_q",
-    "cqr_apply_q", "cqr_tsqr_r", "cqr_tsqr_factor", "cqr_tsqr_form_q", "cqr_stack_qr", "cqr_stack_form_q",
+    "cqr_apply_q", "cqr_solve_ls", "cqr_tsqr_r", "cqr_tsqr_factor", "cqr_tsqr_form_q", "cqr_stack_qr", "cqr_stack_form_q",
     "cqr_geqrf_batched", "cqr_gemm", "cqr_gemm_tf32x3", "cqr_set_identity", "cqr_version",
 ]
 
@@ -87,6 +87,7 @@ def _load() -> ctypes.CDLL:
     lib.cqr_extract_r.argtypes = [_VP, _VP, i, i, i, _VP, i, i]
     lib.cqr_form_q.argtypes = [_VP, _VP, i, i, i, _VP, _VP, i, i]
     lib.cqr_apply_q.argtypes = [_VP, i, _VP, i, i, i, _VP, _VP, i, i]
+    lib.cqr_solve_ls.argtypes = [_VP, _VP, i, i, i, _VP, _VP, i, i]
     lib.cqr_tsqr_r.argtypes = [_VP, _VP, i, ll, i, _VP, i]
     lib.cqr_tsqr_factor.argtypes = [_VP, _VP, i, ll, i, _VP, i]
     lib.cqr_tsqr_form_q.argtypes = [_VP, _VP, i, _VP, i]
@@ -309,6 +310,11 @@ class Context:
         m, n = A.shape
         _check(lib.cqr_apply_q(self.h, 1 if trans else 0, _dptr(A), _ld(A), m, n, _dptr(tau), _dptr(C), _ld(C),
                                C.shape[1]), "cqr_apply_q")
+
+    def solve_ls(self, A, tau, B):
+        """min ||A x - b|| for every column b of B (m x nrhs) from geqrf's output: X is left in B[:n]."""
+        m, n = A.shape
+        _check(lib.cqr_solve_ls(self.h, _dptr(A), _ld(A), m, n, _dptr(tau), _dptr(B), _ld(B), B.shape[1]), "cqr_solve_ls")
 
     # -- TSQR -----------------------------------------------------------------------------
     def tsqr_r(self, A, R):

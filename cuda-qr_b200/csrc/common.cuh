@@ -159,6 +159,9 @@ void launch_extract_r(const float* a, long long lda, int m, int n, float* r, lon
 void launch_extract_v(const float* a, long long lda, long long mp, int b, int d0, float* v, long long ldv,
                       cudaStream_t s);
 
+// x = R^-1 b for one kb x kb (kb <= 64) upper-triangular block and nrhs right-hand sides, in place; *singular = 1 on a zero pivot
+void launch_trsm_upper_block(const float* r, long long ldr, int kb, float* b, long long ldb, int nrhs, int* singular, cudaStream_t s);
+
 // ---- tcgen05 3xTF32 GEMMs: gemm_umma.cu -------------------------------------------------------
 // Both return false (nothing launched) when shape/alignment rules out the TMA path.
 bool umma_available();

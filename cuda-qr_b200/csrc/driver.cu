@@ -450,6 +450,7 @@ const char* cqr_error_string(int status) {
     case CQR_ENOMEM: return "workspace allocation failed";
     case CQR_ESTATE: return "call out of order";
     case CQR_EUNSUPPORTED: return "unsupported shape";
+    case CQR_ESINGULAR: return "R is exactly singular";
     default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown";
   }
 }
@@ -895,6 +896,32 @@ int cqr_apply_q(cqr_context* c, int trans, const float* dA, int lda, int m, int 
                 int ldc, int nc) {
   if (!c || !dA || !dtau || !dC || n < 1 || m < n || lda < m || ldc < m || nc < 1) return CQR_EINVAL;
   return apply_q_impl(c, trans ? 1 : 0, dA, lda, m, n, dtau, dC, ldc, nc, false);
+}
+
+// Least squares min ||A x - b|| through the factorisation (the natural consumer of mmqr's output; the
+// reference only forms dense Q, qr.c:330-438): B <- Q^T B, then back substitution with R by 64-row diagonal blocks
+// (one small kernel each) and GEMM updates of the rows above.  X is left in the first n rows of B.
+int cqr_solve_ls(cqr_context* c, const float* dA, int lda, int m, int n, const float* dtau, float* dB, int ldb, int nrhs) {
+  if (!c || !dA || !dtau || !dB || n < 1 || m < n || lda < m || ldb < m || nrhs < 1) return CQR_EINVAL;
+  int rc = apply_q_impl(c, 1, dA, lda, m, n, dtau, dB, ldb, nrhs, false);
+  if (rc) return rc;
+  cudaStream_t st = c->stream;
+  CQR_CUDA(cudaMemsetAsync(c->hh_err + 1, 0, sizeof(int), st));
+  const bool tensor = tensor_ok(c, dB, ldb) && tensor_ok(c, dA, lda) && nrhs >= 64;
+  for (int k0 = ((n - 1) / 64) * 64; k0 >= 0; k0 -= 64) {
+    const int kb = n - k0 < 64 ? n - k0 : 64;
+    launch_trsm_upper_block(dA + k0 + (long long)k0 * lda, lda, kb, dB + k0, ldb, nrhs, c->hh_err + 1, st);
+    if (k0 > 0) {   // rows above: B(0:k0, :) -= R(0:k0, k0:k0+kb) X_k
+      Operand R{dA + (long long)k0 * lda, lda};
+      Operand X{dB + k0, ldb};
+      gemm_nn(c, k0, nrhs, kb, -1.f, R, X, 1.f, dB, ldb, tensor && k0 >= 128);
+    }
+  }
+  int sing = 0;
+  CQR_CUDA(cudaMemcpyAsync(&sing, c->hh_err + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CQR_CUDA(cudaStreamSynchronize(st));
+  if (sing) return CQR_ESINGULAR;
+  return (int)cudaGetLastError();
 }
 
 // ---- TSQR ---------------------------------------------------------------------------------------

@@ -271,4 +271,43 @@ void launch_extract_v(const float* a, long long lda, long long mp, int b, int d0
   elementwise_kernel<5><<<ew_grid(mp, b), 256, 0, s>>>(mp, b, a, lda, v, ldv, d0);
 }
 
+// Back substitution with one kb x kb upper-triangular diagonal block (kb <= 64): X = R^-1 B in place, one thread
+// per right-hand side, R staged in shared memory.  The off-diagonal part of the solve is GEMM work (driver.cu).
+__global__ void __launch_bounds__(128) trsm_upper_block_kernel(const float* __restrict__ r, long long ldr, int kb, float* __restrict__ b,
+                                                               long long ldb, int nrhs, int* __restrict__ singular) {
+  __shared__ float rs[64][65];
+  for (int idx = threadIdx.x; idx < kb * kb; idx += blockDim.x) {
+    const int i = idx % kb, j = idx / kb;
+    rs[i][j] = (i <= j) ? r[i + (long long)j * ldr] : 0.f;
+  }
+  __syncthreads();
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= nrhs) return;
+  float* bc = b + (long long)col * ldb;
+  float x[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) x[i] = (i < kb) ? bc[i] : 0.f;
+#pragma unroll
+  for (int i = 63; i >= 0; --i) {
+    if (i < kb) {
+      const float d = rs[i][i];
+      if (d == 0.f && col == 0) *singular = 1;
+      const float xi = x[i] / d;
+      x[i] = xi;
+#pragma unroll
+      for (int k = 0; k < 64; ++k)
+        if (k < i) x[k] = fmaf(-rs[k][i], xi, x[k]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 64; ++i)
+    if (i < kb) bc[i] = x[i];
+}
+
+void launch_trsm_upper_block(const float* r, long long ldr, int kb, float* b, long long ldb, int nrhs, int* singular, cudaStream_t s) {
+  if (kb <= 0 || nrhs <= 0) return;
+  ++g_launches;
+  trsm_upper_block_kernel<<<(nrhs + 127) / 128, 128, 0, s>>>(r, ldr, kb, b, ldb, nrhs, singular);
+}
+
 }  // namespace cqr

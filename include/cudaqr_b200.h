@@ -64,7 +64,8 @@ enum {
   CQR_EINVAL = -1,      /* bad shape / pointer / leading dimension            */
   CQR_ENOMEM = -2,      /* workspace allocation failed                        */
   CQR_ESTATE = -3,      /* call order (e.g. tsqr_form_q without tsqr_factor)  */
-  CQR_EUNSUPPORTED = -4
+  CQR_EUNSUPPORTED = -4,
+  CQR_ESINGULAR = -5    /* cqr_solve_ls: R has an exactly zero diagonal entry */
 };
 
 /* Options for cqr_set_option. */
@@ -116,6 +117,12 @@ int cqr_form_q(cqr_context* ctx, const float* dA, int lda, int m, int n, const f
 /* C <- Q*C (trans = 0) or Q^T*C (trans = 1); C is m x nc. */
 int cqr_apply_q(cqr_context* ctx, int trans, const float* dA, int lda, int m, int n, const float* dtau,
                 float* dC, int ldc, int nc);
+
+/* Least squares through the factorisation: B (m x nrhs, ldb >= m) <- Q^T B, then R X = B(0:n, :) by blocked back
+ * substitution; X is returned in the first n rows of B (rows n..m-1 hold the residual's Q^T components).
+ * Blocking (reads a singularity flag back).  The natural consumer of mmqr's output (the reference only forms a dense
+ * Q, qr.c:330-438). */
+int cqr_solve_ls(cqr_context* ctx, const float* dA, int lda, int m, int n, const float* dtau, float* dB, int ldb, int nrhs);
 
 /* Communication-avoiding tall-skinny QR (n <= 64).  R-only: A is read once, never written. */
 int cqr_tsqr_r(cqr_context* ctx, const float* dA, int lda, long long m, int n, float* dR, int ldr);

@@ -57,3 +57,13 @@ def test_no_product_import_of_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle", src, flags=re.M), f
                 assert "liboracle" not in src and "oracle/_ref" not in src, f
+
+
+def test_cli_builds_and_prints_the_reference_usage_line():
+    """qr_device is built next to the library (csrc/Makefile) and, like qr.cu:715-719, exits 1 with the usage line
+    before touching the GPU when the sizes are missing."""
+    import subprocess
+    exe = os.path.join(ROOT, "cuda-qr_b200", "qr_device")
+    assert os.path.exists(exe), "run __graft_entry__.build() first"
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 1 and out.stdout.strip() == "Usage: ./qr_device m n"

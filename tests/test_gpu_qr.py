@@ -323,6 +323,47 @@ def test_apply_q_and_qt_roundtrip(pkg, torch, ctx):
     assert np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref) < 1e-3
 
 
+@pytest.mark.parametrize("m,n,nrhs", [(2000, 700, 5), (4096, 1024, 128), (300, 300, 1), (100, 7, 3)])
+def test_solve_least_squares_matches_fp64_lstsq(pkg, torch, ctx, m, n, nrhs):
+    """cqr_solve_ls (Q^T b, blocked back substitution) against numpy's fp64 least squares on the same data."""
+    rng = np.random.default_rng(21)
+    A = np.asfortranarray(rng.random((m, n), dtype=np.float32))
+    B = np.asfortranarray(rng.standard_normal((m, nrhs)).astype(np.float32))
+    dA, dB = dev(pkg, torch, A), dev(pkg, torch, B)
+    tau = torch.zeros(n, device="cuda")
+    ctx.geqrf(dA, tau)
+    ctx.solve_ls(dA, tau, dB)
+    ctx.synchronize()
+    X = host(dB)[:n]
+    X64 = np.linalg.lstsq(A.astype(np.float64), B.astype(np.float64), rcond=None)[0]
+    cond = np.linalg.cond(A.astype(np.float64))
+    assert np.linalg.norm(X - X64) / np.linalg.norm(X64) < 50 * cond * metrics.EPS32
+    # the normal equations hold to working precision: A^T (A x - b) ~ 0
+    res = A.astype(np.float64) @ X.astype(np.float64) - B.astype(np.float64)
+    assert np.linalg.norm(A.astype(np.float64).T @ res) / (np.linalg.norm(A) ** 2 * np.linalg.norm(X64)) < 50 * metrics.EPS32
+    # exactly singular R is reported, not divided through
+    A0 = A.copy(order="F"); A0[:, n - 1] = 0.0
+    dA0 = dev(pkg, torch, A0)
+    ctx.geqrf(dA0, tau)
+    with pytest.raises(pkg.CudaQRError):
+        ctx.solve_ls(dA0, tau, dev(pkg, torch, B))
+
+
+def test_cli_qr_device_matches_reference_interface(pkg):
+    """cuda-qr_b200/qr_device (C, legacy entry points only): the reference's size rounding (qr.cu:722-734), result line
+    (qr.cu:789) and -- with `check` -- its commented-out residual validation (qr.cu:822-850)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(pkg.__file__), "qr_device")
+    out = subprocess.run([exe, "512", "512", "check"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "Exact problem size: 484x484" in out.stdout
+    assert "MMQR ran QR on 484x484 matrix in" in out.stdout and "(avg over 3)" in out.stdout
+    units = float(out.stdout.split("in units of n*eps:")[1].split(")")[0])
+    assert units <= metrics.TOL_BACKWARD
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 1 and "Usage: ./qr_device m n" in out.stdout
+
+
 # ---------------------------------------------------------------------------------------------
 # TSQR (config 3), batched (config 4)
 # ---------------------------------------------------------------------------------------------

@@ -86,9 +86,25 @@ struct FlatTsqrParams {
   float* r_out;                    // chain k's 64 x 64 R -> r_out + (k / fan) * r_tile_stride + (k % fan) * 64, ld r_ld
   long long r_tile_stride, r_ld;
   int fan;
+  // implicit-Q variant only: reflectors are written over the source (a_out == a) and taus to tau_out[block][64]
+  float* a_out;
+  float* tau_out;
+};
+struct FlatApplyParams {
+  const float* v; long long ldv;   // the factored matrix (V blocks as written by the implicit-Q leaf)
+  const float* tau;                // [blocks][64]
+  long long m; int n;              // rows, reflectors per block
+  int nc;                          // output columns (<= 64)
+  long long rows_per_chain; int chains;
+  const float* x;                  // seeds: chain k reads the 64-row slot x + (k / fan) * x_tile_stride + (k % fan) * 64, ld x_ld
+  long long x_tile_stride, x_ld;   //   (nullptr = identity)
+  int x_rows, fan;
+  float* q; long long ldq;         // output m x nc
 };
 int flat_tsqr_max_chains(int sm_count);   // chains resident in one wave
 void launch_tsqr_flat_r(const FlatTsqrParams& p, cudaStream_t s);
+void launch_tsqr_flat_keep(const FlatTsqrParams& p, cudaStream_t s);
+void launch_tsqr_flat_apply(const FlatApplyParams& p, cudaStream_t s);
 // batched QR of m x n matrices (m, n <= 64), one warp per matrix, LAPACK storage in place, tau[b * n + j]
 void launch_batched_qr_warp(float* base, long long stride, long long lda, int m, int n, int batch, float* tau, cudaStream_t s);
 

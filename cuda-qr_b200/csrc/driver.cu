@@ -236,7 +236,7 @@ struct Carver {   // size pass (base == nullptr) and carve pass share one code p
 // ---- TSQR plan ---------------------------------------------------------------------------
 // flat_chains > 0: the leaf level is the warp-resident flat tree (R only) with at most that many chains in flight;
 // each chain gets at least 8 blocks of 64 rows so the leaf level shrinks the problem at least 8x.
-void plan_tsqr(TsqrPlan& P, long long m, int n, int th, Carver& cv, int flat_chains = 0) {
+void plan_tsqr(TsqrPlan& P, long long m, int n, int th, Carver& cv, int flat_chains = 0, bool flat_keep = false) {
   P.m = m; P.n = n; P.th = th; P.fan = th / CQR_SLOT;
   P.lv.clear();
   TsqrLevel l0;
@@ -249,6 +249,7 @@ void plan_tsqr(TsqrPlan& P, long long m, int n, int th, Carver& cv, int flat_cha
     P.flat_rows = bpc * 64;
     l0.tiles = (int)((blocks + bpc - 1) / bpc);
     l0.rows_total = m;
+    if (flat_keep) l0.tau = cv.take(blocks * 64);   // one tau row per 64-row block
   } else {
     l0.tiles = (int)((m + th - 1) / th);
     l0.rows_total = m;
@@ -284,7 +285,8 @@ void run_tsqr_factor(cqr_context* c, const TsqrPlan& P, float* a, long long lda,
       FlatTsqrParams f{};
       f.a = a; f.lda = lda; f.m = P.m; f.n = P.n; f.rows_per_chain = P.flat_rows; f.chains = P.lv[0].tiles;
       f.r_out = P.lv[1].store; f.r_tile_stride = (long long)P.th * 64; f.r_ld = P.th; f.fan = P.fan;
-      launch_tsqr_flat_r(f, cur_stream(c));
+      if (keep_q) { f.a_out = a; f.tau_out = P.lv[0].tau; launch_tsqr_flat_keep(f, cur_stream(c)); }
+      else launch_tsqr_flat_r(f, cur_stream(c));
       continue;
     }
     TileQRParams p{};
@@ -305,6 +307,15 @@ void run_tsqr_form_q(cqr_context* c, const TsqrPlan& P, const float* a, long lon
                      int nc, float* q, long long ldq) {
   const int L = (int)P.lv.size();
   for (int l = L - 1; l >= 0; --l) {
+    if (l == 0 && P.flat) {   // flat leaf: chains walk their blocks last to first from the level-1 seeds
+      FlatApplyParams f{};
+      f.v = a; f.ldv = lda; f.tau = P.lv[0].tau; f.m = P.m; f.n = P.n; f.nc = nc;
+      f.rows_per_chain = P.flat_rows; f.chains = P.lv[0].tiles;
+      f.x = P.lv[1].xbuf; f.x_tile_stride = (long long)P.th * 64; f.x_ld = P.th; f.x_rows = P.n; f.fan = P.fan;
+      f.q = q; f.ldq = ldq;
+      launch_tsqr_flat_apply(f, cur_stream(c));
+      continue;
+    }
     TileApplyParams p{};
     p.v = level_src(P, l, const_cast<float*>(a), lda);
     p.tau = P.lv[l].tau;
@@ -932,7 +943,7 @@ static int tsqr_common(cqr_context* c, float* dA, int lda, long long m, int n, f
   TsqrPlan plan;
   for (int pass = 0; pass < 2; ++pass) {
     Carver cv(pass ? (keep ? c->ts : c->ws) : nullptr);
-    plan_tsqr(plan, m, n, th, cv, (!keep && c->opt_flat && m >= 16384) ? flat_tsqr_max_chains(c->sm_count) : 0);
+    plan_tsqr(plan, m, n, th, cv, (c->opt_flat && m >= 16384) ? flat_tsqr_max_chains(c->sm_count) : 0, keep);
     if (!pass) {
       if (keep) {
         if (cv.off > c->ts_bytes) {

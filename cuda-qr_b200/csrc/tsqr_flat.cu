@@ -154,9 +154,12 @@ struct FlatGroups<8> {
 // and nw[i] = -(tau s_i / u) per slot (0 = nothing pending).  Iteration (I0, jj) touches slots >= I0 only: the pending
 // reflector of the group's first iteration has its pivot in slot I0-1's last column, whose remaining active columns all
 // lie in slots >= I0.
-template <int I0>
+// KEEP: the reflector is stored -- column j of the block becomes x / u (the part of v below the carried R; v's unit entry
+// sits on R's row j and is implicit) and tau goes to tau_blk[j] -- so tsqr_flat_apply_kernel can expand the implicit Q.
+template <int I0, bool KEEP>
 __device__ __forceinline__ void flat_steps_pipe(f32x2 (&b)[8][8], f32x2 (&xp)[8], float (&nw)[8], float* __restrict__ Rs,
-                                                float* __restrict__ xs, const int q, const int h, const int n) {
+                                                float* __restrict__ xs, const int q, const int h, const int n,
+                                                float* __restrict__ tau_blk) {
 #pragma unroll 1
   for (int jj = 0; jj < 8; ++jj) {
     const int j = 8 * I0 + jj;
@@ -244,6 +247,14 @@ __device__ __forceinline__ void flat_steps_pipe(f32x2 (&b)[8][8], f32x2 (&xp)[8]
       for (int i = IM; i < 8; ++i) d[i] += __shfl_xor_sync(kFull, d[i], 16);
     }
     if (q == jj && h == 0) Rj[j] = ok ? bc : alpha;
+    if (KEEP) {
+      if (q == jj) {                         // nothing pending touches this column any more (its nw stays 0)
+        const f32x2 iu2 = fpack2(inv_u, inv_u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(b[I0][k]) : "l"(b[I0][k]), "l"(iu2));
+        if (h == 0) tau_blk[j] = tau;
+      }
+    }
 #pragma unroll
     for (int i = I0; i < 8; ++i) {
       const bool act = (i > I0) || (q > jj);
@@ -256,20 +267,22 @@ __device__ __forceinline__ void flat_steps_pipe(f32x2 (&b)[8][8], f32x2 (&xp)[8]
   }
 }
 
-template <int I0>
+template <int I0, bool KEEP>
 struct FlatGroupsPipe {
-  static __device__ __forceinline__ void run(f32x2 (&b)[8][8], f32x2 (&xp)[8], float (&nw)[8], float* Rs, float* xs, int q, int h, int n) {
-    flat_steps_pipe<I0>(b, xp, nw, Rs, xs, q, h, n);
-    FlatGroupsPipe<I0 + 1>::run(b, xp, nw, Rs, xs, q, h, n);
+  static __device__ __forceinline__ void run(f32x2 (&b)[8][8], f32x2 (&xp)[8], float (&nw)[8], float* Rs, float* xs, int q, int h, int n,
+                                             float* tau_blk) {
+    flat_steps_pipe<I0, KEEP>(b, xp, nw, Rs, xs, q, h, n, tau_blk);
+    FlatGroupsPipe<I0 + 1, KEEP>::run(b, xp, nw, Rs, xs, q, h, n, tau_blk);
   }
 };
-template <>
-struct FlatGroupsPipe<8> {
-  static __device__ __forceinline__ void run(f32x2 (&)[8][8], f32x2 (&)[8], float (&)[8], float*, float*, int, int, int) {}
+template <bool KEEP>
+struct FlatGroupsPipe<8, KEEP> {
+  static __device__ __forceinline__ void run(f32x2 (&)[8][8], f32x2 (&)[8], float (&)[8], float*, float*, int, int, int, float*) {}
 };
 
-template <int WPC, int MINB, bool PIPE>
+template <int WPC, int MINB, bool PIPE, bool KEEP = false>
 __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_r_kernel(FlatTsqrParams p) {
+  static_assert(PIPE || !KEEP, "the reflector store lives in the pipelined step body");
   extern __shared__ __align__(16) float flat_smem[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane & 7, h = lane >> 3;
   const long long chain = (long long)blockIdx.x * WPC + w;
@@ -323,9 +336,36 @@ __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_r_kernel(FlatTsqrPar
     if (PIPE) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) nw[i] = 0.f;       // nothing pending at the top of a block
-      FlatGroupsPipe<0>::run(b, xp, nw, Rs, xs, q, h, n);
+      FlatGroupsPipe<0, KEEP>::run(b, xp, nw, Rs, xs, q, h, n, KEEP ? p.tau_out + (rb >> 6) * 64 : nullptr);
     } else {
       FlatGroups<0>::run(b, Rs, xs, q, h, n);
+    }
+    if (KEEP) {                              // V block over the source rows (same addressing as the load)
+      float* dstv = p.a_out + rb + 16 * h;
+      if (aligned && rb + 64 <= row1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = q + 8 * i;
+          if (c < n) {
+            ulonglong2* d4 = reinterpret_cast<ulonglong2*>(dstv + (long long)c * p.lda);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { ulonglong2 v; v.x = b[i][2 * k]; v.y = b[i][2 * k + 1]; d4[k] = v; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = q + 8 * i;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const long long r = rb + 16 * h + 2 * k;
+            float lo, hi;
+            funpack2(b[i][k], lo, hi);
+            if (c < n && r < row1) dstv[(long long)c * p.lda + 2 * k] = lo;
+            if (c < n && r + 1 < row1) dstv[(long long)c * p.lda + 2 * k + 1] = hi;
+          }
+        }
+      }
     }
   }
   __syncwarp();
@@ -337,6 +377,142 @@ __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_r_kernel(FlatTsqrPar
     for (int rr = 0; rr < 2; ++rr) {
       const int r = lane + 32 * rr;
       dst[r + (long long)c * p.r_ld] = (r <= c && c < n) ? Rs[r * 64 + c] : 0.f;
+    }
+  }
+}
+
+// out = Q_leaf * [X; 0] for the implicit Q of the flat leaf (KEEP): every chain starts from its 64 x nc seed X (rows of the
+// carried R: what the tree level above hands down) and walks its blocks last to first; in a block the reflectors are
+// applied in reverse, s = Y_R(j, c) + v_j^T Y_B(:, c), Y_R(j, c) -= tau s, Y_B(:, c) -= tau s v_j, and the finished
+// Y_B is the block's 64 rows of the output.  Same lane layout as the factorisation (no slot ever dies here: every
+// reflector touches all nc columns); v_j comes straight from global memory one step ahead of its use (all eight column
+// groups read the same 256 bytes), the next block is prefetched into L2.  The chain's virtual R rows end as ~0 and are dropped.
+template <int WPC, int MINB>
+__global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_apply_kernel(FlatApplyParams p) {
+  extern __shared__ __align__(16) float flat_smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane & 7, h = lane >> 3;
+  const long long chain = (long long)blockIdx.x * WPC + w;
+  if (chain >= p.chains) return;
+  float* Ys = flat_smem + w * (64 * 64);     // Y_R, row-major: Ys[j * 64 + c]
+  const int n = p.n, nc = p.nc;
+  {
+    const float* xs = p.x ? p.x + (chain / p.fan) * p.x_tile_stride + (chain % p.fan) * CQR_SLOT : nullptr;
+    for (int c = 0; c < 64; ++c) {
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int r = lane + 32 * rr;
+        float v = 0.f;
+        if (c < nc && r < p.x_rows) v = xs ? xs[r + (long long)c * p.x_ld] : (r == c ? 1.f : 0.f);
+        Ys[r * 64 + c] = v;
+      }
+    }
+  }
+  __syncwarp();
+  const long long row0 = chain * p.rows_per_chain;
+  const long long row1 = (row0 + p.rows_per_chain < p.m) ? row0 + p.rows_per_chain : p.m;
+  const bool aligned = (p.ldv % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.v) & 15) == 0);
+  const bool oaligned = (p.ldq % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.q) & 15) == 0);
+  const long long nblk = (row1 - row0 + 63) / 64;
+  for (long long t = nblk - 1; t >= 0; --t) {
+    const long long rb = row0 + 64 * t;
+    const bool full = rb + 64 <= row1;
+    const float* vsrc = p.v + rb + 16 * h;
+    const float* tau_blk = p.tau + (rb >> 6) * 64;
+    if (t > 0 && aligned) {                  // next block (one up) into L2: 64 columns x 256 B, four 128-byte lines per lane
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = lane + 32 * i;       // column idx / 2, half idx % 2
+        if ((idx >> 1) < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.v + rb - 64 + (long long)(idx >> 1) * p.ldv + 32 * (idx & 1)));
+      }
+    }
+    f32x2 b[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) b[i][k] = 0ull;
+    auto load_v = [&](int j, f32x2 (&v)[8]) {
+      const float* col = vsrc + (long long)j * p.ldv;
+      if (aligned && full) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const ulonglong2 t4 = *reinterpret_cast<const ulonglong2*>(col + 4 * k);
+          v[2 * k] = t4.x; v[2 * k + 1] = t4.y;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const long long r = rb + 16 * h + 2 * k;
+          v[k] = fpack2(r < row1 ? col[2 * k] : 0.f, r + 1 < row1 ? col[2 * k + 1] : 0.f);
+        }
+      }
+    };
+    f32x2 vn[8];
+    load_v(n - 1, vn);
+    float taun = tau_blk[n - 1];
+#pragma unroll 1
+    for (int j = n - 1; j >= 0; --j) {
+      f32x2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = vn[k];
+      const float tau = taun;
+      if (j > 0) { load_v(j - 1, vn); taun = tau_blk[j - 1]; }
+      float* Yj = Ys + j * 64;
+      float yr[8], d[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) yr[i] = Yj[q + 8 * i];
+      {
+        f32x2 d2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d2[i] = 0ull;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d2[i] = ffma2(v[k], b[i][k], d2[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = fsum2(d2[i]);
+      }
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        float t8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t8[i] = __shfl_xor_sync(kFull, d[i], o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] += t8[i];
+      }
+      __syncwarp();                          // every lane has read row j of Y_R before part 0 rewrites it
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float wv = tau * (yr[i] + d[i]);
+        if (h == 0) Yj[q + 8 * i] = yr[i] - wv;
+        const f32x2 nw2 = fpack2(-wv, -wv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) b[i][k] = ffma2(nw2, v[k], b[i][k]);
+      }
+    }
+    float* dst = p.q + rb + 16 * h;
+    if (oaligned && full) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = q + 8 * i;
+        if (c < nc) {
+          ulonglong2* d4 = reinterpret_cast<ulonglong2*>(dst + (long long)c * p.ldq);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { ulonglong2 t4; t4.x = b[i][2 * k]; t4.y = b[i][2 * k + 1]; d4[k] = t4; }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = q + 8 * i;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const long long r = rb + 16 * h + 2 * k;
+          float lo, hi;
+          funpack2(b[i][k], lo, hi);
+          if (c < nc && r < row1) dst[(long long)c * p.ldq + 2 * k] = lo;
+          if (c < nc && r + 1 < row1) dst[(long long)c * p.ldq + 2 * k + 1] = hi;
+        }
+      }
     }
   }
 }
@@ -377,6 +553,26 @@ static void flat_init() {
 int flat_tsqr_max_chains(int sm_count) {
   flat_init();
   return sm_count * g_flat_per_sm;
+}
+
+// Implicit-Q variant (reflectors over A, taus to p.tau_out) and its expansion: 2 CTAs x 4 warps per SM, so the chain
+// geometry is the one flat_tsqr_max_chains reports for the pipelined R-only kernel.
+void launch_tsqr_flat_keep(const FlatTsqrParams& p, cudaStream_t s) {
+  if (p.chains <= 0) return;
+  ++g_launches;
+  constexpr size_t smem = (size_t)4 * kFlatWarpFloats * sizeof(float);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(tsqr_flat_r_kernel<4, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  tsqr_flat_r_kernel<4, 2, true, true><<<(p.chains + 3) / 4, 128, smem, s>>>(p);
+}
+
+void launch_tsqr_flat_apply(const FlatApplyParams& p, cudaStream_t s) {
+  if (p.chains <= 0) return;
+  ++g_launches;
+  constexpr size_t smem = (size_t)4 * 64 * 64 * sizeof(float);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(tsqr_flat_apply_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  tsqr_flat_apply_kernel<4, 2><<<(p.chains + 3) / 4, 128, smem, s>>>(p);
 }
 
 void launch_tsqr_flat_r(const FlatTsqrParams& p, cudaStream_t s) {

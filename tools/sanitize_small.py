@@ -1,0 +1,21 @@
+"""Small-shape workload for compute-sanitizer (memcheck / racecheck) over the warp-resident kernels and the legacy path:
+   compute-sanitizer --tool racecheck python tools/sanitize_small.py"""
+import importlib, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+pkg = importlib.import_module("cuda-qr_b200")
+ctx = pkg.Context(0); ctx.use_torch_stream()
+g = torch.Generator(device="cuda").manual_seed(1)
+for m, n in [(16444, 64), (20011, 17)]:                    # flat TSQR leaf: aligned and ragged / unaligned
+    A = pkg.colmajor(m, n); A.copy_(torch.rand((m, n), device="cuda", generator=g))
+    R = pkg.colmajor(n, n); ctx.tsqr_r(A, R); ctx.synchronize()
+    G = A.t().double() @ A.double(); Rd = torch.triu(R.double())
+    print("tsqr_r", m, n, float((Rd.t() @ Rd - G).norm() / G.norm()))
+for m, n, batch in [(64, 64, 40), (50, 33, 9)]:            # batched warp kernel
+    A3 = torch.rand((batch, n, m), device="cuda", generator=g); tau = torch.zeros((batch, n), device="cuda")
+    O = A3.clone(); ctx.geqrf_batched(A3, tau); ctx.synchronize()
+    Rd = torch.triu(A3.transpose(1, 2)[:, :n, :].double()); G = O.double() @ O.double().transpose(1, 2)
+    print("batched", m, n, float(((Rd.transpose(1, 2) @ Rd - G).flatten(1).norm(dim=1) / G.flatten(1).norm(dim=1)).max()))
+A = np.asfortranarray(np.random.default_rng(0).random((300, 200), dtype=np.float32))
+RV = A.copy(order="F"); tau = pkg.mmqr(RV); Q, R = pkg.explicitQR(RV, tau)
+print("legacy 300x200 residual", float(np.linalg.norm(Q.astype(np.float64) @ R.astype(np.float64) - A) / np.linalg.norm(A)))

@@ -323,6 +323,21 @@ def bench_tsqr(args, pkg, ctx, torch, dist, dev, rank, world, timed_steps, pk):
                        "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": _traffic("tsqr_flat") if world == 1 else None,
                        "note": "per-GPU algorithmic bytes 4*m_loc*n over the whole step (leaves + tree + NCCL hops); "
                                "SIMT Householder is FMA-issue bound at this shape (32 flop/B): the fp32 FMA floor is 2mn^2 / (148 SMs x 128 lanes x 2 x clock) ~ 1.0 ms = 33 % of the HBM roof, see DESIGN.md"}
+    if world == 1:
+        # implicit-Q variant and thin-Q expansion (north_star item 4) on the same matrix: A is overwritten by the
+        # reflectors, so it is restored from a copy outside the timed region
+        A_keep = A_loc.clone()
+        Rq = pkg.colmajor(n, n, device=dev)
+        Q = pkg.colmajor(m_loc, n, device=dev)
+        fq = lambda: ctx.tsqr_factor(A_keep, Rq)
+        fq(); ctx.tsqr_form_q(Q); torch.cuda.synchronize()
+        ms_f, _ = timed_steps(fq, lambda: A_keep.copy_(A_loc), 5, 2)
+        ms_q, _ = timed_steps(lambda: ctx.tsqr_form_q(Q), lambda: None, 5, 2)
+        eye = torch.eye(n, device=dev, dtype=torch.float64)
+        res["implicit_q"] = {"factor_ms": ms_f, "form_thin_q_ms": ms_q,
+                             "orthogonality_over_n_eps": float((Q.t().double() @ Q.double() - eye).norm()) / (n * 2.0 ** -23),
+                             "algorithmic_bytes": {"factor": 8.0 * m_loc * n, "form_q": 8.0 * m_loc * n}}
+        del A_keep, Q
     # Gram check of the combined R against the distributed A: A^T A = sum over ranks of A_loc^T A_loc
     G = A_loc.t().double() @ A_loc.double()
     if world > 1:

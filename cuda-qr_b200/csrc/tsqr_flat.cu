@@ -532,7 +532,13 @@ struct FlatCfg {
     return nb * WPC;
   }
   static void launch(const FlatTsqrParams& p, cudaStream_t s) {
-    tsqr_flat_r_kernel<WPC, MINB, PIPE><<<(p.chains + WPC - 1) / WPC, 32 * WPC, smem, s>>>(p);
+    static size_t pad = (size_t)-1;          // CQR_FLAT_SMEM_PAD=bytes: occupancy experiments (extra dynamic shared memory)
+    if (pad == (size_t)-1) {
+      const char* e = getenv("CQR_FLAT_SMEM_PAD");
+      pad = e ? (size_t)atol(e) : 0;
+      if (pad) cudaFuncSetAttribute(tsqr_flat_r_kernel<WPC, MINB, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + pad));
+    }
+    tsqr_flat_r_kernel<WPC, MINB, PIPE><<<(p.chains + WPC - 1) / WPC, 32 * WPC, smem + pad, s>>>(p);
   }
 };
 

@@ -501,6 +501,48 @@ def test_batched_geqrf(pkg, torch, ctx, port, m, n, batch):
     assert float(err.max()) < 1e-5
 
 
+def test_random_shapes_all_entry_points(pkg, torch, ctx):
+    """Seeded sweep over ragged shapes (odd leading dimensions included through row slicing): every device entry point
+    against fp64 on the same data -- geqrf + form_q, R-only / implicit-Q TSQR on both leaf kinds, batched."""
+    rng = np.random.default_rng(2026)
+    for _ in range(6):                                        # blocked Householder, any m >= n
+        n = int(rng.integers(1, 700)); m = n + int(rng.integers(0, 900))
+        A = np.asfortranarray(rng.standard_normal((m, n)).astype(np.float32))
+        dA = dev(pkg, torch, A); tau = torch.zeros(n, device="cuda")
+        ctx.geqrf(dA, tau)
+        Q = pkg.colmajor(m, n); ctx.form_q(dA, tau, Q)
+        R = pkg.colmajor(n, n); ctx.extract_r(dA, R)
+        ctx.synchronize()
+        check_factorisation(A, host(Q), host(R), np.linalg.qr(A.astype(np.float64), mode="r"))
+    for _ in range(6):                                        # tall-skinny: below and above the flat-leaf threshold
+        n = int(rng.integers(1, 65)); m = int(rng.integers(max(n, 200), 60000))
+        A = np.asfortranarray(rng.random((m, n), dtype=np.float32))
+        big = pkg.colmajor(m + 3, n); big.zero_()
+        dA = big[1:m + 1]                                     # ld = m + 3 (not a multiple of 4 in general), offset base
+        dA.copy_(torch.from_numpy(A).cuda())
+        R1 = pkg.colmajor(n, n); ctx.tsqr_r(dA, R1)
+        R2 = pkg.colmajor(n, n); ctx.tsqr_factor(dA, R2)
+        Q = pkg.colmajor(m, n); ctx.tsqr_form_q(Q)
+        ctx.synchronize()
+        r_ref = np.linalg.qr(A.astype(np.float64), mode="r")
+        check_factorisation(A, host(Q), host(R2), r_ref)
+        assert metrics.r_rel_diff(host(R1), r_ref) <= 1e-5
+        assert float(big[0].abs().max()) == 0.0 and float(big[m + 1:].abs().max()) == 0.0   # nothing written outside
+    for _ in range(4):                                        # batched, m <= 64 (warp kernel) with padding between matrices
+        n = int(rng.integers(1, 65)); m = int(rng.integers(n, 65)); batch = int(rng.integers(1, 40)); lda = m + int(rng.integers(0, 5))
+        buf = torch.rand((batch, n, lda), device="cuda")
+        orig = buf.clone()
+        tau = torch.zeros((batch, n), device="cuda")
+        pkg._check(pkg.lib.cqr_geqrf_batched(ctx.h, pkg._dptr(buf), lda, n * lda, m, n, batch, pkg._dptr(tau)), "cqr_geqrf_batched")
+        ctx.synchronize()
+        assert torch.equal(buf[:, :, m:], orig[:, :, m:])      # padding rows untouched
+        for b in range(batch):
+            A = orig[b, :, :m].t().cpu().numpy()
+            V = buf[b, :, :m].t().cpu().numpy()
+            Qb = metrics.householder_q(V, tau[b].cpu().numpy(), full=False)
+            check_factorisation(A, Qb, np.triu(V[:n]), np.linalg.qr(A.astype(np.float64), mode="r"))
+
+
 # ---------------------------------------------------------------------------------------------
 # BASELINE-size property checks (the oracle cannot reach these)
 # ---------------------------------------------------------------------------------------------

@@ -103,7 +103,9 @@ struct FlatApplyParams {
 };
 int flat_tsqr_max_chains(int sm_count);   // chains resident in one wave
 void launch_tsqr_flat_r(const FlatTsqrParams& p, cudaStream_t s);
-void launch_tsqr_flat_keep(const FlatTsqrParams& p, cudaStream_t s);
+void launch_tsqr_flat_keep(const FlatTsqrParams& p, cudaStream_t s);   // after launch_tsqr_flat_first_blocks
+void launch_tsqr_flat_first_blocks(float* a, long long lda, long long m, int n, long long rows_per_chain, int chains, float* tau,
+                                   cudaStream_t s);
 void launch_tsqr_flat_apply(const FlatApplyParams& p, cudaStream_t s);
 // batched QR of m x n matrices (m, n <= 64), one warp per matrix, LAPACK storage in place, tau[b * n + j]
 void launch_batched_qr_warp(float* base, long long stride, long long lda, int m, int n, int batch, float* tau, cudaStream_t s);

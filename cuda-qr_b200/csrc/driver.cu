@@ -285,7 +285,11 @@ void run_tsqr_factor(cqr_context* c, const TsqrPlan& P, float* a, long long lda,
       FlatTsqrParams f{};
       f.a = a; f.lda = lda; f.m = P.m; f.n = P.n; f.rows_per_chain = P.flat_rows; f.chains = P.lv[0].tiles;
       f.r_out = P.lv[1].store; f.r_tile_stride = (long long)P.th * 64; f.r_ld = P.th; f.fan = P.fan;
-      if (keep_q) { f.a_out = a; f.tau_out = P.lv[0].tau; launch_tsqr_flat_keep(f, cur_stream(c)); }
+      if (keep_q) {
+        f.a_out = a; f.tau_out = P.lv[0].tau;
+        launch_tsqr_flat_first_blocks(a, lda, P.m, P.n, P.flat_rows, P.lv[0].tiles, P.lv[0].tau, cur_stream(c));
+        launch_tsqr_flat_keep(f, cur_stream(c));
+      }
       else launch_tsqr_flat_r(f, cur_stream(c));
       continue;
     }

@@ -291,6 +291,17 @@ __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_r_kernel(FlatTsqrPar
   float* xs = Rs + 64 * 64;
   for (int i = lane; i < 64 * 64 / 4; i += 32) reinterpret_cast<float4*>(Rs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
+  if (KEEP) {                                // the chain's first block is already factored (launch_tsqr_flat_first_blocks): R = its upper triangle
+    const long long r0 = chain * p.rows_per_chain;
+    for (int c = 0; c < p.n; ++c) {
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int r = lane + 32 * rr;
+        if (r <= c && r0 + r < p.m) Rs[r * 64 + c] = p.a[r0 + r + (long long)c * p.lda];
+      }
+    }
+    __syncwarp();
+  }
 
   f32x2 xp[8];
   float nw[8];
@@ -300,7 +311,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_r_kernel(FlatTsqrPar
   const long long row0 = chain * p.rows_per_chain;
   const long long row1 = (row0 + p.rows_per_chain < p.m) ? row0 + p.rows_per_chain : p.m;
   const bool aligned = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.a) & 15) == 0);
-  for (long long rb = row0; rb < row1; rb += 64) {
+  for (long long rb = row0 + (KEEP ? 64 : 0); rb < row1; rb += 64) {
     f32x2 b[8][8];
     const float* src = p.a + rb + 16 * h;
     if (aligned && rb + 64 <= row1) {
@@ -386,7 +397,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_r_kernel(FlatTsqrPar
 // applied in reverse, s = Y_R(j, c) + v_j^T Y_B(:, c), Y_R(j, c) -= tau s, Y_B(:, c) -= tau s v_j, and the finished
 // Y_B is the block's 64 rows of the output.  Same lane layout as the factorisation (no slot ever dies here: every
 // reflector touches all nc columns); v_j comes straight from global memory one step ahead of its use (all eight column
-// groups read the same 256 bytes), the next block is prefetched into L2.  The chain's virtual R rows end as ~0 and are dropped.
+// groups read the same 256 bytes), the next block is prefetched into L2.  The chain's first block is a dense QR of real rows (no virtual rows): it is expanded last.
 template <int WPC, int MINB>
 __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_apply_kernel(FlatApplyParams p) {
   extern __shared__ __align__(16) float flat_smem[];
@@ -413,12 +424,12 @@ __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_apply_kernel(FlatApp
   const bool aligned = (p.ldv % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.v) & 15) == 0);
   const bool oaligned = (p.ldq % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.q) & 15) == 0);
   const long long nblk = (row1 - row0 + 63) / 64;
-  for (long long t = nblk - 1; t >= 0; --t) {
+  for (long long t = nblk - 1; t >= 1; --t) {
     const long long rb = row0 + 64 * t;
     const bool full = rb + 64 <= row1;
     const float* vsrc = p.v + rb + 16 * h;
     const float* tau_blk = p.tau + (rb >> 6) * 64;
-    if (t > 0 && aligned) {                  // next block (one up) into L2: 64 columns x 256 B, four 128-byte lines per lane
+    if (aligned) {                           // next block (one up) into L2: 64 columns x 256 B, four 128-byte lines per lane
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int idx = lane + 32 * i;       // column idx / 2, half idx % 2
@@ -484,6 +495,89 @@ __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_apply_kernel(FlatApp
       for (int i = 0; i < 8; ++i) {
         const float wv = tau * (yr[i] + d[i]);
         if (h == 0) Yj[q + 8 * i] = yr[i] - wv;
+        const f32x2 nw2 = fpack2(-wv, -wv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) b[i][k] = ffma2(nw2, v[k], b[i][k]);
+      }
+    }
+    float* dst = p.q + rb + 16 * h;
+    if (oaligned && full) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = q + 8 * i;
+        if (c < nc) {
+          ulonglong2* d4 = reinterpret_cast<ulonglong2*>(dst + (long long)c * p.ldq);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { ulonglong2 t4; t4.x = b[i][2 * k]; t4.y = b[i][2 * k + 1]; d4[k] = t4; }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = q + 8 * i;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const long long r = rb + 16 * h + 2 * k;
+          float lo, hi;
+          funpack2(b[i][k], lo, hi);
+          if (c < nc && r < row1) dst[(long long)c * p.ldq + 2 * k] = lo;
+          if (c < nc && r + 1 < row1) dst[(long long)c * p.ldq + 2 * k + 1] = hi;
+        }
+      }
+    }
+  }
+  // The chain's first block holds a dense Householder QR (launch_tsqr_flat_first_blocks): the carried rows ARE this
+  // block's rows, so Y_R moves into registers and the block's reflectors v_j = [0; 1; v(j+1:)] are applied in reverse.
+  {
+    const long long rb = row0;
+    const bool full = rb + 64 <= row1;
+    const float* vsrc = p.v + rb + 16 * h;
+    const float* tau_blk = p.tau + (rb >> 6) * 64;
+    __syncwarp();
+    f32x2 b[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) b[i][k] = fpack2(Ys[(16 * h + 2 * k) * 64 + q + 8 * i], Ys[(16 * h + 2 * k + 1) * 64 + q + 8 * i]);
+#pragma unroll 1
+    for (int j = n - 1; j >= 0; --j) {
+      const float tau = tau_blk[j];
+      if (tau == 0.f) continue;              // warp-uniform
+      const float* col = vsrc + (long long)j * p.ldv;
+      f32x2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int rl = 16 * h + 2 * k;       // block-local rows rl, rl + 1
+        float lo = 0.f, hi = 0.f;
+        if (rl > j && rb + rl < row1) lo = col[2 * k];
+        if (rl + 1 > j && rb + rl + 1 < row1) hi = col[2 * k + 1];
+        if (rl == j) lo = 1.f;
+        if (rl + 1 == j) hi = 1.f;
+        v[k] = fpack2(lo, hi);
+      }
+      float d[8];
+      {
+        f32x2 d2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d2[i] = 0ull;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d2[i] = ffma2(v[k], b[i][k], d2[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = fsum2(d2[i]);
+      }
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        float t8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t8[i] = __shfl_xor_sync(kFull, d[i], o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] += t8[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float wv = tau * d[i];
         const f32x2 nw2 = fpack2(-wv, -wv);
 #pragma unroll
         for (int k = 0; k < 8; ++k) b[i][k] = ffma2(nw2, v[k], b[i][k]);
@@ -721,7 +815,8 @@ constexpr int kDenseWarpFloats = 2 * 72 + 64;   // double-buffered x (+ alpha) a
 
 template <int WPC, int MINB>
 __global__ void __launch_bounds__(32 * WPC, MINB) batched_qr_warp_kernel(float* __restrict__ base, long long stride, long long lda,
-                                                                         int m, int n, int batch, float* __restrict__ tau_out) {
+                                                                         int m, int n, int batch, float* __restrict__ tau_out,
+                                                                         long long tau_stride, long long rows_total) {
   __shared__ __align__(16) float dsm[WPC * kDenseWarpFloats];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane & 7, h = lane >> 3;
   const long long mat = (long long)blockIdx.x * WPC + w;
@@ -729,6 +824,10 @@ __global__ void __launch_bounds__(32 * WPC, MINB) batched_qr_warp_kernel(float* 
   float* xs = dsm + w * kDenseWarpFloats;
   float* staus = xs + 2 * 72;
   float* A = base + mat * stride;
+  if (rows_total > 0) {                      // matrices are row blocks `stride` rows apart of one tall matrix: the last may be short
+    const long long rem = rows_total - mat * stride;
+    if (rem < m) m = (int)rem;
+  }
   const bool vec = (lda % 2 == 0) && (stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(base) & 7) == 0);
   f32x2 b[8][8];
 #pragma unroll
@@ -768,14 +867,27 @@ __global__ void __launch_bounds__(32 * WPC, MINB) batched_qr_warp_kernel(float* 
       }
     }
   }
-  for (int j = lane; j < n; j += 32) tau_out[mat * n + j] = staus[j];
+  for (int j = lane; j < n; j += 32) tau_out[mat * tau_stride + j] = staus[j];
 }
 
 void launch_batched_qr_warp(float* base, long long stride, long long lda, int m, int n, int batch, float* tau, cudaStream_t s) {
   if (batch <= 0) return;
   ++g_launches;
   constexpr int WPC = 4;
-  batched_qr_warp_kernel<WPC, 2><<<(batch + WPC - 1) / WPC, 32 * WPC, 0, s>>>(base, stride, lda, m, n, batch, tau);
+  batched_qr_warp_kernel<WPC, 2><<<(batch + WPC - 1) / WPC, 32 * WPC, 0, s>>>(base, stride, lda, m, n, batch, tau, (long long)n, 0);
+}
+
+// First 64-row block of every chain of the implicit-Q flat leaf: a dense Householder QR in place (R in the block's upper
+// triangle, v below it, tau into the chain's first row of the [block][64] table).  Starting the chains from a true QR of
+// real rows -- instead of from R = 0 on 64 virtual rows -- keeps the thin Q orthonormal for rank-deficient and badly
+// conditioned inputs: with virtual rows, [0; A] = Q R puts part of Q's columns into the virtual rows whenever R is
+// (nearly) singular, and dropping those rows loses orthogonality (1.5e3 n eps on a graded matrix with a duplicated column).
+void launch_tsqr_flat_first_blocks(float* a, long long lda, long long m, int n, long long rows_per_chain, int chains, float* tau,
+                                   cudaStream_t s) {
+  if (chains <= 0) return;
+  ++g_launches;
+  constexpr int WPC = 4;
+  batched_qr_warp_kernel<WPC, 2><<<(chains + WPC - 1) / WPC, 32 * WPC, 0, s>>>(a, rows_per_chain, lda, 64, n, chains, tau, rows_per_chain, m);
 }
 
 }  // namespace cqr

@@ -78,6 +78,8 @@ class DistCAQR:
             self.stackR = pkg.colmajor(world * kb, kb, device=device)
             self.stackC = pkg.colmajor(world * kb, n, device=device)
         self.bytes_exchanged = 0
+        self.profile = False                 # True: CUDA-event brackets per step, summed into self.step_ms after factor()
+        self.step_ms = {}
 
     # -- steps -----------------------------------------------------------------------------------------------
     def _blk(self, A, k0, w, r0):
@@ -129,7 +131,24 @@ class DistCAQR:
             if cs is not None:
                 A_loc[r0:r0 + w, k0 + w:].copy_(cs[me * w:(me + 1) * w])
 
-        caqr_generic(self.rank, self.world, self.m_loc, n, kb, local_qr, local_apply, gather, tree_qr, tree_apply, put_back)
+        steps = dict(local_qr=local_qr, local_apply=local_apply, gather=gather, tree_qr=tree_qr, tree_apply=tree_apply, put_back=put_back)
+        evs = []
+        if self.profile:
+            def timed(name, fn):
+                def run(*a):
+                    e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+                    e0.record(); out = fn(*a); e1.record()
+                    evs.append((name, e0, e1))
+                    return out
+                return run
+            steps = {k: timed(k, v) for k, v in steps.items()}
+        caqr_generic(self.rank, self.world, self.m_loc, n, kb, steps["local_qr"], steps["local_apply"], steps["gather"],
+                     steps["tree_qr"], steps["tree_apply"], steps["put_back"])
+        if self.profile:
+            t.cuda.synchronize()
+            self.step_ms = {}
+            for name, e0, e1 in evs:
+                self.step_ms[name] = self.step_ms.get(name, 0.0) + e0.elapsed_time(e1)
         return A_loc
 
     def extract_r(self, A_loc, R):

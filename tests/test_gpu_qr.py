@@ -387,8 +387,9 @@ def test_tsqr_r_and_thin_q(pkg, torch, ctx, port, m, n):
     if m < 16384:
         assert np.array_equal(host(R1), host(R2))          # same 256-row tile leaves
     else:
-        # both run the warp-resident flat-tree leaf (tsqr_flat.cu): the same arithmetic with and without the reflector store
-        assert metrics.r_rel_diff(host(R1), host(R2)) < 1e-6
+        # both run the warp-resident flat-tree leaf (tsqr_flat.cu); the implicit-Q variant starts every chain from a dense
+        # QR of its first block instead of from R = 0, so the two R agree up to row signs and rounding
+        assert metrics.r_rel_diff(host(R1), host(R2)) < 2e-5
         # ... and the 256-row tile leaves (CQR_OPT_FLAT_TSQR = 0) give the same R up to row signs and fp32 rounding
         ctx.set_option(pkg.OPT_FLAT_TSQR, 0)
         R3 = pkg.colmajor(n, n)
@@ -541,6 +542,57 @@ def test_random_shapes_all_entry_points(pkg, torch, ctx):
             V = buf[b, :, :m].t().cpu().numpy()
             Qb = metrics.householder_q(V, tau[b].cpu().numpy(), full=False)
             check_factorisation(A, Qb, np.triu(V[:n]), np.linalg.qr(A.astype(np.float64), mode="r"))
+
+
+def test_badly_scaled_and_rank_deficient_inputs(pkg, torch, ctx):
+    """Householder QR is backward stable whatever the conditioning: graded column scales (1e-6 .. 1e6), duplicated
+    columns (exact rank deficiency) and an all-zero matrix through the blocked path, both TSQR leaves and the batched
+    kernel -- backward error and orthogonality within the north_star bounds, never a NaN (the reference divides by a zero
+    norm there)."""
+    rng = np.random.default_rng(77)
+    def graded(m, n):
+        A = rng.standard_normal((m, n)) * np.logspace(-6, 6, n)[None, :]
+        A[:, n // 2] = A[:, n // 3]                                     # exact duplicate column
+        return np.asfortranarray(A.astype(np.float32))
+    # blocked Householder
+    A = graded(1500, 320)
+    dA = dev(pkg, torch, A); tau = torch.zeros(320, device="cuda")
+    ctx.geqrf(dA, tau)
+    Q = pkg.colmajor(1500, 320); ctx.form_q(dA, tau, Q)
+    R = pkg.colmajor(320, 320); ctx.extract_r(dA, R)
+    ctx.synchronize()
+    assert np.isfinite(host(Q)).all() and np.isfinite(host(R)).all()
+    check_factorisation(A, host(Q), host(R))
+    # TSQR: tile leaves (m < 16384) and flat leaves
+    for m in (3000, 40000):
+        A = graded(m, 64)
+        dA = dev(pkg, torch, A)
+        R1 = pkg.colmajor(64, 64); ctx.tsqr_r(dA, R1)
+        R2 = pkg.colmajor(64, 64); ctx.tsqr_factor(dA, R2)
+        Qt = pkg.colmajor(m, 64); ctx.tsqr_form_q(Qt)
+        ctx.synchronize()
+        assert np.isfinite(host(Qt)).all() and np.isfinite(host(R1)).all()
+        check_factorisation(A, host(Qt), host(R2))
+        # columnwise: |R^T R - A^T A| relative to the column norms (a normwise Gram check would hide the small columns)
+        G = A.astype(np.float64).T @ A.astype(np.float64)
+        Rd = np.triu(host(R1).astype(np.float64))
+        cn = np.sqrt(np.diag(G))
+        assert np.max(np.abs(Rd.T @ Rd - G) / np.outer(cn, cn)) < 1e-4
+    # batched
+    A3 = torch.from_numpy(np.stack([graded(64, 64).T.copy() for _ in range(8)])).cuda()
+    A3[3].zero_()                                                        # one all-zero matrix
+    orig = A3.clone(); tb = torch.zeros((8, 64), device="cuda")
+    ctx.geqrf_batched(A3, tb)
+    ctx.synchronize()
+    assert bool(torch.isfinite(A3).all()) and bool(torch.isfinite(tb).all())
+    assert float(A3[3].abs().max()) == 0.0 and float(tb[3].abs().max()) == 0.0
+    for b in (0, 5):
+        Ab = orig[b].t().cpu().numpy(); V = A3[b].t().cpu().numpy()
+        check_factorisation(Ab, metrics.householder_q(V, tb[b].cpu().numpy(), full=False), np.triu(V))
+    # all-zero tall matrix through the flat leaf: R = 0, no NaN
+    Z = pkg.colmajor(20000, 64); Z.zero_()
+    Rz = pkg.colmajor(64, 64); ctx.tsqr_r(Z, Rz); ctx.synchronize()
+    assert float(Rz.abs().max()) == 0.0
 
 
 # ---------------------------------------------------------------------------------------------

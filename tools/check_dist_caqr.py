@@ -51,6 +51,10 @@ for it in range(4):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ts.append(float(t))
+cq.profile = True
+A.copy_(A0); cq.factor(A); cq.profile = False
+if rank == 0:
+    print("per-step device ms (rank 0, one factorisation): " + "  ".join(f"{k} {v:.2f}" for k, v in cq.step_ms.items()), flush=True)
 G = A0.t().double() @ A0.double()
 if world > 1:
     dist.all_reduce(G)

@@ -563,9 +563,20 @@ def test_badly_scaled_and_rank_deficient_inputs(pkg, torch, ctx):
     ctx.synchronize()
     assert np.isfinite(host(Q)).all() and np.isfinite(host(R)).all()
     check_factorisation(A, host(Q), host(R))
+    # duplicates and a zero column inside one 64-column panel, plus a zero row block
+    A = np.asfortranarray(rng.standard_normal((2000, 256)).astype(np.float32))
+    A[:, 9] = A[:, 5]; A[:, 20] = 0.0; A[:, 70] = 2.0 * A[:, 66]; A[512:1024, :] = 0.0
+    dA = dev(pkg, torch, A); tau = torch.zeros(256, device="cuda")
+    ctx.geqrf(dA, tau)
+    Q = pkg.colmajor(2000, 256); ctx.form_q(dA, tau, Q)
+    R = pkg.colmajor(256, 256); ctx.extract_r(dA, R)
+    ctx.synchronize()
+    assert np.isfinite(host(Q)).all() and np.isfinite(host(R)).all()
+    check_factorisation(A, host(Q), host(R))
     # TSQR: tile leaves (m < 16384) and flat leaves
     for m in (3000, 40000):
         A = graded(m, 64)
+        A[:, 7] = 0.0; A[:, 12] = A[:, 11]                                # also inside the first 8-column slot group
         dA = dev(pkg, torch, A)
         R1 = pkg.colmajor(64, 64); ctx.tsqr_r(dA, R1)
         R2 = pkg.colmajor(64, 64); ctx.tsqr_factor(dA, R2)
@@ -576,7 +587,7 @@ def test_badly_scaled_and_rank_deficient_inputs(pkg, torch, ctx):
         # columnwise: |R^T R - A^T A| relative to the column norms (a normwise Gram check would hide the small columns)
         G = A.astype(np.float64).T @ A.astype(np.float64)
         Rd = np.triu(host(R1).astype(np.float64))
-        cn = np.sqrt(np.diag(G))
+        cn = np.sqrt(np.diag(G)); cn[cn == 0] = 1.0                      # the zero column: absolute check
         assert np.max(np.abs(Rd.T @ Rd - G) / np.outer(cn, cn)) < 1e-4
     # batched
     A3 = torch.from_numpy(np.stack([graded(64, 64).T.copy() for _ in range(8)])).cuda()

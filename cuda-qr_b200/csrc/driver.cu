@@ -676,6 +676,16 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
   if (!c || !dA || !dtau || n < 1 || m < n || lda < m) return CQR_EINVAL;
   cudaSetDevice(c->device);
   cudaStream_t st = c->stream;
+  if (m <= 64) {   // one 64 x 64 tile: the one-warp Householder kernel (same LAPACK storage), a single launch
+    launch_batched_qr_warp(dA, 0, lda, m, n, 1, dtau, st);
+    if (c->host_out) {   // legacy mmqr: the result goes back on the copy stream like every finished block below
+      CQR_CUDA(cudaEventRecord(c->ev_panel[0], st));
+      CQR_CUDA(cudaStreamWaitEvent(c->copy, c->ev_panel[0], 0));
+      CQR_CUDA(cudaMemcpy2DAsync(c->host_out, (size_t)m * sizeof(float), dA, (size_t)lda * sizeof(float), (size_t)m * sizeof(float), n,
+                                 cudaMemcpyDeviceToHost, c->copy));
+    }
+    return (int)cudaGetLastError();
+  }
   const int th = c->opt_tile_rows;
   const int KB = c->opt_outer < n ? c->opt_outer : (int)round_up(n, 64);
   const bool tensor = tensor_ok(c, dA, lda) && m >= 128 && n > 64;

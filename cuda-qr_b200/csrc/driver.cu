@@ -74,14 +74,15 @@ struct cqr_context {
   cudaStream_t cur = nullptr;      // stream the launch helpers use right now (nullptr = `stream`)
   bool cur_chain = false;          // `cur` is the panel-chain stream (profiling classes CQR_PROF_CHAIN_*)
   int cur_ctas = 0;                // SMs behind `cur` (0 = the whole device): caps persistent grids and split-K choices
-  SmPartition part[3];             // [0] unpartitioned (side/work streams), [1] 16 + 132 SMs, [2] 2 x 16 + 116 SMs
+  SmPartition part[5];             // [0] unpartitioned (side/work streams), [g] g x 16 SMs for the panel stream, the rest for the GEMMs (g = 1..4)
   int opt_partition = 1;
   // legacy mmqr: finished column blocks are copied back to the caller's host matrix (column-major, ld = m) on
   // `copy` while later blocks are still being factored
   float* host_out = nullptr;
   cudaStream_t copy = nullptr;
   cudaEvent_t ev_start = nullptr, ev_a = nullptr, ev_g = nullptr, ev_panel[2] = {nullptr, nullptr};
-  int opt_gemm = 1, opt_outer = 256, opt_tile_rows = 256, opt_splitk = 0, opt_lookahead = 1, opt_panel = 1, opt_cluster = 1, opt_flat = 1;
+  cudaEvent_t ev_pp[2][8] = {};    // per-panel completion (panel-wise look-ahead slices, opt_lookahead == 2)
+  int opt_gemm = 1, opt_outer = 256, opt_tile_rows = 256, opt_splitk = 0, opt_lookahead = 2, opt_panel = 1, opt_cluster = 1, opt_flat = 1;
   // multi-CTA panel kernel (panel_hh.cu): cross-CTA exchange slots, launch epoch, spin-timeout flag
   uint2* hh_slots = nullptr;
   int* hh_err = nullptr;
@@ -151,7 +152,7 @@ bool make_partition(int device, int groups, int prio_hi, SmPartition& out) {
   DrvApi& d = drv_api();
   if (!d.ok) return false;
   CUdevice dev;
-  CUdevResource all, res[2], rem;
+  CUdevResource all, res[8], rem;
   if (d.DeviceGet(&dev, device) != CUDA_SUCCESS) return false;
   if (d.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
   unsigned int n = (unsigned)groups;
@@ -496,6 +497,8 @@ int cqr_create(cqr_context** out, int device) {
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_g, cudaEventDisableTiming));
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_panel[0], cudaEventDisableTiming));
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_panel[1], cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 8; ++j) CQR_CUDA(cudaEventCreateWithFlags(&c->ev_pp[i][j], cudaEventDisableTiming));
   CQR_CUDA(cudaMalloc((void**)&c->hh_slots, panel_hh_slot_bytes() + 256));
   CQR_CUDA(cudaMemset(c->hh_slots, 0, panel_hh_slot_bytes() + 256));
   c->hh_err = reinterpret_cast<int*>(reinterpret_cast<char*>(c->hh_slots) + panel_hh_slot_bytes());
@@ -503,9 +506,13 @@ int cqr_create(cqr_context** out, int device) {
   c->part[0].sp = c->side; c->part[0].sg = c->work; c->part[0].sm_p = c->part[0].sm_g = c->sm_count; c->part[0].ok = true;
   if (c->opt_partition) {
     CQR_CUDA(cudaFree(0));   // the primary context must exist before green contexts are carved out of it
-    if (!make_partition(device, 1, prio_hi, c->part[1]) || !make_partition(device, 2, prio_hi, c->part[2])) c->opt_partition = 0;
+    int gmax = 2;   // 16 and 32 SMs for the panel stream; CQR_PGROUPS_SMALL / _BIG = 3 or 4 (tuning) need the bigger ones too
+    for (const char* k : {"CQR_PGROUPS_SMALL", "CQR_PGROUPS_BIG"})
+      if (const char* e = getenv(k)) { const int v = atoi(e); if (v > gmax) gmax = v > 4 ? 4 : v; }
+    for (int g = 1; g <= gmax && c->opt_partition; ++g)
+      if (!make_partition(device, g, prio_hi, c->part[g])) c->opt_partition = 0;
   }
-  if (const char* e = getenv("CQR_LOOKAHEAD")) c->opt_lookahead = atoi(e) != 0;
+  if (const char* e = getenv("CQR_LOOKAHEAD")) { const int v = atoi(e); c->opt_lookahead = v < 0 ? 0 : (v > 2 ? 2 : v); }
   if (const char* e = getenv("CQR_PANEL")) c->opt_panel = atoi(e) != 0;
   if (const char* e = getenv("CQR_CLUSTER")) c->opt_cluster = atoi(e) != 0;   // debugging aid: 0 = global-flag exchange only
   if (const char* e = getenv("CQR_GEMM")) c->opt_gemm = (strcmp(e, "simt") == 0) ? 0 : 1;   // debugging aid
@@ -524,7 +531,7 @@ int cqr_destroy(cqr_context* c) {
   if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
   if (c->work) { cudaStreamSynchronize(c->work); cudaStreamDestroy(c->work); }
   if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
-  for (int i = 1; i < 3; ++i) {
+  for (int i = 1; i < 5; ++i) {
     SmPartition& pt = c->part[i];
     if (pt.sp) { cudaStreamSynchronize(pt.sp); cudaStreamDestroy(pt.sp); }
     if (pt.sg) { cudaStreamSynchronize(pt.sg); cudaStreamDestroy(pt.sg); }
@@ -532,6 +539,8 @@ int cqr_destroy(cqr_context* c) {
     if (pt.gg) drv_api().GreenCtxDestroy(pt.gg);
   }
   for (cudaEvent_t e : {c->ev_start, c->ev_a, c->ev_g, c->ev_panel[0], c->ev_panel[1]}) if (e) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 8; ++j) if (c->ev_pp[i][j]) cudaEventDestroy(c->ev_pp[i][j]);
   delete c;
   return 0;
 }
@@ -545,7 +554,7 @@ int cqr_set_option(cqr_context* c, int opt, int v) {
     case CQR_OPT_OUTER_BLOCK: if (v < 64 || v > 512 || v % 64) return CQR_EINVAL; c->opt_outer = v; return 0;
     case CQR_OPT_TILE_ROWS: if (v != 128 && v != 256) return CQR_EINVAL; c->opt_tile_rows = v; return 0;
     case CQR_OPT_SPLITK: if (v < 0 || v > kMaxSplits) return CQR_EINVAL; c->opt_splitk = v; return 0;
-    case CQR_OPT_LOOKAHEAD: if (v != 0 && v != 1) return CQR_EINVAL; c->opt_lookahead = v; return 0;
+    case CQR_OPT_LOOKAHEAD: if (v < 0 || v > 2) return CQR_EINVAL; c->opt_lookahead = v; return 0;
     case CQR_OPT_PANEL: if (v != 0 && v != 1) return CQR_EINVAL; c->opt_panel = v; return 0;
     case CQR_OPT_FLAT_TSQR: if (v != 0 && v != 1) return CQR_EINVAL; c->opt_flat = v; return 0;
   }
@@ -697,7 +706,7 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
   struct BlockBufs { float *vbuf, *tbig; } bb[2];
   TsqrPlan plan;
   float *gram = nullptr, *gpart = nullptr, *qthin = nullptr, *rt = nullptr, *uinv = nullptr, *gsmall = nullptr;
-  BlockWs bw_main{}, bw_side{};
+  BlockWs bw_main{}, bw_side{}, bw_slice{};
   for (int pass = 0; pass < 2; ++pass) {
     Carver cv(pass ? c->ws : nullptr);
     plan_tsqr(plan, m, n < 64 ? n : 64, th, cv);
@@ -713,12 +722,13 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
     gsmall = cv.take(64 * 64);
     bw_main = carve_block_ws(cv, KB, ncmax);
     bw_side = carve_block_ws(cv, 64, KB);   // inner updates: 64 reflectors on < KB columns
+    bw_slice = carve_block_ws(cv, 64, KB);  // panel-wise look-ahead slices on the GEMM stream (opt_lookahead == 2)
     if (!pass) { int rc = ws_ensure(c, cv.off); if (rc) return rc; }
   }
 
   // Panels + inner updates of the outer block starting at column K0 (runs on the current stream):
   // fills B.vbuf/B.tbig (aggregated V and T of the block) and dtau[K0 .. K0+kbw).
-  auto do_panels = [&](int K0, BlockBufs& B) {
+  auto do_panels = [&](int K0, BlockBufs& B, cudaEvent_t* panel_done = nullptr) {
     cudaStream_t s = cur_stream(c);
     const int kbw = (n - K0 < KB) ? n - K0 : KB;
     const long long mK = m - K0;
@@ -760,6 +770,7 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
       launch_hr_rows(hp, s);
       pps.finish();
       }
+      if (panel_done) cudaEventRecord(panel_done[off / 64], s);   // V_j, T_j and the panel's columns are final
       // (4) inner update: remaining columns of this outer block
       const int ninner = K0 + kbw - (j0 + b);
       if (ninner > 0) {
@@ -816,7 +827,10 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
   // SM sets (16 or 2 x 16 SMs for the panel clusters, the rest for the GEMMs), chosen per block by panel height.
   auto pair_for = [&](long long mp) -> SmPartition& {
     if (!c->opt_partition || c->opt_panel != 1 || !c->opt_cluster || mp > 16384) return c->part[0];
-    return mp > 8192 ? c->part[2] : c->part[1];
+    // panel-stream SMs: two clusters need 32 above 8192 rows; below, the chain's K = 64 updates are what the extra SMs buy
+    static const int small_groups = getenv("CQR_PGROUPS_SMALL") ? atoi(getenv("CQR_PGROUPS_SMALL")) : 2;   // tuning knob
+    static const int big_groups = getenv("CQR_PGROUPS_BIG") ? atoi(getenv("CQR_PGROUPS_BIG")) : 2;       // tuning knob (>= 2)
+    return mp > 8192 ? c->part[big_groups < 2 ? 2 : (big_groups > 4 ? 4 : big_groups)] : c->part[small_groups < 1 ? 1 : (small_groups > 4 ? 4 : small_groups)];
   };
   auto use = [&](cudaStream_t s, int ctas, bool chain) { c->cur = s; c->cur_ctas = ctas; c->cur_chain = chain; };
   CQR_CUDA(cudaEventRecord(c->ev_start, st));
@@ -826,12 +840,14 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
   // While the remaining matrix is tall the GEMM stream is the busy one (it also owns fewer SMs then), so the block's
   // aggregated T is built on the panel stream right after its last panel; later the panel chain is the critical
   // path and the GEMM stream builds T.
-  auto t_on_chain = [&](int K0) { return c->opt_partition && (m - K0) > 8192; };
+  static const long long tchain_rows = getenv("CQR_TCHAIN_ROWS") ? atoll(getenv("CQR_TCHAIN_ROWS")) : 12288;   // tuning knob
+  auto t_on_chain = [&](int K0) { return c->opt_partition && (m - K0) > tchain_rows; };
   use(prev_p, pp->sm_p, true);
   do_panels(0, bb[0]);
   CQR_CUDA(cudaEventRecord(c->ev_panel[0], prev_p));
   ship(0, c->ev_panel[0]);
   if (t_on_chain(0)) { do_block_t(0, bb[0]); CQR_CUDA(cudaEventRecord(c->ev_panel[0], prev_p)); }
+  bool slice_done = false;   // the current block's look-ahead slice is already on the GEMM stream (panel-wise, see below)
   for (int blk = 0; blk < nblk; ++blk) {
     const int K0 = blk * KB;
     const int kbw = (n - K0 < KB) ? n - K0 : KB;
@@ -844,21 +860,49 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
       CQR_CUDA(cudaEventRecord(c->ev_g, prev_g));
       CQR_CUDA(cudaStreamWaitEvent(G, c->ev_g, 0));
     }
-    CQR_CUDA(cudaStreamWaitEvent(G, c->ev_panel[blk & 1], 0));
-    use(G, pr.sm_g, false);
-    if (!t_on_chain(K0)) do_block_t(K0, bb[blk & 1]);
     const int la = nrest < KB ? nrest : KB;
-    do_update(K0, bb[blk & 1], cnext, cnext + la);
-    CQR_CUDA(cudaEventRecord(c->ev_a, G));
+    if (!slice_done) {
+      CQR_CUDA(cudaStreamWaitEvent(G, c->ev_panel[blk & 1], 0));
+      use(G, pr.sm_g, false);
+      if (!t_on_chain(K0)) do_block_t(K0, bb[blk & 1]);
+      do_update(K0, bb[blk & 1], cnext, cnext + la);
+      CQR_CUDA(cudaEventRecord(c->ev_a, G));
+    }
     if (prev_p != P) CQR_CUDA(cudaStreamWaitEvent(P, c->ev_panel[blk & 1], 0));
     CQR_CUDA(cudaStreamWaitEvent(P, c->ev_a, 0));
+    // Panel-wise look-ahead (opt_lookahead == 2, panel-bound phase only): the NEXT block's panels are applied to the block
+    // after it one by one on the GEMM stream while the panel chain is still running, so when its last panel is done
+    // only one K = 64 update separates the chain from the following block -- not the aggregated T plus a K = 256 slice.
+    const int c2 = cnext + la;               // first column right of the next block
+    static const long long pws_rows = getenv("CQR_PWS_ROWS") ? atoll(getenv("CQR_PWS_ROWS")) : 14336;   // tuning knob
+    const bool pws = c->opt_lookahead == 2 && (m - cnext) <= pws_rows && c2 < n && KB / 64 <= 8;
     use(P, pr.sm_p, true);
-    do_panels(cnext, bb[(blk + 1) & 1]);
+    do_panels(cnext, bb[(blk + 1) & 1], pws ? c->ev_pp[(blk + 1) & 1] : nullptr);
     CQR_CUDA(cudaEventRecord(c->ev_panel[(blk + 1) & 1], P));
     ship(cnext, c->ev_panel[(blk + 1) & 1]);
     if (t_on_chain(cnext)) { do_block_t(cnext, bb[(blk + 1) & 1]); CQR_CUDA(cudaEventRecord(c->ev_panel[(blk + 1) & 1], P)); }
     use(G, pr.sm_g, false);
+    if (slice_done) {                        // this block's slice was applied panel by panel: T and the rest are what is left
+      CQR_CUDA(cudaStreamWaitEvent(G, c->ev_panel[blk & 1], 0));
+      if (!t_on_chain(K0)) do_block_t(K0, bb[blk & 1]);
+    }
     do_update(K0, bb[blk & 1], cnext + la, n);
+    slice_done = false;
+    if (pws) {
+      use(G, pr.sm_g, true);                 // profiled with the chain classes: K = 64 look-ahead work, not the trailing update
+      BlockBufs& Bn = bb[(blk + 1) & 1];
+      const int w2 = (n - c2 < KB) ? n - c2 : KB;
+      for (int j0 = cnext; j0 < cnext + la; j0 += 64) {
+        const int b = (cnext + la - j0 < 64) ? cnext + la - j0 : 64;
+        const int off = j0 - cnext;
+        CQR_CUDA(cudaStreamWaitEvent(G, c->ev_pp[(blk + 1) & 1][off / 64], 0));
+        Operand V{Bn.vbuf + off + (long long)off * ldv, ldv};
+        Operand T{Bn.tbig + off + (long long)off * KB, KB};
+        apply_block(c, m - j0, b, w2, V, T, dA + j0 + (long long)c2 * lda, lda, 1, bw_slice, tensor);
+      }
+      CQR_CUDA(cudaEventRecord(c->ev_a, G));
+      slice_done = true;
+    }
     prev_g = G; prev_p = P;
   }
   use(nullptr, 0, false);

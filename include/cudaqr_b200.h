@@ -74,7 +74,8 @@ enum {
   CQR_OPT_OUTER_BLOCK = 2,  /* aggregated block width for the trailing update: 64..512 (default 256) */
   CQR_OPT_TILE_ROWS = 3,    /* TSQR leaf height: 128 or 256 (default 256)                            */
   CQR_OPT_SPLITK = 4,       /* 0 = automatic                                                        */
-  CQR_OPT_LOOKAHEAD = 5,    /* 1 (default): next block's panels overlap the trailing update on a side stream */
+  CQR_OPT_LOOKAHEAD = 5,    /* 0: none; 1: next block's panels overlap the trailing update on a side stream; 2 (default): as 1, and in the
+                             * panel-bound phase each finished panel is applied to the block after next's columns at once (panel-wise slices) */
   CQR_OPT_PANEL = 6,        /* 1 (default): one-launch multi-CTA Householder panel; 0: TSQR tree + Householder reconstruction */
   CQR_OPT_FLAT_TSQR = 7     /* 1 (default): cqr_tsqr_r on >= 16384 rows uses the warp-resident flat-tree leaf; 0: 256-row tile leaves */
 };

@@ -23,6 +23,7 @@
 // {l, l+32, ...} (RI of them).  CTAs spin on each other: the grid must be co-resident (P <= #SMs, one
 // CTA per SM); spins are bounded by a clock64 timeout that raises an error flag instead of hanging.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace cqr {
 
@@ -633,6 +634,15 @@ bool panel_hh_cluster_plan(long long mp, int* rr, int* cs, int* ncl) {
   if (mp > 2 * 16 * 512) return false;
   if (mp > 16 * 512) { *rr = 64; *cs = 16; *ncl = 2; return true; }
   int r = 8;
+  {
+    // short panels: one CTA holding the whole panel (no cluster exchange at all) up to `single` rows (tuning knob)
+    static const long long single = getenv("CQR_PANEL_SINGLE_ROWS") ? atoll(getenv("CQR_PANEL_SINGLE_ROWS")) : 256;
+    if (mp <= single && mp <= 512) {
+      while (8 * r < mp) r *= 2;
+      *rr = r; *cs = 1; *ncl = 1;
+      return true;
+    }
+  }
   while ((mp + 8 * r - 1) / (8 * r) > 16) r *= 2;
   const int P = (int)((mp + 8 * r - 1) / (8 * r));
   int c = 1;

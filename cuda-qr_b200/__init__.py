@@ -34,7 +34,7 @@ GEMM_SIMT, GEMM_TF32X3 = 0, 1
 EXPORTS = [
     "getPanelDims", "mmqr", "mmqr_alloc", "explicitQR", "dgemm", "identity", "printMat",
     "cqr_create", "cqr_destroy", "cqr_set_stream", "cqr_set_option", "cqr_get_option", "cqr_synchronize",
-    "cqr_error_string", "cqr_launch_count", "cqr_profile_begin", "cqr_profile_end", "cqr_profile_timeline", "cqr_reserve", "cqr_geqrf", "cqr_extract_r", "cqr_form_q",
+    "cqr_error_string", "cqr_launch_count", "cqr_profile_begin", "cqr_profile_end", "cqr_profile_timeline", "cqr_reserve", "cqr_geqrf", "cqr_geqrf_partial", "cqr_extract_r", "cqr_form_q",
     "cqr_apply_q", "cqr_solve_ls", "cqr_tsqr_r", "cqr_tsqr_factor", "cqr_tsqr_form_q", "cqr_stack_qr", "cqr_stack_form_q",
     "cqr_geqrf_batched", "cqr_gemm", "cqr_gemm_tf32x3", "cqr_set_identity", "cqr_version",
 ]
@@ -84,6 +84,7 @@ def _load() -> ctypes.CDLL:
     lib.cqr_profile_timeline.argtypes = [_VP, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                          ctypes.POINTER(ctypes.c_int), i]
     lib.cqr_geqrf.argtypes = [_VP, _VP, i, i, i, _VP]
+    lib.cqr_geqrf_partial.argtypes = [_VP, _VP, i, i, i, i, _VP]
     lib.cqr_extract_r.argtypes = [_VP, _VP, i, i, i, _VP, i, i]
     lib.cqr_form_q.argtypes = [_VP, _VP, i, i, i, _VP, _VP, i, i]
     lib.cqr_apply_q.argtypes = [_VP, i, _VP, i, i, i, _VP, _VP, i, i]
@@ -297,6 +298,11 @@ class Context:
     def geqrf(self, A, tau):
         m, n = A.shape
         _check(lib.cqr_geqrf(self.h, _dptr(A), _ld(A), m, n, _dptr(tau)), "cqr_geqrf")
+
+    def geqrf_partial(self, A, tau, nfact: int):
+        """QR of the first nfact columns of A, Q^T applied to all of A's columns (cqr_geqrf_partial)."""
+        m, n = A.shape
+        _check(lib.cqr_geqrf_partial(self.h, _dptr(A), _ld(A), m, n, nfact, _dptr(tau)), "cqr_geqrf_partial")
 
     def extract_r(self, A, R):
         m, n = A.shape

@@ -681,11 +681,12 @@ int cqr_gemm_tf32x3(cqr_context* c, int transA, int M, int N, int K, float alpha
 }
 
 // ---- blocked Householder QR ----------------------------------------------------------------------
-int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
-  if (!c || !dA || !dtau || n < 1 || m < n || lda < m) return CQR_EINVAL;
+// nf <= n: Householder QR of the first nf columns, Q^T applied to all n (nf == n: the plain factorisation).
+static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, float* dtau) {
+  if (!c || !dA || !dtau || nf < 1 || nf > n || m < nf || lda < m) return CQR_EINVAL;
   cudaSetDevice(c->device);
   cudaStream_t st = c->stream;
-  if (m <= 64) {   // one 64 x 64 tile: the one-warp Householder kernel (same LAPACK storage), a single launch
+  if (m <= 64 && nf == n) {   // one 64 x 64 tile: the one-warp Householder kernel (same LAPACK storage), a single launch
     launch_batched_qr_warp(dA, 0, lda, m, n, 1, dtau, st);
     if (c->host_out) {   // legacy mmqr: the result goes back on the copy stream like every finished block below
       CQR_CUDA(cudaEventRecord(c->ev_panel[0], st));
@@ -696,10 +697,10 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
     return (int)cudaGetLastError();
   }
   const int th = c->opt_tile_rows;
-  const int KB = c->opt_outer < n ? c->opt_outer : (int)round_up(n, 64);
+  const int KB = c->opt_outer < nf ? c->opt_outer : (int)round_up(nf, 64);
   const bool tensor = tensor_ok(c, dA, lda) && m >= 128 && n > 64;
   const long long ldv = round_up(m, 4);
-  const int nblk = (n + KB - 1) / KB;
+  const int nblk = (nf + KB - 1) / KB;
   const bool look = c->opt_lookahead && nblk > 1;
   const int ncmax = n > 64 ? n - 64 : 1;
 
@@ -730,7 +731,7 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
   // fills B.vbuf/B.tbig (aggregated V and T of the block) and dtau[K0 .. K0+kbw).
   auto do_panels = [&](int K0, BlockBufs& B, cudaEvent_t* panel_done = nullptr) {
     cudaStream_t s = cur_stream(c);
-    const int kbw = (n - K0 < KB) ? n - K0 : KB;
+    const int kbw = (nf - K0 < KB) ? nf - K0 : KB;
     const long long mK = m - K0;
     launch_fill_zero(B.vbuf, ldv, mK, kbw, s);
     for (int j0 = K0; j0 < K0 + kbw; j0 += 64) {
@@ -784,7 +785,7 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
   // Aggregated T of the whole block from the Gram matrix V^T V (only needed when something is left to update).
   // Runs on the stream that applies the block: it is off the panel chain.
   auto do_block_t = [&](int K0, BlockBufs& B) {
-    const int kbw = (n - K0 < KB) ? n - K0 : KB;
+    const int kbw = (nf - K0 < KB) ? nf - K0 : KB;
     if (n - (K0 + kbw) > 0 && kbw > 64) {
       Operand V{B.vbuf, ldv};
       gemm_tn(c, kbw, kbw, (int)(m - K0), V, V, gpart, gram, KB, kMaxSplits, tensor);
@@ -795,7 +796,7 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
   // Columns [K0, K0 + kbw) are final once the block's panel chain is done (event ev): R above, V below.
   auto ship = [&](int K0, cudaEvent_t ev) {
     if (!c->host_out) return;
-    const int kbw = (n - K0 < KB) ? n - K0 : KB;
+    const int kbw = (nf - K0 < KB) ? nf - K0 : KB;
     cudaStreamWaitEvent(c->copy, ev, 0);
     cudaMemcpy2DAsync(c->host_out + (size_t)K0 * m, (size_t)m * sizeof(float), dA + (size_t)K0 * lda, (size_t)lda * sizeof(float),
                       (size_t)m * sizeof(float), kbw, cudaMemcpyDeviceToHost, c->copy);
@@ -803,17 +804,47 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
   // Trailing update of columns [c0, c1) with block K0's aggregated reflector (current stream).
   auto do_update = [&](int K0, BlockBufs& B, int c0, int c1) {
     if (c1 <= c0) return;
-    const int kbw = (n - K0 < KB) ? n - K0 : KB;
+    const int kbw = (nf - K0 < KB) ? nf - K0 : KB;
     Operand V{B.vbuf, ldv};
     Operand T{B.tbig, KB};
     float* cp = dA + K0 + (long long)c0 * lda;
     apply_block(c, m - K0, kbw, c1 - c0, V, T, cp, lda, 1, bw_main, tensor);
   };
 
+  // (only while the trailing part is narrow: four K = 64 updates of a wide C cost more HBM traffic than the chain hides --
+  // 16384 x 3840: 4 x 0.37 ms against 0.39 ms for one K = 256 update)
+  static const int partial_overlap_cols = getenv("CQR_PARTIAL_OVERLAP_COLS") ? atoi(getenv("CQR_PARTIAL_OVERLAP_COLS")) : 1536;
+  if (nblk == 1 && n > nf && n - nf <= partial_overlap_cols && c->opt_lookahead == 2 && c->opt_partition && c->opt_panel == 1 &&
+      c->opt_cluster && m <= 16384 && KB / 64 <= 8) {
+    // One block to factor, many columns to update (the local step of CAQR): the panel chain runs on the panel partition
+    // while the GEMM partition applies every finished 64-column panel (V_j, T_j) to all the trailing columns -- no
+    // aggregated T, and only the last panel's update is not hidden under the chain.
+    SmPartition& pr = c->part[2];
+    CQR_CUDA(cudaEventRecord(c->ev_start, st));
+    CQR_CUDA(cudaStreamWaitEvent(pr.sp, c->ev_start, 0));
+    CQR_CUDA(cudaStreamWaitEvent(pr.sg, c->ev_start, 0));
+    c->cur = pr.sp; c->cur_ctas = pr.sm_p; c->cur_chain = true;
+    do_panels(0, bb[0], c->ev_pp[0]);
+    CQR_CUDA(cudaEventRecord(c->ev_panel[0], pr.sp));
+    c->cur = pr.sg; c->cur_ctas = pr.sm_g; c->cur_chain = false;
+    for (int j0 = 0; j0 < nf; j0 += 64) {
+      const int b = (nf - j0 < 64) ? nf - j0 : 64;
+      CQR_CUDA(cudaStreamWaitEvent(pr.sg, c->ev_pp[0][j0 / 64], 0));
+      Operand V{bb[0].vbuf + j0 + (long long)j0 * ldv, ldv};
+      Operand T{bb[0].tbig + j0 + (long long)j0 * KB, KB};
+      apply_block(c, m - j0, b, n - nf, V, T, dA + j0 + (long long)nf * lda, lda, 1, bw_main, tensor);
+    }
+    CQR_CUDA(cudaEventRecord(c->ev_g, pr.sg));
+    c->cur = nullptr; c->cur_ctas = 0; c->cur_chain = false;
+    CQR_CUDA(cudaStreamWaitEvent(st, c->ev_panel[0], 0));
+    CQR_CUDA(cudaStreamWaitEvent(st, c->ev_g, 0));
+    return (int)cudaGetLastError();
+  }
+
   if (!look) {
     for (int blk = 0; blk < nblk; ++blk) {
       const int K0 = blk * KB;
-      const int kbw = (n - K0 < KB) ? n - K0 : KB;
+      const int kbw = (nf - K0 < KB) ? nf - K0 : KB;
       do_panels(K0, bb[0]);
       if (c->host_out) { CQR_CUDA(cudaEventRecord(c->ev_panel[0], st)); ship(K0, c->ev_panel[0]); }
       do_block_t(K0, bb[0]);
@@ -850,7 +881,7 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
   bool slice_done = false;   // the current block's look-ahead slice is already on the GEMM stream (panel-wise, see below)
   for (int blk = 0; blk < nblk; ++blk) {
     const int K0 = blk * KB;
-    const int kbw = (n - K0 < KB) ? n - K0 : KB;
+    const int kbw = (nf - K0 < KB) ? nf - K0 : KB;
     const int cnext = K0 + kbw;
     const int nrest = n - cnext;
     if (nrest <= 0) break;
@@ -860,7 +891,15 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
       CQR_CUDA(cudaEventRecord(c->ev_g, prev_g));
       CQR_CUDA(cudaStreamWaitEvent(G, c->ev_g, 0));
     }
-    const int la = nrest < KB ? nrest : KB;
+    if (cnext >= nf) {             // partial factorisation: nothing left to factor, the columns right of nf only get Q^T
+      CQR_CUDA(cudaStreamWaitEvent(G, c->ev_panel[blk & 1], 0));
+      use(G, pr.sm_g, false);
+      if (!t_on_chain(K0)) do_block_t(K0, bb[blk & 1]);
+      do_update(K0, bb[blk & 1], cnext, n);
+      prev_g = G;
+      break;
+    }
+    const int la = (nf - cnext < KB) ? nf - cnext : KB;
     if (!slice_done) {
       CQR_CUDA(cudaStreamWaitEvent(G, c->ev_panel[blk & 1], 0));
       use(G, pr.sm_g, false);
@@ -875,7 +914,7 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
     // only one K = 64 update separates the chain from the following block -- not the aggregated T plus a K = 256 slice.
     const int c2 = cnext + la;               // first column right of the next block
     static const long long pws_rows = getenv("CQR_PWS_ROWS") ? atoll(getenv("CQR_PWS_ROWS")) : 14336;   // tuning knob
-    const bool pws = c->opt_lookahead == 2 && (m - cnext) <= pws_rows && c2 < n && KB / 64 <= 8;
+    const bool pws = c->opt_lookahead == 2 && (m - cnext) <= pws_rows && c2 < nf && KB / 64 <= 8;
     use(P, pr.sm_p, true);
     do_panels(cnext, bb[(blk + 1) & 1], pws ? c->ev_pp[(blk + 1) & 1] : nullptr);
     CQR_CUDA(cudaEventRecord(c->ev_panel[(blk + 1) & 1], P));
@@ -913,6 +952,15 @@ int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
     CQR_CUDA(cudaStreamWaitEvent(st, c->ev_g, 0));
   }
   return (int)cudaGetLastError();
+}
+
+int cqr_geqrf(cqr_context* c, float* dA, int lda, int m, int n, float* dtau) {
+  if (m < n) return CQR_EINVAL;
+  return geqrf_impl(c, dA, lda, m, n, n, dtau);
+}
+
+int cqr_geqrf_partial(cqr_context* c, float* dA, int lda, int m, int n, int nfact, float* dtau) {
+  return geqrf_impl(c, dA, lda, m, n, nfact, dtau);
 }
 
 // Shared by form_q / apply_q: walk the outer blocks, rebuild (V, T) from LAPACK-format storage.

@@ -75,8 +75,9 @@ class DistCAQR:
             # exchange buffers: [R_i | top rows of the trailing block] packed per rank as one (kb x (kb + n)) slab, ld = kb
             self.send = torch.empty((kb + n, kb), dtype=torch.float32, device=device)            # storage (cols, ld)
             self.recv = torch.empty(world * (kb + n) * kb, dtype=torch.float32, device=device)
-            self.stackR = pkg.colmajor(world * kb, kb, device=device)
-            self.stackC = pkg.colmajor(world * kb, n, device=device)
+            # stacked [R_0; ...; R_{P-1} | top rows of the trailing blocks] as ONE column-major matrix, so the tree step is a
+            # single partial factorisation (QR of the first w columns, Q^T applied to the rest)
+            self.stack = pkg.colmajor(world * kb, kb + n, device=device)
         self.bytes_exchanged = 0
         self.profile = False                 # True: CUDA-event brackets per step, summed into self.step_ms after factor()
         self.step_ms = {}
@@ -92,10 +93,12 @@ class DistCAQR:
         import torch.distributed as dist
 
         def local_qr(k0, w, r0):
-            self.ctx.geqrf(self._blk(A_loc, k0, w, r0), self.tau_loc[k0:k0 + w])
+            # steps 1 + 2 in one call: QR of the block's w columns with Q_i^T applied to the trailing columns while the
+            # panel chain is still running (cqr_geqrf_partial)
+            self.ctx.geqrf_partial(A_loc[r0:, k0:], self.tau_loc[k0:k0 + w], w)
 
         def local_apply(k0, w, r0):
-            self.ctx.apply_q(self._blk(A_loc, k0, w, r0), self.tau_loc[k0:k0 + w], A_loc[r0:, k0 + w:], trans=True)
+            pass                                               # done by local_qr
 
         def gather(k0, w, r0):
             nt = n - (k0 + w)
@@ -108,8 +111,9 @@ class DistCAQR:
             out = self.recv[:P * (w + nt) * kb].view(P, w + nt, kb)
             dist.all_gather_into_tensor(out, chunk)
             self.bytes_exchanged += chunk.numel() * 4 * (P - 1)
-            rs = self.stackR[:P * w, :w]
-            cs = self.stackC[:P * w, :nt] if nt else None
+            S = self.stack[:P * w, :w + nt]
+            rs = S[:, :w]
+            cs = S[:, w:] if nt else None
             for p in range(P):
                 blk = out[p].t()                               # (kb, w + nt)
                 rs[p * w:(p + 1) * w].copy_(blk[:w, :w])
@@ -118,10 +122,11 @@ class DistCAQR:
             return rs, cs
 
         def tree_qr(k0, w, rs):
-            self.ctx.geqrf(rs, self.tau_tree[k0 // kb, :w])
+            nt = n - (k0 + w)
+            self.ctx.geqrf_partial(self.stack[:P * w, :w + nt], self.tau_tree[k0 // kb, :w], w)   # tree QR + its update of the top rows
 
         def tree_apply(k0, w, rs, cs):
-            self.ctx.apply_q(rs, self.tau_tree[k0 // kb, :w], cs, trans=True)
+            pass                                               # done by tree_qr
 
         def put_back(k0, w, r0, rs, cs):
             me = self.rank

@@ -105,6 +105,11 @@ int cqr_reserve(cqr_context* ctx, size_t bytes);
 
 /* Blocked Householder QR (device core of mmqr).  A: m x n, lda >= m.  tau: n floats. */
 int cqr_geqrf(cqr_context* ctx, float* dA, int lda, int m, int n, float* dtau);
+/* Partial factorisation: Householder QR of the first nfact columns (m >= nfact) with Q^T applied to all n columns
+ * (n may exceed m): what one outer step of a blocked / communication-avoiding driver needs, without rebuilding (V, T)
+ * for a separate cqr_apply_q.  With one outer block to factor the finished 64-column panels are applied to the
+ * trailing columns while the panel chain is still running. */
+int cqr_geqrf_partial(cqr_context* ctx, float* dA, int lda, int m, int n, int nfact, float* dtau);
 
 /* R = triu(A) into dR (r_rows x n, r_rows = m reproduces explicitQR's m x n R; r_rows = n
  * gives the square factor). */

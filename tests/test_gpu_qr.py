@@ -672,6 +672,35 @@ def test_square_properties_up_to_the_baseline_size(pkg, torch, ctx, size):
     assert orth <= metrics.TOL_ORTH
 
 
+@pytest.mark.parametrize("m,n,nf", [(3000, 1000, 256), (16384, 2048, 256), (2048, 4096, 256), (5000, 900, 512), (700, 300, 100),
+                                    (512, 1200, 512)])
+def test_geqrf_partial_equals_factor_then_apply(pkg, torch, ctx, m, n, nf):
+    """cqr_geqrf_partial (QR of the first nf columns, Q^T applied to all n; n may exceed m) against cqr_geqrf on the
+    first nf columns followed by cqr_apply_q on the rest, and against fp64: [Q^T A](:, nf:) and R of A(:, :nf)."""
+    rng = np.random.default_rng(31)
+    A = np.asfortranarray(rng.standard_normal((m, n)).astype(np.float32))
+    d1 = dev(pkg, torch, A); t1 = torch.zeros(nf, device="cuda")
+    ctx.geqrf_partial(d1, t1, nf)
+    d2 = dev(pkg, torch, A); t2 = torch.zeros(nf, device="cuda")
+    ctx.geqrf(d2[:, :nf], t2)
+    ctx.apply_q(d2[:, :nf], t2, d2[:, nf:], trans=True)
+    ctx.synchronize()
+    H1, H2 = host(d1), host(d2)
+    # same panels, same reflectors (the K = 64 updates inside the block may pick different split-K counts on the panel partition)
+    assert np.linalg.norm(H1[:, :nf] - H2[:, :nf]) / np.linalg.norm(H2[:, :nf]) < 5e-6
+    assert np.linalg.norm(host(t1) - host(t2)) / np.linalg.norm(host(t2)) < 5e-6
+    dq = np.linalg.norm(H1[:, nf:] - H2[:, nf:]) / np.linalg.norm(H2[:, nf:])
+    assert dq < 2e-5, f"Q^T C differs by {dq}"                                              # same Q^T C up to GEMM grouping (K = 64 x 4 vs K = 256)
+    Q64, R64 = np.linalg.qr(A[:, :nf].astype(np.float64), mode="complete")
+    sgn = np.sign(np.diag(R64[:nf])) * np.sign(np.diag(H1[:nf, :nf]))
+    want = (Q64.T @ A[:, nf:].astype(np.float64))
+    want[:nf] *= sgn[:, None]                                                                   # row signs of the first nf rows follow R's
+    got = H1[:, nf:].astype(np.float64)
+    assert np.linalg.norm(got[:nf] - want[:nf]) / np.linalg.norm(want[:nf]) < 1e-4
+    # the rows below nf are only determined up to the orthogonal completion: compare their Gram matrix
+    assert np.linalg.norm(got[nf:].T @ got[nf:] - want[nf:].T @ want[nf:]) / max(1e-30, np.linalg.norm(want[nf:].T @ want[nf:])) < 1e-4
+
+
 def test_caqr_single_rank_blocks_match_fp64(pkg, torch, ctx):
     """cuda-qr_b200/dist_caqr.py with world = 1: the per-block local steps (cqr_geqrf / cqr_apply_q on sub-views of
     the local slab) must reproduce the fp64 R; the cross-rank steps are covered by tools/check_dist_caqr.py on 2 GPUs

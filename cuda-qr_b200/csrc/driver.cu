@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <vector>
 
 #pragma GCC visibility push(default)   // the C ABI is the only exported surface (-fvisibility=hidden elsewhere)
@@ -729,7 +730,13 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
 
   // Panels + inner updates of the outer block starting at column K0 (runs on the current stream):
   // fills B.vbuf/B.tbig (aggregated V and T of the block) and dtau[K0 .. K0+kbw).
-  auto do_panels = [&](int K0, BlockBufs& B, cudaEvent_t* panel_done = nullptr) {
+  // Hooks of the panel-wise look-ahead: `panel_done[j]` is recorded after panel j and `after(j0, b)` runs on the host right
+  // behind it (it enqueues the GEMM stream's application of panel j to the next block's columns and must leave the
+  // current stream as it found it).  Tried and dropped: also handing the GEMM stream the block's own columns beyond the
+  // next panel (the chain then only updates 64 columns per panel): +-1 % up to 8192^2, +13 % run time at 16384^2, where
+  // the chain ends up waiting for the busier GEMM stream.
+  struct PanelHook { cudaEvent_t* panel_done = nullptr; std::function<void(int, int)> after; };
+  auto do_panels = [&](int K0, BlockBufs& B, PanelHook* hk = nullptr) {
     cudaStream_t s = cur_stream(c);
     const int kbw = (nf - K0 < KB) ? nf - K0 : KB;
     const long long mK = m - K0;
@@ -771,7 +778,8 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
       launch_hr_rows(hp, s);
       pps.finish();
       }
-      if (panel_done) cudaEventRecord(panel_done[off / 64], s);   // V_j, T_j and the panel's columns are final
+      if (hk && hk->panel_done) cudaEventRecord(hk->panel_done[off / 64], s);   // V_j, T_j and the panel's columns are final
+      if (hk && hk->after) hk->after(j0, b);
       // (4) inner update: remaining columns of this outer block
       const int ninner = K0 + kbw - (j0 + b);
       if (ninner > 0) {
@@ -824,7 +832,8 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
     CQR_CUDA(cudaStreamWaitEvent(pr.sp, c->ev_start, 0));
     CQR_CUDA(cudaStreamWaitEvent(pr.sg, c->ev_start, 0));
     c->cur = pr.sp; c->cur_ctas = pr.sm_p; c->cur_chain = true;
-    do_panels(0, bb[0], c->ev_pp[0]);
+    PanelHook hk0; hk0.panel_done = c->ev_pp[0];
+    do_panels(0, bb[0], &hk0);
     CQR_CUDA(cudaEventRecord(c->ev_panel[0], pr.sp));
     c->cur = pr.sg; c->cur_ctas = pr.sm_g; c->cur_chain = false;
     for (int j0 = 0; j0 < nf; j0 += 64) {
@@ -915,11 +924,7 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
     const int c2 = cnext + la;               // first column right of the next block
     static const long long pws_rows = getenv("CQR_PWS_ROWS") ? atoll(getenv("CQR_PWS_ROWS")) : 14336;   // tuning knob
     const bool pws = c->opt_lookahead == 2 && (m - cnext) <= pws_rows && c2 < nf && KB / 64 <= 8;
-    use(P, pr.sm_p, true);
-    do_panels(cnext, bb[(blk + 1) & 1], pws ? c->ev_pp[(blk + 1) & 1] : nullptr);
-    CQR_CUDA(cudaEventRecord(c->ev_panel[(blk + 1) & 1], P));
-    ship(cnext, c->ev_panel[(blk + 1) & 1]);
-    if (t_on_chain(cnext)) { do_block_t(cnext, bb[(blk + 1) & 1]); CQR_CUDA(cudaEventRecord(c->ev_panel[(blk + 1) & 1], P)); }
+    // GEMM stream first (host order only): what is left of block K's update, then -- behind it -- the panel-wise share
     use(G, pr.sm_g, false);
     if (slice_done) {                        // this block's slice was applied panel by panel: T and the rest are what is left
       CQR_CUDA(cudaStreamWaitEvent(G, c->ev_panel[blk & 1], 0));
@@ -927,21 +932,31 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
     }
     do_update(K0, bb[blk & 1], cnext + la, n);
     slice_done = false;
+    use(P, pr.sm_p, true);
     if (pws) {
-      use(G, pr.sm_g, true);                 // profiled with the chain classes: K = 64 look-ahead work, not the trailing update
       BlockBufs& Bn = bb[(blk + 1) & 1];
       const int w2 = (n - c2 < KB) ? n - c2 : KB;
-      for (int j0 = cnext; j0 < cnext + la; j0 += 64) {
-        const int b = (cnext + la - j0 < 64) ? cnext + la - j0 : 64;
+      PanelHook hk;
+      hk.panel_done = c->ev_pp[(blk + 1) & 1];
+      hk.after = [&](int j0, int b) {        // GEMM stream: panel j onto the next block's columns
         const int off = j0 - cnext;
-        CQR_CUDA(cudaStreamWaitEvent(G, c->ev_pp[(blk + 1) & 1][off / 64], 0));
+        const int col0 = c2;
+        use(G, pr.sm_g, true);               // profiled with the chain classes: K = 64 look-ahead work, not the trailing update
+        cudaStreamWaitEvent(G, c->ev_pp[(blk + 1) & 1][off / 64], 0);
         Operand V{Bn.vbuf + off + (long long)off * ldv, ldv};
         Operand T{Bn.tbig + off + (long long)off * KB, KB};
-        apply_block(c, m - j0, b, w2, V, T, dA + j0 + (long long)c2 * lda, lda, 1, bw_slice, tensor);
-      }
+        apply_block(c, m - j0, b, c2 + w2 - col0, V, T, dA + j0 + (long long)col0 * lda, lda, 1, bw_slice, tensor);
+        use(P, pr.sm_p, true);
+      };
+      do_panels(cnext, bb[(blk + 1) & 1], &hk);
       CQR_CUDA(cudaEventRecord(c->ev_a, G));
       slice_done = true;
+    } else {
+      do_panels(cnext, bb[(blk + 1) & 1]);
     }
+    CQR_CUDA(cudaEventRecord(c->ev_panel[(blk + 1) & 1], P));
+    ship(cnext, c->ev_panel[(blk + 1) & 1]);
+    if (t_on_chain(cnext)) { do_block_t(cnext, bb[(blk + 1) & 1]); CQR_CUDA(cudaEventRecord(c->ev_panel[(blk + 1) & 1], P)); }
     prev_g = G; prev_p = P;
   }
   use(nullptr, 0, false);

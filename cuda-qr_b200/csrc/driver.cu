@@ -758,8 +758,14 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
         hp.a = ap; hp.lda = lda; hp.mp = mp; hp.b = b; hp.tau = dtau + j0;
         hp.vbuf = vj; hp.ldv = ldv; hp.t = tj; hp.ldt = KB;
         hp.slots = c->hh_slots; hp.pmax = kPanelHHMaxCtas; hp.epoch = ++c->hh_epoch; hp.err = c->hh_err;
-        int rr = 0, cs = 0, ncl = 0;
-        if (!(c->opt_cluster && panel_hh_cluster_plan(mp, &rr, &cs, &ncl) && launch_panel_hh_cluster(hp, rr, cs, ncl, s)))
+        int rr = 0, cs = 0, ncl = 0, wpc = 0;
+        // warp-block panel kernel (panel_wb.cu): faster than the one-column-per-thread kernel from about 3072 rows up (156 vs
+        // 162 us at 4096, 173 vs 197 us at 8192), slower below (a CTA is then one or two warps).  CQR_PANEL_WB=0 disables it,
+        // CQR_PANEL_WB_MIN_ROWS moves the threshold (1 = every panel of at most 8192 rows).
+        static const bool use_wb = !(getenv("CQR_PANEL_WB") && atoi(getenv("CQR_PANEL_WB")) == 0);
+        static const long long wb_min = getenv("CQR_PANEL_WB_MIN_ROWS") ? atoll(getenv("CQR_PANEL_WB_MIN_ROWS")) : 3072;
+        if (use_wb && mp >= wb_min && c->opt_cluster && panel_wb_plan(mp, &wpc, &cs) && launch_panel_wb(hp, wpc, cs, s)) {
+        } else if (!(c->opt_cluster && panel_hh_cluster_plan(mp, &rr, &cs, &ncl) && launch_panel_hh_cluster(hp, rr, cs, ncl, s)))
           launch_panel_hh(hp, hh_ri, hh_ctas, s);
       } else {
       // (1) panel TSQR: R_tsqr + implicit Q   (2) explicit thin Q   (3) Householder reconstruction

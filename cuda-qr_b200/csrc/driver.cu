@@ -764,7 +764,8 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
         // CQR_PANEL_WB_MIN_ROWS moves the threshold (1 = every panel of at most 8192 rows).
         static const bool use_wb = !(getenv("CQR_PANEL_WB") && atoi(getenv("CQR_PANEL_WB")) == 0);
         static const long long wb_min = getenv("CQR_PANEL_WB_MIN_ROWS") ? atoll(getenv("CQR_PANEL_WB_MIN_ROWS")) : 3072;
-        if (use_wb && mp >= wb_min && c->opt_cluster && panel_wb_plan(mp, &wpc, &cs) && launch_panel_wb(hp, wpc, cs, s)) {
+        static const long long wb_small = getenv("CQR_PANEL_WB_SMALL_ROWS") ? atoll(getenv("CQR_PANEL_WB_SMALL_ROWS")) : 0;   // one-CTA variant up to this height
+        if (use_wb && (mp >= wb_min || mp <= wb_small) && c->opt_cluster && panel_wb_plan(mp, &wpc, &cs) && launch_panel_wb(hp, wpc, cs, s)) {
         } else if (!(c->opt_cluster && panel_hh_cluster_plan(mp, &rr, &cs, &ncl) && launch_panel_hh_cluster(hp, rr, cs, ncl, s)))
           launch_panel_hh(hp, hh_ri, hh_ctas, s);
       } else {

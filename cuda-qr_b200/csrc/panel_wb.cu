@@ -383,6 +383,11 @@ bool panel_wb_plan(long long mp, int* wpc, int* cs) {
   if (mp < 1 || mp > 8192) return false;
   const int nw = (int)((mp + 63) / 64);
   int w = 1;
+  if (nw <= 8) {                 // up to 512 rows: one CTA, no cluster exchange at all
+    while (w < nw) w *= 2;
+    *wpc = w; *cs = 1;
+    return true;
+  }
   while ((nw + w - 1) / w > 16) w *= 2;
   const int P = (nw + w - 1) / w;
   int c = 1;

@@ -148,9 +148,9 @@ void launch_panel_hh(const PanelHHParams& p, int ri, int ctas, cudaStream_t s);
 // size cs, cluster count ncl; launch returns false if the launch failed
 bool panel_hh_cluster_plan(long long mp, int* rr, int* cs, int* ncl);
 bool launch_panel_hh_cluster(const PanelHHParams& p, int rr, int cs, int ncl, cudaStream_t s);
-// warp-block layout (panel_wb.cu), m_p <= 8192: warps per CTA wpc (1, 2, 4, 8), cluster size cs
-bool panel_wb_plan(long long mp, int* wpc, int* cs);
-bool launch_panel_wb(const PanelHHParams& p, int wpc, int cs, cudaStream_t s);
+// warp-block layout (panel_wb.cu), m_p <= 16384: warps per CTA wpc (1, 2, 4, 8), cluster size cs, clusters ncl (1 or 2)
+bool panel_wb_plan(long long mp, int* wpc, int* cs, int* ncl);
+bool launch_panel_wb(const PanelHHParams& p, int wpc, int cs, int ncl, cudaStream_t s);
 #ifdef CQR_HH_TRACE
 void panel_hh_read_trace(long long* out);
 #endif

@@ -765,7 +765,10 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
         static const bool use_wb = !(getenv("CQR_PANEL_WB") && atoi(getenv("CQR_PANEL_WB")) == 0);
         static const long long wb_min = getenv("CQR_PANEL_WB_MIN_ROWS") ? atoll(getenv("CQR_PANEL_WB_MIN_ROWS")) : 3072;
         static const long long wb_small = getenv("CQR_PANEL_WB_SMALL_ROWS") ? atoll(getenv("CQR_PANEL_WB_SMALL_ROWS")) : 0;   // one-CTA variant up to this height
-        if (use_wb && (mp >= wb_min || mp <= wb_small) && c->opt_cluster && panel_wb_plan(mp, &wpc, &cs) && launch_panel_wb(hp, wpc, cs, s)) {
+        static const long long wb_max = getenv("CQR_PANEL_WB_MAX_ROWS") ? atoll(getenv("CQR_PANEL_WB_MAX_ROWS")) : 8192;   // > 8192: two clusters
+        int wncl = 1;
+        if (use_wb && ((mp >= wb_min && mp <= wb_max) || mp <= wb_small) && c->opt_cluster && panel_wb_plan(mp, &wpc, &cs, &wncl) &&
+            launch_panel_wb(hp, wpc, cs, wncl, s)) {
         } else if (!(c->opt_cluster && panel_hh_cluster_plan(mp, &rr, &cs, &ncl) && launch_panel_hh_cluster(hp, rr, cs, ncl, s)))
           launch_panel_hh(hp, hh_ri, hh_ctas, s);
       } else {

@@ -13,10 +13,11 @@
 // and the pivot row back to every peer), driven here by warp 0 of each CTA.  Reflector scalars follow qr.c:144-152
 // (MUFU rsqrt / rcp + one Newton step); a zero column gives tau = 0 (H = I).
 //
-// Status (round 1): validated against the parity tests with every panel of at most 8192 rows routed here
-// (CQR_PANEL_WB_MIN_ROWS=1); used by default from 3072 rows up: 173 us against 197 us at 8192 rows and 156 against 162
-// at 4096, but 164 against 130 at 1024, where a CTA is a single warp -- the step is still dominated by the cluster
-// exchange and this kernel's own serial parts (scalar chain in every thread, T by 64 barrier-separated columns).
+// Status (round 1): validated against the parity tests with every panel routed here (CQR_PANEL_WB_MIN_ROWS=1,
+// CQR_PANEL_WB_MAX_ROWS=16384); used by default between 3072 and 8192 rows: 173 us against 197 us at 8192 rows and 156
+// against 162 at 4096, but 164 against 130 at 1024, where a CTA is a single warp, and only 221 against 229 at 16384, where
+// the two clusters exchange through global-memory flags -- the step is dominated by the exchange (ncu: issue slots 15 %
+// busy, the warps sit in the mbarrier wait and the CTA barrier), no longer by the local work.
 #include "common.cuh"
 
 namespace cqr {
@@ -50,6 +51,14 @@ __device__ __forceinline__ void wb_mbar_init(unsigned long long* bar, unsigned c
 __device__ __forceinline__ void wb_mbar_expect(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void wb_st_flag(uint2* p, float v, unsigned tag) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 wb_ld_flag(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+  return r;
+}
 // bounded wait: a protocol error must not hang the device; *err is set and the caller's results are void
 __device__ __forceinline__ void wb_mbar_wait(unsigned long long* bar, unsigned parity, int* err) {
   unsigned ok, a = (unsigned)__cvta_generic_to_shared(bar);
@@ -77,6 +86,8 @@ struct WbShared {
   float prs_in[2][16][4];      // phase 1: pivot-row entries of my columns (from CTA 0)
   float tot_in[2][64];         // phase 2: cluster totals
   float prow[2][64];           // phase 2: row j
+  float tot_x[2][64];          // two clusters: totals over both clusters, row j
+  float prow_x[2][64];
   unsigned long long mbar1[2], mbar2[2];
   float gs[64][65];            // CTA 0: G(c, j) = v_c^T v_j (c < j)
   float ts[64][65];
@@ -86,10 +97,12 @@ struct WbShared {
 struct WbCtx {
   int q, h, w, lane;
   bool top;                    // this warp holds the panel's first 64 rows (the pivot rows)
-  unsigned rank, CS;
+  unsigned rank, CS, cl, ncl;   // CTA rank in its cluster, cluster size, cluster index, number of clusters (1 or 2)
   int nb;
   int* err;
   float* tau_out;
+  uint2* slots;                // two clusters: {value, tag} exchange slots in global memory [2 buffers][3][64]
+  unsigned epoch;
 };
 
 // steps j = 8 I0 .. 8 I0 + 7
@@ -179,12 +192,12 @@ __device__ __forceinline__ void wb_steps(f32x2 (&b)[8][8], WbShared<W>& sm, cons
         const unsigned CS = cx.CS, rank = cx.rank;
         const unsigned wpo = 16u / CS;                  // groups of four columns per owner CTA
         if (lane == 0) {
-          wb_mbar_expect(&sm.mbar1[buf], (16 + wpo) * 16);
-          wb_mbar_expect(&sm.mbar2[buf], (16 + 16) * 16);
+          wb_mbar_expect(&sm.mbar1[buf], (16 + (cx.cl == 0 ? wpo : 0)) * 16);
+          wb_mbar_expect(&sm.mbar2[buf], (16 + (cx.cl == 0 ? 16 : 0)) * 16);
         }
         const unsigned owner = ((unsigned)l16 * CS) >> 4, wl = (unsigned)l16 - owner * wpo;
         if (lane < 16) wb_st_async_v4(&sm.rs_in[buf][rank * wpo + wl][0], &sm.mbar1[buf], owner, sv);
-        else if (rank == 0) wb_st_async_v4(&sm.prs_in[buf][wl][0], &sm.mbar1[buf], owner, pv);
+        else if (rank == 0 && cx.cl == 0) wb_st_async_v4(&sm.prs_in[buf][wl][0], &sm.mbar1[buf], owner, pv);
         wb_mbar_wait(&sm.mbar1[buf], par, cx.err);
         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
         if (lane < 16) t = *reinterpret_cast<const float4*>(&sm.rs_in[buf][lane][0]);
@@ -198,13 +211,51 @@ __device__ __forceinline__ void wb_steps(f32x2 (&b)[8][8], WbShared<W>& sm, cons
         tv.z = __shfl_sync(kFull, t.z, slot); tv.w = __shfl_sync(kFull, t.w, slot);
         const unsigned col4 = 4u * (rank * wpo + slot);
         if (lane < 16) wb_st_async_v4(&sm.tot_in[buf][col4], &sm.mbar2[buf], peer, tv);
-        else wb_st_async_v4(&sm.prow[buf][col4], &sm.mbar2[buf], peer, *reinterpret_cast<const float4*>(&sm.prs_in[buf][slot][0]));
+        else if (cx.cl == 0) wb_st_async_v4(&sm.prow[buf][col4], &sm.mbar2[buf], peer, *reinterpret_cast<const float4*>(&sm.prs_in[buf][slot][0]));
       }
     }
     if (cx.CS == 1) __syncthreads();
     else wb_mbar_wait(&sm.mbar2[buf], par, cx.err);
+    const float* tot = sm.tot_in[buf];
+    const float* prw = sm.prow[buf];
+    if (cx.ncl > 1) {
+      // two clusters: the leaders publish their 64 cluster sums (cluster 0 also row j) as {value, tag} pairs in global
+      // memory, warp 0 of every CTA polls the other cluster's slots (two columns per lane) and adds in the same order on
+      // both sides (cluster 0 + cluster 1), so all 32 CTAs hold bit-identical totals
+      if (w == 0) {
+        const unsigned tag = cx.epoch * 64u + (unsigned)j + 1u;
+        uint2* mys = cx.slots + ((size_t)buf * 3 + cx.cl) * 64;
+        const uint2* oth = cx.slots + ((size_t)buf * 3 + (cx.cl ^ 1u)) * 64;
+        uint2* piv = cx.slots + ((size_t)buf * 3 + 2) * 64;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = lane + 32 * e;
+          const float mine = sm.tot_in[buf][c];
+          if (cx.rank == 0) {
+            wb_st_flag(mys + c, mine, tag);
+            if (cx.cl == 0) wb_st_flag(piv + c, sm.prow[buf][c], tag);
+          }
+          float so = 0.f, po = 0.f;
+          long long t0 = 0;
+          for (;;) {
+            const uint2 r = wb_ld_flag(oth + c);
+            uint2 qv; qv.x = 0u; qv.y = tag;
+            if (cx.cl != 0) qv = wb_ld_flag(piv + c);
+            so = __uint_as_float(r.x); po = __uint_as_float(qv.x);
+            if (r.y == tag && qv.y == tag) break;
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 2000000000LL) { atomicExch(cx.err, 1); break; }
+          }
+          sm.tot_x[buf][c] = (cx.cl == 0) ? (mine + so) : (so + mine);
+          sm.prow_x[buf][c] = (cx.cl == 0) ? sm.prow[buf][c] : po;
+        }
+      }
+      __syncthreads();
+      tot = sm.tot_x[buf];
+      prw = sm.prow_x[buf];
+    }
     // ---- reflector scalars (redundant in every thread: bit-identical inputs)
-    const float sig = sm.tot_in[buf][j], alpha = sm.prow[buf][j];
+    const float sig = tot[j], alpha = prw[j];
     const float sj = fmaf(alpha, alpha, sig);
     const bool ok = sj >= 1.2e-38f;          // like panel_hh.cu and the reference: a length-1 reflector (x = 0, alpha != 0) flips the sign, tau = 2
     const float sjs = ok ? sj : 1.f;
@@ -226,7 +277,7 @@ __device__ __forceinline__ void wb_steps(f32x2 (&b)[8][8], WbShared<W>& sm, cons
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = q + 8 * i;
-      const float s = fmaf(sm.tot_in[buf][c], inv_u, sm.prow[buf][c]);      // v_j^T a_c  (for c < j: v_c^T v_j)
+      const float s = fmaf(tot[c], inv_u, prw[c]);      // v_j^T a_c  (for c < j: v_c^T v_j)
       if (i <= I0 && cx.top && h == 0 && c < j) sm.gs[c][j] = s;
       if (i >= I0) {
         const bool act = (i > I0) || (q > jj);
@@ -274,7 +325,8 @@ __global__ void __launch_bounds__(32 * W, 1) panel_wb_kernel(PanelHHParams p) {
   WbCtx cx;
   cx.lane = threadIdx.x & 31; cx.w = threadIdx.x >> 5; cx.q = cx.lane & 7; cx.h = cx.lane >> 3;
   cx.rank = wb_ctarank(); cx.CS = wb_nctarank();
-  cx.nb = p.b; cx.err = p.err; cx.tau_out = p.tau;
+  cx.cl = blockIdx.x / cx.CS; cx.ncl = gridDim.x / cx.CS;
+  cx.nb = p.b; cx.err = p.err; cx.tau_out = p.tau; cx.slots = p.slots; cx.epoch = p.epoch;
   const int q = cx.q, h = cx.h;
   const long long gw = (long long)blockIdx.x * W + cx.w;        // warp block index: rows 64 gw .. 64 gw + 63
   cx.top = (gw == 0);
@@ -358,14 +410,14 @@ __global__ void __launch_bounds__(32 * W, 1) panel_wb_kernel(PanelHHParams p) {
 }
 
 template <int W>
-cudaError_t launch_wb_t(const PanelHHParams& p, int cs, cudaStream_t s) {
+cudaError_t launch_wb_t(const PanelHHParams& p, int cs, int ncl, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(panel_wb_kernel<W>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     attr_done = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cs, 1, 1);
+  cfg.gridDim = dim3(cs * ncl, 1, 1);
   cfg.blockDim = dim3(32 * W, 1, 1);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = s;
@@ -378,9 +430,12 @@ cudaError_t launch_wb_t(const PanelHHParams& p, int cs, cudaStream_t s) {
 
 }  // namespace
 
-// Warps per CTA and cluster size for an m_p-row panel (m_p <= 16 x 8 x 64 = 8192): as many CTAs as the cluster allows.
-bool panel_wb_plan(long long mp, int* wpc, int* cs) {
-  if (mp < 1 || mp > 8192) return false;
+// Warps per CTA, cluster size and cluster count for an m_p-row panel: one cluster of up to 16 CTAs x 8 warps x 64 rows up
+// to 8192 rows, two such clusters (exchange through global-memory flags) up to 16384.
+bool panel_wb_plan(long long mp, int* wpc, int* cs, int* ncl) {
+  if (mp < 1 || mp > 16384) return false;
+  *ncl = 1;
+  if (mp > 8192) { *wpc = 8; *cs = 16; *ncl = 2; return true; }
   const int nw = (int)((mp + 63) / 64);
   int w = 1;
   if (nw <= 8) {                 // up to 512 rows: one CTA, no cluster exchange at all
@@ -396,13 +451,13 @@ bool panel_wb_plan(long long mp, int* wpc, int* cs) {
   return true;
 }
 
-bool launch_panel_wb(const PanelHHParams& p, int wpc, int cs, cudaStream_t s) {
+bool launch_panel_wb(const PanelHHParams& p, int wpc, int cs, int ncl, cudaStream_t s) {
   ++g_launches;
   cudaError_t e;
-  if (wpc == 1) e = launch_wb_t<1>(p, cs, s);
-  else if (wpc == 2) e = launch_wb_t<2>(p, cs, s);
-  else if (wpc == 4) e = launch_wb_t<4>(p, cs, s);
-  else e = launch_wb_t<8>(p, cs, s);
+  if (wpc == 1) e = launch_wb_t<1>(p, cs, ncl, s);
+  else if (wpc == 2) e = launch_wb_t<2>(p, cs, ncl, s);
+  else if (wpc == 4) e = launch_wb_t<4>(p, cs, ncl, s);
+  else e = launch_wb_t<8>(p, cs, ncl, s);
   if (e != cudaSuccess) { cudaGetLastError(); --g_launches; return false; }
   return true;
 }

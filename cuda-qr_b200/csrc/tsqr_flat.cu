@@ -611,8 +611,9 @@ __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_apply_kernel(FlatApp
   }
 }
 
-// Variants: CQR_FLAT_CFG = 0: plain step body, 3 CTAs x 4 warps per SM (168 registers);  1: plain, 2 x 4 (236 registers);
-// 2: software-pipelined, 2 x 4;  3: software-pipelined, 2 x 5.
+// Variants: CQR_FLAT_CFG = 0: plain step body, 3 CTAs x 4 warps per SM (168 registers, a few spills);  1: plain, 2 x 4
+// (236 registers);  2 (default): software-pipelined, 2 x 4 (218 registers).  Registers are allotted per 4 warps, so 8
+// or 12 resident warps per SM are the only useful occupancies (a 2 x 5 variant compiles to the 168-register budget).
 template <int WPC, int MINB, bool PIPE>
 struct FlatCfg {
   static constexpr size_t smem = (size_t)WPC * kFlatWarpFloats * sizeof(float);
@@ -640,12 +641,11 @@ static int g_flat_cfg = -1, g_flat_per_sm = 0;
 static void flat_init() {
   if (g_flat_cfg >= 0) return;
   const char* e = getenv("CQR_FLAT_CFG");
-  g_flat_cfg = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : kFlatDefaultCfg;
+  g_flat_cfg = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : kFlatDefaultCfg;
   switch (g_flat_cfg) {
     case 0: g_flat_per_sm = FlatCfg<4, 3, false>::per_sm(); break;
     case 1: g_flat_per_sm = FlatCfg<4, 2, false>::per_sm(); break;
-    case 2: g_flat_per_sm = FlatCfg<4, 2, true>::per_sm(); break;
-    default: g_flat_per_sm = FlatCfg<5, 2, true>::per_sm(); break;
+    default: g_flat_per_sm = FlatCfg<4, 2, true>::per_sm(); break;
   }
 }
 
@@ -682,8 +682,7 @@ void launch_tsqr_flat_r(const FlatTsqrParams& p, cudaStream_t s) {
   switch (g_flat_cfg) {
     case 0: FlatCfg<4, 3, false>::launch(p, s); break;
     case 1: FlatCfg<4, 2, false>::launch(p, s); break;
-    case 2: FlatCfg<4, 2, true>::launch(p, s); break;
-    default: FlatCfg<5, 2, true>::launch(p, s); break;
+    default: FlatCfg<4, 2, true>::launch(p, s); break;
   }
 }
 

@@ -14,7 +14,7 @@
 // (MUFU rsqrt / rcp + one Newton step); a zero column gives tau = 0 (H = I).
 //
 // Status (round 1): validated against the parity tests with every panel routed here (CQR_PANEL_WB_MIN_ROWS=1,
-// CQR_PANEL_WB_MAX_ROWS=16384); used by default between 3072 and 8192 rows: 173 us against 197 us at 8192 rows and 156
+// CQR_PANEL_WB_MAX_ROWS=16384); used by default between 3072 and 8192 rows: 166 us against 197 us at 8192 rows and 152
 // against 162 at 4096, but 164 against 130 at 1024, where a CTA is a single warp, and only 221 against 229 at 16384, where
 // the two clusters exchange through global-memory flags -- the step is dominated by the exchange (ncu: issue slots 15 %
 // busy, the warps sit in the mbarrier wait and the CTA barrier), no longer by the local work.
@@ -385,22 +385,22 @@ __global__ void __launch_bounds__(32 * W, 1) panel_wb_kernel(PanelHHParams p) {
       }
     }
   }
-  // ---- compact-WY T (CTA 0): T(c,c) = tau_c, T(0:c, c) = -tau_c T(0:c, 0:c) G(0:c, c), column by column (larft)
+  // ---- compact-WY T (CTA 0).  T^-1 = diag(1 / tau) + striu(V^T V), so column c of T is a back substitution that does
+  // not depend on the other columns: T(c,c) = tau_c, T(i,c) = -tau_i sum_{k=i+1..c} G(i,k) T(k,c) for i = c-1 .. 0
+  // (tau_i = 0, H_i = I, gives a zero row).  One thread per column, no barrier inside; G(i,k) is a broadcast read and
+  // ts[k][c] is conflict-free across the threads (row stride 65).
   if (blockIdx.x == 0 && p.t != nullptr) {
     __syncthreads();
     const int nb = p.b, nt = 32 * W;
-    for (int idx = threadIdx.x; idx < 64 * 64; idx += nt) sm.ts[idx / 64][idx % 64] = 0.f;
-    __syncthreads();
-    for (int c = 0; c < nb; ++c) {
-      const float tc = sm.staus[c];
-      for (int i = threadIdx.x; i < c; i += nt) {
+    for (int c = threadIdx.x; c < nb; c += nt) {
+      sm.ts[c][c] = sm.staus[c];
+      for (int i = c - 1; i >= 0; --i) {
         float acc = 0.f;
-        for (int k = i; k < c; ++k) acc = fmaf(sm.ts[i][k], sm.gs[k][c], acc);
-        sm.ts[i][c] = -tc * acc;
+        for (int k = i + 1; k <= c; ++k) acc = fmaf(sm.gs[i][k], sm.ts[k][c], acc);
+        sm.ts[i][c] = -sm.staus[i] * acc;
       }
-      if (threadIdx.x == 0) sm.ts[c][c] = tc;
-      __syncthreads();
     }
+    __syncthreads();
     for (int idx = threadIdx.x; idx < nb * nb; idx += nt) {
       const int i = idx % nb, cc = idx / nb;
       p.t[i + (long long)cc * p.ldt] = (i <= cc) ? sm.ts[i][cc] : 0.f;

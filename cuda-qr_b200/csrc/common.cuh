@@ -151,6 +151,8 @@ bool launch_panel_hh_cluster(const PanelHHParams& p, int rr, int cs, int ncl, cu
 // warp-block layout (panel_wb.cu), m_p <= 16384: warps per CTA wpc (1, 2, 4, 8), cluster size cs, clusters ncl (1 or 2)
 bool panel_wb_plan(long long mp, int* wpc, int* cs, int* ncl);
 bool launch_panel_wb(const PanelHHParams& p, int wpc, int cs, int ncl, cudaStream_t s);
+// experimental (panel_wb2.cu, CQR_PANEL_PAIR): same plan, two pivot columns per cluster exchange; b == 64, ncl == 1 only
+bool launch_panel_wb2(const PanelHHParams& p, int wpc, int cs, int ncl, int mode, cudaStream_t s);
 #ifdef CQR_HH_TRACE
 void panel_hh_read_trace(long long* out);
 #endif

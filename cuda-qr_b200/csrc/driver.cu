@@ -766,9 +766,12 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
         static const long long wb_min = getenv("CQR_PANEL_WB_MIN_ROWS") ? atoll(getenv("CQR_PANEL_WB_MIN_ROWS")) : 3072;
         static const long long wb_small = getenv("CQR_PANEL_WB_SMALL_ROWS") ? atoll(getenv("CQR_PANEL_WB_SMALL_ROWS")) : 0;   // one-CTA variant up to this height
         static const long long wb_max = getenv("CQR_PANEL_WB_MAX_ROWS") ? atoll(getenv("CQR_PANEL_WB_MAX_ROWS")) : 8192;   // > 8192: two clusters
+        // CQR_PANEL_PAIR=1|2 (experimental, default off): two pivot columns per exchange (panel_wb2.cu) where it applies
+        static const int wb_pair = getenv("CQR_PANEL_PAIR") ? atoi(getenv("CQR_PANEL_PAIR")) : 0;
         int wncl = 1;
-        if (use_wb && ((mp >= wb_min && mp <= wb_max) || mp <= wb_small) && c->opt_cluster && panel_wb_plan(mp, &wpc, &cs, &wncl) &&
-            launch_panel_wb(hp, wpc, cs, wncl, s)) {
+        const bool wb_range = use_wb && ((mp >= wb_min && mp <= wb_max) || mp <= wb_small) && c->opt_cluster && panel_wb_plan(mp, &wpc, &cs, &wncl);
+        if (wb_range && wb_pair > 0 && launch_panel_wb2(hp, wpc, cs, wncl, wb_pair, s)) {
+        } else if (wb_range && launch_panel_wb(hp, wpc, cs, wncl, s)) {
         } else if (!(c->opt_cluster && panel_hh_cluster_plan(mp, &rr, &cs, &ncl) && launch_panel_hh_cluster(hp, rr, cs, ncl, s)))
           launch_panel_hh(hp, hh_ri, hh_ctas, s);
       } else {

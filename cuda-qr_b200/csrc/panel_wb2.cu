@@ -1,0 +1,489 @@
+// panel_wb2.cu -- Householder panel (m_p x 64) on the warp-block layout with TWO pivot columns per cluster exchange.
+//
+// EXPERIMENTAL, off by default (CQR_PANEL_PAIR=1 routes the panels that panel_wb.cu takes today through this kernel;
+// =2 forces the cancellation fallback in every pair, which exercises the single-step code of this file).  Same contract,
+// register layout and st.async all-reduce as panel_wb.cu (which replaces the reference's one-CTA panelHouseholderKernel,
+// qr.cu:60-333); what changes is the number of exchanges: panel_wb.cu's ncu capture shows the 64 exchanges, not the local
+// work, are the run time (profiles/r01_panel_wb8192_summary.txt), so here one exchange serves the reflectors j and j+1.
+//
+// Algebra (fp32 numpy spec with the failure cases: tools/two_column_step.py).  x = column j, y = column j+1, both BEFORE
+// reflector j touches anything and both restricted to the rows below j+1.  One exchange delivers, for every column c,
+// p_c = x^T a_c and q_c = y^T a_c plus the rows j and j+1 of the panel (r1, r2).  Then
+//   reflector j:    sigma_1 = p_j + r2_j^2, alpha_1 = r1_j               -> beta_1, u_1, tau_1   (qr.c:144-152 convention)
+//   any column c:   d1_c = r1_c + (p_c + r2_j r2_c) / u_1,  t_c = tau_1 d1_c,  e_c = t_c / u_1
+//   column j+1:     a1 = e_{j+1};  y' = y - a1 x;  alpha_2 = r2_{j+1} - a1 r2_j;
+//                   sigma_2 = q_{j+1} - 2 a1 p_{j+1} + a1^2 p_j                             -> beta_2, u_2, tau_2
+//   any column c:   a'(j+1,c) = r2_c - e_c r2_j;  y'^T a'_c = q_c - e_c p_{j+1} - a1 p_c + a1 e_c p_j;
+//                   d2_c = a'(j+1,c) + y'^T a'_c / u_2,  f_c = tau_2 d2_c / u_2
+//   update:         a_c -= (e_c - f_c a1) x + f_c y   below row j+1 (two FFMA2 per register pair, the work of two single
+//                   steps);  a(j,c) = r1_c - t_c,  a(j+1,c) = a'(j+1,c) - tau_2 d2_c
+//   V^T V for T:    the same d1_c, d2_c of the finished columns (with e_c = 0), and G(j,j+1) = r2_j/u_1 + (p_{j+1} - a1 p_j)/(u_1 u_2).
+// Cancellation guard (mandatory): when sigma_2 < 1e-3 q_{j+1} the expansion is noise (neighbouring
+// columns nearly dependent); the pair then finishes step j from the data it has and runs step j+1 as a single step with
+// one more exchange of the true y'.  The decision is taken on bit-identical totals in every thread of the cluster, so it is
+// uniform.  One cluster only (m_p <= 8192); b must be 64.
+#include "common.cuh"
+
+namespace cqr {
+namespace {
+
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 wpk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void wupk(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 wfma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 wmul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float wsum2(f32x2 v) { float lo, hi; wupk(v, lo, hi); return lo + hi; }
+__device__ __forceinline__ float wrsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float wrcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return fmaf(r, fmaf(-x, r, 1.f), r); }
+
+__device__ __forceinline__ unsigned wb_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned wb_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void wb_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void wb_st_async_v4(float* local_dst, unsigned long long* local_bar, unsigned rank, float4 v) {
+  unsigned la = (unsigned)__cvta_generic_to_shared(local_dst), lb = (unsigned)__cvta_generic_to_shared(local_bar), ra, rb;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(lb), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(ra),
+               "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)), "r"(rb)
+               : "memory");
+}
+__device__ __forceinline__ void wb_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void wb_mbar_expect(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol error must not hang the device; *err is set and the caller's results are void
+__device__ __forceinline__ void wb_mbar_wait(unsigned long long* bar, unsigned parity, int* err) {
+  unsigned ok, a = (unsigned)__cvta_generic_to_shared(bar);
+  long long t0 = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (t0 == 0) t0 = clock64();
+    else if (clock64() - t0 > 200000000LL) { atomicExch(err, 1); break; }
+  }
+}
+
+template <int W>
+struct Wb2Shared {
+  float xs[W][2][64];          // per-warp x (column j, or the lone column j+1 of a fallen-back pair) of the warp's 64 rows
+  float ys[W][2][64];          // per-warp y (column j+1)
+  float part[2][W][128];       // per-warp column sums: [0,64) x^T a_c, [64,128) y^T a_c
+  float prl[2][128];           // CTA 0: rows j and j+1 of the panel
+  float rs_in[2][32][4];       // phase 1 inbox of the group owner (one float4 per sender and owned group)
+  float prs_in[2][32][4];      // phase 1: pivot-row entries of my groups (from CTA 0)
+  float tot_in[2][128];        // phase 2: cluster totals p (0..63), q (64..127)
+  float prow[2][128];          // phase 2: rows j (0..63), j+1 (64..127)
+  unsigned long long mbar1[2], mbar2[2];
+  float gs[64][65];            // CTA 0: G(c, j) = v_c^T v_j (c < j)
+  float ts[64][65];
+  float staus[64];
+};
+
+struct Wb2Ctx {
+  int q, h, w, lane;
+  bool top;                    // this warp holds the panel's first 64 rows (the pivot rows)
+  unsigned rank, CS;           // CTA rank in the cluster, cluster size
+  int nb, mode;                // mode 2: every pair takes the fallback
+  int* err;
+  float* tau_out;
+};
+
+struct Refl { float bc, inv_u, tau; bool ok; };
+// beta = -sign(alpha) norm, u = alpha - beta, tau = -u / beta (qr.c:144-152); MUFU rsqrt / rcp + one Newton step as in
+// panel_wb.cu; a zero column gives tau = 0 (H = I)
+__device__ __forceinline__ Refl wb2_scalars(float alpha, float sig) {
+  Refl r;
+  const float sj = fmaf(alpha, alpha, sig);
+  r.ok = sj >= 1.2e-38f;
+  const float sjs = r.ok ? sj : 1.f;
+  const float rs = wrsqrt(sjs);
+  float nrm = sjs * rs;
+  nrm = fmaf(fmaf(-nrm, nrm, sjs), 0.5f * rs, nrm);
+  r.bc = (alpha < 0.f) ? nrm : -nrm;
+  const float u = alpha - r.bc;
+  r.inv_u = r.ok ? wrcp(u) : 0.f;
+  r.tau = r.ok ? -u * wrcp(r.bc) : 0.f;
+  return r;
+}
+
+// columns j = 8 I0 .. 8 I0 + 7, two per exchange; ex counts the exchanges of this launch (buffer and mbarrier parity)
+template <int I0, int W>
+__device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, const Wb2Ctx& cx, unsigned& ex) {
+  const int q = cx.q, h = cx.h, w = cx.w, lane = cx.lane;
+  int jj = 0;
+  bool second = false;                       // this pass is the lone step j+1 of a pair that failed the guard
+#pragma unroll 1
+  while (jj < 8) {
+    const int j = 8 * I0 + jj;               // even
+    if (j >= cx.nb) break;                   // uniform over the whole cluster
+    const int buf = ex & 1;
+    const unsigned par = (ex >> 1) & 1;
+    ++ex;
+    const int hj = jj >> 1;                  // rows j, j+1 are the (lo, hi) of pair I0 in the lanes h == hj of the top warp
+    const int qx = second ? jj + 1 : jj, qy = jj + 1;
+    float* xb = sm.xs[w][buf];
+    float* yb = sm.ys[w][buf];
+    // ---- publish x and y (this warp's rows; the top warp masks rows 0 .. j+1) and rows j, j+1
+    if (q == qx || q == qy) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        f32x2 v = b[I0][k];
+        if (cx.top && (k < I0 || (k == I0 && h <= hj))) v = 0ull;
+        if (q == qx) *reinterpret_cast<f32x2*>(xb + 8 * k + 2 * h) = v;
+        if (q == qy) *reinterpret_cast<f32x2*>(yb + 8 * k + 2 * h) = v;
+      }
+    }
+    if (cx.top && h == hj) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float lo, hi;
+        wupk(b[i][I0], lo, hi);
+        sm.prl[buf][q + 8 * i] = lo;
+        sm.prl[buf][64 + q + 8 * i] = hi;
+      }
+    }
+    __syncwarp();
+    f32x2 x[8], y[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      x[k] = *reinterpret_cast<const f32x2*>(xb + 8 * k + 2 * h);
+      y[k] = *reinterpret_cast<const f32x2*>(yb + 8 * k + 2 * h);
+    }
+    // ---- warp-level column sums for all 64 columns against x and y.  First shuffle stage swaps halves (odd h keeps the
+    // y sums, even h the x sums), so the 16 sums cost 16 shuffles; lanes h == 0 end with x^T a_c, lanes h == 1 with y^T a_c
+    {
+      f32x2 d2[8], e2[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { d2[i] = 0ull; e2[i] = 0ull; }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          d2[i] = wfma2(x[k], b[i][k], d2[i]);
+          e2[i] = wfma2(y[k], b[i][k], e2[i]);
+        }
+      const bool odd = (h & 1) != 0;
+      float keep[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float dx = wsum2(d2[i]), dy = wsum2(e2[i]);
+        const float give = odd ? dx : dy;
+        keep[i] = (odd ? dy : dx) + __shfl_xor_sync(kFull, give, 8);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) keep[i] += __shfl_xor_sync(kFull, keep[i], 16);
+      if (h < 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sm.part[buf][w][64 * h + q + 8 * i] = keep[i];
+      }
+    }
+    __syncthreads();
+    // ---- CTA sums, then the cluster all-reduce (warp 0): lane g handles the float4 group g of the 128 sums
+    if (w == 0) {
+      float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int ww = 0; ww < W; ++ww) {
+        const float4 t = *reinterpret_cast<const float4*>(&sm.part[buf][ww][4 * lane]);
+        sv.x += t.x; sv.y += t.y; sv.z += t.z; sv.w += t.w;
+      }
+      const float4 pv = *reinterpret_cast<const float4*>(&sm.prl[buf][4 * lane]);   // meaningful in CTA 0 only
+      if (cx.CS == 1) {
+        *reinterpret_cast<float4*>(&sm.tot_in[buf][4 * lane]) = sv;
+        *reinterpret_cast<float4*>(&sm.prow[buf][4 * lane]) = pv;
+      } else {
+        const unsigned CS = cx.CS, rank = cx.rank;
+        const unsigned wpo = 32u / CS;                  // float4 groups per owner CTA
+        if (lane == 0) {
+          wb_mbar_expect(&sm.mbar1[buf], (32 + wpo) * 16);
+          wb_mbar_expect(&sm.mbar2[buf], (32 + 32) * 16);
+        }
+        const unsigned owner = ((unsigned)lane * CS) >> 5, wl = (unsigned)lane - owner * wpo;
+        wb_st_async_v4(&sm.rs_in[buf][rank * wpo + wl][0], &sm.mbar1[buf], owner, sv);
+        if (rank == 0) wb_st_async_v4(&sm.prs_in[buf][wl][0], &sm.mbar1[buf], owner, pv);
+        wb_mbar_wait(&sm.mbar1[buf], par, cx.err);
+        float4 t = *reinterpret_cast<const float4*>(&sm.rs_in[buf][lane][0]);    // entry = sender * wpo + my group
+        for (unsigned o = 16; o >= wpo; o >>= 1) {
+          t.x += __shfl_xor_sync(kFull, t.x, o); t.y += __shfl_xor_sync(kFull, t.y, o);
+          t.z += __shfl_xor_sync(kFull, t.z, o); t.w += __shfl_xor_sync(kFull, t.w, o);
+        }
+        const unsigned slot = (unsigned)lane % wpo, peer = (unsigned)lane / wpo;   // lane holds the total of group `slot`
+        const unsigned col4 = 4u * (rank * wpo + slot);
+        wb_st_async_v4(&sm.tot_in[buf][col4], &sm.mbar2[buf], peer, t);
+        wb_st_async_v4(&sm.prow[buf][col4], &sm.mbar2[buf], peer, *reinterpret_cast<const float4*>(&sm.prs_in[buf][slot][0]));
+      }
+    }
+    if (cx.CS == 1) __syncthreads();
+    else wb_mbar_wait(&sm.mbar2[buf], par, cx.err);
+    const float* P = sm.tot_in[buf];
+    const float* Q = sm.tot_in[buf] + 64;
+    const float* R1 = sm.prow[buf];
+    const float* R2 = sm.prow[buf] + 64;
+
+    if (!second) {
+      // ---- reflector j and what it does to column j+1 (redundant in every thread: bit-identical inputs)
+      const float xj1 = R2[j], yj1 = R2[j + 1];
+      const Refl s1 = wb2_scalars(R1[j], fmaf(xj1, xj1, P[j]));
+      const float iu1 = s1.inv_u, t1 = s1.tau;
+      const float d1n = fmaf(fmaf(xj1, yj1, P[j + 1]), iu1, R1[j + 1]);
+      const float tn = t1 * d1n;
+      const float a1 = tn * iu1;
+      const float alpha2 = fmaf(-a1, xj1, yj1);
+      const float sig2 = fmaf(a1 * a1, P[j], fmaf(-2.f * a1, P[j + 1], Q[j + 1]));
+      const bool fb = (cx.mode == 2) || (sig2 < 1e-3f * Q[j + 1]);
+      if (cx.top && lane == 0) { cx.tau_out[j] = t1; sm.staus[j] = t1; }
+      if (!fb) {
+        const Refl s2 = wb2_scalars(alpha2, fmaxf(sig2, 0.f));
+        const float iu2 = s2.inv_u, t2 = s2.tau;
+        if (cx.top && lane == 0) { cx.tau_out[j + 1] = t2; sm.staus[j + 1] = t2; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = q + 8 * i;
+          const float d1 = fmaf(fmaf(xj1, R2[c], P[c]), iu1, R1[c]);          // v_j^T a_c  (c < j: v_c^T v_j)
+          if (i <= I0 && cx.top && h == 0) {
+            if (c < j) { sm.gs[c][j] = d1; sm.gs[c][j + 1] = fmaf(fmaf(-a1, P[c], Q[c]), iu2, R2[c]); }
+            else if (c == j) sm.gs[j][j + 1] = fmaf(iu1 * iu2, fmaf(-a1, P[j], P[j + 1]), xj1 * iu1);
+          }
+          if (i >= I0) {
+            const bool act = (i > I0) || (q > jj + 1);
+            const float tc = t1 * d1, ec = tc * iu1;
+            const float r2c = fmaf(-ec, xj1, R2[c]);                          // a'(j+1, c)
+            const float inner = fmaf(a1 * ec, P[j], fmaf(-a1, P[c], fmaf(-ec, P[j + 1], Q[c])));
+            const float sc2 = t2 * fmaf(inner, iu2, r2c), fc = sc2 * iu2;
+            const float cxv = act ? fmaf(fc, a1, -ec) : 0.f, cyv = act ? -fc : 0.f;
+            const f32x2 cx2 = wpk(cxv, cxv), cy2 = wpk(cyv, cyv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) b[i][k] = wfma2(cx2, x[k], wfma2(cy2, y[k], b[i][k]));
+            if (act && cx.top && h == hj) b[i][I0] = wpk(R1[c] - tc, r2c - sc2);   // rows j, j+1 (x, y are masked there)
+          }
+        }
+        if (q == jj + 1) {                   // column j+1: R(j, j+1), beta_2, v = (y - a1 x) / u_2 below
+          const float m2 = s2.ok ? iu2 : 1.f;
+          const f32x2 m22 = wpk(m2, m2), na2 = wpk(-a1, -a1);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const f32x2 nv = wmul2(wfma2(na2, x[k], b[I0][k]), m22);
+            if (!cx.top || k > I0 || (k == I0 && h > hj)) b[I0][k] = nv;
+          }
+          if (cx.top && h == hj) b[I0][I0] = wpk(R1[j + 1] - tn, s2.ok ? s2.bc : alpha2);
+        }
+      } else {
+        // ---- cancellation fallback, first half: step j alone from the data of this exchange (x^T a_c over the rows
+        // below j is p_c + r2_j r2_c); step j+1 follows as a single step with its own exchange
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = q + 8 * i;
+          const float d1 = fmaf(fmaf(xj1, R2[c], P[c]), iu1, R1[c]);
+          if (i <= I0 && cx.top && h == 0 && c < j) sm.gs[c][j] = d1;
+          if (i >= I0) {
+            const bool act = (i > I0) || (q > jj);
+            const float tc = t1 * d1, ec = tc * iu1;
+            const float cxv = act ? -ec : 0.f;
+            const f32x2 cx2 = wpk(cxv, cxv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) b[i][k] = wfma2(cx2, x[k], b[i][k]);
+            if (act && cx.top && h == hj) b[i][I0] = wpk(R1[c] - tc, fmaf(-ec, xj1, R2[c]));
+          }
+        }
+      }
+      if (q == jj && s1.ok) {                // column j: beta_1 on the diagonal, v = x / u_1 below (row j+1 included)
+        const f32x2 iu12 = wpk(iu1, iu1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (!cx.top || k > I0 || (k == I0 && h > hj)) b[I0][k] = wmul2(b[I0][k], iu12);
+        if (cx.top && h == hj) b[I0][I0] = wpk(s1.bc, xj1 * iu1);
+      }
+      if (fb) second = true;
+      else jj += 2;
+    } else {
+      // ---- lone step j+1: x is the true column j+1 below row j+1, R2 the current row j+1
+      const Refl s2 = wb2_scalars(R2[j + 1], P[j + 1]);
+      const float iu2 = s2.inv_u, t2 = s2.tau;
+      if (cx.top && lane == 0) { cx.tau_out[j + 1] = t2; sm.staus[j + 1] = t2; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = q + 8 * i;
+        const float d2 = fmaf(P[c], iu2, R2[c]);
+        if (i <= I0 && cx.top && h == 0 && c < j + 1) sm.gs[c][j + 1] = d2;
+        if (i >= I0) {
+          const bool act = (i > I0) || (q > jj + 1);
+          const float sc2 = t2 * d2, fc = sc2 * iu2;
+          const float cxv = act ? -fc : 0.f;
+          const f32x2 cx2 = wpk(cxv, cxv);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) b[i][k] = wfma2(cx2, x[k], b[i][k]);
+          if (act && cx.top && h == hj) {
+            float lo, hi;
+            wupk(b[i][I0], lo, hi);
+            b[i][I0] = wpk(lo, R2[c] - sc2);
+          }
+        }
+      }
+      if (q == jj + 1 && s2.ok) {
+        const f32x2 iu22 = wpk(iu2, iu2);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (!cx.top || k > I0 || (k == I0 && h > hj)) b[I0][k] = wmul2(b[I0][k], iu22);
+        if (cx.top && h == hj) {
+          float lo, hi;
+          wupk(b[I0][I0], lo, hi);
+          b[I0][I0] = wpk(lo, s2.bc);
+        }
+      }
+      second = false;
+      jj += 2;
+    }
+  }
+}
+
+template <int I0, int W>
+struct Wb2Groups {
+  static __device__ __forceinline__ void run(f32x2 (&b)[8][8], Wb2Shared<W>& sm, const Wb2Ctx& cx, unsigned& ex) {
+    wb2_steps<I0, W>(b, sm, cx, ex);
+    Wb2Groups<I0 + 1, W>::run(b, sm, cx, ex);
+  }
+};
+template <int W>
+struct Wb2Groups<8, W> {
+  static __device__ __forceinline__ void run(f32x2 (&)[8][8], Wb2Shared<W>&, const Wb2Ctx&, unsigned&) {}
+};
+
+extern __shared__ __align__(16) unsigned char wb2_smem[];
+
+template <int W>
+__global__ void __launch_bounds__(32 * W, 1) panel_wb2_kernel(PanelHHParams p) {
+  Wb2Shared<W>& sm = *reinterpret_cast<Wb2Shared<W>*>(wb2_smem);
+  Wb2Ctx cx;
+  cx.lane = threadIdx.x & 31; cx.w = threadIdx.x >> 5; cx.q = cx.lane & 7; cx.h = cx.lane >> 3;
+  cx.rank = wb_ctarank(); cx.CS = wb_nctarank();
+  cx.nb = p.b; cx.err = p.err; cx.tau_out = p.tau; cx.mode = p.pmax;
+  const int q = cx.q, h = cx.h;
+  const long long gw = (long long)blockIdx.x * W + cx.w;        // warp block index: rows 64 gw .. 64 gw + 63
+  cx.top = (gw == 0);
+  const long long row0 = 64 * gw;
+  const int b_cols = p.b;
+  const bool vec = (p.lda % 2 == 0) && (p.ldv % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.a) & 7) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(p.vbuf) & 7) == 0);
+  f32x2 b[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = q + 8 * i;
+    const float* col = p.a + row0 + (long long)c * p.lda + 2 * h;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long r0 = row0 + 8 * k + 2 * h;
+      if (c < b_cols && vec && r0 + 1 < p.mp) {
+        b[i][k] = *reinterpret_cast<const f32x2*>(col + 8 * k);
+      } else {
+        const float lo = (c < b_cols && r0 < p.mp) ? col[8 * k] : 0.f;
+        const float hi = (c < b_cols && r0 + 1 < p.mp) ? col[8 * k + 1] : 0.f;
+        b[i][k] = wpk(lo, hi);
+      }
+    }
+  }
+  if (cx.CS > 1) {
+    if (threadIdx.x == 0) {
+      wb_mbar_init(&sm.mbar1[0], 1); wb_mbar_init(&sm.mbar1[1], 1);
+      wb_mbar_init(&sm.mbar2[0], 1); wb_mbar_init(&sm.mbar2[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    wb_cluster_sync();   // every peer's barriers exist before anyone pushes
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 64) sm.staus[threadIdx.x] = 0.f;
+
+  unsigned ex = 0;
+  Wb2Groups<0, W>::run(b, sm, cx, ex);
+
+  // ---- results: LAPACK storage into the panel, explicit V (unit diagonal, zeros above) into vbuf
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = q + 8 * i;
+    float* acol = p.a + row0 + (long long)c * p.lda + 2 * h;
+    float* vcol = p.vbuf + row0 + (long long)c * p.ldv + 2 * h;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long r0 = row0 + 8 * k + 2 * h;
+      float lo, hi;
+      wupk(b[i][k], lo, hi);
+      const float vlo = r0 > c ? lo : (r0 == c ? 1.f : 0.f);
+      const float vhi = r0 + 1 > c ? hi : (r0 + 1 == c ? 1.f : 0.f);
+      if (c < b_cols && vec && r0 + 1 < p.mp) {
+        *reinterpret_cast<f32x2*>(acol + 8 * k) = b[i][k];
+        *reinterpret_cast<f32x2*>(vcol + 8 * k) = wpk(vlo, vhi);
+      } else {
+        if (c < b_cols && r0 < p.mp) { acol[8 * k] = lo; vcol[8 * k] = vlo; }
+        if (c < b_cols && r0 + 1 < p.mp) { acol[8 * k + 1] = hi; vcol[8 * k + 1] = vhi; }
+      }
+    }
+  }
+  // ---- compact-WY T (CTA 0), as in panel_wb.cu: column c of T is an independent back substitution on
+  // T^-1 = diag(1 / tau) + striu(V^T V); one thread per column
+  if (blockIdx.x == 0 && p.t != nullptr) {
+    __syncthreads();
+    const int nb = p.b, nt = 32 * W;
+    for (int c = threadIdx.x; c < nb; c += nt) {
+      sm.ts[c][c] = sm.staus[c];
+      for (int i = c - 1; i >= 0; --i) {
+        float acc = 0.f;
+        for (int k = i + 1; k <= c; ++k) acc = fmaf(sm.gs[i][k], sm.ts[k][c], acc);
+        sm.ts[i][c] = -sm.staus[i] * acc;
+      }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nb * nb; idx += nt) {
+      const int i = idx % nb, cc = idx / nb;
+      p.t[i + (long long)cc * p.ldt] = (i <= cc) ? sm.ts[i][cc] : 0.f;
+    }
+  }
+  if (cx.CS > 1) wb_cluster_sync();   // no CTA leaves while pushes addressed to it (or by it) are in flight
+}
+
+template <int W>
+cudaError_t launch_wb2_t(const PanelHHParams& p, int cs, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(panel_wb2_kernel<W>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(panel_wb2_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Wb2Shared<W>));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cs, 1, 1);
+  cfg.blockDim = dim3(32 * W, 1, 1);
+  cfg.dynamicSmemBytes = sizeof(Wb2Shared<W>);
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, panel_wb2_kernel<W>, p);
+}
+
+}  // namespace
+
+// Same plan as panel_wb.cu (wpc warps per CTA, one cluster of cs CTAs); mode 1 = pairs with the cancellation guard,
+// 2 = every pair falls back to two single steps.  Returns false when the shape is not covered (b != 64, more than one
+// cluster) or the launch failed; the caller then takes the one-column-per-exchange kernels.
+bool launch_panel_wb2(const PanelHHParams& p, int wpc, int cs, int ncl, int mode, cudaStream_t s) {
+  if (p.b != 64 || ncl != 1 || cs > 16) return false;
+  PanelHHParams pp = p;
+  pp.pmax = mode;
+  ++g_launches;
+  cudaError_t e;
+  if (wpc == 1) e = launch_wb2_t<1>(pp, cs, s);
+  else if (wpc == 2) e = launch_wb2_t<2>(pp, cs, s);
+  else if (wpc == 4) e = launch_wb2_t<4>(pp, cs, s);
+  else e = launch_wb2_t<8>(pp, cs, s);
+  if (e != cudaSuccess) { cudaGetLastError(); --g_launches; return false; }
+  return true;
+}
+
+}  // namespace cqr

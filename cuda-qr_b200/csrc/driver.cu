@@ -766,12 +766,17 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
         static const long long wb_min = getenv("CQR_PANEL_WB_MIN_ROWS") ? atoll(getenv("CQR_PANEL_WB_MIN_ROWS")) : 3072;
         static const long long wb_small = getenv("CQR_PANEL_WB_SMALL_ROWS") ? atoll(getenv("CQR_PANEL_WB_SMALL_ROWS")) : 0;   // one-CTA variant up to this height
         static const long long wb_max = getenv("CQR_PANEL_WB_MAX_ROWS") ? atoll(getenv("CQR_PANEL_WB_MAX_ROWS")) : 8192;   // > 8192: two clusters
-        // CQR_PANEL_PAIR=1|2 (experimental, default off): two pivot columns per exchange (panel_wb2.cu) where it applies
-        static const int wb_pair = getenv("CQR_PANEL_PAIR") ? atoi(getenv("CQR_PANEL_PAIR")) : 0;
+        // CQR_PANEL_PAIR (default 1): two pivot columns per exchange (panel_wb2.cu: 8192 rows 166 -> 132 us, 4096 rows
+        // 152 -> 121 us, 2048 rows 120 us) from CQR_PANEL_PAIR_MIN_ROWS (2048) up to 8192 rows; 0 = off, 2 = forced fallback
+        static const int wb_pair = getenv("CQR_PANEL_PAIR") ? atoi(getenv("CQR_PANEL_PAIR")) : 1;
+        static const long long pair_min = getenv("CQR_PANEL_PAIR_MIN_ROWS") ? atoll(getenv("CQR_PANEL_PAIR_MIN_ROWS"))
+                                          : (getenv("CQR_PANEL_WB_MIN_ROWS") ? wb_min : 2048);
         int wncl = 1;
-        const bool wb_range = use_wb && ((mp >= wb_min && mp <= wb_max) || mp <= wb_small) && c->opt_cluster && panel_wb_plan(mp, &wpc, &cs, &wncl);
-        if (wb_range && wb_pair > 0 && launch_panel_wb2(hp, wpc, cs, wncl, wb_pair, s)) {
-        } else if (wb_range && launch_panel_wb(hp, wpc, cs, wncl, s)) {
+        const bool wb_planned = use_wb && c->opt_cluster && panel_wb_plan(mp, &wpc, &cs, &wncl);
+        const bool in_wb = wb_planned && ((mp >= wb_min && mp <= wb_max) || mp <= wb_small);
+        const bool in_pair = wb_planned && wb_pair > 0 && b == 64 && wncl == 1 && mp >= pair_min;
+        if (in_pair && launch_panel_wb2(hp, wpc, cs, wncl, wb_pair, s)) {
+        } else if (in_wb && launch_panel_wb(hp, wpc, cs, wncl, s)) {
         } else if (!(c->opt_cluster && panel_hh_cluster_plan(mp, &rr, &cs, &ncl) && launch_panel_hh_cluster(hp, rr, cs, ncl, s)))
           launch_panel_hh(hp, hh_ri, hh_ctas, s);
       } else {

@@ -1,7 +1,7 @@
 // panel_wb2.cu -- Householder panel (m_p x 64) on the warp-block layout with TWO pivot columns per cluster exchange.
 //
-// EXPERIMENTAL, off by default (CQR_PANEL_PAIR=1 routes the panels that panel_wb.cu takes today through this kernel;
-// =2 forces the cancellation fallback in every pair, which exercises the single-step code of this file).  Same contract,
+// Default for panels of 2048 .. 8192 rows (CQR_PANEL_PAIR=0 goes back to one column per exchange, =2 forces the
+// cancellation fallback in every pair, which exercises the single-step code of this file).  Same contract,
 // register layout and st.async all-reduce as panel_wb.cu (which replaces the reference's one-CTA panelHouseholderKernel,
 // qr.cu:60-333); what changes is the number of exchanges: panel_wb.cu's ncu capture shows the 64 exchanges, not the local
 // work, are the run time (profiles/r01_panel_wb8192_summary.txt), so here one exchange serves the reflectors j and j+1.
@@ -21,7 +21,9 @@
 // Cancellation guard (mandatory): when sigma_2 < 1e-3 q_{j+1} the expansion is noise (neighbouring
 // columns nearly dependent); the pair then finishes step j from the data it has and runs step j+1 as a single step with
 // one more exchange of the true y'.  The decision is taken on bit-identical totals in every thread of the cluster, so it is
-// uniform.  One cluster only (m_p <= 8192); b must be 64.
+// uniform.  One cluster only (m_p <= 8192); b must be 64.  Measured on B200 (tools/panel_bench.py, zero fill + panel):
+// 8192 rows 166 -> 132 us, 4096 rows 152 -> 121 us, 2048 rows 120 us; the lane-level numpy replay of this file is
+// tools/emulate_pair_panel.py.
 #include "common.cuh"
 
 namespace cqr {
@@ -109,10 +111,11 @@ __device__ __forceinline__ Refl wb2_scalars(float alpha, float sig) {
   const float rs = wrsqrt(sjs);
   float nrm = sjs * rs;
   nrm = fmaf(fmaf(-nrm, nrm, sjs), 0.5f * rs, nrm);
-  r.bc = (alpha < 0.f) ? nrm : -nrm;
+  const bool len1 = (sig == 0.f);             // nothing below the pivot: exact sign flip, tau = 2 like the reference's division
+  r.bc = len1 ? -alpha : ((alpha < 0.f) ? nrm : -nrm);
   const float u = alpha - r.bc;
   r.inv_u = r.ok ? wrcp(u) : 0.f;
-  r.tau = r.ok ? -u * wrcp(r.bc) : 0.f;
+  r.tau = r.ok ? (len1 ? 2.f : -u * wrcp(r.bc)) : 0.f;
   return r;
 }
 

@@ -18,9 +18,10 @@ def scalars(alpha, sig):
     ok = sj >= F(1.2e-38)
     sjs = sj if ok else F(1)
     nrm = F(np.sqrt(sjs))
-    bc = nrm if alpha < 0 else -nrm
+    len1 = sig == 0
+    bc = -alpha if len1 else (nrm if alpha < 0 else -nrm)
     u = F(alpha - bc)
-    return bc, (F(1) / u if ok else F(0)), (F(-u / bc) if ok else F(0)), ok
+    return bc, (F(1) / u if ok else F(0)), ((F(2) if len1 else F(-u / bc)) if ok else F(0)), ok
 
 
 def run(A, W, CS, mode=1):

@@ -774,7 +774,8 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
         int wncl = 1;
         const bool wb_planned = use_wb && c->opt_cluster && panel_wb_plan(mp, &wpc, &cs, &wncl);
         const bool in_wb = wb_planned && ((mp >= wb_min && mp <= wb_max) || mp <= wb_small);
-        const bool in_pair = wb_planned && wb_pair > 0 && b == 64 && wncl == 1 && mp >= pair_min;
+        static const long long pair_max = getenv("CQR_PANEL_PAIR_MAX_ROWS") ? atoll(getenv("CQR_PANEL_PAIR_MAX_ROWS")) : 8192;   // > 8192: two clusters
+        const bool in_pair = wb_planned && wb_pair > 0 && b == 64 && mp >= pair_min && mp <= pair_max;
         if (in_pair && launch_panel_wb2(hp, wpc, cs, wncl, wb_pair, s)) {
         } else if (in_wb && launch_panel_wb(hp, wpc, cs, wncl, s)) {
         } else if (!(c->opt_cluster && panel_hh_cluster_plan(mp, &rr, &cs, &ncl) && launch_panel_hh_cluster(hp, rr, cs, ncl, s)))

@@ -21,7 +21,8 @@
 // Cancellation guard (mandatory): when sigma_2 < 1e-3 q_{j+1} the expansion is noise (neighbouring
 // columns nearly dependent); the pair then finishes step j from the data it has and runs step j+1 as a single step with
 // one more exchange of the true y'.  The decision is taken on bit-identical totals in every thread of the cluster, so it is
-// uniform.  One cluster only (m_p <= 8192); b must be 64.  Measured on B200 (tools/panel_bench.py, zero fill + panel):
+// uniform.  b must be 64.  One cluster up to 8192 rows (default); two clusters up to 16384 rows exchange through
+// global-memory flags exactly like panel_wb.cu (CQR_PANEL_PAIR_MAX_ROWS=16384, not yet measured: off by default).  Measured on B200 (tools/panel_bench.py, zero fill + panel):
 // 8192 rows 166 -> 132 us, 4096 rows 152 -> 121 us, 2048 rows 120 us; the lane-level numpy replay of this file is
 // tools/emulate_pair_panel.py.
 #include "common.cuh"
@@ -57,6 +58,14 @@ __device__ __forceinline__ void wb_mbar_init(unsigned long long* bar, unsigned c
 __device__ __forceinline__ void wb_mbar_expect(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void wb_st_flag(uint2* p, float v, unsigned tag) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 wb_ld_flag(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+  return r;
+}
 // bounded wait: a protocol error must not hang the device; *err is set and the caller's results are void
 __device__ __forceinline__ void wb_mbar_wait(unsigned long long* bar, unsigned parity, int* err) {
   unsigned ok, a = (unsigned)__cvta_generic_to_shared(bar);
@@ -71,7 +80,7 @@ __device__ __forceinline__ void wb_mbar_wait(unsigned long long* bar, unsigned p
         : "memory");
     if (ok) break;
     if (t0 == 0) t0 = clock64();
-    else if (clock64() - t0 > 200000000LL) { atomicExch(err, 1); break; }
+    else if (clock64() - t0 > 2000000000LL) { atomicExch(err, 1); break; }
   }
 }
 
@@ -89,12 +98,16 @@ struct Wb2Shared {
   float gs[64][65];            // CTA 0: G(c, j) = v_c^T v_j (c < j)
   float ts[64][65];
   float staus[64];
+  float tot_x[2][128];         // two clusters: totals over both clusters, rows j and j+1
+  float prow_x[2][128];
 };
 
 struct Wb2Ctx {
   int q, h, w, lane;
   bool top;                    // this warp holds the panel's first 64 rows (the pivot rows)
-  unsigned rank, CS;           // CTA rank in the cluster, cluster size
+  unsigned rank, CS, cl, ncl;  // CTA rank in its cluster, cluster size, cluster index, number of clusters (1 or 2)
+  uint2* slots;                // two clusters: {value, tag} exchange slots in global memory [2 buffers][3][128]
+  unsigned epoch;
   int nb, mode;                // mode 2: every pair takes the fallback
   int* err;
   float* tau_out;
@@ -120,7 +133,7 @@ __device__ __forceinline__ Refl wb2_scalars(float alpha, float sig) {
 }
 
 // columns j = 8 I0 .. 8 I0 + 7, two per exchange; ex counts the exchanges of this launch (buffer and mbarrier parity)
-template <int I0, int W>
+template <int I0, int W, bool X2>
 __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, const Wb2Ctx& cx, unsigned& ex) {
   const int q = cx.q, h = cx.h, w = cx.w, lane = cx.lane;
   int jj = 0;
@@ -207,12 +220,12 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
         const unsigned CS = cx.CS, rank = cx.rank;
         const unsigned wpo = 32u / CS;                  // float4 groups per owner CTA
         if (lane == 0) {
-          wb_mbar_expect(&sm.mbar1[buf], (32 + wpo) * 16);
-          wb_mbar_expect(&sm.mbar2[buf], (32 + 32) * 16);
+          wb_mbar_expect(&sm.mbar1[buf], (32 + ((!X2 || cx.cl == 0) ? wpo : 0)) * 16);
+          wb_mbar_expect(&sm.mbar2[buf], (32 + ((!X2 || cx.cl == 0) ? 32 : 0)) * 16);
         }
         const unsigned owner = ((unsigned)lane * CS) >> 5, wl = (unsigned)lane - owner * wpo;
         wb_st_async_v4(&sm.rs_in[buf][rank * wpo + wl][0], &sm.mbar1[buf], owner, sv);
-        if (rank == 0) wb_st_async_v4(&sm.prs_in[buf][wl][0], &sm.mbar1[buf], owner, pv);
+        if (rank == 0 && (!X2 || cx.cl == 0)) wb_st_async_v4(&sm.prs_in[buf][wl][0], &sm.mbar1[buf], owner, pv);
         wb_mbar_wait(&sm.mbar1[buf], par, cx.err);
         float4 t = *reinterpret_cast<const float4*>(&sm.rs_in[buf][lane][0]);    // entry = sender * wpo + my group
         for (unsigned o = 16; o >= wpo; o >>= 1) {
@@ -222,15 +235,55 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
         const unsigned slot = (unsigned)lane % wpo, peer = (unsigned)lane / wpo;   // lane holds the total of group `slot`
         const unsigned col4 = 4u * (rank * wpo + slot);
         wb_st_async_v4(&sm.tot_in[buf][col4], &sm.mbar2[buf], peer, t);
-        wb_st_async_v4(&sm.prow[buf][col4], &sm.mbar2[buf], peer, *reinterpret_cast<const float4*>(&sm.prs_in[buf][slot][0]));
+        if (!X2 || cx.cl == 0) wb_st_async_v4(&sm.prow[buf][col4], &sm.mbar2[buf], peer, *reinterpret_cast<const float4*>(&sm.prs_in[buf][slot][0]));
       }
     }
     if (cx.CS == 1) __syncthreads();
     else wb_mbar_wait(&sm.mbar2[buf], par, cx.err);
     const float* P = sm.tot_in[buf];
-    const float* Q = sm.tot_in[buf] + 64;
     const float* R1 = sm.prow[buf];
-    const float* R2 = sm.prow[buf] + 64;
+    if constexpr (X2) {
+      // two clusters (as in panel_wb.cu): the leaders publish their 128 cluster sums (cluster 0 also rows j, j+1) as
+      // {value, tag} pairs in global memory, warp 0 of every CTA polls the other cluster's slots (four values per lane) and
+      // adds in the same order on both sides (cluster 0 + cluster 1), so all 32 CTAs hold bit-identical totals
+      if (w == 0) {
+        const unsigned tag = cx.epoch * 64u + ex;        // ex = 1 .. 64 inside a launch, epoch unique per launch
+        uint2* mys = cx.slots + ((size_t)buf * 3 + cx.cl) * 128;
+        const uint2* oth = cx.slots + ((size_t)buf * 3 + (cx.cl ^ 1u)) * 128;
+        uint2* piv = cx.slots + ((size_t)buf * 3 + 2) * 128;
+        if (cx.rank == 0) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = lane + 32 * e;
+            wb_st_flag(mys + c, sm.tot_in[buf][c], tag);
+            if (cx.cl == 0) wb_st_flag(piv + c, sm.prow[buf][c], tag);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = lane + 32 * e;
+          const float mine = sm.tot_in[buf][c];
+          float so = 0.f, po = 0.f;
+          long long t0 = 0;
+          for (;;) {
+            const uint2 r = wb_ld_flag(oth + c);
+            uint2 qv; qv.x = 0u; qv.y = tag;
+            if (cx.cl != 0) qv = wb_ld_flag(piv + c);
+            so = __uint_as_float(r.x); po = __uint_as_float(qv.x);
+            if (r.y == tag && qv.y == tag) break;
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 2000000000LL) { atomicExch(cx.err, 1); break; }
+          }
+          sm.tot_x[buf][c] = (cx.cl == 0) ? (mine + so) : (so + mine);
+          sm.prow_x[buf][c] = (cx.cl == 0) ? sm.prow[buf][c] : po;
+        }
+      }
+      __syncthreads();
+      P = sm.tot_x[buf];
+      R1 = sm.prow_x[buf];
+    }
+    const float* Q = P + 64;
+    const float* R2 = R1 + 64;
 
     if (!second) {
       // ---- reflector j and what it does to column j+1 (redundant in every thread: bit-identical inputs)
@@ -348,27 +401,28 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
   }
 }
 
-template <int I0, int W>
+template <int I0, int W, bool X2>
 struct Wb2Groups {
   static __device__ __forceinline__ void run(f32x2 (&b)[8][8], Wb2Shared<W>& sm, const Wb2Ctx& cx, unsigned& ex) {
-    wb2_steps<I0, W>(b, sm, cx, ex);
-    Wb2Groups<I0 + 1, W>::run(b, sm, cx, ex);
+    wb2_steps<I0, W, X2>(b, sm, cx, ex);
+    Wb2Groups<I0 + 1, W, X2>::run(b, sm, cx, ex);
   }
 };
-template <int W>
-struct Wb2Groups<8, W> {
+template <int W, bool X2>
+struct Wb2Groups<8, W, X2> {
   static __device__ __forceinline__ void run(f32x2 (&)[8][8], Wb2Shared<W>&, const Wb2Ctx&, unsigned&) {}
 };
 
 extern __shared__ __align__(16) unsigned char wb2_smem[];
 
-template <int W>
+template <int W, bool X2>
 __global__ void __launch_bounds__(32 * W, 1) panel_wb2_kernel(PanelHHParams p) {
   Wb2Shared<W>& sm = *reinterpret_cast<Wb2Shared<W>*>(wb2_smem);
   Wb2Ctx cx;
   cx.lane = threadIdx.x & 31; cx.w = threadIdx.x >> 5; cx.q = cx.lane & 7; cx.h = cx.lane >> 3;
   cx.rank = wb_ctarank(); cx.CS = wb_nctarank();
-  cx.nb = p.b; cx.err = p.err; cx.tau_out = p.tau; cx.mode = p.pmax;
+  cx.cl = blockIdx.x / cx.CS; cx.ncl = gridDim.x / cx.CS;
+  cx.nb = p.b; cx.err = p.err; cx.tau_out = p.tau; cx.mode = p.pmax; cx.slots = p.slots; cx.epoch = p.epoch;
   const int q = cx.q, h = cx.h;
   const long long gw = (long long)blockIdx.x * W + cx.w;        // warp block index: rows 64 gw .. 64 gw + 63
   cx.top = (gw == 0);
@@ -404,7 +458,7 @@ __global__ void __launch_bounds__(32 * W, 1) panel_wb2_kernel(PanelHHParams p) {
   if (blockIdx.x == 0 && threadIdx.x < 64) sm.staus[threadIdx.x] = 0.f;
 
   unsigned ex = 0;
-  Wb2Groups<0, W>::run(b, sm, cx, ex);
+  Wb2Groups<0, W, X2>::run(b, sm, cx, ex);
 
   // ---- results: LAPACK storage into the panel, explicit V (unit diagonal, zeros above) into vbuf
 #pragma unroll
@@ -450,16 +504,16 @@ __global__ void __launch_bounds__(32 * W, 1) panel_wb2_kernel(PanelHHParams p) {
   if (cx.CS > 1) wb_cluster_sync();   // no CTA leaves while pushes addressed to it (or by it) are in flight
 }
 
-template <int W>
-cudaError_t launch_wb2_t(const PanelHHParams& p, int cs, cudaStream_t s) {
+template <int W, bool X2>
+cudaError_t launch_wb2_t(const PanelHHParams& p, int cs, int ncl, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(panel_wb2_kernel<W>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    cudaFuncSetAttribute(panel_wb2_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Wb2Shared<W>));
+    cudaFuncSetAttribute(panel_wb2_kernel<W, X2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(panel_wb2_kernel<W, X2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Wb2Shared<W>));
     attr_done = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cs, 1, 1);
+  cfg.gridDim = dim3(cs * ncl, 1, 1);
   cfg.blockDim = dim3(32 * W, 1, 1);
   cfg.dynamicSmemBytes = sizeof(Wb2Shared<W>);
   cfg.stream = s;
@@ -467,7 +521,7 @@ cudaError_t launch_wb2_t(const PanelHHParams& p, int cs, cudaStream_t s) {
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, panel_wb2_kernel<W>, p);
+  return cudaLaunchKernelEx(&cfg, panel_wb2_kernel<W, X2>, p);
 }
 
 }  // namespace
@@ -476,15 +530,18 @@ cudaError_t launch_wb2_t(const PanelHHParams& p, int cs, cudaStream_t s) {
 // 2 = every pair falls back to two single steps.  Returns false when the shape is not covered (b != 64, more than one
 // cluster) or the launch failed; the caller then takes the one-column-per-exchange kernels.
 bool launch_panel_wb2(const PanelHHParams& p, int wpc, int cs, int ncl, int mode, cudaStream_t s) {
-  if (p.b != 64 || ncl != 1 || cs > 16) return false;
+  if (p.b != 64 || ncl < 1 || ncl > 2 || cs > 16) return false;
+  if (ncl == 2 && (wpc != 8 || cs != 16)) return false;
+  if (ncl == 2 && panel_hh_slot_bytes() < (size_t)2 * 3 * 128 * sizeof(uint2)) return false;
   PanelHHParams pp = p;
   pp.pmax = mode;
   ++g_launches;
   cudaError_t e;
-  if (wpc == 1) e = launch_wb2_t<1>(pp, cs, s);
-  else if (wpc == 2) e = launch_wb2_t<2>(pp, cs, s);
-  else if (wpc == 4) e = launch_wb2_t<4>(pp, cs, s);
-  else e = launch_wb2_t<8>(pp, cs, s);
+  if (ncl == 2) e = launch_wb2_t<8, true>(pp, cs, ncl, s);       // panel_wb_plan: two clusters are always 16 CTAs x 8 warps
+  else if (wpc == 1) e = launch_wb2_t<1, false>(pp, cs, ncl, s);
+  else if (wpc == 2) e = launch_wb2_t<2, false>(pp, cs, ncl, s);
+  else if (wpc == 4) e = launch_wb2_t<4, false>(pp, cs, ncl, s);
+  else e = launch_wb2_t<8, false>(pp, cs, ncl, s);
   if (e != cudaSuccess) { cudaGetLastError(); --g_launches; return false; }
   return true;
 }

@@ -24,10 +24,10 @@ def scalars(alpha, sig):
     return bc, (F(1) / u if ok else F(0)), ((F(2) if len1 else F(-u / bc)) if ok else F(0)), ok
 
 
-def run(A, W, CS, mode=1):
+def run(A, W, CS, mode=1, NCL=1):
     mp, nb = A.shape
     assert nb == 64
-    nwt = W * CS
+    nwt = W * CS * NCL
     assert mp <= 64 * nwt
     Ap = np.zeros((64 * nwt, 64), F); Ap[:mp] = A
     lanes = np.arange(32); qv = lanes & 7; hv = lanes >> 3
@@ -87,36 +87,41 @@ def run(A, W, CS, mode=1):
                     q, h = qv[lane], hv[lane]
                     if h < 2:
                         for i in range(8): part[gw, 64 * h + q + 8 * i] = keep2[lane, i]
-            # CTA sums and the cluster exchange, message by message
-            tot_in = np.full((CS, 128), np.nan, F); prow = np.full((CS, 128), np.nan, F)
-            sv = np.zeros((CS, 32, 4), F)
-            for r in range(CS):
-                for lane in range(32):
-                    for ww in range(W): sv[r, lane] += part[r * W + ww, 4 * lane: 4 * lane + 4]
-            if CS == 1:
-                tot_in[0] = sv[0].reshape(128); prow[0] = prl
-            else:
-                wpo = 32 // CS
-                rs_in = np.full((CS, 32, 4), np.nan, F); prs_in = np.full((CS, 32, 4), np.nan, F)
+            # CTA sums and the cluster exchange, message by message (per cluster), then the two-cluster sum
+            cl_tot = []; cl_prow = []
+            for cl in range(NCL):
+                tot_in = np.full((CS, 128), np.nan, F); prow = np.full((CS, 128), np.nan, F)
+                sv = np.zeros((CS, 32, 4), F)
                 for r in range(CS):
                     for lane in range(32):
-                        owner = (lane * CS) >> 5; wl = lane - owner * wpo
-                        rs_in[owner, r * wpo + wl] = sv[r, lane]
-                        if r == 0: prs_in[owner, wl] = prl[4 * lane: 4 * lane + 4]
-                for r in range(CS):      # owner r
-                    t = rs_in[r].copy()
-                    assert not np.isnan(t).any()
-                    o = 16
-                    while o >= wpo:
-                        t = t + t[lanes ^ o]; o >>= 1
-                    for lane in range(32):
-                        slot, peer = lane % wpo, lane // wpo
-                        col4 = 4 * (r * wpo + slot)
-                        tot_in[peer, col4: col4 + 4] = t[lane]
-                        prow[peer, col4: col4 + 4] = prs_in[r, slot]
-            assert not np.isnan(tot_in).any() and not np.isnan(prow).any()
-            for r in range(1, CS):
-                assert (tot_in[r] == tot_in[0]).all() and (prow[r] == prow[0]).all()
+                        for ww in range(W): sv[r, lane] += part[(cl * CS + r) * W + ww, 4 * lane: 4 * lane + 4]
+                if CS == 1:
+                    tot_in[0] = sv[0].reshape(128); prow[0] = prl
+                else:
+                    wpo = 32 // CS
+                    rs_in = np.full((CS, 32, 4), np.nan, F); prs_in = np.full((CS, 32, 4), np.nan, F)
+                    for r in range(CS):
+                        for lane in range(32):
+                            owner = (lane * CS) >> 5; wl = lane - owner * wpo
+                            rs_in[owner, r * wpo + wl] = sv[r, lane]
+                            if r == 0 and cl == 0: prs_in[owner, wl] = prl[4 * lane: 4 * lane + 4]
+                    for r in range(CS):      # owner r
+                        t = rs_in[r].copy()
+                        assert not np.isnan(t).any()
+                        o = 16
+                        while o >= wpo:
+                            t = t + t[lanes ^ o]; o >>= 1
+                        for lane in range(32):
+                            slot, peer = lane % wpo, lane // wpo
+                            col4 = 4 * (r * wpo + slot)
+                            tot_in[peer, col4: col4 + 4] = t[lane]
+                            if cl == 0: prow[peer, col4: col4 + 4] = prs_in[r, slot]
+                assert not np.isnan(tot_in).any() and (cl > 0 or not np.isnan(prow).any())
+                for r in range(1, CS):
+                    assert (tot_in[r] == tot_in[0]).all() and (cl > 0 or (prow[r] == prow[0]).all())
+                cl_tot.append(tot_in[0]); cl_prow.append(prow[0])
+            tot_in = (cl_tot[0] + cl_tot[1])[None] if NCL == 2 else cl_tot[0][None]
+            prow = cl_prow[0][None]
             P, Q, R1, R2 = tot_in[0, :64], tot_in[0, 64:], prow[0, :64], prow[0, 64:]
 
             def colmask(top, k, h):   # registers that hold rows >= j+2
@@ -212,9 +217,9 @@ def run(A, W, CS, mode=1):
     return out[:mp], tau, T, nex, fallbacks
 
 
-def check(name, A, W, CS, mode=1):
+def check(name, A, W, CS, mode=1, NCL=1):
     S, ts = sweep_single(A)
-    out, tau, T, nex, fb = run(A, W, CS, mode)
+    out, tau, T, nex, fb = run(A, W, CS, mode, NCL)
     n = 64; eps = 2.0 ** -23
     Qm = q_from(out.astype(np.float64), tau)
     R = np.triu(out[:n].astype(np.float64))
@@ -227,7 +232,7 @@ def check(name, A, W, CS, mode=1):
     Qfull_thin = (np.eye(A.shape[0]) - V @ T.astype(np.float64) @ V.T)[:, :n]
     dT = np.linalg.norm(Qfull_thin - Qm) / (n * eps)
     ok = be < 10 and orth < 10 and dT < 50
-    print(f"{name:44s} W={W} CS={CS:2d} mode={mode} exchanges {nex:3d} fallbacks {fb:2d}  backward {be:6.3f} orth {orth:6.3f} "
+    print(f"{name:44s} W={W} CS={CS:2d} NCL={NCL} mode={mode} exchanges {nex:3d} fallbacks {fb:2d}  backward {be:6.3f} orth {orth:6.3f} "
           f"|dR| {dR:.1e} |dV| {dV:.1e} T-vs-Q {dT:6.2f}  {'ok' if ok else 'FAIL'}")
     return ok
 
@@ -242,5 +247,6 @@ if __name__ == "__main__":
     B = rng.standard_normal((512, 64)).astype(F)
     B[:, 11] = B[:, 10] * F(1.0 + 1e-6); B[:, 21] = B[:, 20]; B[:, 40] = 0
     good &= check("dependent neighbours + zero column", B, 4, 2)
+    good &= check("uniform 2000x64, two clusters of 16 CTAs", rng.random((2000, 64)).astype(F), 1, 16, NCL=2)
     good &= check("graded N(0,1) 1e-6..1e6", (rng.standard_normal((256, 64)) * np.logspace(-6, 6, 64)).astype(F), 2, 2)
     sys.exit(0 if good else 1)

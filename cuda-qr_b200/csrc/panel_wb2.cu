@@ -18,7 +18,7 @@
 //   update:         a_c -= (e_c - f_c a1) x + f_c y   below row j+1 (two FFMA2 per register pair, the work of two single
 //                   steps);  a(j,c) = r1_c - t_c,  a(j+1,c) = a'(j+1,c) - tau_2 d2_c
 //   V^T V for T:    the same d1_c, d2_c of the finished columns (with e_c = 0), and G(j,j+1) = r2_j/u_1 + (p_{j+1} - a1 p_j)/(u_1 u_2).
-// Cancellation guard (mandatory): when sigma_2 < 1e-3 q_{j+1} the expansion is noise (neighbouring
+// Cancellation guard (mandatory): when sigma_2 < 0.1 q_{j+1} the expansion loses too much (neighbouring
 // columns nearly dependent); the pair then finishes step j from the data it has and runs step j+1 as a single step with
 // one more exchange of the true y'.  The decision is taken on bit-identical totals in every thread of the cluster, so it is
 // uniform.  b must be 64.  One cluster up to 8192 rows (default); two clusters up to 16384 rows exchange through
@@ -112,6 +112,12 @@ struct Wb2Ctx {
   int* err;
   float* tau_out;
 };
+
+// Cancellation guard: sigma_2 and every y'^T a'_c come from an expansion whose relative error grows like
+// q_{j+1} / sigma_2.  Measured on the fp32 spec with EVERY pair at the same angle (tools/two_column_step.py `guard_study`):
+// orthogonality 2.4 n eps at sigma_2 / q = 0.1, 8 at 0.03, 24 at 0.01, 177 at 0.0015 (acceptance: 10) -- so pairs below 0.1
+// take the fallback; uniform[0,1) data sits at 0.25 in its first pair (the common mean) and near 1 afterwards.
+constexpr float kPairGuard = 0.1f;
 
 struct Refl { float bc, inv_u, tau; bool ok; };
 // beta = -sign(alpha) norm, u = alpha - beta, tau = -u / beta (qr.c:144-152); MUFU rsqrt / rcp + one Newton step as in
@@ -295,7 +301,7 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
       const float a1 = tn * iu1;
       const float alpha2 = fmaf(-a1, xj1, yj1);
       const float sig2 = fmaf(a1 * a1, P[j], fmaf(-2.f * a1, P[j + 1], Q[j + 1]));
-      const bool fb = (cx.mode == 2) || (sig2 < 1e-3f * Q[j + 1]);
+      const bool fb = (cx.mode == 2) || (sig2 < kPairGuard * Q[j + 1]);
       if (cx.top && lane == 0) { cx.tau_out[j] = t1; sm.staus[j] = t1; }
       if (!fb) {
         const Refl s2 = wb2_scalars(alpha2, fmaxf(sig2, 0.f));

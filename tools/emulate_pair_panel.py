@@ -133,7 +133,7 @@ def run(A, W, CS, mode=1, NCL=1):
                 d1n = F(F(xj1 * yj1 + P[j + 1]) * iu1 + R1[j + 1])
                 tn = F(t1 * d1n); a1 = F(tn * iu1); alpha2 = F(-a1 * xj1 + yj1)
                 sig2 = F(F(a1 * a1) * P[j] + F(F(-2 * a1) * P[j + 1] + Q[j + 1]))
-                fb = mode == 2 or sig2 < F(1e-3) * Q[j + 1]
+                fb = mode == 2 or sig2 < F(0.1) * Q[j + 1]
                 tau[j] = t1
                 if not fb:
                     bc2, iu2, t2, ok2 = scalars(alpha2, max(sig2, F(0)))

@@ -5,7 +5,9 @@ One "exchange" delivers, for every column c, the sums p_c = x^T a_c and q_c = y^
 Everything else -- both reflectors' scalars, every column's two inner products, the update coefficients and the two new
 columns of V^T V -- follows algebraically.  This script checks the algebra against the plain column-by-column Householder
 sweep in fp32 (same reflector convention as the kernels: beta = -sign(alpha) * norm, u = alpha - beta, tau = -u / beta)
-and shows why the cancellation guard on sigma_2 is mandatory.   python tools/two_column_step.py"""
+and shows why the cancellation guard on sigma_2 is mandatory.   python tools/two_column_step.py [guard_study]"""
+import sys
+
 import numpy as np
 
 F = np.float32
@@ -42,7 +44,7 @@ def sweep_single(A):
     return A, tau
 
 
-def sweep_pairs(A, guard=1e-3, use_guard=True):
+def sweep_pairs(A, guard=0.1, use_guard=True):
     """two columns per exchange; n even"""
     A = A.astype(F).copy()
     m, n = A.shape
@@ -133,7 +135,36 @@ def report(name, A, **kw):
     print(f"{name:34s} {out[0]}   {out[1]}   |R_pairs - R_single|/|R| {dR:.1e}  guard fallbacks {fb}")
 
 
+def guard_study(guard, trials=4):
+    """Worst case for a given guard: EVERY odd column nearly parallel to its left neighbour, sin^2(angle) = ratio, so that
+    sigma_2 / q_{j+1} ~ ratio in all 32 pairs.  Prints the acceptance numbers of the pair sweep and of the single sweep."""
+    rng = np.random.default_rng(1)
+    eps = 2.0 ** -23
+    print(f"guard = {guard}")
+    for ratio in (0.5, 0.1, 3e-2, 1e-2, 3e-3, 1.5e-3):
+        worst = [0.0, 0.0, 0.0, 0.0]
+        fbs = 0
+        for _ in range(trials):
+            A = rng.standard_normal((512, 64)).astype(F)
+            for j in range(0, 64, 2):
+                A[:, j + 1] = (np.sqrt(1 - ratio) * A[:, j] + np.sqrt(ratio) * A[:, j + 1]).astype(F)
+            Pp, tp, fb = sweep_pairs(A, guard=guard)
+            S, ts = sweep_single(A)
+            fbs += fb
+            for k, (V, tau) in enumerate(((Pp, tp), (S, ts))):
+                Q = q_from(V.astype(np.float64), tau)
+                R = np.triu(V[:64].astype(np.float64))
+                worst[2 * k] = max(worst[2 * k], np.linalg.norm(A - Q @ R) / (np.linalg.norm(A) * 64 * eps))
+                worst[2 * k + 1] = max(worst[2 * k + 1], np.linalg.norm(Q.T @ Q - np.eye(64)) / (64 * eps))
+        print(f"  sin^2 = {ratio:7.1e}: pairs backward {worst[0]:7.3f} orth {worst[1]:8.3f}   single backward {worst[2]:6.3f} "
+              f"orth {worst[3]:6.3f}   fallbacks {fbs}")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "guard_study":
+        for g in (1e-3, 0.05, 0.1):
+            guard_study(g)
+        sys.exit(0)
     rng = np.random.default_rng(3)
     A = rng.random((512, 64)).astype(F)
     report("uniform[0,1) 512x64", A)

@@ -25,64 +25,10 @@
 // global-memory flags exactly like panel_wb.cu (CQR_PANEL_PAIR_MAX_ROWS=16384, not yet measured: off by default).  Measured on B200 (tools/panel_bench.py, zero fill + panel):
 // 8192 rows 166 -> 132 us, 4096 rows 152 -> 121 us, 2048 rows 120 us; the lane-level numpy replay of this file is
 // tools/emulate_pair_panel.py.
-#include "common.cuh"
+#include "panel_wb_common.cuh"
 
 namespace cqr {
 namespace {
-
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 wpk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void wupk(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 wfma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f32x2 wmul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ float wsum2(f32x2 v) { float lo, hi; wupk(v, lo, hi); return lo + hi; }
-__device__ __forceinline__ float wrsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float wrcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return fmaf(r, fmaf(-x, r, 1.f), r); }
-
-__device__ __forceinline__ unsigned wb_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ unsigned wb_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void wb_cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void wb_st_async_v4(float* local_dst, unsigned long long* local_bar, unsigned rank, float4 v) {
-  unsigned la = (unsigned)__cvta_generic_to_shared(local_dst), lb = (unsigned)__cvta_generic_to_shared(local_bar), ra, rb;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(lb), "r"(rank));
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(ra),
-               "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)), "r"(rb)
-               : "memory");
-}
-__device__ __forceinline__ void wb_mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void wb_mbar_expect(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void wb_st_flag(uint2* p, float v, unsigned tag) {
-  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
-}
-__device__ __forceinline__ uint2 wb_ld_flag(const uint2* p) {
-  uint2 r;
-  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
-  return r;
-}
-// bounded wait: a protocol error must not hang the device; *err is set and the caller's results are void
-__device__ __forceinline__ void wb_mbar_wait(unsigned long long* bar, unsigned parity, int* err) {
-  unsigned ok, a = (unsigned)__cvta_generic_to_shared(bar);
-  long long t0 = 0;
-  for (;;) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(a), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (t0 == 0) t0 = clock64();
-    else if (clock64() - t0 > 2000000000LL) { atomicExch(err, 1); break; }
-  }
-}
 
 template <int W>
 struct Wb2Shared {

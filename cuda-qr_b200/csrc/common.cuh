@@ -155,6 +155,7 @@ bool launch_panel_wb(const PanelHHParams& p, int wpc, int cs, int ncl, cudaStrea
 bool launch_panel_wb2(const PanelHHParams& p, int wpc, int cs, int ncl, int mode, cudaStream_t s);
 #ifdef CQR_HH_TRACE
 void panel_hh_read_trace(long long* out);
+void panel_wb2_read_trace(long long* steps, long long* marks);   // [2][8][64][8] and [2][8][5] clock64 values
 #endif
 
 // ---- fp32 SIMT GEMMs and element-wise utilities: gemm_simt.cu -------------------------------

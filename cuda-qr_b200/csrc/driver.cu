@@ -456,6 +456,7 @@ extern "C" {
 
 #ifdef CQR_HH_TRACE
 __attribute__((visibility("default"))) void cqr_debug_hh_trace(long long* out) { cqr::panel_hh_read_trace(out); }
+__attribute__((visibility("default"))) void cqr_debug_wb2_trace(long long* steps, long long* marks) { cqr::panel_wb2_read_trace(steps, marks); }
 #endif
 
 const char* cqr_version(void) { return "cudaqr_b200 0.1;sm_100a;tsqr+hr+wy;tcgen05-3xtf32"; }

@@ -65,6 +65,27 @@ struct Wb2Ctx {
 // take the fallback; uniform[0,1) data sits at 0.25 in its first pair (the common mean) and near 1 afterwards.
 constexpr float kPairGuard = 0.1f;
 
+// Optional phase trace (debug builds only: make TRACE=1 -> -DCQR_HH_TRACE; tools/wb2_trace.py): clock64 of lane 0 of every
+// warp of CTA 0 and of the last CTA at eight points of each exchange step -> g_wb2_trace[cta01][warp][exchange][8], and at
+// five points of the kernel -> g_wb2_marks[cta01][warp][5] (entry, panel loaded, steps done, results stored, T done).
+#ifdef CQR_HH_TRACE
+__device__ long long g_wb2_trace[2][8][64][8];
+__device__ long long g_wb2_marks[2][8][5];
+#define WB2_TRACE(k)                                                                                          \
+  do {                                                                                                        \
+    if (cx.lane == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))                                    \
+      g_wb2_trace[blockIdx.x == 0 ? 0 : 1][cx.w][(ex - 1) & 63][k] = clock64();                              \
+  } while (0)
+#define WB2_MARK(k)                                                                                           \
+  do {                                                                                                        \
+    if (cx.lane == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))                                    \
+      g_wb2_marks[blockIdx.x == 0 ? 0 : 1][cx.w][k] = clock64();                                             \
+  } while (0)
+#else
+#define WB2_TRACE(k) do { } while (0)
+#define WB2_MARK(k) do { } while (0)
+#endif
+
 struct Refl { float bc, inv_u, tau; bool ok; };
 // beta = -sign(alpha) norm, u = alpha - beta, tau = -u / beta (qr.c:144-152); MUFU rsqrt / rcp + one Newton step as in
 // panel_wb.cu; a zero column gives tau = 0 (H = I)
@@ -97,6 +118,7 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
     const int buf = ex & 1;
     const unsigned par = (ex >> 1) & 1;
     ++ex;
+    WB2_TRACE(0);
     const int hj = jj >> 1;                  // rows j, j+1 are the (lo, hi) of pair I0 in the lanes h == hj of the top warp
     const int qx = second ? jj + 1 : jj, qy = jj + 1;
     float* xb = sm.xs[w][buf];
@@ -127,6 +149,7 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
       x[k] = *reinterpret_cast<const f32x2*>(xb + 8 * k + 2 * h);
       y[k] = *reinterpret_cast<const f32x2*>(yb + 8 * k + 2 * h);
     }
+    WB2_TRACE(1);
     // ---- warp-level column sums for all 64 columns against x and y.  First shuffle stage swaps halves (odd h keeps the
     // y sums, even h the x sums), so the 16 sums cost 16 shuffles; lanes h == 0 end with x^T a_c, lanes h == 1 with y^T a_c
     {
@@ -155,7 +178,9 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
         for (int i = 0; i < 8; ++i) sm.part[buf][w][64 * h + q + 8 * i] = keep[i];
       }
     }
+    WB2_TRACE(2);
     __syncthreads();
+    WB2_TRACE(3);
     // ---- CTA sums, then the cluster all-reduce (warp 0): lane g handles the float4 group g of the 128 sums
     if (w == 0) {
       float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -179,6 +204,7 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
         wb_st_async_v4(&sm.rs_in[buf][rank * wpo + wl][0], &sm.mbar1[buf], owner, sv);
         if (rank == 0 && (!X2 || cx.cl == 0)) wb_st_async_v4(&sm.prs_in[buf][wl][0], &sm.mbar1[buf], owner, pv);
         wb_mbar_wait(&sm.mbar1[buf], par, cx.err);
+        WB2_TRACE(4);
         float4 t = *reinterpret_cast<const float4*>(&sm.rs_in[buf][lane][0]);    // entry = sender * wpo + my group
         for (unsigned o = 16; o >= wpo; o >>= 1) {
           t.x += __shfl_xor_sync(kFull, t.x, o); t.y += __shfl_xor_sync(kFull, t.y, o);
@@ -236,6 +262,7 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
     }
     const float* Q = P + 64;
     const float* R2 = R1 + 64;
+    WB2_TRACE(5);
 
     if (!second) {
       // ---- reflector j and what it does to column j+1 (redundant in every thread: bit-identical inputs)
@@ -249,6 +276,7 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
       const float sig2 = fmaf(a1 * a1, P[j], fmaf(-2.f * a1, P[j + 1], Q[j + 1]));
       const bool fb = (cx.mode == 2) || (sig2 < kPairGuard * Q[j + 1]);
       if (cx.top && lane == 0) { cx.tau_out[j] = t1; sm.staus[j] = t1; }
+      WB2_TRACE(6);
       if (!fb) {
         const Refl s2 = wb2_scalars(alpha2, fmaxf(sig2, 0.f));
         const float iu2 = s2.inv_u, t2 = s2.tau;
@@ -312,6 +340,7 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
       }
       if (fb) second = true;
       else jj += 2;
+      WB2_TRACE(7);
     } else {
       // ---- lone step j+1: x is the true column j+1 below row j+1, R2 the current row j+1
       const Refl s2 = wb2_scalars(R2[j + 1], P[j + 1]);
@@ -349,6 +378,7 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
       }
       second = false;
       jj += 2;
+      WB2_TRACE(7);
     }
   }
 }
@@ -382,6 +412,7 @@ __global__ void __launch_bounds__(32 * W, 1) panel_wb2_kernel(PanelHHParams p) {
   const int b_cols = p.b;
   const bool vec = (p.lda % 2 == 0) && (p.ldv % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.a) & 7) == 0) &&
                    ((reinterpret_cast<uintptr_t>(p.vbuf) & 7) == 0);
+  WB2_MARK(0);
   f32x2 b[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -410,7 +441,9 @@ __global__ void __launch_bounds__(32 * W, 1) panel_wb2_kernel(PanelHHParams p) {
   if (blockIdx.x == 0 && threadIdx.x < 64) sm.staus[threadIdx.x] = 0.f;
 
   unsigned ex = 0;
+  WB2_MARK(1);
   Wb2Groups<0, W, X2>::run(b, sm, cx, ex);
+  WB2_MARK(2);
 
   // ---- results: LAPACK storage into the panel, explicit V (unit diagonal, zeros above) into vbuf
 #pragma unroll
@@ -434,6 +467,7 @@ __global__ void __launch_bounds__(32 * W, 1) panel_wb2_kernel(PanelHHParams p) {
       }
     }
   }
+  WB2_MARK(3);
   // ---- compact-WY T (CTA 0), as in panel_wb.cu: column c of T is an independent back substitution on
   // T^-1 = diag(1 / tau) + striu(V^T V); one thread per column
   if (blockIdx.x == 0 && p.t != nullptr) {
@@ -453,6 +487,7 @@ __global__ void __launch_bounds__(32 * W, 1) panel_wb2_kernel(PanelHHParams p) {
       p.t[i + (long long)cc * p.ldt] = (i <= cc) ? sm.ts[i][cc] : 0.f;
     }
   }
+  WB2_MARK(4);
   if (cx.CS > 1) wb_cluster_sync();   // no CTA leaves while pushes addressed to it (or by it) are in flight
 }
 
@@ -477,6 +512,13 @@ cudaError_t launch_wb2_t(const PanelHHParams& p, int cs, int ncl, cudaStream_t s
 }
 
 }  // namespace
+
+#ifdef CQR_HH_TRACE
+void panel_wb2_read_trace(long long* steps, long long* marks) {
+  cudaMemcpyFromSymbol(steps, g_wb2_trace, sizeof(g_wb2_trace));
+  cudaMemcpyFromSymbol(marks, g_wb2_marks, sizeof(g_wb2_marks));
+}
+#endif
 
 // Same plan as panel_wb.cu (wpc warps per CTA, one cluster of cs CTAs); mode 1 = pairs with the cancellation guard,
 // 2 = every pair falls back to two single steps.  Returns false when the shape is not covered (b != 64, more than one

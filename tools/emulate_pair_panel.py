@@ -3,7 +3,8 @@ register layout, masks, exchange index maps and algebra on the CPU: every warp i
 array exactly as in the kernel (lane = 8 h + q owns columns q + 8 i and rows 8 k + 2 h + {0,1} of its 64-row block),
 the cluster all-reduce is replayed message by message (owner / slot / peer maps of the kernel), and the result (LAPACK
 storage, tau, T) is compared with the plain column-by-column sweep of tools/two_column_step.py.
-    python tools/emulate_pair_panel.py            # a few shapes, pairs / forced fallback / dependent columns"""
+    python tools/emulate_pair_panel.py            # a few shapes, pairs / forced fallback / dependent columns
+    python tools/emulate_pair_panel.py fuzz [seed] # random plans, heights, data kinds and modes"""
 import os, sys
 import numpy as np
 
@@ -237,7 +238,30 @@ def check(name, A, W, CS, mode=1, NCL=1):
     return ok
 
 
+def fuzz(seed, cases=24):
+    """random plans (warps per CTA, cluster size, one or two clusters, ragged heights), data kinds (uniform, normal, zero
+    columns, nearly dependent neighbours, columns graded over 16 decades, zero rows) and modes"""
+    rng = np.random.default_rng(seed)
+    bad = 0
+    for t in range(cases):
+        W = int(rng.choice([1, 2, 4])); CS = int(rng.choice([1, 2, 4, 8])); NCL = 2 if (CS > 1 and rng.random() < 0.25) else 1
+        rows_max = 64 * W * CS * NCL
+        mp = int(rng.integers(max(64, rows_max - 63 * W), rows_max + 1))
+        kind = int(rng.integers(0, 6))
+        A = rng.standard_normal((mp, 64)) if kind % 2 else rng.random((mp, 64))
+        if kind == 2: A[:, rng.integers(0, 64, 3)] = 0
+        if kind == 3:
+            for _ in range(3):
+                j = int(rng.integers(0, 63)); A[:, j + 1] = A[:, j] * (1 + rng.standard_normal() * 1e-5)
+        if kind == 4: A *= np.logspace(-8, 8, 64)[rng.permutation(64)]
+        if kind == 5: A[rng.integers(0, mp, mp // 2)] = 0
+        bad += not check(f"fuzz {t} kind {kind} {mp}x64", A.astype(F), W, CS, mode=int(rng.choice([1, 1, 1, 2])), NCL=NCL)
+    return bad == 0
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "fuzz":
+        sys.exit(0 if fuzz(int(sys.argv[2]) if len(sys.argv) > 2 else 0) else 1)
     rng = np.random.default_rng(5)
     good = True
     good &= check("uniform 128x64 (one CTA)", rng.random((128, 64)).astype(F), 2, 1)

@@ -293,28 +293,6 @@ def test_geqrf_panel_hh_edge_cases(pkg, torch, ctx):
     check_factorisation(S, host(Q), host(R), np.linalg.qr(S.astype(np.float64), mode="r"))
 
 
-def test_geqrf_pair_step_cancellation_fallback(pkg, torch, ctx):
-    """Panels of 2048 .. 8192 rows take two pivot columns per cluster exchange (panel_wb2.cu).  Nearly dependent
-    NEIGHBOURING columns make the algebraic update of the pair cancel; the kernel must notice (sigma_2 guard) and fall
-    back to two single steps.  Same acceptance numbers as everywhere else; tools/two_column_step.py shows them at
-    1e4 n eps without the guard."""
-    rng = np.random.default_rng(21)
-    A = np.asfortranarray(rng.standard_normal((3000, 128)).astype(np.float32))
-    A[:, 11] = A[:, 10] * np.float32(1.0 + 1e-6)
-    A[:, 21] = A[:, 20]
-    A[:, 64] = A[:, 65] + np.float32(1e-4) * A[:, 66]
-    dA = dev(pkg, torch, A)
-    tau = torch.zeros(128, device="cuda")
-    ctx.geqrf(dA, tau)
-    Q = pkg.colmajor(3000, 128)
-    ctx.form_q(dA, tau, Q)
-    R = pkg.colmajor(128, 128)
-    ctx.extract_r(dA, R)
-    ctx.synchronize()
-    assert np.isfinite(host(dA)).all() and np.isfinite(tau.cpu().numpy()).all()
-    check_factorisation(A, host(Q), host(R))
-
-
 def test_apply_q_and_qt_roundtrip(pkg, torch, ctx):
     m, n, nc = 1500, 300, 77
     rng = np.random.default_rng(1)
@@ -752,3 +730,25 @@ def test_profile_timeline_brackets_are_ordered(pkg, torch, ctx):
     assert len(tl) > 0 and all(t1 >= t0 >= 0.0 for t0, t1, _ in tl)
     assert {c for _, _, c in tl} <= set(pkg.Context.PROF_CLASSES)
     assert abs(sum(t1 - t0 for t0, t1, _ in tl) - sum(v["ms"] for v in prof.values())) < 1e-3 * max(1.0, len(tl))
+
+
+def test_geqrf_pair_step_cancellation_fallback(pkg, torch, ctx):
+    """Panels of 2048 .. 8192 rows take two pivot columns per cluster exchange (panel_wb2.cu).  Nearly dependent
+    NEIGHBOURING columns make the algebraic update of the pair cancel; the kernel must notice (sigma_2 guard) and fall
+    back to two single steps.  Same acceptance numbers as everywhere else; tools/two_column_step.py shows them at
+    1e4 n eps without the guard."""
+    rng = np.random.default_rng(21)
+    A = np.asfortranarray(rng.standard_normal((3000, 128)).astype(np.float32))
+    A[:, 11] = A[:, 10] * np.float32(1.0 + 1e-6)
+    A[:, 21] = A[:, 20]
+    A[:, 64] = A[:, 65] + np.float32(1e-4) * A[:, 66]
+    dA = dev(pkg, torch, A)
+    tau = torch.zeros(128, device="cuda")
+    ctx.geqrf(dA, tau)
+    Q = pkg.colmajor(3000, 128)
+    ctx.form_q(dA, tau, Q)
+    R = pkg.colmajor(128, 128)
+    ctx.extract_r(dA, R)
+    ctx.synchronize()
+    assert np.isfinite(host(dA)).all() and np.isfinite(tau.cpu().numpy()).all()
+    check_factorisation(A, host(Q), host(R))

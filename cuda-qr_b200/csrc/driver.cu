@@ -1233,8 +1233,10 @@ void mmqr(float* mat, float* tau, int m, int n) {
   const int rc = cqr_geqrf(c, dA, (int)lda, m, n, dtau);
   c->host_out = nullptr;
   LEGACY_CHECK(rc);
+  // unused slots zero, qr.c:62 -- done while the device is still factoring (cqr_geqrf only enqueues): the reference-sized
+  // tau grid is rowPanels * colPanels * PC floats (18 MB at 16384^2), of which the first n are overwritten below
+  memset(tau, 0, tau_count * sizeof(float));
   LEGACY_CHECK(cudaStreamSynchronize(c->copy));
-  memset(tau, 0, tau_count * sizeof(float));   // unused slots zero, qr.c:62
   LEGACY_CHECK(cudaMemcpy(tau, dtau, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
 }
 

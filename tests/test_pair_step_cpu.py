@@ -50,3 +50,24 @@ def test_kernel_replay_forced_fallback_and_two_clusters():
     rng = np.random.default_rng(6)
     assert emu.check("replay 256x64 fallback", rng.random((256, 64)).astype(F), 1, 4, mode=2)
     assert emu.check("replay 250x64 two clusters", rng.random((250, 64)).astype(F), 1, 2, NCL=2)
+
+
+def _every_pair_at(ratio, seed):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((256, 64)).astype(F)
+    for j in range(0, 64, 2):            # odd column nearly parallel to its left neighbour: sin^2(angle) = ratio
+        A[:, j + 1] = (np.sqrt(1 - ratio) * A[:, j] + np.sqrt(ratio) * A[:, j + 1]).astype(F)
+    return A
+
+
+def test_guard_threshold_keeps_the_acceptance_bounds_in_the_worst_case():
+    """Why the kernel's guard is 0.1 and not the first estimate 1e-3 (profiles/r01_pair_guard_study.txt): with EVERY pair
+    just above the guard, the pair sweep must still meet orthogonality <= 10 n eps."""
+    for ratio in (0.5, 0.12, 0.1, 0.05, 0.01):
+        A = _every_pair_at(ratio, 2)
+        P, t, _ = spec.sweep_pairs(A)                       # default guard = the kernel's kPairGuard
+        be, orth = _metrics(A, P, t)
+        assert be <= 10 and orth <= 10, (ratio, be, orth)
+    A = _every_pair_at(1.5e-3, 2)
+    P, t, fb = spec.sweep_pairs(A, guard=1e-3)
+    assert fb == 0 and _metrics(A, P, t)[1] > 10            # the old guard lets these pairs through and fails

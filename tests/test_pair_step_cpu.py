@@ -71,3 +71,25 @@ def test_guard_threshold_keeps_the_acceptance_bounds_in_the_worst_case():
     A = _every_pair_at(1.5e-3, 2)
     P, t, fb = spec.sweep_pairs(A, guard=1e-3)
     assert fb == 0 and _metrics(A, P, t)[1] > 10            # the old guard lets these pairs through and fails
+
+
+def test_k_column_step_spec_meets_the_bounds_for_k_up_to_8():
+    """tools/k_column_step.py: k pivot columns per exchange through k x k Gram algebra (study for a 16-exchange panel
+    kernel); random, graded and nearly dependent data, and the in-group chain adversary at the guard."""
+    import k_column_step as ks
+    rng = np.random.default_rng(8)
+    cases = [rng.random((300, 64)), rng.standard_normal((300, 64)) * np.logspace(-6, 6, 64)]
+    B = rng.standard_normal((300, 64)); B[:, 11] = B[:, 10] * (1.0 + 1e-6); B[:, 21] = B[:, 20]; B[:, 40] = 0
+    cases.append(B)
+    C = rng.standard_normal((300, 64))
+    for j in range(0, 64, 4):                                # chain adversary just above the guard of 0.25
+        for r in range(1, 4):
+            C[:, j + r] = np.sqrt(1 - 0.26) * C[:, j + r - 1] + np.sqrt(0.26) * C[:, j + r]
+    cases.append(C)
+    for A in cases:
+        A = A.astype(F)
+        for k in (2, 4, 8):
+            V, tau, nex = ks.sweep_k(A, k, guard=0.25)
+            be, orth = ks.metrics(A, V, tau)
+            assert be <= 10 and orth <= 10, (k, be, orth)
+            assert nex <= 64

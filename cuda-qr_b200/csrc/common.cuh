@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 
 #ifndef CQR_SLOT
 #define CQR_SLOT 64            // panel width / height of one R slot in the TSQR tree
@@ -10,6 +11,20 @@
 namespace cqr {
 
 constexpr unsigned kFull = 0xffffffffu;
+
+// One-time per-DEVICE setup guard (cudaFuncSetAttribute and the device queries apply to the current device, not the
+// process): `static PerDeviceOnce once; if (once.first()) { ... }`.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+  void retry() { int d = 0; if (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) done[d] = false; }
+};
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -197,6 +212,6 @@ bool launch_gemm_nn_umma(int M, int N, int K, float alpha, const float* a, long 
                          float beta, float* d, long long ldd, int max_ctas, cudaStream_t s);
 
 // global launch counter (gpu_launches evidence)
-extern long long g_launches;
+extern std::atomic<long long> g_launches;   // host threads may drive contexts on several devices
 
 }  // namespace cqr

@@ -106,6 +106,16 @@ namespace {
     if (e__ != cudaSuccess) return (int)e__; \
   } while (0)
 
+// Entry points run on the context's device and leave the caller's current device as they found it.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 inline cudaStream_t cur_stream(cqr_context* c) { return c->cur ? c->cur : c->stream; }
 inline int cur_ctas(cqr_context* c) { return (c->cur && c->cur_ctas > 0) ? c->cur_ctas : c->sm_count; }
 
@@ -473,21 +483,12 @@ const char* cqr_error_string(int status) {
   }
 }
 
-int cqr_create(cqr_context** out, int device) {
-  if (!out) return CQR_EINVAL;
-  int ndev = 0;
-  CQR_CUDA(cudaGetDeviceCount(&ndev));
-  if (device < 0 || device >= ndev) return CQR_EINVAL;
-  CQR_CUDA(cudaSetDevice(device));
-  cqr_context* c = new cqr_context();
+static int create_impl(cqr_context* c, int device) {
   c->device = device;
-  cudaDeviceProp prop;
-  CQR_CUDA(cudaGetDeviceProperties(&prop, device));
-  c->sm_count = prop.multiProcessorCount;
-  if (prop.major != 10) {   // sm_100a-only binary: fail loudly instead of faulting at first launch
-    delete c;
-    return (int)cudaErrorNoKernelImageForDevice;
-  }
+  int major = 0;
+  CQR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  CQR_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+  if (major != 10) return (int)cudaErrorNoKernelImageForDevice;   // sm_100a-only binary: fail loudly instead of faulting at first launch
   c->launches0 = g_launches;
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -518,13 +519,26 @@ int cqr_create(cqr_context** out, int device) {
   if (const char* e = getenv("CQR_PANEL")) c->opt_panel = atoi(e) != 0;
   if (const char* e = getenv("CQR_CLUSTER")) c->opt_cluster = atoi(e) != 0;   // debugging aid: 0 = global-flag exchange only
   if (const char* e = getenv("CQR_GEMM")) c->opt_gemm = (strcmp(e, "simt") == 0) ? 0 : 1;   // debugging aid
+  return 0;
+}
+
+int cqr_create(cqr_context** out, int device) {
+  if (!out) return CQR_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  CQR_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return CQR_EINVAL;
+  DeviceGuard dg__(device);
+  cqr_context* c = new cqr_context();
+  const int rc = create_impl(c, device);
+  if (rc) { c->device = device; cqr_destroy(c); return rc; }   // one cleanup path: streams, events, green contexts made so far
   *out = c;
   return 0;
 }
 
 int cqr_destroy(cqr_context* c) {
   if (!c) return CQR_EINVAL;
-  cudaSetDevice(c->device);
+  DeviceGuard dg__(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->ws) cudaFree(c->ws);
   if (c->ts) cudaFree(c->ts);
@@ -612,21 +626,21 @@ int cqr_profile_end(cqr_context* c, double* ms, double* flops, double* bytes, lo
 }
 
 int cqr_profile_timeline(cqr_context* c, double* t0_ms, double* t1_ms, int* cls, int cap) {
-  if (!c || !t0_ms || !t1_ms || !cls || cap < 0) return -CQR_EINVAL;
-  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -CQR_ESTATE;
+  if (!c || !t0_ms || !t1_ms || !cls || cap < 0) return CQR_EINVAL;   // the CQR_E* codes are negative already
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return CQR_ESTATE;
   int n = 0;
   for (auto& r : c->prof) {
     if (n >= cap) break;
     float a = 0.f, b = 0.f;
-    if (cudaEventElapsedTime(&a, c->prof[0].e0, r.e0) != cudaSuccess) return -CQR_ESTATE;
-    if (cudaEventElapsedTime(&b, c->prof[0].e0, r.e1) != cudaSuccess) return -CQR_ESTATE;
+    if (cudaEventElapsedTime(&a, c->prof[0].e0, r.e0) != cudaSuccess) return CQR_ESTATE;
+    if (cudaEventElapsedTime(&b, c->prof[0].e0, r.e1) != cudaSuccess) return CQR_ESTATE;
     t0_ms[n] = a; t1_ms[n] = b; cls[n] = r.cat;
     ++n;
   }
   return n;
 }
 
-int cqr_reserve(cqr_context* c, size_t bytes) { if (!c) return CQR_EINVAL; cudaSetDevice(c->device); return ws_ensure(c, bytes); }
+int cqr_reserve(cqr_context* c, size_t bytes) { if (!c) return CQR_EINVAL; DeviceGuard dg__(c->device); return ws_ensure(c, bytes); }
 
 int cqr_set_identity(cqr_context* c, float* dA, int lda, int m, int n) {
   if (!c || !dA || m < 1 || n < 1 || lda < m) return CQR_EINVAL;
@@ -644,7 +658,7 @@ int cqr_gemm(cqr_context* c, int transA, int M, int N, int K, float alpha, const
              int ldb, float beta, float* dD, int ldd) {
   if (!c || !dA || !dB || !dD || M < 1 || N < 1 || K < 1 || ldd < M || ldb < K) return CQR_EINVAL;
   if (transA ? lda < K : lda < M) return CQR_EINVAL;
-  cudaSetDevice(c->device);
+  DeviceGuard dg__(c->device);
   if (!transA) {
     launch_gemm_nn_simt(M, N, K, alpha, dA, lda, dB, ldb, beta, dD, ldd, c->stream);
   } else {
@@ -661,7 +675,7 @@ int cqr_gemm_tf32x3(cqr_context* c, int transA, int M, int N, int K, float alpha
   if (!c || !dA || !dB || !dD || M < 1 || N < 1 || K < 1 || ldd < M || ldb < K) return CQR_EINVAL;
   if (transA ? lda < K : lda < M) return CQR_EINVAL;
   if (transA && (alpha != 1.f || beta != 0.f)) return CQR_EUNSUPPORTED;
-  cudaSetDevice(c->device);
+  DeviceGuard dg__(c->device);
   if (!umma_available()) return CQR_EUNSUPPORTED;
   float* part = nullptr;
   int splits = transA ? umma_effective_splits(K, pick_splits(c, M, N, K, 128, 128)) : 1;
@@ -686,7 +700,7 @@ int cqr_gemm_tf32x3(cqr_context* c, int transA, int M, int N, int K, float alpha
 // nf <= n: Householder QR of the first nf columns, Q^T applied to all n (nf == n: the plain factorisation).
 static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, float* dtau) {
   if (!c || !dA || !dtau || nf < 1 || nf > n || m < nf || lda < m) return CQR_EINVAL;
-  cudaSetDevice(c->device);
+  DeviceGuard dg__(c->device);
   cudaStream_t st = c->stream;
   if (m <= 64 && nf == n) {   // one 64 x 64 tile: the one-warp Householder kernel (same LAPACK storage), a single launch
     launch_batched_qr_warp(dA, 0, lda, m, n, 1, dtau, st);
@@ -704,7 +718,9 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
   const long long ldv = round_up(m, 4);
   const int nblk = (nf + KB - 1) / KB;
   const bool look = c->opt_lookahead && nblk > 1;
-  const int ncmax = n > 64 ? n - 64 : 1;
+  // widest update any path below issues with the block scratch: everything right of the first outer block, whose width is
+  // min(nf, KB) -- for nf < 64 (cqr_geqrf_partial with a narrow factor part) that is more than n - 64 columns
+  const int ncmax = n - (nf < KB ? nf : KB) > 0 ? n - (nf < KB ? nf : KB) : 1;
 
   struct BlockBufs { float *vbuf, *tbig; } bb[2];
   TsqrPlan plan;
@@ -775,7 +791,8 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
         int wncl = 1;
         const bool wb_planned = use_wb && c->opt_cluster && panel_wb_plan(mp, &wpc, &cs, &wncl);
         const bool in_wb = wb_planned && ((mp >= wb_min && mp <= wb_max) || mp <= wb_small);
-        static const long long pair_max = getenv("CQR_PANEL_PAIR_MAX_ROWS") ? atoll(getenv("CQR_PANEL_PAIR_MAX_ROWS")) : 8192;   // > 8192: two clusters
+        // > 8192 rows: two clusters exchanging through global flags (16384 rows: 232 -> 168 us, profiles/r02_panel_bench_pair16384.txt)
+        static const long long pair_max = getenv("CQR_PANEL_PAIR_MAX_ROWS") ? atoll(getenv("CQR_PANEL_PAIR_MAX_ROWS")) : 16384;
         const bool in_pair = wb_planned && wb_pair > 0 && b == 64 && mp >= pair_min && mp <= pair_max;
         if (in_pair && launch_panel_wb2(hp, wpc, cs, wncl, wb_pair, s)) {
         } else if (in_wb && launch_panel_wb(hp, wpc, cs, wncl, s)) {
@@ -1001,7 +1018,7 @@ int cqr_geqrf_partial(cqr_context* c, float* dA, int lda, int m, int n, int nfac
 // Shared by form_q / apply_q: walk the outer blocks, rebuild (V, T) from LAPACK-format storage.
 static int apply_q_impl(cqr_context* c, int trans, const float* dA, int lda, int m, int n, const float* dtau,
                         float* dC, int ldc, int nc, bool c_is_identity_start) {
-  cudaSetDevice(c->device);
+  DeviceGuard dg__(c->device);
   cudaStream_t st = c->stream;
   const int KB = c->opt_outer < n ? c->opt_outer : (int)round_up(n, 64);
   const bool tensor = tensor_ok(c, dC, ldc) && m >= 128 && nc >= 64 && n >= 64;
@@ -1039,7 +1056,7 @@ static int apply_q_impl(cqr_context* c, int trans, const float* dA, int lda, int
 int cqr_form_q(cqr_context* c, const float* dA, int lda, int m, int n, const float* dtau, float* dQ, int ldq,
                int q_cols) {
   if (!c || !dA || !dtau || !dQ || n < 1 || m < n || lda < m || ldq < m || q_cols < 1 || q_cols > m) return CQR_EINVAL;
-  cudaSetDevice(c->device);
+  DeviceGuard dg__(c->device);
   launch_set_identity(dQ, ldq, m, q_cols, c->stream);
   return apply_q_impl(c, 0, dA, lda, m, n, dtau, dQ, ldq, q_cols, true);
 }
@@ -1069,17 +1086,18 @@ int cqr_solve_ls(cqr_context* c, const float* dA, int lda, int m, int n, const f
       gemm_nn(c, k0, nrhs, kb, -1.f, R, X, 1.f, dB, ldb, tensor && k0 >= 128);
     }
   }
-  int sing = 0;
-  CQR_CUDA(cudaMemcpyAsync(&sing, c->hh_err + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  int flags[2] = {0, 0};   // [0] panel spin timeout (void factorisation upstream), [1] zero pivot in R
+  CQR_CUDA(cudaMemcpyAsync(flags, c->hh_err, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   CQR_CUDA(cudaStreamSynchronize(st));
-  if (sing) return CQR_ESINGULAR;
+  if (flags[0]) { cudaMemset(c->hh_err, 0, sizeof(int)); return CQR_ESTATE; }
+  if (flags[1]) return CQR_ESINGULAR;
   return (int)cudaGetLastError();
 }
 
 // ---- TSQR ---------------------------------------------------------------------------------------
 static int tsqr_common(cqr_context* c, float* dA, int lda, long long m, int n, float* dR, int ldr, bool keep) {
   if (!c || !dA || !dR || n < 1 || n > 64 || m < n || lda < m || ldr < n) return CQR_EINVAL;
-  cudaSetDevice(c->device);
+  DeviceGuard dg__(c->device);
   const int th = c->opt_tile_rows;
   TsqrPlan plan;
   for (int pass = 0; pass < 2; ++pass) {
@@ -1120,7 +1138,7 @@ int cqr_tsqr_form_q(cqr_context* c, const float* dX, int ldx, float* dQ, int ldq
   if (!c->ts_valid) return CQR_ESTATE;
   const TsqrPlan& P = c->ts_plan;
   if (ldq < P.m || (dX && ldx < P.n)) return CQR_EINVAL;
-  cudaSetDevice(c->device);
+  DeviceGuard dg__(c->device);
   run_tsqr_form_q(c, P, c->ts_a, c->ts_lda, dX, ldx, P.n, dQ, ldq);
   return (int)cudaGetLastError();
 }
@@ -1128,7 +1146,7 @@ int cqr_tsqr_form_q(cqr_context* c, const float* dX, int ldx, float* dQ, int ldq
 int cqr_stack_qr(cqr_context* c, float* dRs, int ldrs, int nblk, int n, float* dtau, float* dR, int ldr) {
   if (!c || !dRs || !dtau || !dR || n < 1 || n > 64 || nblk < 1 || ldrs < nblk * n || ldr < n) return CQR_EINVAL;
   if (nblk * n > 256) return CQR_EUNSUPPORTED;
-  cudaSetDevice(c->device);
+  DeviceGuard dg__(c->device);
   TileQRParams p{};
   p.a.base = dRs; p.a.tile_stride = 0; p.a.ld = ldrs; p.a.rows_total = (long long)nblk * n;
   p.ncols = n; p.write_back = 1; p.tau = dtau; p.tau_stride = 64;
@@ -1141,7 +1159,7 @@ int cqr_stack_form_q(cqr_context* c, const float* dRs, int ldrs, int nblk, int n
                      int ldx, float* dQs, int ldqs) {
   if (!c || !dRs || !dtau || !dQs || n < 1 || n > 64 || nblk < 1 || ldrs < nblk * n || ldqs < nblk * n) return CQR_EINVAL;
   if (nblk * n > 256) return CQR_EUNSUPPORTED;
-  cudaSetDevice(c->device);
+  DeviceGuard dg__(c->device);
   TileApplyParams p{};
   p.v.base = const_cast<float*>(dRs); p.v.tile_stride = 0; p.v.ld = ldrs; p.v.rows_total = (long long)nblk * n;
   p.tau = dtau; p.nref = n; p.nc = n;
@@ -1153,7 +1171,7 @@ int cqr_stack_form_q(cqr_context* c, const float* dRs, int ldrs, int nblk, int n
 
 int cqr_geqrf_batched(cqr_context* c, float* dA, int lda, long long stride, int m, int n, int batch, float* dtau) {
   if (!c || !dA || !dtau || n < 1 || n > 64 || m < n || m > 256 || lda < m || batch < 1) return CQR_EINVAL;
-  cudaSetDevice(c->device);
+  DeviceGuard dg__(c->device);
   if (m <= 64) {   // one warp per matrix (tsqr_flat.cu); CQR_BATCHED_CTA=1 selects the older two-threads-per-column CTA kernel
     static const bool cta_kernel = getenv("CQR_BATCHED_CTA") != nullptr;
     if (cta_kernel) launch_batched_qr_col(dA, stride, lda, m, n, batch, dtau, c->stream);
@@ -1238,6 +1256,10 @@ void mmqr(float* mat, float* tau, int m, int n) {
   memset(tau, 0, tau_count * sizeof(float));
   LEGACY_CHECK(cudaStreamSynchronize(c->copy));
   LEGACY_CHECK(cudaMemcpy(tau, dtau, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+  // a panel kernel's cross-CTA spin timed out (its CTAs were never co-resident): the factorisation is void -- fail like
+  // every other device error here instead of handing back a silently wrong result (cqr_synchronize reports it to
+  // device-API callers)
+  LEGACY_CHECK(cqr_synchronize(c));
 }
 
 void mmqr_alloc(float* mat, float** tau, int m, int n) {

@@ -8,7 +8,7 @@
 
 namespace cqr {
 
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 
 constexpr int BT = 64;   // output tile edge
 constexpr int BK = 16;   // K chunk

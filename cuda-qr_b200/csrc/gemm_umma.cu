@@ -420,15 +420,15 @@ bool make_map(CUtensorMap* tm, const float* base, long long dim0, long long dim1
 
 bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
-int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+int sm_count() {   // per device: a process may hold contexts on several GPUs
+  static int n[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!n[dev]) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
 template <int BN, bool kAMn>
@@ -445,13 +445,13 @@ bool launch_umma(int M, int N, int K, const float* a, long long lda, const float
   if (!ok) return false;
   Epilogue e2 = ep;
   constexpr size_t smem = (size_t)kRing * 2 * (BM * BK * 4 + BN * BK * 4) + 1024 + 256;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     if (cudaFuncSetAttribute(umma_gemm_kernel<BN, kAMn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       cudaGetLastError();
+      once.retry();
       return false;
     }
-    attr_done = true;
   }
   int kper = ((K + splits - 1) / splits + BK - 1) / BK * BK;
   if (kper < BK) kper = BK;
@@ -462,21 +462,24 @@ bool launch_umma(int M, int N, int K, const float* a, long long lda, const float
   const int grid = (int)(total < max_ctas ? total : max_ctas);
   ++g_launches;
   umma_gemm_kernel<BN, kAMn><<<grid, kThreadsP, smem, s>>>(ta, tb, td, e2, M, N, K, kper, tiles_m, tiles_n, splits);
+  if (cudaGetLastError() != cudaSuccess) { --g_launches; return false; }   // launch refused: the caller falls back to the SIMT GEMM
   return true;
 }
 
 }  // namespace
 
-bool umma_available() {
-  static int state = -1;
-  if (state < 0) {
-    int dev = 0;
-    cudaDeviceProp prop;
-    state = (get_encode() != nullptr && cudaGetDevice(&dev) == cudaSuccess &&
-             cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.major == 10)
-                ? 1 : 0;
+bool umma_available() {   // per device
+  static signed char state[64];
+  static bool init = false;
+  if (!init) { for (int i = 0; i < 64; ++i) state[i] = -1; init = true; }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  if (state[dev] < 0) {
+    int major = 0;
+    state[dev] = (get_encode() != nullptr && cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess &&
+                  major == 10) ? 1 : 0;
   }
-  return state == 1;
+  return state[dev] == 1;
 }
 
 // Number of K splits the kernel will really use for a request (the reduction must agree).

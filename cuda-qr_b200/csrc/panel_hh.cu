@@ -653,10 +653,9 @@ bool panel_hh_cluster_plan(long long mp, int* rr, int* cs, int* ncl) {
 
 template <int RR>
 static cudaError_t launch_cluster_t(const PanelHHParams& p, int cs, int ncl, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(panel_hh_cluster_kernel<RR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    attr_done = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cs * ncl, 1, 1);

@@ -357,10 +357,9 @@ __global__ void __launch_bounds__(32 * W, 1) panel_wb_kernel(PanelHHParams p) {
 
 template <int W>
 cudaError_t launch_wb_t(const PanelHHParams& p, int cs, int ncl, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(panel_wb_kernel<W>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    attr_done = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cs * ncl, 1, 1);

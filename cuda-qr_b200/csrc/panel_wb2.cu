@@ -493,11 +493,10 @@ __global__ void __launch_bounds__(32 * W, 1) panel_wb2_kernel(PanelHHParams p) {
 
 template <int W, bool X2>
 cudaError_t launch_wb2_t(const PanelHHParams& p, int cs, int ncl, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(panel_wb2_kernel<W, X2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaFuncSetAttribute(panel_wb2_kernel<W, X2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Wb2Shared<W>));
-    attr_done = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cs * ncl, 1, 1);

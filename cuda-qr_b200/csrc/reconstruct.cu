@@ -155,10 +155,9 @@ __global__ void __launch_bounds__(256) hr_rows_kernel(HrParams p) {
 void launch_hr_top(const HrParams& p, cudaStream_t s) {
   ++g_launches;
   constexpr size_t smem = (4 * 64 * 65 + 128) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(hr_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
   }
   hr_top_kernel<<<1, 256, smem, s>>>(p);
 }

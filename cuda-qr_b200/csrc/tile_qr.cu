@@ -399,11 +399,10 @@ void launch_tile_apply_q(const TileApplyParams& p, int tiles, int tile_rows, cud
   if (tiles <= 0) return;
   ++g_launches;
   const size_t smem = (size_t)tile_rows * CQR_SLOT * sizeof(float) + CQR_SLOT * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(tile_apply_q_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * CQR_SLOT * 4 + 256);
     cudaFuncSetAttribute(tile_apply_q_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * CQR_SLOT * 4 + 256);
-    attr_done = true;
   }
   if (tile_rows == 64) tile_apply_q_kernel<2><<<tiles, 256, smem, s>>>(p);
   else if (tile_rows == 128) tile_apply_q_kernel<4><<<tiles, 256, smem, s>>>(p);

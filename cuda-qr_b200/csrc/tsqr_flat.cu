@@ -344,6 +344,9 @@ __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_r_kernel(FlatTsqrPar
         }
       }
     }
+    // the x buffers are reused from block to block: for odd n the previous block's last step read buffer 0, which this
+    // block's first step rewrites (racecheck, 20011 x 17) -- order them
+    __syncwarp();
     if (PIPE) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) nw[i] = 0.f;       // nothing pending at the top of a block
@@ -633,6 +636,8 @@ struct FlatCfg {
       pad = e ? (size_t)atol(e) : 0;
       if (pad) cudaFuncSetAttribute(tsqr_flat_r_kernel<WPC, MINB, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + pad));
     }
+    static PerDeviceOnce once;             // per_sm() set the attribute on the device that ran flat_init() only
+    if (once.first()) cudaFuncSetAttribute(tsqr_flat_r_kernel<WPC, MINB, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + pad));
     tsqr_flat_r_kernel<WPC, MINB, PIPE><<<(p.chains + WPC - 1) / WPC, 32 * WPC, smem + pad, s>>>(p);
   }
 };
@@ -661,8 +666,8 @@ void launch_tsqr_flat_keep(const FlatTsqrParams& p, cudaStream_t s) {
   if (p.chains <= 0) return;
   ++g_launches;
   constexpr size_t smem = (size_t)4 * kFlatWarpFloats * sizeof(float);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(tsqr_flat_r_kernel<4, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  static PerDeviceOnce once;
+  if (once.first()) cudaFuncSetAttribute(tsqr_flat_r_kernel<4, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   tsqr_flat_r_kernel<4, 2, true, true><<<(p.chains + 3) / 4, 128, smem, s>>>(p);
 }
 
@@ -670,8 +675,8 @@ void launch_tsqr_flat_apply(const FlatApplyParams& p, cudaStream_t s) {
   if (p.chains <= 0) return;
   ++g_launches;
   constexpr size_t smem = (size_t)4 * 64 * 64 * sizeof(float);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(tsqr_flat_apply_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  static PerDeviceOnce once;
+  if (once.first()) cudaFuncSetAttribute(tsqr_flat_apply_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   tsqr_flat_apply_kernel<4, 2><<<(p.chains + 3) / 4, 128, smem, s>>>(p);
 }
 

@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- QR GFLOP/s (2mn^2 - 2n^3/3) of the B200-native hot path, one process per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload square|tsqr|batched]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-extra] [--no-e2e] [--no-cpu] [--config1-full]
 
-Workloads (BASELINE.json configs): `square` = config 2, 16384 x 16384 blocked Householder QR on one
-GPU (the default; at N > 1 every rank factors its own matrix: replicas only);
-`tsqr` = config 3, 8 388 608 x 64 row-partitioned over the N ranks with the R factors combined
-in a binary tree over NCCL point-to-point (strong scaling); `batched` = config 4, 65 536
-independent 64 x 64 matrices split across ranks.  The default run reports `square` as the
-headline line and carries the TSQR and batched numbers in the same JSON object.
+Workloads (BASELINE.json configs).  The headline line is config 2: 16384 x 16384 blocked Householder QR on one GPU
+(at N > 1 every rank factors its own matrix: replicas only).  The same JSON object carries, under the keys
+`tsqr`, `batched` and (N > 1) `caqr`: config 3, 8 388 608 x 64 row-partitioned over the N ranks with the R factors
+combined in a binary tree (strong scaling; `tsqr.efficiency_vs_ideal` from the in-run per-rank leaf time); config 4,
+65 536 independent 64 x 64 matrices split across ranks; config 5, CAQR with 16384 rows per rank, with its three
+acceptance numbers.  `--no-extra` drops those, `--no-e2e` / `--no-cpu` drop the host-buffer and CPU legs.
+`cpu_baseline` also times config 1 (the reference's own CPU case, 512 x 512) as BASELINE.md section 3 specifies;
+`--config1-full` runs its six-minute full-Q leg instead of the bounded sample.
 
 One JSON line is printed by rank 0.  `value` is device-resident throughput (CUDA events, max over
 ranks); `e2e` is the same metric through the reference-facing legacy call mmqr(host buffers) with
@@ -106,6 +108,37 @@ def cpu_reference_run(m: int, n: int, steps: int, warmup: int):
         run()
     dt = (time.perf_counter() - t0) / steps
     return kind, dt, qr_flops(m, n) / dt / 1e9
+
+
+def cpu_config1(full: bool) -> dict:
+    """BASELINE config 1 / BASELINE.md section 3: the reference's CPU path on the 512 x 512 srand(12) matrix, 1 core:
+    mmqr alone with PR=4/PC=2 (qr.c as shipped) and PR=64/PC=8, and mmqr + explicitQR (full Q and R).  explicitQR is
+    O(m^3) per reflector (qr.c:415-429): 512^2 with PR=64/PC=8 takes about six minutes, so the default run times that
+    leg on a bounded 304 x 304 sample (PR=64/PC=4, legal: 304 = 64 + 4*60) and `full` runs the named size."""
+    import numpy as np
+    import oracle
+    from oracle import metrics
+    out = {"cores": 1, "host_cores": os.cpu_count()}
+    A = oracle.rand_matrix(512, 512, 12)
+    for PR, PC in ((4, 2), (64, 8)):
+        if not oracle.Ref.available(PR, PC):
+            continue
+        ref = oracle.Ref(PR, PC)
+        t0 = time.perf_counter(); rv, tau = ref.mmqr(A); dt = time.perf_counter() - t0
+        out[f"mmqr_512x512_pr{PR}_pc{PC}"] = {"seconds": dt, "gflops": qr_flops(512, 512) / dt / 1e9,
+                                               "gram_error": metrics.gram_error(A, rv)}
+    m, PR, PC = (512, 64, 8) if full else (304, 64, 4)
+    if oracle.Ref.available(PR, PC):
+        ref = oracle.Ref(PR, PC)
+        As = oracle.rand_matrix(m, m, 12)
+        t0 = time.perf_counter(); rv, tau = ref.mmqr(As); t1 = time.perf_counter()
+        Q, R = ref.explicitQR(rv, tau); t2 = time.perf_counter()
+        out[f"mmqr_explicitQR_{m}x{m}_pr{PR}_pc{PC}"] = {
+            "mmqr_seconds": t1 - t0, "explicitQR_seconds": t2 - t1, "gflops": qr_flops(m, m) / (t2 - t0) / 1e9,
+            "residual_fro": float(np.linalg.norm(Q.astype(np.float64) @ R.astype(np.float64) - As)),
+            "backward_over_n_eps": metrics.backward_error(As, Q, R),
+            "note": "the named config-1 size" if full else "bounded sample of config 1 (512x512 full Q: ~6 min, see profiles/r02_config1_cpu.json)"}
+    return out
 
 
 def main_reference(args, rank: int):
@@ -230,7 +263,13 @@ def main_ours(args, rank: int, world: int, local_rank: int):
                 "avg_launch_ms": nn["ms"] / max(1, nn["launches"]), "share_of_step": nn["ms"] / tot_ms if tot_ms else None,
                 "hbm_GBps_algorithmic": nn["bytes"] / (nn["ms"] * 1e-3) / 1e9 if nn["ms"] > 0 else None,
                 "by_class_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
-                "by_class_launches": {k: v["launches"] for k, v in prof.items()}}
+                "by_class_launches": {k: v["launches"] for k, v in prof.items()},
+                # algorithmic TFLOP/s of every class over its own event brackets (the two streams overlap, so the class
+                # times do not add up to the step), and the whole step against the same roof
+                "by_class_tflops": {k: round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) for k, v in prof.items() if v["ms"] > 0 and v["flops"] > 0},
+                "by_class_flops": {k: v["flops"] for k, v in prof.items() if v["flops"] > 0},
+                "gemm_tn_frac": (prof["gemm_tn"]["flops"] / (prof["gemm_tn"]["ms"] * 1e-3) / 1e12 / peak) if prof["gemm_tn"]["ms"] > 0 else None,
+                "step_tflops": flops / (ms * 1e-3) / 1e12, "step_frac": flops / (ms * 1e-3) / 1e12 / peak}
         # measured DRAM traffic of the dominant kernel from the committed ncu --set full capture (one launch at the
         # first-block shape; `achieved` above averages all launches of the step, whose shapes shrink)
         try:
@@ -274,7 +313,9 @@ def main_ours(args, rank: int, world: int, local_rank: int):
     if rank == 0 and not args.no_cpu:
         kind, dt, gf = cpu_reference_run(args.ref_size, args.ref_size, 1, 0)
         cpu = {"value": gf, "unit": "GFLOP/s", "cores": 1, "kind": kind, "seconds": dt,
-               "sample": f"{args.ref_size}x{args.ref_size} srand(12) uniform[0,1) matrix, reference mmqr only (qr.c as shipped, PR=4/PC=2), 1 of {os.cpu_count()} host cores"}
+               "sample": f"{args.ref_size}x{args.ref_size} srand(12) uniform[0,1) matrix (bounded sample of the 16384x16384 workload: a rate-vs-rate comparison "
+                         f"across sizes, not the same input), reference mmqr only (qr.c as shipped, PR=4/PC=2), 1 of {os.cpu_count()} host cores",
+               "config1": cpu_config1(args.config1_full)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -323,6 +364,35 @@ def bench_tsqr(args, pkg, ctx, torch, dist, dev, rank, world, timed_steps, pk):
                        "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": _traffic("tsqr_flat") if world == 1 else None,
                        "note": "per-GPU algorithmic bytes 4*m_loc*n over the whole step (leaves + tree + NCCL hops); "
                                "SIMT Householder is FMA-issue bound at this shape (32 flop/B): the fp32 FMA floor is 2mn^2 / (148 SMs x 128 lanes x 2 x clock) ~ 1.0 ms = 33 % of the HBM roof, see DESIGN.md"}
+    # both roofline fractions: the leaf is compute-bound long before it is HBM-bound (32 flop/B), so the arithmetic rate is
+    # stated against the fp32 FMA ceiling (148 SMs x 128 lanes x 2 x max clock) as well
+    fma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    res["roofline"]["fp32_fma"] = {"achieved": flops / world / (ms * 1e-3) / 1e12, "peak": fma_peak, "unit": "TFLOP/s per GPU",
+                                   "frac": flops / world / (ms * 1e-3) / 1e12 / fma_peak}
+    # in-run scaling record: this rank's local TSQR alone (leaf + on-GPU tree, no cross-GPU step) and, on rank 0, the
+    # whole matrix on one GPU; efficiency = t_1 / (N t_N)
+    R_loc = pkg.colmajor(n, n, device=dev)
+    ms_local, _ = timed_steps(lambda: ctx.tsqr_r(A_loc, R_loc), lambda: None, 10, 3)
+    res["local_ms"] = ms_local
+    res["cross_gpu_ms"] = ms - ms_local
+    if world > 1:
+        t1 = torch.zeros(1, device=dev, dtype=torch.float64)
+        if rank == 0:
+            A_full = pkg.colmajor(m_total, n, device=dev)
+            A_full.copy_(torch.rand((m_total, n), device=dev, generator=g))
+            for _ in range(3):
+                ctx.tsqr_r(A_full, R_loc)
+            torch.cuda.synchronize()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+            for e0, e1 in ev:
+                e0.record(); ctx.tsqr_r(A_full, R_loc); e1.record()
+            torch.cuda.synchronize()
+            t1[0] = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+            del A_full
+        dist.all_reduce(t1)
+        res["one_gpu_ms_same_run"] = float(t1.item())
+        res["efficiency_vs_ideal"] = float(t1.item()) / (world * ms)
+        res["leaf_efficiency"] = float(t1.item()) / (world * ms_local)
     if world == 1:
         # implicit-Q variant and thin-Q expansion (north_star item 4) on the same matrix: A is overwritten by the
         # reflectors, so it is restored from a copy outside the timed region
@@ -372,11 +442,35 @@ def bench_caqr(args, pkg, ctx, torch, dist, dev, rank, world, timed_steps, pk):
     res["nvlink_bytes_per_rank_per_step"] = int(cq.bytes_exchanged)
     G = A0.t().double() @ A0.double()
     dist.all_reduce(G)
+    R = pkg.colmajor(n, n, device=dev)
     if rank == 0:
-        R = pkg.colmajor(n, n, device=dev)
         cq.extract_r(A, R)
         Rd = torch.triu(R.double())
         res["gram_error"] = float((Rd.t() @ Rd - G).norm() / G.norm())
+    # the three acceptance numbers of north_star on this configuration: thin Q through the local and tree reflectors
+    # (DistCAQR.form_q), backward error and orthogonality in fp64 over all ranks' rows, R against the Gram matrix
+    Q = pkg.colmajor(m_loc, n, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); cq.form_q(A, Q); e1.record(); torch.cuda.synchronize()
+    res["form_thin_q_ms"] = e0.elapsed_time(e1)
+    dist.broadcast(R.t(), src=0)                              # colmajor(n, n): R.t() is the contiguous storage
+    Rt = torch.triu(R).double()
+    num = torch.zeros((), device=dev, dtype=torch.float64)
+    den = torch.zeros((), device=dev, dtype=torch.float64)
+    for r0 in range(0, m_loc, 4096):                          # blocked fp64 products: bounded memory
+        d = A0[r0:r0 + 4096].double() - Q[r0:r0 + 4096].double() @ Rt
+        num += (d * d).sum(); den += (A0[r0:r0 + 4096].double() ** 2).sum()
+    GQ = torch.zeros((n, n), device=dev, dtype=torch.float64)
+    for r0 in range(0, m_loc, 4096):
+        q = Q[r0:r0 + 4096].double()
+        GQ += q.t() @ q
+    pack = torch.stack([num, den])
+    dist.all_reduce(pack); dist.all_reduce(GQ)
+    if rank == 0:
+        eps = 2.0 ** -23
+        res["backward_error_over_n_eps"] = float((pack[0] / pack[1]).sqrt()) / (n * eps)
+        res["orthogonality_over_n_eps"] = float((GQ - torch.eye(n, device=dev, dtype=torch.float64)).norm()) / (n * eps)
+        res["residual"] = float((pack[0] / pack[1]).sqrt())
     return res
 
 
@@ -417,10 +511,16 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--config1-full", action="store_true", help="time config 1's full-Q leg at 512x512 (about six minutes of CPU)")
+    ap.add_argument("--config1-only", action="store_true", help="print only the config-1 CPU timings (no GPU work)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.config1_only:
+        if rank == 0:
+            print(json.dumps({"config1": cpu_config1(args.config1_full)}), flush=True)
+        return
     if args.impl == "reference":
         main_reference(args, rank)
         return

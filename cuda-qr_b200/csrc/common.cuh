@@ -125,6 +125,21 @@ void launch_tsqr_flat_apply(const FlatApplyParams& p, cudaStream_t s);
 // batched QR of m x n matrices (m, n <= 64), one warp per matrix, LAPACK storage in place, tau[b * n + j]
 void launch_batched_qr_warp(float* base, long long stride, long long lda, int m, int n, int batch, float* tau, cudaStream_t s);
 
+// ---- tensor-pipe flat-tree TSQR (R only): tsqr_mma.cu ------------------------------------------
+// One launch turns an m x n matrix into one 64 x 64 R per CTA: warp chains of 64-row blocks, then the CTA's warps are
+// combined.  CTA b writes rows [64 b, 64 b + out_rows) of r_out (column-major, ld r_ld): out_rows = 64 for a level that
+// feeds the next launch (the stacked R's are its input matrix), n for the last one (a single CTA).
+struct MmaTsqrParams {
+  const float* a; long long lda;
+  long long m; int n;
+  long long rows_per_chain;        // multiple of 64
+  int chains;
+  float* r_out; long long r_ld;
+  int out_rows;
+};
+int mma_tsqr_warps_per_cta();
+void launch_tsqr_mma_r(const MmaTsqrParams& p, cudaStream_t s);
+
 // ---- Householder reconstruction + T builder: reconstruct.cu ---------------------------------
 struct HrParams {
   const float* q;  long long ldq;     // thin Q of the panel (mp x b)

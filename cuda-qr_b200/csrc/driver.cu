@@ -505,6 +505,10 @@ static int create_impl(cqr_context* c, int device) {
   CQR_CUDA(cudaMalloc((void**)&c->hh_slots, panel_hh_slot_bytes() + 256));
   CQR_CUDA(cudaMemset(c->hh_slots, 0, panel_hh_slot_bytes() + 256));
   c->hh_err = reinterpret_cast<int*>(reinterpret_cast<char*>(c->hh_slots) + panel_hh_slot_bytes());
+  // Profilers that inject into the process (ncu: CUDA_INJECTION64_PATH / NV_COMPUTE_PROFILER_PERFWORKS_DIR) cannot follow
+  // launches on green-context streams (ncu 2025.2 dies at the first one), so the spatial partition is off under them and
+  // the look-ahead runs on two plain streams; CQR_PARTITION=1 forces it on, =0 off.
+  if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NV_NSIGHT_INJECTION_PORT_BASE")) c->opt_partition = 0;
   if (const char* e = getenv("CQR_PARTITION")) c->opt_partition = atoi(e) != 0;   // debugging aid: 0 = no green contexts
   c->part[0].sp = c->side; c->part[0].sg = c->work; c->part[0].sm_p = c->part[0].sm_g = c->sm_count; c->part[0].ok = true;
   if (c->opt_partition) {

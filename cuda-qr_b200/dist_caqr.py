@@ -63,11 +63,15 @@ def caqr_generic(rank: int, world: int, m_loc: int, n: int, kb: int, local_qr: C
 class DistCAQR:
     """CAQR of a row-partitioned m x n matrix (n <= local rows); one instance per rank (one process per GPU)."""
 
-    def __init__(self, pkg, ctx, m_loc: int, n: int, rank: int, world: int, device, kb: int = 256):
+    def __init__(self, pkg, ctx, m_loc: int, n: int, rank: int, world: int, device, kb: int = 256, comm=None):
         import torch
         self.torch, self.pkg, self.ctx = torch, pkg, ctx
         self.m_loc, self.n, self.rank, self.world, self.device, self.kb = m_loc, n, rank, world, device, kb
         check_shape(m_loc, n, kb, world)
+        if comm is None and world > 1:
+            from .comm import Comm
+            comm = Comm()
+        self.comm = comm                     # transport only (NCCL; gloo stages through the host, see comm.py)
         nblk = (n + kb - 1) // kb
         self.tau_loc = torch.zeros(n, device=device)                       # local reflectors, LAPACK tau per column
         self.tau_tree = torch.zeros((nblk, kb), device=device)             # tree reflectors per block (replicated)
@@ -90,7 +94,6 @@ class DistCAQR:
         """In-place CAQR of the local slab A_loc (m_loc x n column-major device tensor).  Afterwards rank 0 holds R
         in the upper triangle of its first n rows."""
         t, kb, n, P = self.torch, self.kb, self.n, self.world
-        import torch.distributed as dist
 
         def local_qr(k0, w, r0):
             # steps 1 + 2 in one call: QR of the block's w columns with Q_i^T applied to the trailing columns while the
@@ -109,7 +112,7 @@ class DistCAQR:
                 s[:w, w:].copy_(A_loc[r0:r0 + w, k0 + w:])
             chunk = self.send[:w + nt]                         # contiguous prefix of the slab storage
             out = self.recv[:P * (w + nt) * kb].view(P, w + nt, kb)
-            dist.all_gather_into_tensor(out, chunk)
+            self.comm.all_gather_into(out, chunk)
             self.bytes_exchanged += chunk.numel() * 4 * (P - 1)
             S = self.stack[:P * w, :w + nt]
             rs = S[:, :w]
@@ -160,3 +163,59 @@ class DistCAQR:
         """R (n x n) from rank 0's slab (valid on rank 0)."""
         self.ctx.extract_r(A_loc[:self.n], R)
         return R
+
+    # -- implicit Q ---------------------------------------------------------------------------------------------
+    # A = Q R with Q = prod_K diag_i(Q_i,K) Q_tree,K (K ascending): block K's local reflectors (V_i below the diagonal of
+    # A_loc[r0:, K0:K0+w], tau_loc) followed by the tree reflectors of the stacked triangles.  Column j of V_tree is
+    # e_j on rank 0's rows and an upper triangle on every other rank's top w rows (kept by factor() in the upper
+    # triangle of that rank's top block); tau_tree is replicated.  The reference's contract is A = Q R with an explicit
+    # Q (qr.c:330-438); here Q is applied or formed by blocks, never as m x m.
+    def _tree_v(self, A_loc, k0, w, r0):
+        """The block's V_tree (P w x w, LAPACK storage) assembled on every rank from the ranks' upper-triangle slices."""
+        t, P = self.torch, self.world
+        mine = t.zeros((w, w), dtype=t.float32, device=self.device)            # storage (cols, rows): column-major w x w
+        if self.rank > 0:
+            mine.t().copy_(t.triu(A_loc[r0:r0 + w, k0:k0 + w]))
+        allv = t.empty((P, w, w), dtype=t.float32, device=self.device)
+        self.comm.all_gather_into(allv, mine)
+        Vt = self.pkg.colmajor(P * w, w, device=self.device)
+        for p in range(P):
+            Vt[p * w:(p + 1) * w].copy_(allv[p].t())
+        return Vt
+
+    def apply_q(self, A_loc, C_loc, trans: bool):
+        """C <- Q^T C (trans) or Q C on the row-partitioned C (every rank passes its m_loc x nc slab; all ranks the same nc).
+        Per block: the local reflectors through cqr_apply_q, the tree reflectors redundantly on the gathered top rows."""
+        t, P, n = self.torch, self.world, self.n
+        nc = C_loc.shape[1]
+        plan = block_plan(self.m_loc, n, self.kb, self.rank)
+        for (k0, w, r0) in (plan if trans else reversed(plan)):
+            def local():
+                self.ctx.apply_q(A_loc[r0:, k0:k0 + w], self.tau_loc[k0:k0 + w], C_loc[r0:], trans)
+
+            def tree():
+                if P == 1:
+                    return
+                Vt = self._tree_v(A_loc, k0, w, r0)
+                top = t.empty((nc, w), dtype=t.float32, device=self.device)    # my top rows, column-major w x nc
+                top.t().copy_(C_loc[r0:r0 + w])
+                alltop = t.empty((P, nc, w), dtype=t.float32, device=self.device)
+                self.comm.all_gather_into(alltop, top)
+                Cs = self.pkg.colmajor(P * w, nc, device=self.device)
+                for p in range(P):
+                    Cs[p * w:(p + 1) * w].copy_(alltop[p].t())
+                self.ctx.apply_q(Vt, self.tau_tree[k0 // self.kb, :w], Cs, trans)
+                C_loc[r0:r0 + w].copy_(Cs[self.rank * w:(self.rank + 1) * w])
+
+            if trans:
+                local(); tree()
+            else:
+                tree(); local()
+        return C_loc
+
+    def form_q(self, A_loc, Q_loc):
+        """This rank's rows of the thin Q (m_loc x n): Q [I_n; 0]."""
+        Q_loc.zero_()
+        if self.rank == 0:
+            self.ctx.set_identity(Q_loc[:self.n])
+        return self.apply_q(A_loc, Q_loc, False)

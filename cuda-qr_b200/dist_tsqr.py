@@ -55,10 +55,14 @@ def reduce_r(rank: int, world: int, r_local, combine: Callable, send: Callable, 
 class DistTSQR:
     """TSQR of a row-partitioned tall-skinny matrix; one instance per rank (one process per GPU)."""
 
-    def __init__(self, pkg, ctx, n: int, rank: int, world: int, device):
+    def __init__(self, pkg, ctx, n: int, rank: int, world: int, device, comm=None):
         import torch
         self.torch, self.pkg, self.ctx = torch, pkg, ctx
         self.n, self.rank, self.world, self.device = n, rank, world, device
+        if comm is None and world > 1:
+            from .comm import Comm
+            comm = Comm()
+        self.comm = comm                     # transport only (NCCL; gloo stages through the host, see comm.py)
         depth = tree_depth(world)
         # per tree level: the stacked [R_mine; R_recv] tile (kept: it holds the level's reflectors) and its tau
         self.stack = [pkg.colmajor(2 * n, n, device=device) for _ in range(depth)]
@@ -66,10 +70,6 @@ class DistTSQR:
         self.rbuf = pkg.colmajor(n, n, device=device)
         self.R = pkg.colmajor(n, n, device=device)
         self.steps = rtree_steps(rank, world)
-
-    def _dist(self):
-        import torch.distributed as dist
-        return dist
 
     @staticmethod
     def _wire(t):
@@ -87,18 +87,18 @@ class DistTSQR:
             self.ctx.tsqr_r(A_local, self.R)
         for kind, peer, level in self.steps:
             if kind == "send":
-                self._dist().send(self._wire(self.R), peer)
+                self.comm.send(self._wire(self.R), peer)
                 break
             st = self.stack[level]
             st[:n].copy_(self.R)
-            self._dist().recv(self._wire(self.rbuf), peer)
+            self.comm.recv(self._wire(self.rbuf), peer)
             st[n:].copy_(self.rbuf)
             self.ctx.stack_qr(st, n, self.tau[level], self.R)
         return self.R
 
     def broadcast_r(self):
         if self.world > 1:
-            self._dist().broadcast(self._wire(self.R), src=0)
+            self.comm.broadcast(self._wire(self.R), 0)
         return self.R
 
     def form_q(self, Q_local):
@@ -110,14 +110,14 @@ class DistTSQR:
         mine = list(self.steps)
         if mine and mine[-1][0] == "send":
             X = self.pkg.colmajor(n, n, device=self.device)
-            self._dist().recv(self._wire(X), mine[-1][1])
+            self.comm.recv(self._wire(X), mine[-1][1])
             mine = mine[:-1]
         for kind, peer, level in reversed(mine):
             Qs = self.pkg.colmajor(2 * n, n, device=self.device)
             self.ctx.stack_form_q(self.stack[level], n, self.tau[level], Qs, X)
             Xp = self.pkg.colmajor(n, n, device=self.device)
             Xp.copy_(Qs[n:])
-            self._dist().send(self._wire(Xp), peer)
+            self.comm.send(self._wire(Xp), peer)
             X = self.pkg.colmajor(n, n, device=self.device)
             X.copy_(Qs[:n])
         self.ctx.tsqr_form_q(Q_local, X)

@@ -140,6 +140,28 @@ def test_legacy_edge_cases(pkg):
     check_factorisation(A, Q, R, A)
 
 
+def test_legacy_mmqr_alloc_and_printmat(pkg, port, capfd):
+    """The qr.c:55 overload (callee mallocs tau, caller frees) and printMat's text (qr.c:21-33) through the C ABI."""
+    import ctypes
+    A = oracle.rand_matrix(124, 64, 12)
+    RV = A.copy(order="F")
+    tau_p = ctypes.POINTER(ctypes.c_float)()
+    pkg.lib.mmqr_alloc(RV.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), ctypes.byref(tau_p), 124, 64)
+    n_tau = pkg.tau_size(124, 64)
+    tau = np.ctypeslib.as_array(tau_p, shape=(n_tau,)).copy()
+    ctypes.CDLL(None).free(tau_p)
+    RV2 = A.copy(order="F")
+    tau2 = pkg.mmqr(RV2)
+    assert np.array_equal(RV, RV2) and np.array_equal(tau, tau2)
+    Q, R = pkg.explicitQR(RV, tau)
+    assert metrics.backward_error(A, Q, R) <= metrics.TOL_BACKWARD
+    small = np.asfortranarray(np.array([[1.0, 2.5], [-3.0, 4.0], [0.125, 6.0]], dtype=np.float32))
+    pkg.printMat(small)
+    ctypes.CDLL(None).fflush(None)
+    text = capfd.readouterr().out
+    assert text == "Matrix 3 x 2, row by row:\n 1.000000  2.500000 \n-3.000000  4.000000 \n 0.125000  6.000000 \n\n"
+
+
 def test_legacy_dgemm_and_identity_vs_oracle(pkg, port):
     rng = np.random.default_rng(0)
     for k, m, n in [(6, 6, 4), (33, 70, 129), (200, 64, 200), (1, 5, 1)]:
@@ -673,7 +695,9 @@ def test_square_properties_up_to_the_baseline_size(pkg, torch, ctx, size):
 
 
 @pytest.mark.parametrize("m,n,nf", [(3000, 1000, 256), (16384, 2048, 256), (2048, 4096, 256), (5000, 900, 512), (700, 300, 100),
-                                    (512, 1200, 512)])
+                                    (512, 1200, 512),
+                                    # narrow factor parts (nf < 64): the block scratch must cover n - nf columns
+                                    (400, 48, 8), (600, 64, 32), (2000, 700, 8), (4096, 1300, 32), (300, 40, 24)])
 def test_geqrf_partial_equals_factor_then_apply(pkg, torch, ctx, m, n, nf):
     """cqr_geqrf_partial (QR of the first nf columns, Q^T applied to all n; n may exceed m) against cqr_geqrf on the
     first nf columns followed by cqr_apply_q on the rest, and against fp64: [Q^T A](:, nf:) and R of A(:, :nf)."""
@@ -730,6 +754,11 @@ def test_profile_timeline_brackets_are_ordered(pkg, torch, ctx):
     assert len(tl) > 0 and all(t1 >= t0 >= 0.0 for t0, t1, _ in tl)
     assert {c for _, _, c in tl} <= set(pkg.Context.PROF_CLASSES)
     assert abs(sum(t1 - t0 for t0, t1, _ in tl) - sum(v["ms"] for v in prof.values())) < 1e-3 * max(1.0, len(tl))
+    # errors are reported as the (negative) status codes, not as a positive bracket count
+    import ctypes
+    z = (ctypes.c_double * 1)()
+    assert pkg.lib.cqr_profile_timeline(ctx.h, z, z, (ctypes.c_int * 1)(), -1) < 0
+    assert pkg.lib.cqr_profile_timeline(ctx.h, None, z, (ctypes.c_int * 1)(), 1) < 0
 
 
 def test_geqrf_pair_step_cancellation_fallback(pkg, torch, ctx):

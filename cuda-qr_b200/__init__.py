@@ -22,7 +22,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libcudaqr_b200.so")
+_LIB_PATH = os.environ.get("CQR_LIB") or os.path.join(_HERE, "libcudaqr_b200.so")   # CQR_LIB: an instrumented build (tools/mma_trace.py)
 _FP = ctypes.POINTER(ctypes.c_float)
 _IP = ctypes.POINTER(ctypes.c_int)
 _VP = ctypes.c_void_p
@@ -37,6 +37,7 @@ EXPORTS = [
     "cqr_error_string", "cqr_launch_count", "cqr_profile_begin", "cqr_profile_end", "cqr_profile_timeline", "cqr_reserve", "cqr_geqrf", "cqr_geqrf_partial", "cqr_extract_r", "cqr_form_q",
     "cqr_apply_q", "cqr_solve_ls", "cqr_tsqr_r", "cqr_tsqr_factor", "cqr_tsqr_form_q", "cqr_stack_qr", "cqr_stack_form_q",
     "cqr_geqrf_batched", "cqr_gemm", "cqr_gemm_tf32x3", "cqr_set_identity", "cqr_version",
+    "cqr_compare_cusolver_sgeqrf",
 ]
 
 
@@ -99,6 +100,7 @@ def _load() -> ctypes.CDLL:
     lib.cqr_gemm_tf32x3.argtypes = [_VP, i, i, i, i, f, _VP, i, _VP, i, f, _VP, i]
     lib.cqr_set_identity.argtypes = [_VP, _VP, i, i, i]
     lib.cqr_version.restype = ctypes.c_char_p
+    lib.cqr_compare_cusolver_sgeqrf.argtypes = [_FP, _FP, i, i]
     return lib
 
 

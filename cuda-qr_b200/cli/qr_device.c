@@ -8,8 +8,9 @@
  * "Exact problem size" line, srand(12) / rand() uniform [0,1) input in column-major order (qr.cu:765-771), three timed
  * trials of the whole mmqr call with gettimeofday, input restored between trials outside the timing (qr.cu:774-788),
  * and the result line " MMQR ran QR on MxN matrix in T s (avg over 3)" (qr.cu:789).
- * Not kept: the MAGMA comparator (qr.cu:790-806, external library) and the shared-memory bank configuration
- * (qr.cu:741-759, a Kepler setting).  Extras: QR_DEVICE_EXACT=1 skips the rounding (the library takes any m >= n);
+ * The MAGMA comparator slot (qr.cu:790-806: the library's geqrf timed the same way, result not compared) is filled with
+ * cuSOLVER's geqrf when a third or fourth argument "compare" is given and libcusolver is on the box.
+ * Not kept: the shared-memory bank configuration (qr.cu:741-759, a Kepler setting).  Extras: QR_DEVICE_EXACT=1 skips the rounding (the library takes any m >= n);
  * a third argument "check" re-enables the reference's commented-out validation (qr.cu:822-850): explicit Q and R,
  * QR = Q*R with dgemm, and the Frobenius norm of QR - A. */
 #include <math.h>
@@ -30,7 +31,11 @@ int main(int argc, const char** argv) {
   }
   int m = atoi(argv[1]);
   int n = atoi(argv[2]);
-  const int check = argc > 3 && strcmp(argv[3], "check") == 0;
+  int check = 0, compare = 0;
+  for (int i = 3; i < argc; i++) {
+    if (strcmp(argv[i], "check") == 0) check = 1;
+    if (strcmp(argv[i], "compare") == 0) compare = 1;
+  }
   const char* exact = getenv("QR_DEVICE_EXACT");
   if (!(exact && exact[0] == '1')) { /* make m, n fit the reference's window grid */
     int numPanels = (int)((double)(m - PR) / (PR - PC) + 0.5);
@@ -71,6 +76,25 @@ int main(int argc, const char** argv) {
   printf(" MMQR ran QR on %dx%d matrix in %f s (avg over %d)\n", m, n, elapsed / TRIALS, TRIALS);
   const double flops = 2.0 * m * (double)n * n - 2.0 * (double)n * n * n / 3.0;
   printf("%.1f GFLOP/s (2mn^2 - 2n^3/3, host buffers: transfers included)\n", flops / (elapsed / TRIALS) / 1e9);
+  if (compare) { /* qr.cu:790-806 with cuSOLVER in MAGMA's place: same loop, same timing, transfers included */
+    float* CV = (float*)malloc((size_t)m * n * sizeof(float));
+    float* ctau = (float*)malloc((size_t)n * sizeof(float));
+    memcpy(CV, A, (size_t)m * n * sizeof(float));
+    double cmpElapsed = 0;
+    int rc = cqr_compare_cusolver_sgeqrf(CV, ctau, m, n); /* warm-up: library load, handle, workspace */
+    memcpy(CV, A, (size_t)m * n * sizeof(float));
+    gettimeofday(&cur, NULL);
+    for (int i = 0; i < TRIALS && rc == 0; i++) {
+      rc = cqr_compare_cusolver_sgeqrf(CV, ctau, m, n);
+      gettimeofday(&next, NULL);
+      cmpElapsed += (next.tv_sec + 1e-6 * next.tv_usec) - (cur.tv_sec + 1e-6 * cur.tv_usec);
+      if (i != TRIALS - 1) memcpy(CV, A, (size_t)m * n * sizeof(float));
+      gettimeofday(&cur, NULL);
+    }
+    if (rc == 0) printf("cuSOLVER ran QR on %dx%d matrix in %f s (avg over %d)\n", m, n, cmpElapsed / TRIALS, TRIALS);
+    else printf("cuSOLVER comparator unavailable (status %d)\n", rc);
+    free(CV); free(ctau);
+  }
   if (check) {
     if ((double)m * m * 4 > 2e9) {
       puts("check: Q is m x m; use m <= 20000");

@@ -138,6 +138,9 @@ struct MmaTsqrParams {
   int out_rows;
 };
 int mma_tsqr_warps_per_cta();
+#ifdef CQR_MMA_TRACE
+void mma_tsqr_read_trace(long long* out);   // [loads, sub-panels, trailing] clock cycles and block steps of warp 0 of CTA 0
+#endif
 void launch_tsqr_mma_r(const MmaTsqrParams& p, cudaStream_t s);
 
 // ---- Householder reconstruction + T builder: reconstruct.cu ---------------------------------

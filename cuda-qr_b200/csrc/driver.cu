@@ -49,9 +49,11 @@ struct TsqrPlan {
 // Spatial partition of the GPU for look-ahead (CUDA green contexts): the panel chain (latency-bound, a 16-CTA
 // cluster or two) owns `sm_p` SMs, the trailing-update GEMMs the remaining `sm_g`; the two streams are bound to
 // disjoint SM sets, so the persistent GEMM kernels can never hold the SMs a co-resident panel cluster needs.
+constexpr int kMaxInChunks = 8;   // legacy mmqr: column chunks of the host matrix uploaded under the factorisation
 struct SmPartition {
   CUgreenCtx gp = nullptr, gg = nullptr;
   cudaStream_t sp = nullptr, sg = nullptr;
+  cudaStream_t sc[kMaxInChunks] = {};   // catch-up streams on the GEMM partition (lowest priority), one per upload chunk
   int sm_p = 0, sm_g = 0;
   bool ok = false;
 };
@@ -81,9 +83,15 @@ struct cqr_context {
   // `copy` while later blocks are still being factored
   float* host_out = nullptr;
   cudaStream_t copy = nullptr;
+  // legacy mmqr, chunked upload: columns [in_cb[k], in_cb[k + 1]) are on the device once in_ev[k] has fired (copy_in stream)
+  cudaStream_t copy_in = nullptr;
+  int in_n = 0;
+  int in_cb[kMaxInChunks + 1] = {};
+  cudaEvent_t in_ev[kMaxInChunks] = {}, ev_joined[kMaxInChunks] = {};
+  std::vector<cudaEvent_t> ev_t;   // aggregated T of outer block k is final (catch-up streams wait on it)
   cudaEvent_t ev_start = nullptr, ev_a = nullptr, ev_g = nullptr, ev_panel[2] = {nullptr, nullptr};
   cudaEvent_t ev_pp[2][8] = {};    // per-panel completion (panel-wise look-ahead slices, opt_lookahead == 2)
-  int opt_gemm = 1, opt_outer = 256, opt_tile_rows = 256, opt_splitk = 0, opt_lookahead = 2, opt_panel = 1, opt_cluster = 1, opt_flat = 1;
+  int opt_gemm = 1, opt_outer = 256, opt_tile_rows = 256, opt_splitk = 0, opt_lookahead = 2, opt_panel = 1, opt_cluster = 1, opt_flat = 1;   // opt_flat: R-only TSQR leaf 0 = tile tree, 1 = SIMT flat tree (default), 2 = tensor-pipe flat tree (measured slower)
   // multi-CTA panel kernel (panel_hh.cu): cross-CTA exchange slots, launch epoch, spin-timeout flag
   uint2* hh_slots = nullptr;
   int* hh_err = nullptr;
@@ -179,13 +187,18 @@ bool make_partition(int device, int groups, int prio_hi, SmPartition& out) {
   if (d.GreenCtxCreate(&out.gg, dg, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { d.GreenCtxDestroy(out.gp); out.gp = nullptr; return false; }
   CUstream sp = nullptr, sg = nullptr;
   if (d.GreenCtxStreamCreate(&sp, out.gp, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS ||
-      d.GreenCtxStreamCreate(&sg, out.gg, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
+      d.GreenCtxStreamCreate(&sg, out.gg, CU_STREAM_NON_BLOCKING, prio_hi < -1 ? -1 : 0) != CUDA_SUCCESS) {
     if (sp) cudaStreamDestroy((cudaStream_t)sp);
     d.GreenCtxDestroy(out.gp); d.GreenCtxDestroy(out.gg);
     out.gp = out.gg = nullptr;
     return false;
   }
   out.sp = (cudaStream_t)sp; out.sg = (cudaStream_t)sg;
+  for (int k = 0; k < kMaxInChunks; ++k) {   // catch-up work yields to the look-ahead slices and trailing updates of sg
+    CUstream sk = nullptr;
+    if (d.GreenCtxStreamCreate(&sk, out.gg, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) sk = nullptr;
+    out.sc[k] = (cudaStream_t)sk;
+  }
   out.sm_p = 16 * groups; out.sm_g = (int)rem.sm.smCount;
   out.ok = true;
   return true;
@@ -464,6 +477,9 @@ bool tensor_ok(cqr_context* c, const void* a, long long lda) {
 // ================================================================================================
 extern "C" {
 
+#ifdef CQR_MMA_TRACE
+__attribute__((visibility("default"))) void cqr_debug_mma_trace(long long* out) { cqr::mma_tsqr_read_trace(out); }
+#endif
 #ifdef CQR_HH_TRACE
 __attribute__((visibility("default"))) void cqr_debug_hh_trace(long long* out) { cqr::panel_hh_read_trace(out); }
 __attribute__((visibility("default"))) void cqr_debug_wb2_trace(long long* steps, long long* marks) { cqr::panel_wb2_read_trace(steps, marks); }
@@ -495,6 +511,12 @@ static int create_impl(cqr_context* c, int device) {
   CQR_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi));
   CQR_CUDA(cudaStreamCreateWithFlags(&c->work, cudaStreamNonBlocking));
   CQR_CUDA(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+  CQR_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+  for (int k = 0; k < kMaxInChunks; ++k) {
+    CQR_CUDA(cudaEventCreateWithFlags(&c->in_ev[k], cudaEventDisableTiming));
+    CQR_CUDA(cudaEventCreateWithFlags(&c->ev_joined[k], cudaEventDisableTiming));
+    CQR_CUDA(cudaStreamCreateWithPriority(&c->part[0].sc[k], cudaStreamNonBlocking, prio_lo));
+  }
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_g, cudaEventDisableTiming));
@@ -523,6 +545,7 @@ static int create_impl(cqr_context* c, int device) {
   if (const char* e = getenv("CQR_PANEL")) c->opt_panel = atoi(e) != 0;
   if (const char* e = getenv("CQR_CLUSTER")) c->opt_cluster = atoi(e) != 0;   // debugging aid: 0 = global-flag exchange only
   if (const char* e = getenv("CQR_GEMM")) c->opt_gemm = (strcmp(e, "simt") == 0) ? 0 : 1;   // debugging aid
+  if (const char* e = getenv("CQR_TSQR_LEAF")) c->opt_flat = strcmp(e, "mma") == 0 ? 2 : (strcmp(e, "flat") == 0 ? 1 : (strcmp(e, "tile") == 0 ? 0 : c->opt_flat));
   return 0;
 }
 
@@ -551,8 +574,16 @@ int cqr_destroy(cqr_context* c) {
   if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
   if (c->work) { cudaStreamSynchronize(c->work); cudaStreamDestroy(c->work); }
   if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
+  if (c->copy_in) { cudaStreamSynchronize(c->copy_in); cudaStreamDestroy(c->copy_in); }
+  for (int k = 0; k < kMaxInChunks; ++k) {
+    if (c->in_ev[k]) cudaEventDestroy(c->in_ev[k]);
+    if (c->ev_joined[k]) cudaEventDestroy(c->ev_joined[k]);
+    if (c->part[0].sc[k]) { cudaStreamSynchronize(c->part[0].sc[k]); cudaStreamDestroy(c->part[0].sc[k]); }
+  }
+  for (cudaEvent_t e : c->ev_t) cudaEventDestroy(e);
   for (int i = 1; i < 5; ++i) {
     SmPartition& pt = c->part[i];
+    for (int k = 0; k < kMaxInChunks; ++k) if (pt.sc[k]) { cudaStreamSynchronize(pt.sc[k]); cudaStreamDestroy(pt.sc[k]); }
     if (pt.sp) { cudaStreamSynchronize(pt.sp); cudaStreamDestroy(pt.sp); }
     if (pt.sg) { cudaStreamSynchronize(pt.sg); cudaStreamDestroy(pt.sg); }
     if (pt.gp) drv_api().GreenCtxDestroy(pt.gp);
@@ -576,7 +607,7 @@ int cqr_set_option(cqr_context* c, int opt, int v) {
     case CQR_OPT_SPLITK: if (v < 0 || v > kMaxSplits) return CQR_EINVAL; c->opt_splitk = v; return 0;
     case CQR_OPT_LOOKAHEAD: if (v < 0 || v > 2) return CQR_EINVAL; c->opt_lookahead = v; return 0;
     case CQR_OPT_PANEL: if (v != 0 && v != 1) return CQR_EINVAL; c->opt_panel = v; return 0;
-    case CQR_OPT_FLAT_TSQR: if (v != 0 && v != 1) return CQR_EINVAL; c->opt_flat = v; return 0;
+    case CQR_OPT_FLAT_TSQR: if (v < 0 || v > 2) return CQR_EINVAL; c->opt_flat = v; return 0;
   }
   return CQR_EINVAL;
 }
@@ -726,17 +757,54 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
   // min(nf, KB) -- for nf < 64 (cqr_geqrf_partial with a narrow factor part) that is more than n - 64 columns
   const int ncmax = n - (nf < KB ? nf : KB) > 0 ? n - (nf < KB ? nf : KB) : 1;
 
-  struct BlockBufs { float *vbuf, *tbig; } bb[2];
+  // Chunked upload (legacy mmqr on pinned memory, see mmqr below): the right-looking schedule runs on the columns that
+  // have "joined"; upload chunk k joins at outer block jn[k], after a catch-up stream has applied the block reflectors
+  // 0 .. jn[k] - 1 it missed -- so V and T of those blocks are kept (nkeep of them) instead of two look-ahead sets.
+  // The schedule is static (an upload-time model); events make it safe when the model is off, only slower.
+  int nin = 0, jn[kMaxInChunks] = {}, nkeep = 0;
+  if (c->in_n > 1 && look && nf == n) {
+    nin = c->in_n;
+    static const double gbps = getenv("CQR_H2D_GBPS") ? atof(getenv("CQR_H2D_GBPS")) : 50.0;      // tuning knobs of the model
+    static const double blk_ms = getenv("CQR_H2D_BLOCK_MS") ? atof(getenv("CQR_H2D_BLOCK_MS")) : 1.0;
+    const double t_col = (double)m * 4.0 / (gbps * 1e9);      // seconds per uploaded column (PCIe 5 x16, pinned: ~50 GB/s)
+    const double t_blk = blk_ms * 1e-3 * (double)m / 16384.0 * (KB / 256.0);   // an underestimate of a block's time: chunks join late rather than stall
+    for (int k = 1; k < nin; ++k) {
+      int j = (int)((c->in_cb[k + 1] * t_col * 1.15 + 0.3e-3 - c->in_cb[1] * t_col) / t_blk) + 1;
+      const int need = c->in_cb[k] / KB - 3;                   // the chain needs column block b + 3 joined at block b
+      // Join as late as the chain allows (default): what a late chunk has missed is worked off by its low-priority
+      // catch-up stream in the GEMM partition's idle time, the trailing updates on the chain's critical path stay
+      // small, and the deferred work never queues in front of a look-ahead slice.  Joining at the modelled arrival
+      // instead (CQR_H2D_JOIN=model) leaves the GEMM stream a backlog right when it is the busy one: 80.7 against 77 ms.
+      static const bool join_late = !(getenv("CQR_H2D_JOIN") && strcmp(getenv("CQR_H2D_JOIN"), "model") == 0);
+      if (join_late || j > need) j = need;
+      if (j < jn[k - 1]) j = jn[k - 1];
+      if (j < 0) j = 0;
+      jn[k] = j;
+      if (j > nkeep) nkeep = j;
+    }
+  }
+  const bool chunked = nin > 1;
+  if (c->in_n > 0 && !chunked)                                // a path that does not join chunks: wait for the whole upload first
+    for (int k = 0; k < c->in_n; ++k) CQR_CUDA(cudaStreamWaitEvent(st, c->in_ev[k], 0));
+  struct BlockBufs { float *vbuf, *tbig; };
+  std::vector<BlockBufs> bbv((size_t)nkeep + 2);
+  auto bb = [&](int blk) -> BlockBufs& { return bbv[blk < nkeep ? blk : nkeep + ((blk - nkeep) & 1)]; };
+  auto njoin = [&](int blk) { int e = n; if (chunked) { e = c->in_cb[1]; for (int k = 1; k < nin; ++k) if (jn[k] <= blk) e = c->in_cb[k + 1]; } return e; };
+  constexpr int kCatchCols = 2048;                           // catch-up updates go in slices of at most this many columns (scratch size)
+  static const int catch_cols = getenv("CQR_CATCH_COLS") ? (atoi(getenv("CQR_CATCH_COLS")) < 256 ? 256 : (atoi(getenv("CQR_CATCH_COLS")) > kCatchCols ? kCatchCols : atoi(getenv("CQR_CATCH_COLS")))) : kCatchCols;
+  static const int catch_ctas_pct = getenv("CQR_CATCH_CTAS_PCT") ? atoi(getenv("CQR_CATCH_CTAS_PCT")) : 100;   // share of the GEMM partition a catch-up kernel may fill
+  BlockWs bw_catch[kMaxInChunks] = {};
   TsqrPlan plan;
   float *gram = nullptr, *gpart = nullptr, *qthin = nullptr, *rt = nullptr, *uinv = nullptr, *gsmall = nullptr;
   BlockWs bw_main{}, bw_side{}, bw_slice{};
   for (int pass = 0; pass < 2; ++pass) {
     Carver cv(pass ? c->ws : nullptr);
     plan_tsqr(plan, m, n < 64 ? n : 64, th, cv);
-    for (int i = 0; i < 2; ++i) {
-      bb[i].vbuf = cv.take(ldv * KB);
-      bb[i].tbig = cv.take((long long)KB * KB);
+    for (auto& b : bbv) {
+      b.vbuf = cv.take(ldv * KB);
+      b.tbig = cv.take((long long)KB * KB);
     }
+    for (int k = 1; k < nin; ++k) if (jn[k] > 0) bw_catch[k] = carve_block_ws(cv, KB, kCatchCols);
     gram = cv.take((long long)KB * KB);
     gpart = cv.take((long long)KB * KB * kMaxSplits);
     qthin = cv.take(ldv * 64);
@@ -841,6 +909,28 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
       ProfScope pbt(c, CQR_PROF_MISC, 0.0, 0.0);
       launch_build_t(gram, KB, dtau + K0, B.tbig, KB, kbw, 1, cur_stream(c));
     }
+    if (!chunked) return;
+    // Block K0's reflector is complete: the upload chunks that have not joined yet get it on their catch-up streams.
+    const int blk = K0 / KB;
+    if (blk >= nkeep) return;
+    cudaEventRecord(c->ev_t[blk], cur_stream(c));
+    cudaStream_t s0 = c->cur; const int ctas0 = c->cur_ctas; const bool chain0 = c->cur_chain;
+    SmPartition& pr = (c->opt_partition && c->opt_panel == 1 && c->opt_cluster && m <= 16384) ? c->part[2] : c->part[0];
+    for (int k = 1; k < nin; ++k) {
+      if (jn[k] <= blk) continue;
+      cudaStream_t sc = pr.sc[k] ? pr.sc[k] : c->part[0].sc[k];
+      if (blk == 0) cudaStreamWaitEvent(sc, c->in_ev[k], 0);
+      cudaStreamWaitEvent(sc, c->ev_t[blk], 0);
+      c->cur = sc; c->cur_ctas = pr.sm_g * catch_ctas_pct / 100 > 8 ? pr.sm_g * catch_ctas_pct / 100 : 8; c->cur_chain = false;
+      Operand V{B.vbuf, ldv};
+      Operand T{B.tbig, KB};
+      for (int c0 = c->in_cb[k]; c0 < c->in_cb[k + 1]; c0 += catch_cols) {
+        const int w = c->in_cb[k + 1] - c0 < catch_cols ? c->in_cb[k + 1] - c0 : catch_cols;
+        apply_block(c, m - K0, kbw, w, V, T, dA + K0 + (long long)c0 * lda, lda, 1, bw_catch[k], tensor);
+      }
+      if (blk == jn[k] - 1) cudaEventRecord(c->ev_joined[k], sc);
+    }
+    c->cur = s0; c->cur_ctas = ctas0; c->cur_chain = chain0;
   };
   // Columns [K0, K0 + kbw) are final once the block's panel chain is done (event ev): R above, V below.
   auto ship = [&](int K0, cudaEvent_t ev) {
@@ -852,6 +942,13 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
   };
   // Trailing update of columns [c0, c1) with block K0's aggregated reflector (current stream).
   auto do_update = [&](int K0, BlockBufs& B, int c0, int c1) {
+    if (chunked) {
+      const int blk = K0 / KB;
+      for (int k = 1; k < nin; ++k)                            // chunks joining at this block: caught up (or just arrived)
+        if (jn[k] == blk) cudaStreamWaitEvent(cur_stream(c), jn[k] > 0 ? c->ev_joined[k] : c->in_ev[k], 0);
+      const int nj = njoin(blk);
+      if (c1 > nj) c1 = nj;
+    }
     if (c1 <= c0) return;
     const int kbw = (nf - K0 < KB) ? nf - K0 : KB;
     Operand V{B.vbuf, ldv};
@@ -874,14 +971,14 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
     CQR_CUDA(cudaStreamWaitEvent(pr.sg, c->ev_start, 0));
     c->cur = pr.sp; c->cur_ctas = pr.sm_p; c->cur_chain = true;
     PanelHook hk0; hk0.panel_done = c->ev_pp[0];
-    do_panels(0, bb[0], &hk0);
+    do_panels(0, bb(0), &hk0);
     CQR_CUDA(cudaEventRecord(c->ev_panel[0], pr.sp));
     c->cur = pr.sg; c->cur_ctas = pr.sm_g; c->cur_chain = false;
     for (int j0 = 0; j0 < nf; j0 += 64) {
       const int b = (nf - j0 < 64) ? nf - j0 : 64;
       CQR_CUDA(cudaStreamWaitEvent(pr.sg, c->ev_pp[0][j0 / 64], 0));
-      Operand V{bb[0].vbuf + j0 + (long long)j0 * ldv, ldv};
-      Operand T{bb[0].tbig + j0 + (long long)j0 * KB, KB};
+      Operand V{bb(0).vbuf + j0 + (long long)j0 * ldv, ldv};
+      Operand T{bb(0).tbig + j0 + (long long)j0 * KB, KB};
       apply_block(c, m - j0, b, n - nf, V, T, dA + j0 + (long long)nf * lda, lda, 1, bw_main, tensor);
     }
     CQR_CUDA(cudaEventRecord(c->ev_g, pr.sg));
@@ -895,10 +992,10 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
     for (int blk = 0; blk < nblk; ++blk) {
       const int K0 = blk * KB;
       const int kbw = (nf - K0 < KB) ? nf - K0 : KB;
-      do_panels(K0, bb[0]);
+      do_panels(K0, bb(0));
       if (c->host_out) { CQR_CUDA(cudaEventRecord(c->ev_panel[0], st)); ship(K0, c->ev_panel[0]); }
-      do_block_t(K0, bb[0]);
-      do_update(K0, bb[0], K0 + kbw, n);
+      do_block_t(K0, bb(0));
+      do_update(K0, bb(0), K0 + kbw, n);
     }
     return (int)cudaGetLastError();
   }
@@ -923,11 +1020,15 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
   // path and the GEMM stream builds T.
   static const long long tchain_rows = getenv("CQR_TCHAIN_ROWS") ? atoll(getenv("CQR_TCHAIN_ROWS")) : 12288;   // tuning knob
   auto t_on_chain = [&](int K0) { return c->opt_partition && (m - K0) > tchain_rows; };
+  if (chunked) {
+    while ((int)c->ev_t.size() < nkeep) { cudaEvent_t e; CQR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev_t.push_back(e); }
+    CQR_CUDA(cudaStreamWaitEvent(prev_p, c->in_ev[0], 0));   // the first chunk holds the first outer blocks' columns
+  }
   use(prev_p, pp->sm_p, true);
-  do_panels(0, bb[0]);
+  do_panels(0, bb(0));
   CQR_CUDA(cudaEventRecord(c->ev_panel[0], prev_p));
   ship(0, c->ev_panel[0]);
-  if (t_on_chain(0)) { do_block_t(0, bb[0]); CQR_CUDA(cudaEventRecord(c->ev_panel[0], prev_p)); }
+  if (t_on_chain(0)) { do_block_t(0, bb(0)); CQR_CUDA(cudaEventRecord(c->ev_panel[0], prev_p)); }
   bool slice_done = false;   // the current block's look-ahead slice is already on the GEMM stream (panel-wise, see below)
   for (int blk = 0; blk < nblk; ++blk) {
     const int K0 = blk * KB;
@@ -944,8 +1045,8 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
     if (cnext >= nf) {             // partial factorisation: nothing left to factor, the columns right of nf only get Q^T
       CQR_CUDA(cudaStreamWaitEvent(G, c->ev_panel[blk & 1], 0));
       use(G, pr.sm_g, false);
-      if (!t_on_chain(K0)) do_block_t(K0, bb[blk & 1]);
-      do_update(K0, bb[blk & 1], cnext, n);
+      if (!t_on_chain(K0)) do_block_t(K0, bb(blk));
+      do_update(K0, bb(blk), cnext, n);
       prev_g = G;
       break;
     }
@@ -953,8 +1054,8 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
     if (!slice_done) {
       CQR_CUDA(cudaStreamWaitEvent(G, c->ev_panel[blk & 1], 0));
       use(G, pr.sm_g, false);
-      if (!t_on_chain(K0)) do_block_t(K0, bb[blk & 1]);
-      do_update(K0, bb[blk & 1], cnext, cnext + la);
+      if (!t_on_chain(K0)) do_block_t(K0, bb(blk));
+      do_update(K0, bb(blk), cnext, cnext + la);
       CQR_CUDA(cudaEventRecord(c->ev_a, G));
     }
     if (prev_p != P) CQR_CUDA(cudaStreamWaitEvent(P, c->ev_panel[blk & 1], 0));
@@ -969,13 +1070,13 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
     use(G, pr.sm_g, false);
     if (slice_done) {                        // this block's slice was applied panel by panel: T and the rest are what is left
       CQR_CUDA(cudaStreamWaitEvent(G, c->ev_panel[blk & 1], 0));
-      if (!t_on_chain(K0)) do_block_t(K0, bb[blk & 1]);
+      if (!t_on_chain(K0)) do_block_t(K0, bb(blk));
     }
-    do_update(K0, bb[blk & 1], cnext + la, n);
+    do_update(K0, bb(blk), cnext + la, n);
     slice_done = false;
     use(P, pr.sm_p, true);
     if (pws) {
-      BlockBufs& Bn = bb[(blk + 1) & 1];
+      BlockBufs& Bn = bb(blk + 1);
       const int w2 = (n - c2 < KB) ? n - c2 : KB;
       PanelHook hk;
       hk.panel_done = c->ev_pp[(blk + 1) & 1];
@@ -989,15 +1090,15 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
         apply_block(c, m - j0, b, c2 + w2 - col0, V, T, dA + j0 + (long long)col0 * lda, lda, 1, bw_slice, tensor);
         use(P, pr.sm_p, true);
       };
-      do_panels(cnext, bb[(blk + 1) & 1], &hk);
+      do_panels(cnext, bb(blk + 1), &hk);
       CQR_CUDA(cudaEventRecord(c->ev_a, G));
       slice_done = true;
     } else {
-      do_panels(cnext, bb[(blk + 1) & 1]);
+      do_panels(cnext, bb(blk + 1));
     }
     CQR_CUDA(cudaEventRecord(c->ev_panel[(blk + 1) & 1], P));
     ship(cnext, c->ev_panel[(blk + 1) & 1]);
-    if (t_on_chain(cnext)) { do_block_t(cnext, bb[(blk + 1) & 1]); CQR_CUDA(cudaEventRecord(c->ev_panel[(blk + 1) & 1], P)); }
+    if (t_on_chain(cnext)) { do_block_t(cnext, bb(blk + 1)); CQR_CUDA(cudaEventRecord(c->ev_panel[(blk + 1) & 1], P)); }
     prev_g = G; prev_p = P;
   }
   use(nullptr, 0, false);
@@ -1099,9 +1200,48 @@ int cqr_solve_ls(cqr_context* c, const float* dA, int lda, int m, int n, const f
 }
 
 // ---- TSQR ---------------------------------------------------------------------------------------
+// R-only TSQR on the tensor-pipe flat-tree kernel (tsqr_mma.cu): every launch turns its input into one 64 x 64 R per CTA
+// (warp chains of 64-row blocks, then the CTA's warps combined), and the stacked R's of a level are the next level's
+// input matrix; the last level is a single CTA that writes the n x n R.  8M x 64: 1184 chains -> 148 -> 19 -> 3 -> 1.
+static int tsqr_mma_r(cqr_context* c, const float* dA, long long lda, long long m, int n, float* dR, int ldr) {
+  const int wpc = mma_tsqr_warps_per_cta();
+  const long long max_chains = (long long)c->sm_count * wpc;
+  struct Lv { long long m, rpc; int chains, ctas; float* out; };
+  std::vector<Lv> lv;
+  for (long long mm = m;;) {
+    const long long blocks = (mm + 63) / 64;
+    long long bpc = (blocks + max_chains - 1) / max_chains;
+    if (bpc < 1) bpc = 1;
+    const long long chains = (blocks + bpc - 1) / bpc;
+    const int ctas = (int)((chains + wpc - 1) / wpc);
+    lv.push_back(Lv{mm, bpc * 64, (int)chains, ctas, nullptr});
+    if (ctas == 1) break;
+    mm = 64ll * ctas;
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    Carver cv(pass ? c->ws : nullptr);
+    for (size_t l = 0; l + 1 < lv.size(); ++l) lv[l].out = cv.take(64ll * lv[l].ctas * 64);
+    if (!pass) { int rc = ws_ensure(c, cv.off); if (rc) return rc; }
+  }
+  ProfScope ps(c, CQR_PROF_PANEL, 2.0 * m * n * n, 4.0 * (double)m * n);
+  for (size_t l = 0; l < lv.size(); ++l) {
+    const bool last = l + 1 == lv.size();
+    MmaTsqrParams p{};
+    p.a = l ? lv[l - 1].out : dA;
+    p.lda = l ? 64ll * lv[l - 1].ctas : lda;
+    p.m = lv[l].m; p.n = n; p.rows_per_chain = lv[l].rpc; p.chains = lv[l].chains;
+    p.r_out = last ? dR : lv[l].out;
+    p.r_ld = last ? ldr : 64ll * lv[l].ctas;
+    p.out_rows = last ? n : 64;
+    launch_tsqr_mma_r(p, cur_stream(c));
+  }
+  return (int)cudaGetLastError();
+}
+
 static int tsqr_common(cqr_context* c, float* dA, int lda, long long m, int n, float* dR, int ldr, bool keep) {
   if (!c || !dA || !dR || n < 1 || n > 64 || m < n || lda < m || ldr < n) return CQR_EINVAL;
   DeviceGuard dg__(c->device);
+  if (!keep && c->opt_flat == 2 && m >= 16384) return tsqr_mma_r(c, dA, lda, m, n, dR, ldr);
   const int th = c->opt_tile_rows;
   TsqrPlan plan;
   for (int pass = 0; pass < 2; ++pass) {
@@ -1249,11 +1389,37 @@ void mmqr(float* mat, float* tau, int m, int n) {
   const long long lda = round_up(m, 4);
   float* dA = legacy_buf(0, (size_t)lda * n * sizeof(float));
   float* dtau = legacy_buf(1, (size_t)n * sizeof(float));
-  LEGACY_CHECK(cudaMemcpy2D(dA, lda * sizeof(float), mat, (size_t)m * sizeof(float), (size_t)m * sizeof(float), n,
-                            cudaMemcpyHostToDevice));
+  // Upload.  The reference blocks on one cudaMemcpy before its first kernel (qr.cu:498).  From pinned host memory the
+  // matrix goes up in column chunks on a copy stream instead and the factorisation starts on the first chunk: later
+  // chunks join the trailing updates when they have arrived (geqrf_impl), so all but the first chunk's transfer hides
+  // under the panel chain.  Pageable memory (cudaMemcpyAsync would stage and block the host) and small matrices keep the
+  // single blocking copy.  CQR_H2D_OVERLAP=0 turns the chunked upload off.
+  static const bool h2d_overlap = !(getenv("CQR_H2D_OVERLAP") && atoi(getenv("CQR_H2D_OVERLAP")) == 0);
+  cudaPointerAttributes pa{};
+  const bool pinned = cudaPointerGetAttributes(&pa, mat) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  c->in_n = 0;
+  if (h2d_overlap && pinned && n >= 8192 && (size_t)m * n * sizeof(float) >= ((size_t)256 << 20) && m <= 16384 && c->opt_lookahead) {
+    int nb = 0;
+    c->in_cb[0] = 0;
+    for (int e : {1024, 2048, 4096}) if (e < n) c->in_cb[++nb] = e;
+    for (int e = 8192; e < n && nb < kMaxInChunks - 1; e += 4096) c->in_cb[++nb] = e;
+    c->in_cb[++nb] = n;
+    for (int k = 0; k < nb; ++k) {
+      const int c0 = c->in_cb[k], w = c->in_cb[k + 1] - c0;
+      LEGACY_CHECK(cudaMemcpy2DAsync(dA + (size_t)c0 * lda, lda * sizeof(float), mat + (size_t)c0 * m, (size_t)m * sizeof(float),
+                                     (size_t)m * sizeof(float), w, cudaMemcpyHostToDevice, c->copy_in));
+      LEGACY_CHECK(cudaEventRecord(c->in_ev[k], c->copy_in));
+    }
+    c->in_n = nb;
+  } else {
+    LEGACY_CHECK(cudaMemcpy2D(dA, lda * sizeof(float), mat, (size_t)m * sizeof(float), (size_t)m * sizeof(float), n,
+                              cudaMemcpyHostToDevice));
+  }
   c->host_out = mat;   // finished column blocks stream back while the rest is still being factored
   const int rc = cqr_geqrf(c, dA, (int)lda, m, n, dtau);
   c->host_out = nullptr;
+  c->in_n = 0;
   LEGACY_CHECK(rc);
   // unused slots zero, qr.c:62 -- done while the device is still factoring (cqr_geqrf only enqueues): the reference-sized
   // tau grid is rowPanels * colPanels * PC floats (18 MB at 16384^2), of which the first n are overwritten below

@@ -36,11 +36,17 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], unsigned a0, unsigned a1
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-// x = hi + lo: hi = x rounded to TF32 (cvt.rna), lo = the exact remainder (the tensor pipe reads its top 19 bits)
+// x = hi + lo with hi = x rounded to TF32 (11 significant bits, round to nearest on the bit pattern: ties away from zero)
+// and lo = x - hi exactly.  Rounding, not truncating: a truncated head leaves a remainder of x's sign, the dropped
+// lo * lo term and the pipe's own truncation of lo then bias every product the same way, and over a chain of blocks
+// the bias adds up linearly (8M x 64 uniform data: Gram error 2e-4 instead of 5e-7).  cvt.rna.tf32.f32 does the same in
+// five instructions (NaN handling); the integer add + mask is two, and since the head is a computed value it lands in
+// its fragment slot directly -- the block's accumulator registers need the order (c0, c2, c1, c3) as an A fragment.
 __device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
+__device__ __forceinline__ unsigned bits(float x) { return __float_as_uint(x); }
 
 struct Lane { int g, t; };   // lane = 4 g + t: g = column within an 8-column group (fragment row), t = row-pair selector
 
@@ -49,8 +55,7 @@ struct Lane { int g, t; };   // lane = 4 g + t: g = column within an 8-column gr
 
 // Sub-panel P (columns 8 P .. 8 P + 7): Householder column by column on the FMA pipe.  Lane group g owns column 8 P + g.
 // On exit xc holds x~ = x / u of the lane's column, gs the strictly upper triangle of X~^T X, taus the 8 tau values.
-template <int P>
-__device__ __forceinline__ void subpanel(f32x2 (&xc)[8], float* __restrict__ Rs, float* __restrict__ xs, float* __restrict__ gs,
+__device__ __forceinline__ void subpanel(const int P, f32x2 (&xc)[8], float* __restrict__ Rs, float* __restrict__ xs, float* __restrict__ gs,
                                          float* __restrict__ taus, const Lane L) {
   const int g = L.g, t = L.t;
 #pragma unroll 1
@@ -114,7 +119,13 @@ __device__ __forceinline__ void subpanel(f32x2 (&xc)[8], float* __restrict__ Rs,
 
 // Column g of the sub-panel's compact-WY T by back substitution on T^-1 = diag(1/tau) + striu(X~^T X~); returned as
 // the B fragment of Y = T^T W: b0 = T(2 t, g), b1 = T(2 t + 1, g).
-__device__ __forceinline__ void t_fragment(const float* __restrict__ gs, const float* __restrict__ taus, const Lane L, float& b0, float& b1) {
+// T's diagonal (the taus) is returned apart, as tau(2 t), tau(2 t + 1) for the lane's two W columns, and the fragment holds
+// the strictly upper part only: Y = tau . W + striu(T)^T W.  W is R-sized while a chain runs (v_j ~ e_j, tau ~ 2, Y ~ 2 R),
+// and the tensor pipe accumulates with round-toward-zero: a Y shaved by an ulp per block shrinks |R| by as much, and over
+// a chain of 111 blocks that compounds to 1e-5.  The dominant term tau . W is therefore a rounded fp32 multiply on the
+// FMA pipe; striu(T) is O(|x~|^2), small exactly when R is large.
+__device__ __forceinline__ void t_fragment(const float* __restrict__ gs, const float* __restrict__ taus, const Lane L, float& b0, float& b1,
+                                           float& tau0, float& tau1) {
   float G[8][8], tv[8], tc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -134,19 +145,23 @@ __device__ __forceinline__ void t_fragment(const float* __restrict__ gs, const f
     }
     tc[i] = (i == L.g) ? tv[i] : ((i < L.g) ? -tv[i] * (a0 + a1) : 0.f);
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) if (i == L.g) tc[i] = 0.f;
   b0 = (L.t == 0) ? tc[0] : (L.t == 1) ? tc[2] : (L.t == 2) ? tc[4] : tc[6];
   b1 = (L.t == 0) ? tc[1] : (L.t == 1) ? tc[3] : (L.t == 2) ? tc[5] : tc[7];
+  tau0 = (L.t == 0) ? tv[0] : (L.t == 1) ? tv[2] : (L.t == 2) ? tv[4] : tv[6];
+  tau1 = (L.t == 0) ? tv[1] : (L.t == 1) ? tv[3] : (L.t == 2) ? tv[5] : tv[7];
 }
 
 // Columns right of sub-panel P: W = R(J, C) + X~^T B(:, C), Y = T^T W, R(J, C) -= Y, B(:, C) -= X~ Y.
-template <int P>
-__device__ __forceinline__ void trailing(float (&blk)[4][8][4], const f32x2 (&xc)[8], float* __restrict__ Rs, float* __restrict__ xt,
+// P is a run-time value (one copy of this code instead of eight: the fully specialised version was 120 KB of
+// instructions, and eight warps streaming through it at different places were instruction-fetch bound); the 16-column
+// tiles keep static register indices and are skipped by warp-uniform guards.
+__device__ __forceinline__ void trailing(const int P, float (&blk)[4][8][4], const f32x2 (&xc)[8], float* __restrict__ Rs, float* __restrict__ xt,
                                          const float* __restrict__ gs, const float* __restrict__ taus, const Lane L, const int n) {
-  constexpr int MT0 = (P + 1) / 2;             // first 16-column tile entirely right of the sub-panel
-  constexpr bool HALF = (P % 2) == 0;          // P even: the sub-panel is the low half of tile P / 2, its high half is trailing
-  constexpr int MTF = HALF ? P / 2 : MT0;      // first tile that takes part
-  if (P == 7) return;
   const int g = L.g, t = L.t;
+  const bool even = (P & 1) == 0;              // P even: the sub-panel is the low half of tile P / 2, whose high half is trailing
+  const int mtf = (P + 1) >> 1;                // first tile that takes part (for even P this is the shared tile P / 2)
   // X~^T for the update's B fragments: row-major 64 x 8 in shared memory
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
@@ -164,90 +179,130 @@ __device__ __forceinline__ void trailing(float (&blk)[4][8][4], const f32x2 (&xc
     split_tf32(lo, xh[kt][0], xl[kt][0]);
     split_tf32(hi, xh[kt][1], xl[kt][1]);
   }
-  float tb0, tb1;
-  t_fragment(gs, taus, L, tb0, tb1);
-  unsigned th[2], tl[2];
-  split_tf32(tb0, th[0], tl[0]);
-  split_tf32(tb1, th[1], tl[1]);
+  float tb0, tb1, tau0, tau1;
+  t_fragment(gs, taus, L, tb0, tb1, tau0, tau1);
+  unsigned th0, th1, tl0, tl1;
+  split_tf32(tb0, th0, tl0);
+  split_tf32(tb1, th1, tl1);
   float* R0 = Rs + (8 * P + 2 * t) * kRld + g;  // rows 8 P + 2 t (and + 1) of R
   float* R1 = R0 + kRld;
-  unsigned yh[4][4], yl[4][4];                 // A fragments of the update: -Y, split
+  float yn[4][4];                              // A fragments of the update: -Y in fragment order
 #pragma unroll
-  for (int mt = MTF; mt < 4; ++mt) {
-    if (16 * mt >= n) break;                   // warp-uniform: nothing but zero columns from here on
-    const bool half = HALF && mt == P / 2;
-    float r[4];
-    r[0] = R0[16 * mt]; r[1] = R1[16 * mt]; r[2] = R0[16 * mt + 8]; r[3] = R1[16 * mt + 8];
-    // three independent accumulator chains (lo*hi, hi*lo, hi*hi): an HMMA has 20 clk latency and issues every 8
-    float w0[4] = {0.f, 0.f, 0.f, 0.f}, w1[4] = {0.f, 0.f, 0.f, 0.f}, w2[4] = {r[0], r[1], r[2], r[3]};
+  for (int mt = 0; mt < 4; ++mt) {
+    if (mt >= mtf && 16 * mt < n) {            // warp-uniform
+      const bool half = even && 2 * mt == P;
+      float r[4];
+      r[0] = R0[16 * mt]; r[1] = R1[16 * mt]; r[2] = R0[16 * mt + 8]; r[3] = R1[16 * mt + 8];
+      // three independent accumulator chains (lo*hi, hi*lo, hi*hi): an HMMA has 20 clk latency and issues every 8
+      // (all three start from zero: the pipe accumulates with round-toward-zero, and with the large R(J, C) in the
+      // accumulator every HMMA would shave up to an ulp of R off W -- 8 per block, always toward zero, which over a
+      // chain of 111 blocks shrank R by 1e-4; R joins in one rounded fp32 add below)
+      float w0[4] = {0.f, 0.f, 0.f, 0.f}, w1[4] = {0.f, 0.f, 0.f, 0.f}, w2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int kt = 0; kt < 8; ++kt) {
-      unsigned ah[4], al[4];
-      split_tf32(blk[mt][kt][0], ah[0], al[0]);
-      split_tf32(blk[mt][kt][2], ah[1], al[1]);
-      split_tf32(blk[mt][kt][1], ah[2], al[2]);
-      split_tf32(blk[mt][kt][3], ah[3], al[3]);
-      mma_tf32(w0, al[0], al[1], al[2], al[3], xh[kt][0], xh[kt][1]);
-      mma_tf32(w1, ah[0], ah[1], ah[2], ah[3], xl[kt][0], xl[kt][1]);
-      mma_tf32(w2, ah[0], ah[1], ah[2], ah[3], xh[kt][0], xh[kt][1]);
+      for (int kt = 0; kt < 8; ++kt) {
+        unsigned h0, h1, h2, h3, l0, l1, l2, l3;
+        split_tf32(blk[mt][kt][0], h0, l0);
+        split_tf32(blk[mt][kt][2], h1, l1);
+        split_tf32(blk[mt][kt][1], h2, l2);
+        split_tf32(blk[mt][kt][3], h3, l3);
+        mma_tf32(w0, l0, l1, l2, l3, xh[kt][0], xh[kt][1]);
+        mma_tf32(w1, h0, h1, h2, h3, xl[kt][0], xl[kt][1]);
+        mma_tf32(w2, h0, h1, h2, h3, xh[kt][0], xh[kt][1]);
+      }
+      float wv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) wv[e] = r[e] + ((w0[e] + w1[e]) + w2[e]);
+      // Y = T^T W: A = W^T (same k permutation), B = T
+      float y[4] = {0.f, 0.f, 0.f, 0.f};
+      {
+        unsigned h0, h1, h2, h3, l0, l1, l2, l3;
+        split_tf32(wv[0], h0, l0);
+        split_tf32(wv[2], h1, l1);
+        split_tf32(wv[1], h2, l2);
+        split_tf32(wv[3], h3, l3);
+        mma_tf32(y, l0, l1, l2, l3, th0, th1);
+        mma_tf32(y, h0, h1, h2, h3, tl0, tl1);
+        mma_tf32(y, h0, h1, h2, h3, th0, th1);
+      }
+      y[0] = fmaf(tau0, wv[0], y[0]); y[1] = fmaf(tau1, wv[1], y[1]); y[2] = fmaf(tau0, wv[2], y[2]); y[3] = fmaf(tau1, wv[3], y[3]);
+      if (!half) { R0[16 * mt] = r[0] - y[0]; R1[16 * mt] = r[1] - y[1]; }
+      R0[16 * mt + 8] = r[2] - y[2]; R1[16 * mt + 8] = r[3] - y[3];
+      // the sub-panel's own columns (low half of a shared tile) stay as they are: zero rows of -Y
+      yn[mt][0] = half ? 0.f : -y[0]; yn[mt][1] = -y[2]; yn[mt][2] = half ? 0.f : -y[1]; yn[mt][3] = -y[3];
     }
-    float wv[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) wv[e] = (w0[e] + w1[e]) + w2[e];
-    // Y = T^T W: A = W^T (same k permutation), B = T
-    unsigned wh[4], wl[4];
-    split_tf32(wv[0], wh[0], wl[0]);
-    split_tf32(wv[2], wh[1], wl[1]);
-    split_tf32(wv[1], wh[2], wl[2]);
-    split_tf32(wv[3], wh[3], wl[3]);
-    float y[4] = {0.f, 0.f, 0.f, 0.f};
-    mma_tf32(y, wl[0], wl[1], wl[2], wl[3], th[0], th[1]);
-    mma_tf32(y, wh[0], wh[1], wh[2], wh[3], tl[0], tl[1]);
-    mma_tf32(y, wh[0], wh[1], wh[2], wh[3], th[0], th[1]);
-    if (!half) { R0[16 * mt] = r[0] - y[0]; R1[16 * mt] = r[1] - y[1]; }
-    R0[16 * mt + 8] = r[2] - y[2]; R1[16 * mt + 8] = r[3] - y[3];
-    // the sub-panel's own columns (low half of a shared tile) stay as they are: zero rows of -Y
-    split_tf32(half ? 0.f : -y[0], yh[mt][0], yl[mt][0]);
-    split_tf32(-y[2], yh[mt][1], yl[mt][1]);
-    split_tf32(half ? 0.f : -y[1], yh[mt][2], yl[mt][2]);
-    split_tf32(-y[3], yh[mt][3], yl[mt][3]);
   }
   __syncwarp();                                // X~^T is in shared memory
+  unsigned bh[8][2], bl[8][2];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
     const float2 v = *reinterpret_cast<const float2*>(xt + (8 * nt + g) * 8 + 2 * t);   // X~(8 nt + g, 2 t), X~(8 nt + g, 2 t + 1)
-    unsigned bh[2], bl[2];
-    split_tf32(v.x, bh[0], bl[0]);
-    split_tf32(v.y, bh[1], bl[1]);
+    split_tf32(v.x, bh[nt][0], bl[nt][0]);
+    split_tf32(v.y, bh[nt][1], bl[nt][1]);
+  }
 #pragma unroll
-    for (int mt = MTF; mt < 4; ++mt) {
-      if (16 * mt >= n) break;
-      mma_tf32(blk[mt][nt], yl[mt][0], yl[mt][1], yl[mt][2], yl[mt][3], bh[0], bh[1]);
-      mma_tf32(blk[mt][nt], yh[mt][0], yh[mt][1], yh[mt][2], yh[mt][3], bl[0], bl[1]);
-      mma_tf32(blk[mt][nt], yh[mt][0], yh[mt][1], yh[mt][2], yh[mt][3], bh[0], bh[1]);
+  for (int mt = 0; mt < 4; ++mt) {
+    if (mt >= mtf && 16 * mt < n) {
+      unsigned h0, h1, h2, h3, l0, l1, l2, l3;
+      split_tf32(yn[mt][0], h0, l0);
+      split_tf32(yn[mt][1], h1, l1);
+      split_tf32(yn[mt][2], h2, l2);
+      split_tf32(yn[mt][3], h3, l3);
+      // -X~ Y into zero accumulators, then one rounded add per element (same reason as above)
+      float u[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) { u[nt][0] = 0.f; u[nt][1] = 0.f; u[nt][2] = 0.f; u[nt][3] = 0.f; }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) mma_tf32(u[nt], l0, l1, l2, l3, bh[nt][0], bh[nt][1]);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) mma_tf32(u[nt], h0, h1, h2, h3, bl[nt][0], bl[nt][1]);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) mma_tf32(u[nt], h0, h1, h2, h3, bh[nt][0], bh[nt][1]);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) blk[mt][nt][e] += u[nt][e];
     }
   }
   __syncwarp();                                // every lane has read X~^T before the next sub-panel rewrites it
 }
 
-template <int P>
-struct SubPanels {
-  static __device__ __forceinline__ void run(float (&blk)[4][8][4], float* Rs, float* xs, float* xt, float* gs, float* taus, const Lane L, const int n) {
-    if (8 * P < n) {                           // warp-uniform
-      constexpr int MT = P / 2, H = P % 2;
-      f32x2 xc[8];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) xc[nt] = fpack2(blk[MT][nt][2 * H], blk[MT][nt][2 * H + 1]);
-      subpanel<P>(xc, Rs, xs, gs, taus, L);
-      trailing<P>(blk, xc, Rs, xt, gs, taus, L, n);
-      SubPanels<P + 1>::run(blk, Rs, xs, xt, gs, taus, L, n);
+#ifdef CQR_MMA_TRACE
+__device__ long long g_mma_trace[4];           // clock cycles of warp 0 of CTA 0: [0] loads, [1] sub-panels, [2] trailing, [3] blocks
+#define CQR_TR(i, t0) do { if (tr) g_mma_trace[i] += clock64() - (t0); } while (0)
+#else
+#define CQR_TR(i, t0) do { } while (0)
+#endif
+
+// One 64-row block into the running R: eight sub-panels.
+__device__ __forceinline__ void block_step(float (&blk)[4][8][4], float* Rs, float* xs, float* xt, float* gs, float* taus, const Lane L, const int n,
+                                           const bool tr) {
+#pragma unroll 1
+  for (int P = 0; P < 8; ++P) {
+    if (8 * P >= n) break;                     // warp-uniform
+#ifdef CQR_MMA_TRACE
+    long long t0 = clock64();
+#endif
+    f32x2 xc[8];                               // the lane's sub-panel column: tile P / 2, half P % 2 of the block registers
+    switch (P) {
+#define CQR_XC_CASE(PP)                                                                                              \
+      case PP:                                                                                                       \
+        _Pragma("unroll") for (int nt = 0; nt < 8; ++nt) xc[nt] = fpack2(blk[PP / 2][nt][2 * (PP % 2)], blk[PP / 2][nt][2 * (PP % 2) + 1]); \
+        break;
+      CQR_XC_CASE(0) CQR_XC_CASE(1) CQR_XC_CASE(2) CQR_XC_CASE(3) CQR_XC_CASE(4) CQR_XC_CASE(5) CQR_XC_CASE(6)
+      default:
+        _Pragma("unroll") for (int nt = 0; nt < 8; ++nt) xc[nt] = fpack2(blk[3][nt][2], blk[3][nt][3]);
+        break;
+#undef CQR_XC_CASE
     }
+    subpanel(P, xc, Rs, xs, gs, taus, L);
+    CQR_TR(1, t0);
+#ifdef CQR_MMA_TRACE
+    t0 = clock64();
+#endif
+    if (P < 7) trailing(P, blk, xc, Rs, xt, gs, taus, L, n);
+    CQR_TR(2, t0);
   }
-};
-template <>
-struct SubPanels<8> {
-  static __device__ __forceinline__ void run(float (&)[4][8][4], float*, float*, float*, float*, float*, const Lane, const int) {}
-};
+}
 
 }  // namespace
 
@@ -341,7 +396,10 @@ __global__ void __launch_bounds__(32 * WPC, 1) tsqr_mma_r_kernel(MmaTsqrParams p
     }
     if (act) {
       __syncwarp();
-      SubPanels<0>::run(blk, Rs, xs, xt, gs, taus, L, n);
+      block_step(blk, Rs, xs, xt, gs, taus, L, n, blockIdx.x == 0 && w == 0 && lane == 0);
+#ifdef CQR_MMA_TRACE
+      if (blockIdx.x == 0 && w == 0 && lane == 0) g_mma_trace[3] += 1;
+#endif
     }
   }
   __syncwarp();
@@ -358,6 +416,14 @@ __global__ void __launch_bounds__(32 * WPC, 1) tsqr_mma_r_kernel(MmaTsqrParams p
 }
 
 constexpr int kMmaWpc = 8;
+
+#ifdef CQR_MMA_TRACE
+void mma_tsqr_read_trace(long long* out) {
+  cudaMemcpyFromSymbol(out, g_mma_trace, sizeof(long long) * 4);
+  long long z[4] = {0, 0, 0, 0};
+  cudaMemcpyToSymbol(g_mma_trace, z, sizeof(z));
+}
+#endif
 
 int mma_tsqr_warps_per_cta() { return kMmaWpc; }
 

@@ -77,7 +77,7 @@ enum {
   CQR_OPT_LOOKAHEAD = 5,    /* 0: none; 1: next block's panels overlap the trailing update on a side stream; 2 (default): as 1, and in the
                              * panel-bound phase each finished panel is applied to the block after next's columns at once (panel-wise slices) */
   CQR_OPT_PANEL = 6,        /* 1 (default): one-launch multi-CTA Householder panel; 0: TSQR tree + Householder reconstruction */
-  CQR_OPT_FLAT_TSQR = 7     /* 1 (default): cqr_tsqr_r on >= 16384 rows uses the warp-resident flat-tree leaf; 0: 256-row tile leaves */
+  CQR_OPT_FLAT_TSQR = 7     /* R-only cqr_tsqr_r on >= 16384 rows: 1 (default) SIMT flat-tree leaf, 2 tensor-pipe flat-tree leaf (tsqr_mma.cu), 0 256-row tile leaves */
 };
 
 int cqr_create(cqr_context** ctx, int device);
@@ -163,6 +163,12 @@ int cqr_set_identity(cqr_context* ctx, float* dA, int lda, int m, int n);
 
 /* Library build info: "sm_100a;<date>;<features>" */
 const char* cqr_version(void);
+
+/* ---- Part 3: comparator slot of the reference's command line (never on the hot path) ----------------------
+ * The reference can time MAGMA's magma_sgeqrf2_gpu next to mmqr (qr.cu:555-565 magmaQR, qr.cu:790-806; timing only,
+ * compiled out by default).  Same call shape with cuSOLVER's geqrf, dlopen'ed at run time: host matrix up, library
+ * factorisation, matrix and tau[0..n) back.  Returns 0, CQR_EUNSUPPORTED when libcusolver is not on the box. */
+int cqr_compare_cusolver_sgeqrf(float* mat, float* tau, int m, int n);
 
 #ifdef __cplusplus
 }

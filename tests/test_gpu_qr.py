@@ -162,6 +162,45 @@ def test_legacy_mmqr_alloc_and_printmat(pkg, port, capfd):
     assert text == "Matrix 3 x 2, row by row:\n 1.000000  2.500000 \n-3.000000  4.000000 \n 0.125000  6.000000 \n\n"
 
 
+def test_legacy_mmqr_chunked_upload_matches_device_path(pkg, torch):
+    """Legacy mmqr on PINNED host memory uploads in column chunks that join the factorisation late (driver.cu: catch-up
+    streams); the result must agree with the device-resident factorisation of the same matrix and meet the acceptance
+    bounds (R against the Gram matrix, Q^T A = R through apply_q)."""
+    m = n = 8192
+    g = torch.Generator(device="cuda").manual_seed(77)
+    A0 = pkg.colmajor(m, n); A0.copy_(torch.rand((m, n), device="cuda", generator=g))
+    host = torch.empty((n, m), dtype=torch.float32, pin_memory=True)
+    host.copy_(A0.t())
+    hnp = host.numpy().T
+    tau_h = pkg.mmqr(hnp)
+    ctx = pkg.Context(0); ctx.use_torch_stream()
+    dA = A0.clone(); tau = torch.zeros(n, device="cuda")
+    ctx.geqrf(dA, tau); ctx.synchronize()
+    H = torch.from_numpy(np.ascontiguousarray(hnp.T)).cuda().t()          # factored storage from the host path
+    d = float((H - dA).norm() / dA.norm())
+    assert d < 1e-4, f"chunked-upload factorisation differs from the device path by {d}"   # same algorithm, other GEMM grouping (catch-up slices)
+    assert float((torch.from_numpy(tau_h[:n]).cuda() - tau).norm() / tau.norm()) < 1e-4
+    Rh = torch.triu(H[:n]).double()
+    G = A0.t().double() @ A0.double()
+    assert float((Rh.t() @ Rh - G).norm() / G.norm()) < 5e-5
+    ctx.close()
+
+
+def test_comparator_slot_cusolver_agrees(pkg):
+    """cqr_compare_cusolver_sgeqrf (the MAGMA slot of qr.cu:555-565 filled with cuSOLVER): when the library is on the box its
+    R must agree with ours -- the one place the two are compared; the reference itself never compares."""
+    A = oracle.rand_matrix(484, 484, 12)
+    CV = A.copy(order="F"); ctau = np.zeros(484, dtype=np.float32)
+    import ctypes
+    fp = ctypes.POINTER(ctypes.c_float)
+    rc = pkg.lib.cqr_compare_cusolver_sgeqrf(CV.ctypes.data_as(fp), ctau.ctypes.data_as(fp), 484, 484)
+    if rc != 0:
+        assert rc == -4, f"unexpected comparator status {rc}"       # CQR_EUNSUPPORTED: libcusolver not loadable
+        pytest.skip("libcusolver is not on this box")
+    RV = A.copy(order="F"); pkg.mmqr(RV)
+    assert metrics.r_rel_diff(RV, CV) <= metrics.TOL_R
+
+
 def test_legacy_dgemm_and_identity_vs_oracle(pkg, port):
     rng = np.random.default_rng(0)
     for k, m, n in [(6, 6, 4), (33, 70, 129), (200, 64, 200), (1, 5, 1)]:
@@ -376,8 +415,10 @@ def test_cli_qr_device_matches_reference_interface(pkg):
     (qr.cu:789) and -- with `check` -- its commented-out residual validation (qr.cu:822-850)."""
     import subprocess
     exe = os.path.join(os.path.dirname(pkg.__file__), "qr_device")
-    out = subprocess.run([exe, "512", "512", "check"], capture_output=True, text=True, timeout=300)
+    out = subprocess.run([exe, "512", "512", "check", "compare"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
+    # the comparator slot (qr.cu:790-806, MAGMA there): cuSOLVER's geqrf timed the same way, or a clear "unavailable"
+    assert "cuSOLVER ran QR on 484x484 matrix in" in out.stdout or "cuSOLVER comparator unavailable" in out.stdout
     assert "Exact problem size: 484x484" in out.stdout
     assert "MMQR ran QR on 484x484 matrix in" in out.stdout and "(avg over 3)" in out.stdout
     units = float(out.stdout.split("in units of n*eps:")[1].split(")")[0])
@@ -460,6 +501,31 @@ def test_tsqr_flat_leaf_vs_reference_flat_tree(pkg, torch, ctx, port):
     Rh = host(R)
     assert np.isfinite(Rh).all() and np.all(Rh[:, 5][6:] == 0)
     assert metrics.gram_error(A2, Rh) < 1e-5
+
+
+@pytest.mark.parametrize("m,n,kind", [(16384, 64, "u"), (20011, 17, "u"), (65536, 64, "n"), (100003, 40, "u"), (1 << 20, 64, "u")])
+def test_tsqr_r_tensor_pipe_leaf(pkg, torch, ctx, m, n, kind):
+    """CQR_OPT_FLAT_TSQR = 2: the flat-tree leaf with its block products on the tensor pipe (tsqr_mma.cu: mma.sync TF32,
+    three-product split, every R-sized term on the FMA pipe) against the default SIMT leaf, fp64 and the Gram matrix."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    A = pkg.colmajor(m, n)
+    A.copy_(torch.rand((m, n), device="cuda", generator=g) if kind == "u" else torch.randn((m, n), device="cuda", generator=g))
+    G = A.t().double() @ A.double()
+    Rs = {}
+    try:
+        for mode in (2, 1):
+            ctx.set_option(pkg.OPT_FLAT_TSQR, mode)
+            R = pkg.colmajor(n, n); R.fill_(float("nan"))
+            ctx.tsqr_r(A, R); ctx.synchronize()
+            assert float(torch.tril(R, -1).abs().max()) == 0.0 if n > 1 else True
+            Rd = torch.triu(R.double())
+            assert float((Rd.t() @ Rd - G).norm() / G.norm()) < 2e-6
+            Rs[mode] = R.cpu().numpy()
+    finally:
+        ctx.set_option(pkg.OPT_FLAT_TSQR, 1)
+    assert metrics.r_rel_diff(Rs[2], Rs[1]) <= 1e-5
+    if m <= 200000:
+        assert metrics.r_rel_diff(Rs[2], np.linalg.qr(A.cpu().numpy().astype(np.float64), mode="r")) <= 1e-5
 
 
 def test_tsqr_seeded_form_q_is_linear(pkg, torch, ctx):

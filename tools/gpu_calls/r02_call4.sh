@@ -1,0 +1,6 @@
+set -x
+mkdir -p gpurun_out/r02
+timeout 300 python tools/check_tsqr_mma.py > gpurun_out/r02/check_tsqr_mma.txt 2>&1
+cat gpurun_out/r02/check_tsqr_mma.txt
+timeout 300 python tools/tsqr_bench.py 8388608 1048576 > gpurun_out/r02/tsqr_bench_mma.txt 2>&1
+cat gpurun_out/r02/tsqr_bench_mma.txt

@@ -37,7 +37,7 @@ EXPORTS = [
     "cqr_error_string", "cqr_launch_count", "cqr_profile_begin", "cqr_profile_end", "cqr_profile_timeline", "cqr_reserve", "cqr_geqrf", "cqr_geqrf_partial", "cqr_extract_r", "cqr_form_q",
     "cqr_apply_q", "cqr_solve_ls", "cqr_tsqr_r", "cqr_tsqr_factor", "cqr_tsqr_form_q", "cqr_stack_qr", "cqr_stack_form_q",
     "cqr_geqrf_batched", "cqr_gemm", "cqr_gemm_tf32x3", "cqr_set_identity", "cqr_version",
-    "cqr_compare_cusolver_sgeqrf",
+    "cqr_compare_cusolver_sgeqrf", "mmqr_reference_format", "cqr_mmqr_reference_format",
 ]
 
 
@@ -101,6 +101,8 @@ def _load() -> ctypes.CDLL:
     lib.cqr_set_identity.argtypes = [_VP, _VP, i, i, i]
     lib.cqr_version.restype = ctypes.c_char_p
     lib.cqr_compare_cusolver_sgeqrf.argtypes = [_FP, _FP, i, i]
+    lib.mmqr_reference_format.argtypes = [_FP, _FP, i, i]
+    lib.cqr_mmqr_reference_format.argtypes = [_VP, _VP, i, i, i, _VP]
     return lib
 
 
@@ -155,6 +157,21 @@ def mmqr(mat: np.ndarray, tau: np.ndarray | None = None) -> np.ndarray:
     elif tau.size < tau_size(m, n) or tau.dtype != np.float32:
         raise ValueError("tau must hold rowPanels*colPanels*4 float32 values (getPanelDims)")
     lib.mmqr(_p(mat), _p(tau), m, n)
+    return tau
+
+
+def mmqr_reference_format(mat: np.ndarray, tau: np.ndarray | None = None) -> np.ndarray:
+    """mmqr leaving the REFERENCE's storage (window reflector segments + the tau grid of qr.c:300-304, PR = 64, PC = 4) so
+    that the reference's own explicitQR consumes it; legal shapes only (m = 64 + 60 k, 4 | n, n <= m)."""
+    _host(mat)
+    m, n = mat.shape
+    if m < 64 or n < 4 or n > m or (m - 64) % 60 or n % 4:
+        raise ValueError("the reference's window grid needs m = 64 + 60 k and n a multiple of 4, n <= m")
+    if tau is None:
+        tau = np.empty(tau_size(m, n), dtype=np.float32)
+    elif tau.size < tau_size(m, n) or tau.dtype != np.float32:
+        raise ValueError("tau must hold rowPanels*colPanels*4 float32 values (getPanelDims)")
+    lib.mmqr_reference_format(_p(mat), _p(tau), m, n)
     return tau
 
 

@@ -143,6 +143,10 @@ void mma_tsqr_read_trace(long long* out);   // [loads, sub-panels, trailing] clo
 #endif
 void launch_tsqr_mma_r(const MmaTsqrParams& p, cudaStream_t s);
 
+// ---- exporter for the reference's own storage format: legacy_format.cu ------------------------
+bool legacy_format_shape_ok(int m, int n);       // m = 64 + 60 k, n a multiple of 4, n <= m (the reference's legal shapes)
+void launch_legacy_sweep(float* a, long long lda, int m, int n, float* tau, int rowPanels, int colPanels, float* scratch, cudaStream_t s);
+
 // ---- Householder reconstruction + T builder: reconstruct.cu ---------------------------------
 struct HrParams {
   const float* q;  long long ldq;     // thin Q of the panel (mp x b)

@@ -1313,6 +1313,25 @@ int cqr_stack_form_q(cqr_context* c, const float* dRs, int ldrs, int nblk, int n
   return (int)cudaGetLastError();
 }
 
+// The reference's own storage format: its window sweep with PR = 64, PC = 4 on the device, in place; dtau
+// is the reference-sized grid of getPanelDims (rowPanels * colPanels * 4 floats).  Only the shapes the reference itself
+// factors correctly (m = 64 + 60 k, 4 | n, n <= m; it silently mis-factors the others) -- CQR_EUNSUPPORTED otherwise.
+int cqr_mmqr_reference_format(cqr_context* c, float* dA, int lda, int m, int n, float* dtau_grid) {
+  if (!c || !dA || !dtau_grid || m < 1 || n < 1 || m < n || lda < m) return CQR_EINVAL;
+  if (!legacy_format_shape_ok(m, n)) return CQR_EUNSUPPORTED;
+  DeviceGuard dg__(c->device);
+  float* scratch = nullptr;
+  for (int pass = 0; pass < 2; ++pass) {
+    Carver cv(pass ? c->ws : nullptr);
+    scratch = cv.take((long long)m * 4);
+    if (!pass) { int rc = ws_ensure(c, cv.off); if (rc) return rc; }
+  }
+  int rp, cp;
+  getPanelDims(m, n, &rp, &cp);
+  launch_legacy_sweep(dA, lda, m, n, dtau_grid, rp, cp, scratch, c->stream);
+  return (int)cudaGetLastError();
+}
+
 int cqr_geqrf_batched(cqr_context* c, float* dA, int lda, long long stride, int m, int n, int batch, float* dtau) {
   if (!c || !dA || !dtau || n < 1 || n > 64 || m < n || m > 256 || lda < m || batch < 1) return CQR_EINVAL;
   DeviceGuard dg__(c->device);
@@ -1430,6 +1449,25 @@ void mmqr(float* mat, float* tau, int m, int n) {
   // every other device error here instead of handing back a silently wrong result (cqr_synchronize reports it to
   // device-API callers)
   LEGACY_CHECK(cqr_synchronize(c));
+}
+
+// mmqr with the reference's storage format on output (reflector segments per window + the tau grid of qr.c:300-304), so
+// that the reference's own explicitQR (qr.c:330-438) can consume it.  Host buffers, blocking, legal shapes only.
+void mmqr_reference_format(float* mat, float* tau, int m, int n) {
+  if (!(m && n && m >= n)) { printf("mmqr: need m >= n >= 1 (got %d x %d)\n", m, n); exit(1); }
+  if (!legacy_format_shape_ok(m, n)) { printf("mmqr_reference_format: %d x %d is not on the reference's window grid (m = 64 + 60 k, n %% 4 == 0)\n", m, n); exit(1); }
+  cqr_context* c = legacy_ctx();
+  int rp, cp;
+  getPanelDims(m, n, &rp, &cp);
+  const size_t tau_count = (size_t)rp * cp * kLegacyPC;
+  const long long lda = round_up(m, 4);
+  float* dA = legacy_buf(0, (size_t)lda * n * sizeof(float));
+  float* dtau = legacy_buf(1, tau_count * sizeof(float));
+  LEGACY_CHECK(cudaMemcpy2D(dA, lda * sizeof(float), mat, (size_t)m * sizeof(float), (size_t)m * sizeof(float), n, cudaMemcpyHostToDevice));
+  LEGACY_CHECK(cqr_mmqr_reference_format(c, dA, (int)lda, m, n, dtau));
+  LEGACY_CHECK(cudaStreamSynchronize(c->stream));
+  LEGACY_CHECK(cudaMemcpy2D(mat, (size_t)m * sizeof(float), dA, lda * sizeof(float), (size_t)m * sizeof(float), n, cudaMemcpyDeviceToHost));
+  LEGACY_CHECK(cudaMemcpy(tau, dtau, tau_count * sizeof(float), cudaMemcpyDeviceToHost));
 }
 
 void mmqr_alloc(float* mat, float** tau, int m, int n) {

@@ -38,6 +38,13 @@ void mmqr(float* mat, float* tau, int m, int n);
 /* Replaces the CPU variant mmqr, qr.c:55-313: callee malloc()s *tau, caller free()s. */
 void mmqr_alloc(float* mat, float** tau, int m, int n);
 
+/* mmqr with the REFERENCE's storage on output: its window sweep with PR = 64, PC = 4 (qr.cu:21-23) run on
+ * the device, leaving the per-window reflector segments in place (qr.c:109-167) and
+ * tau[(rowPanels*pcCount + prCount)*4 + col] (qr.c:300-304), so that the reference's own explicitQR (qr.c:330-438)
+ * consumes the result unchanged.  tau holds rowPanels*colPanels*4 floats (getPanelDims).  Only the shapes the
+ * reference factors correctly: m = 64 + 60 k, n a multiple of 4, n <= m -- prints and exit(1)s otherwise. */
+void mmqr_reference_format(float* mat, float* tau, int m, int n);
+
 /* Replaces explicitQR, qr.c:330-438 / qr.cu:582-686.  Q is m x m, R is m x n (zero
  * below the diagonal), A = Q*R; all column-major host buffers owned by the caller. */
 void explicitQR(float* A, float* tau, float* Q, float* R, int m, int n);
@@ -143,6 +150,10 @@ int cqr_tsqr_form_q(cqr_context* ctx, const float* dX, int ldx, float* dQ, int l
 int cqr_stack_qr(cqr_context* ctx, float* dRs, int ldrs, int nblk, int n, float* dtau, float* dR, int ldr);
 int cqr_stack_form_q(cqr_context* ctx, const float* dRs, int ldrs, int nblk, int n, const float* dtau,
                      const float* dX, int ldx, float* dQs, int ldqs);
+
+/* Device core of mmqr_reference_format: in place on dA, dtau_grid = rowPanels*colPanels*4 floats (zero-filled here).
+ * CQR_EUNSUPPORTED for shapes off the reference's window grid. */
+int cqr_mmqr_reference_format(cqr_context* ctx, float* dA, int lda, int m, int n, float* dtau_grid);
 
 /* `batch` independent m x n matrices (m <= 256, n <= 64, m >= n), one CTA each; matrix i
  * starts at dA + i*stride, lda >= m.  tau: batch x n. */

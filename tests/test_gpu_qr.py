@@ -186,6 +186,34 @@ def test_legacy_mmqr_chunked_upload_matches_device_path(pkg, torch):
     ctx.close()
 
 
+@pytest.mark.parametrize("m,n", [(64, 64), (124, 64), (244, 124), (484, 484), (1024 - 60, 256)])
+def test_reference_format_export_feeds_the_reference(pkg, port, m, n):
+    """SURVEY 8f-2, the strongest parity check: mmqr_reference_format runs the reference's window sweep (PR = 64, PC = 4)
+    on the GPU; its storage and tau grid must match what the reference's own mmqr leaves (same algorithm, fp32 rounding
+    apart), and the reference's explicitQR (unmodified qr.c when oracle/_ref is built, else the restatement) must turn
+    the GPU output back into A = Q R within the acceptance bounds."""
+    A = oracle.rand_matrix(m, n, 12)
+    RV = A.copy(order="F")
+    tau = pkg.mmqr_reference_format(RV)
+    ref = oracle.Ref(64, 4) if oracle.Ref.available(64, 4) else None
+    rv_ref, tau_ref = ref.mmqr(A) if ref else port.mmqr(A, 64, 4)
+    assert tau.size == tau_ref.size
+    assert np.linalg.norm(RV - rv_ref) / np.linalg.norm(rv_ref) < 2e-5
+    assert np.linalg.norm(tau - tau_ref) / np.linalg.norm(tau_ref) < 2e-5
+    assert np.array_equal(tau == 0, tau_ref == 0)                       # same slots used, the rest zero (qr.c:62)
+    if m <= 244:                                                           # explicitQR is O(m^3) per reflector (qr.c:415-429)
+        Q, R = ref.explicitQR(RV, tau) if ref else port.explicitQR(RV, tau, 64, 4)
+        check_factorisation(A, Q, R, r_ref=rv_ref)
+
+
+def test_reference_format_rejects_shapes_off_the_grid(pkg, torch, ctx):
+    A = pkg.colmajor(512, 512); A.fill_(1.0)
+    tau = torch.zeros(pkg.tau_size(512, 512), device="cuda")
+    assert pkg.lib.cqr_mmqr_reference_format(ctx.h, A.data_ptr(), 512, 512, 512, tau.data_ptr()) == -4   # CQR_EUNSUPPORTED
+    with pytest.raises(ValueError):
+        pkg.mmqr_reference_format(np.zeros((512, 512), dtype=np.float32, order="F"))
+
+
 def test_comparator_slot_cusolver_agrees(pkg):
     """cqr_compare_cusolver_sgeqrf (the MAGMA slot of qr.cu:555-565 filled with cuSOLVER): when the library is on the box its
     R must agree with ours -- the one place the two are compared; the reference itself never compares."""

@@ -352,11 +352,18 @@ def bench_tsqr(args, pkg, ctx, torch, dist, dev, rank, world, timed_steps, pk):
     A_loc = pkg.colmajor(m_loc, n, device=dev)
     A_loc.copy_(torch.rand((m_loc, n), device=dev, generator=g))
     ts = dt.DistTSQR(pkg, ctx, n, rank, world, dev)
+    rtree = "single GPU"
+    if world > 1:
+        if os.environ.get("CQR_BENCH_RTREE", "peer") == "peer":
+            ts.enable_peer()                                # cqr_tsqr_dist_r: one tree kernel per rank, NVLink stores into the receiver's slab
+            rtree = "peer-memory kernel (cudaIpc slabs, cqr_tsqr_dist_r)"
+        else:
+            rtree = "ncclSend/ncclRecv + cqr_stack_qr per level (torch.distributed)"
     step = lambda: ts.factor(A_loc, keep_q=False)          # R-only variant: A is read once, never written
     step(); torch.cuda.synchronize()
     ms, _ = timed_steps(step, lambda: None, max(args.steps, 10), args.warmup)
     flops = qr_flops(m_total, n)
-    res = {"workload": f"tall-skinny {m_total}x{n} fp32 TSQR, R-only, row-partitioned over {world} GPU(s), NCCL p2p R-tree (config 3)",
+    res = {"workload": f"tall-skinny {m_total}x{n} fp32 TSQR, R-only, row-partitioned over {world} GPU(s), binary R-tree (config 3)", "rtree": rtree,
            "value": flops / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms, "scaling": "strong", "n_gpus": world}
     bytes_alg = 4.0 * m_loc * n
     ach = bytes_alg / (ms * 1e-3) / 1e9

@@ -38,6 +38,7 @@ EXPORTS = [
     "cqr_apply_q", "cqr_solve_ls", "cqr_tsqr_r", "cqr_tsqr_factor", "cqr_tsqr_form_q", "cqr_stack_qr", "cqr_stack_form_q",
     "cqr_geqrf_batched", "cqr_gemm", "cqr_gemm_tf32x3", "cqr_set_identity", "cqr_version",
     "cqr_compare_cusolver_sgeqrf", "mmqr_reference_format", "cqr_mmqr_reference_format",
+    "cqr_dist_export", "cqr_dist_attach", "cqr_dist_detach", "cqr_tsqr_dist_r",
 ]
 
 
@@ -103,6 +104,10 @@ def _load() -> ctypes.CDLL:
     lib.cqr_compare_cusolver_sgeqrf.argtypes = [_FP, _FP, i, i]
     lib.mmqr_reference_format.argtypes = [_FP, _FP, i, i]
     lib.cqr_mmqr_reference_format.argtypes = [_VP, _VP, i, i, i, _VP]
+    lib.cqr_dist_export.argtypes = [_VP, ctypes.c_char_p]
+    lib.cqr_dist_attach.argtypes = [_VP, i, i, ctypes.c_char_p]
+    lib.cqr_dist_detach.argtypes = [_VP]
+    lib.cqr_tsqr_dist_r.argtypes = [_VP, _VP, i, ll, i, _VP, i]
     return lib
 
 
@@ -349,6 +354,25 @@ class Context:
     def tsqr_factor(self, A, R):
         m, n = A.shape
         _check(lib.cqr_tsqr_factor(self.h, _dptr(A), _ld(A), m, n, _dptr(R), _ld(R)), "cqr_tsqr_factor")
+
+    # -- row-partitioned TSQR across GPUs, R tree over peer memory (cqr_dist_*) -----------------
+    def dist_export(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        _check(lib.cqr_dist_export(self.h, buf), "cqr_dist_export")
+        return buf.raw
+
+    def dist_attach(self, rank: int, world: int, handles):
+        blob = b"".join(handles)
+        if len(blob) != 64 * world:
+            raise ValueError("need one 64-byte handle per rank")
+        _check(lib.cqr_dist_attach(self.h, rank, world, blob), "cqr_dist_attach")
+
+    def dist_detach(self):
+        _check(lib.cqr_dist_detach(self.h), "cqr_dist_detach")
+
+    def tsqr_dist_r(self, A, R):
+        m, n = A.shape
+        _check(lib.cqr_tsqr_dist_r(self.h, _dptr(A), _ld(A), m, n, _dptr(R), _ld(R)), "cqr_tsqr_dist_r")
 
     def tsqr_form_q(self, Q, X=None):
         _check(lib.cqr_tsqr_form_q(self.h, _dptr(X), _ld(X) if X is not None else 0, _dptr(Q), _ld(Q)),

@@ -143,6 +143,23 @@ void mma_tsqr_read_trace(long long* out);   // [loads, sub-panels, trailing] clo
 #endif
 void launch_tsqr_mma_r(const MmaTsqrParams& p, cudaStream_t s);
 
+// ---- cross-GPU R tree over peer memory: rtree_peer.cu ------------------------------------------
+constexpr int kRtreeMaxLevels = 4, kRtreeMaxWorld = 16;
+struct RtreeSlab {                               // one per rank, cudaMalloc'ed, mapped into every peer with cudaIpc
+  float slot[2][kRtreeMaxLevels][64 * 64];       // [epoch parity][tree level]: the R a peer hands over at that level
+  unsigned ready[2][kRtreeMaxLevels];            // epoch of the R in the slot (written by the sender)
+  unsigned ack[2][kRtreeMaxLevels];              // last epoch the receiver of MY R at that level consumed (written by the receiver)
+};
+struct RtreePeerParams {
+  float* r; long long ldr;                       // this rank's n x n R (in: local TSQR result; out on rank 0: the combined R)
+  int n, rank, world;
+  unsigned epoch;                                // same on every rank, starts at 1, +1 per call
+  unsigned long long timeout_ns;
+  int* err;                                      // set to 1 if a peer never arrived
+  RtreeSlab* slabs[kRtreeMaxWorld];              // slabs[rank] is this rank's own
+};
+void launch_rtree_peer(const RtreePeerParams& p, cudaStream_t s);
+
 // ---- exporter for the reference's own storage format: legacy_format.cu ------------------------
 bool legacy_format_shape_ok(int m, int n);       // m = 64 + 60 k, n a multiple of 4, n <= m (the reference's legal shapes)
 void launch_legacy_sweep(float* a, long long lda, int m, int n, float* tau, int rowPanels, int colPanels, float* scratch, cudaStream_t s);

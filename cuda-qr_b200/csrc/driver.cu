@@ -89,6 +89,11 @@ struct cqr_context {
   int in_cb[kMaxInChunks + 1] = {};
   cudaEvent_t in_ev[kMaxInChunks] = {}, ev_joined[kMaxInChunks] = {};
   std::vector<cudaEvent_t> ev_t;   // aggregated T of outer block k is final (catch-up streams wait on it)
+  // row-partitioned TSQR across GPUs (cqr_dist_*): this rank's exchange slab and the peers' slabs mapped with cudaIpc
+  RtreeSlab* dist_slab = nullptr;
+  RtreeSlab* dist_peers[kRtreeMaxWorld] = {};
+  int dist_rank = -1, dist_world = 0;
+  unsigned dist_epoch = 0;
   cudaEvent_t ev_start = nullptr, ev_a = nullptr, ev_g = nullptr, ev_panel[2] = {nullptr, nullptr};
   cudaEvent_t ev_pp[2][8] = {};    // per-panel completion (panel-wise look-ahead slices, opt_lookahead == 2)
   int opt_gemm = 1, opt_outer = 256, opt_tile_rows = 256, opt_splitk = 0, opt_lookahead = 2, opt_panel = 1, opt_cluster = 1, opt_flat = 1;   // opt_flat: R-only TSQR leaf 0 = tile tree, 1 = SIMT flat tree (default), 2 = tensor-pipe flat tree (measured slower)
@@ -581,6 +586,7 @@ int cqr_destroy(cqr_context* c) {
     if (c->part[0].sc[k]) { cudaStreamSynchronize(c->part[0].sc[k]); cudaStreamDestroy(c->part[0].sc[k]); }
   }
   for (cudaEvent_t e : c->ev_t) cudaEventDestroy(e);
+  cqr_dist_detach(c);
   for (int i = 1; i < 5; ++i) {
     SmPartition& pt = c->part[i];
     for (int k = 0; k < kMaxInChunks; ++k) if (pt.sc[k]) { cudaStreamSynchronize(pt.sc[k]); cudaStreamDestroy(pt.sc[k]); }
@@ -1284,6 +1290,70 @@ int cqr_tsqr_form_q(cqr_context* c, const float* dX, int ldx, float* dQ, int ldq
   if (ldq < P.m || (dX && ldx < P.n)) return CQR_EINVAL;
   DeviceGuard dg__(c->device);
   run_tsqr_form_q(c, P, c->ts_a, c->ts_lda, dX, ldx, P.n, dQ, ldq);
+  return (int)cudaGetLastError();
+}
+
+// ---- row-partitioned TSQR across the GPUs of one box, R tree over peer memory (rtree_peer.cu) ---------------------
+// One process per GPU.  Every rank calls cqr_dist_export (allocates its exchange slab, returns a 64-byte cudaIpc handle),
+// the launcher moves the handles between the ranks by any means (they are plain bytes), every rank calls cqr_dist_attach
+// with all of them, and from then on cqr_tsqr_dist_r is local TSQR + ONE tree kernel whose hand-overs are NVLink stores
+// into the receiver's slab: no NCCL call, no host synchronisation between calls.  Every rank must make the same sequence
+// of cqr_tsqr_dist_r calls (the epoch counter is kept per context).
+int cqr_dist_export(cqr_context* c, void* handle_out) {
+  if (!c || !handle_out) return CQR_EINVAL;
+  DeviceGuard dg__(c->device);
+  if (!c->dist_slab) {
+    CQR_CUDA(cudaMalloc((void**)&c->dist_slab, sizeof(RtreeSlab)));
+    CQR_CUDA(cudaMemset(c->dist_slab, 0, sizeof(RtreeSlab)));
+  }
+  cudaIpcMemHandle_t h;
+  CQR_CUDA(cudaIpcGetMemHandle(&h, c->dist_slab));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpc handles are 64 bytes");
+  memcpy(handle_out, &h, sizeof(h));
+  return 0;
+}
+
+int cqr_dist_attach(cqr_context* c, int rank, int world, const void* handles) {
+  if (!c || !handles || world < 1 || world > kRtreeMaxWorld || rank < 0 || rank >= world) return CQR_EINVAL;
+  if (!c->dist_slab) return CQR_ESTATE;
+  DeviceGuard dg__(c->device);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { c->dist_peers[r] = c->dist_slab; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + 64 * (size_t)r, sizeof(h));
+    void* ptr = nullptr;
+    CQR_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->dist_peers[r] = (RtreeSlab*)ptr;
+  }
+  c->dist_rank = rank; c->dist_world = world; c->dist_epoch = 0;
+  return 0;
+}
+
+int cqr_dist_detach(cqr_context* c) {
+  if (!c) return CQR_EINVAL;
+  for (int r = 0; r < c->dist_world; ++r)
+    if (r != c->dist_rank && c->dist_peers[r]) cudaIpcCloseMemHandle(c->dist_peers[r]);
+  for (auto& q : c->dist_peers) q = nullptr;
+  c->dist_world = 0; c->dist_rank = -1;
+  if (c->dist_slab) { cudaFree(c->dist_slab); c->dist_slab = nullptr; }
+  return 0;
+}
+
+// R-only TSQR of the row-partitioned matrix: this rank's m_loc x n rows in, the combined R (n x n) out on rank 0 (the other
+// ranks' dR holds intermediate factors).  A rank that waits more than 20 s for a peer gives up; cqr_synchronize then
+// returns CQR_ESTATE.
+int cqr_tsqr_dist_r(cqr_context* c, const float* dA, int lda, long long m_loc, int n, float* dR, int ldr) {
+  if (!c || c->dist_world < 1) return c ? CQR_ESTATE : CQR_EINVAL;
+  int rc = tsqr_common(c, const_cast<float*>(dA), lda, m_loc, n, dR, ldr, false);
+  if (rc || c->dist_world == 1) return rc;
+  RtreePeerParams p{};
+  p.r = dR; p.ldr = ldr; p.n = n; p.rank = c->dist_rank; p.world = c->dist_world;
+  p.epoch = ++c->dist_epoch;
+  p.timeout_ns = 20ull * 1000 * 1000 * 1000;
+  p.err = c->hh_err;
+  for (int r = 0; r < c->dist_world; ++r) p.slabs[r] = c->dist_peers[r];
+  DeviceGuard dg__(c->device);
+  launch_rtree_peer(p, c->stream);
   return (int)cudaGetLastError();
 }
 

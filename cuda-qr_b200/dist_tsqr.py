@@ -70,6 +70,22 @@ class DistTSQR:
         self.rbuf = pkg.colmajor(n, n, device=device)
         self.R = pkg.colmajor(n, n, device=device)
         self.steps = rtree_steps(rank, world)
+        self.peer = False                    # True after enable_peer(): the R-only tree runs over peer memory inside the library
+
+    def enable_peer(self):
+        """Switch the R-only path to the library's peer-memory R tree (cqr_dist_*, rtree_peer.cu): every rank exports the
+        cudaIpc handle of its exchange slab, the 64-byte handles are gathered through torch.distributed (any backend), and
+        from then on factor(keep_q=False) is ONE library call per rank -- local TSQR plus a tree kernel whose hand-overs are
+        NVLink stores into the receiver's slab -- with no NCCL message and no host synchronisation between calls."""
+        if self.world == 1:
+            return self
+        import torch.distributed as dist
+        mine = self.ctx.dist_export()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine)
+        self.ctx.dist_attach(self.rank, self.world, handles)
+        self.peer = True
+        return self
 
     @staticmethod
     def _wire(t):
@@ -81,6 +97,9 @@ class DistTSQR:
     def factor(self, A_local, keep_q: bool = False):
         """Local TSQR + R-tree.  The final R is valid on rank 0 (self.R)."""
         n = self.n
+        if self.peer and not keep_q:
+            self.ctx.tsqr_dist_r(A_local, self.R)
+            return self.R
         if keep_q:
             self.ctx.tsqr_factor(A_local, self.R)
         else:

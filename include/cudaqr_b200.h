@@ -155,6 +155,17 @@ int cqr_stack_form_q(cqr_context* ctx, const float* dRs, int ldrs, int nblk, int
  * CQR_EUNSUPPORTED for shapes off the reference's window grid. */
 int cqr_mmqr_reference_format(cqr_context* ctx, float* dA, int lda, int m, int n, float* dtau_grid);
 
+/* Row-partitioned TSQR across the GPUs of one box (BASELINE config 3), one process per GPU, R tree over peer memory:
+ * cqr_dist_export allocates this rank's exchange slab and returns its 64-byte cudaIpc handle; the launcher hands every
+ * rank all `world` handles (rank order, 64 bytes each) for cqr_dist_attach; cqr_tsqr_dist_r is then the local R-only
+ * TSQR of this rank's m_loc x n rows plus one kernel that walks the binary reduction tree, the stacked-R blocks moving
+ * as NVLink stores into the receiver's slab (no NCCL, no host synchronisation between calls).  The combined R is on
+ * rank 0.  Every rank makes the same sequence of calls.  The reference has no multi-GPU path (qr.cu:737). */
+int cqr_dist_export(cqr_context* ctx, void* handle_out_64_bytes);
+int cqr_dist_attach(cqr_context* ctx, int rank, int world, const void* handles);
+int cqr_dist_detach(cqr_context* ctx);
+int cqr_tsqr_dist_r(cqr_context* ctx, const float* dA, int lda, long long m_loc, int n, float* dR, int ldr);
+
 /* `batch` independent m x n matrices (m <= 256, n <= 64, m >= n), one CTA each; matrix i
  * starts at dA + i*stride, lda >= m.  tau: batch x n. */
 int cqr_geqrf_batched(cqr_context* ctx, float* dA, int lda, long long stride, int m, int n, int batch, float* dtau);

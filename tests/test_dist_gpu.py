@@ -114,6 +114,42 @@ def test_dist_tsqr_flat_leaf_ranks(world, keep_q):
         assert metrics.orthogonality(Q) <= metrics.TOL_ORTH
 
 
+def _tsqr_peer_worker(rank, world, port, m, n, reps, out):
+    pkg, ctx, dev = _init(rank, world, port)
+    dt = importlib.import_module("cuda-qr_b200.dist_tsqr")
+    ts = dt.DistTSQR(pkg, ctx, n, rank, world, dev).enable_peer()
+    Rs = []
+    for rep in range(reps):                                     # back-to-back calls: slots are reused with no host sync in between
+        A = _matrix(m, n, 40 + rep)
+        lo, hi = rank * m // world, (rank + 1) * m // world
+        Al = pkg.to_colmajor(torch.from_numpy(np.ascontiguousarray(A[lo:hi])).to(dev))
+        ts.factor(Al, keep_q=False)
+        if rank == 0:
+            Rs.append(ts.R.clone())
+    ctx.synchronize()
+    out.put((rank, [r.cpu().numpy() for r in Rs], ctx.launch_count()))
+    dist.barrier()
+    dist.destroy_process_group()
+    ctx.close()
+
+
+@pytest.mark.parametrize("world,m,n", [(2, 2044, 64), (4, 4 * 20011, 64), (3, 9000, 40), (4, 2044, 64)])
+def test_dist_tsqr_peer_memory_rtree(world, m, n, port):
+    """cqr_tsqr_dist_r: the cross-rank R tree as ONE kernel per rank over cudaIpc-mapped peer slabs (stores into the
+    receiver's slab, flag release / acquire, stacked QR in registers), five calls back to back.  R against fp64, and on
+    the reference-legal shape against the restated qr.c."""
+    from oracle import metrics
+    reps = 5
+    res = _run(_tsqr_peer_worker, world, (m, n, reps))
+    for rep in range(reps):
+        A = _matrix(m, n, 40 + rep)
+        R = np.triu(res[0][1][rep])
+        assert metrics.r_rel_diff(R, np.linalg.qr(A.astype(np.float64), mode="r")) <= metrics.TOL_R
+        if (m - 64) % 60 == 0 and n % 4 == 0 and rep == 0:
+            rv_ref, _ = port.mmqr(A, 64, 4)
+            assert metrics.r_rel_diff(R, rv_ref) <= metrics.TOL_R
+
+
 def _caqr_worker(rank, world, port, m_loc, n, kb, kind, out):
     pkg, ctx, dev = _init(rank, world, port)
     dc = importlib.import_module("cuda-qr_b200.dist_caqr")

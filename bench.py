@@ -273,7 +273,7 @@ def main_ours(args, rank: int, world: int, local_rank: int):
         # measured DRAM traffic of the dominant kernel from the committed ncu --set full capture (one launch at the
         # first-block shape; `achieved` above averages all launches of the step, whose shapes shrink)
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["gemm_nn"]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["gemm_nn"]
             roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
             roof["traffic_detail"] = {"shape": tr["shape"], "algorithmic_bytes": tr["algorithmic_bytes"],
                                       "ratio": (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["algorithmic_bytes"],
@@ -338,7 +338,7 @@ def main_ours(args, rank: int, world: int, local_rank: int):
 def _traffic(key):
     """measured DRAM bytes of one launch at the bench shape, from the committed ncu --set full capture"""
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[key]
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[key]
         return tr["dram_bytes_read"] + tr["dram_bytes_write"]
     except Exception:
         return None

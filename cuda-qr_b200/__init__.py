@@ -39,6 +39,7 @@ EXPORTS = [
     "cqr_geqrf_batched", "cqr_gemm", "cqr_gemm_tf32x3", "cqr_set_identity", "cqr_version",
     "cqr_compare_cusolver_sgeqrf", "mmqr_reference_format", "cqr_mmqr_reference_format",
     "cqr_dist_export", "cqr_dist_attach", "cqr_dist_detach", "cqr_tsqr_dist_r",
+    "mmqr_f64", "explicitQR_f64", "cqr_dgeqrf", "cqr_dform_q", "cqr_dapply_q", "cqr_dextract_r",
 ]
 
 
@@ -104,6 +105,13 @@ def _load() -> ctypes.CDLL:
     lib.cqr_compare_cusolver_sgeqrf.argtypes = [_FP, _FP, i, i]
     lib.mmqr_reference_format.argtypes = [_FP, _FP, i, i]
     lib.cqr_mmqr_reference_format.argtypes = [_VP, _VP, i, i, i, _VP]
+    _DP = ctypes.POINTER(ctypes.c_double)
+    lib.mmqr_f64.argtypes = [_DP, _DP, i, i]
+    lib.explicitQR_f64.argtypes = [_DP, _DP, _DP, _DP, i, i]
+    lib.cqr_dgeqrf.argtypes = [_VP, _VP, i, i, i, _VP]
+    lib.cqr_dform_q.argtypes = [_VP, _VP, i, i, i, _VP, _VP, i, i]
+    lib.cqr_dapply_q.argtypes = [_VP, i, _VP, i, i, i, _VP, _VP, i, i]
+    lib.cqr_dextract_r.argtypes = [_VP, _VP, i, i, i, _VP, i, i]
     lib.cqr_dist_export.argtypes = [_VP, ctypes.c_char_p]
     lib.cqr_dist_attach.argtypes = [_VP, i, i, ctypes.c_char_p]
     lib.cqr_dist_detach.argtypes = [_VP]
@@ -180,6 +188,32 @@ def mmqr_reference_format(mat: np.ndarray, tau: np.ndarray | None = None) -> np.
     return tau
 
 
+def mmqr_f64(mat: np.ndarray, tau: np.ndarray | None = None) -> np.ndarray:
+    """mmqr in double precision (the reference's contemplated `Scalar double`, qr.c:9): factor the column-major float64
+    `mat` IN PLACE, return tau (rowPanels*colPanels*4 doubles, the first n used)."""
+    if not (isinstance(mat, np.ndarray) and mat.dtype == np.float64 and mat.flags["F_CONTIGUOUS"]):
+        raise TypeError("expected a column-major (Fortran-order) float64 numpy array")
+    m, n = mat.shape
+    if m < n or n < 1:
+        raise ValueError("mmqr needs m >= n >= 1 (qr.cu:736)")
+    if tau is None:
+        tau = np.empty(tau_size(m, n), dtype=np.float64)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.mmqr_f64(mat.ctypes.data_as(dp), tau.ctypes.data_as(dp), m, n)
+    return tau
+
+
+def explicitQR_f64(A: np.ndarray, tau: np.ndarray):
+    """(Q m x m, R m x n) in double precision from mmqr_f64's storage."""
+    m, n = A.shape
+    Q = np.empty((m, m), dtype=np.float64, order="F")
+    R = np.empty((m, n), dtype=np.float64, order="F")
+    dp = ctypes.POINTER(ctypes.c_double)
+    t = np.ascontiguousarray(tau, dtype=np.float64)
+    lib.explicitQR_f64(A.ctypes.data_as(dp), t.ctypes.data_as(dp), Q.ctypes.data_as(dp), R.ctypes.data_as(dp), m, n)
+    return Q, R
+
+
 def explicitQR(A: np.ndarray, tau: np.ndarray):
     """qr.c:330 -- (Q m x m, R m x n) from mmqr's in-place storage and tau."""
     _host(A)
@@ -229,12 +263,20 @@ def _dptr(t) -> int:
     return t.data_ptr()
 
 
-def colmajor(m: int, n: int, device="cuda", ld: int | None = None):
-    """Allocate an m x n column-major fp32 device matrix as a torch view (ld >= m): returns a tensor
+def colmajor(m: int, n: int, device="cuda", ld: int | None = None, dtype=None):
+    """Allocate an m x n column-major fp32 (or `dtype`) device matrix as a torch view (ld >= m): returns a tensor
     `a` with a[i, j] at offset i + j*ld, i.e. a = storage(n, ld).T[:m]."""
     import torch
     ld = ld or m
-    return torch.empty((n, ld), dtype=torch.float32, device=device).t()[:m]
+    return torch.empty((n, ld), dtype=dtype or torch.float32, device=device).t()[:m]
+
+
+def _dptr64(t) -> int:
+    if t is None:
+        return 0
+    if not t.is_cuda or str(t.dtype) != "torch.float64":
+        raise TypeError("expected a float64 CUDA tensor")
+    return t.data_ptr()
 
 
 def to_colmajor(x, ld: int | None = None):
@@ -354,6 +396,24 @@ class Context:
     def tsqr_factor(self, A, R):
         m, n = A.shape
         _check(lib.cqr_tsqr_factor(self.h, _dptr(A), _ld(A), m, n, _dptr(R), _ld(R)), "cqr_tsqr_factor")
+
+    # -- double precision (f64_qr.cu) -----------------------------------------------------------
+    def dgeqrf(self, A, tau):
+        m, n = A.shape
+        _check(lib.cqr_dgeqrf(self.h, _dptr64(A), _ld(A), m, n, _dptr64(tau)), "cqr_dgeqrf")
+
+    def dform_q(self, A, tau, Q):
+        m, n = A.shape
+        _check(lib.cqr_dform_q(self.h, _dptr64(A), _ld(A), m, n, _dptr64(tau), _dptr64(Q), _ld(Q), Q.shape[1]), "cqr_dform_q")
+
+    def dapply_q(self, A, tau, C, trans: bool):
+        m, n = A.shape
+        _check(lib.cqr_dapply_q(self.h, 1 if trans else 0, _dptr64(A), _ld(A), m, n, _dptr64(tau), _dptr64(C), _ld(C), C.shape[1]),
+               "cqr_dapply_q")
+
+    def dextract_r(self, A, R):
+        m, n = A.shape
+        _check(lib.cqr_dextract_r(self.h, _dptr64(A), _ld(A), m, n, _dptr64(R), _ld(R), R.shape[0]), "cqr_dextract_r")
 
     # -- row-partitioned TSQR across GPUs, R tree over peer memory (cqr_dist_*) -----------------
     def dist_export(self) -> bytes:

@@ -143,6 +143,14 @@ void mma_tsqr_read_trace(long long* out);   // [loads, sub-panels, trailing] clo
 #endif
 void launch_tsqr_mma_r(const MmaTsqrParams& p, cudaStream_t s);
 
+// ---- double-precision variant: f64_qr.cu -----------------------------------------------------------
+size_t f64_workspace_bytes(long long m, int nc_max);
+int f64_geqrf(double* a, long long lda, long long m, int n, double* tau, void* ws, int sm_count, cudaStream_t s);
+int f64_apply_q(int trans, const double* a, long long lda, long long m, int n, const double* tau, double* c, long long ldc, int nc,
+                bool c_is_identity_start, void* ws, cudaStream_t s);
+void f64_set_identity(double* a, long long lda, long long m, int n, cudaStream_t s);
+void f64_extract_r(const double* a, long long lda, int n, double* r, long long ldr, int r_rows, cudaStream_t s);
+
 // ---- cross-GPU R tree over peer memory: rtree_peer.cu ------------------------------------------
 constexpr int kRtreeMaxLevels = 4, kRtreeMaxWorld = 16;
 struct RtreeSlab {                               // one per rank, cudaMalloc'ed, mapped into every peer with cudaIpc

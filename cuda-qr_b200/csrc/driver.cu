@@ -1293,6 +1293,39 @@ int cqr_tsqr_form_q(cqr_context* c, const float* dX, int ldx, float* dQ, int ldq
   return (int)cudaGetLastError();
 }
 
+// ---- double precision (f64_qr.cu; SURVEY 8f-4: the reference's contemplated `Scalar double`, qr.c:9) ---------------
+int cqr_dgeqrf(cqr_context* c, double* dA, int lda, int m, int n, double* dtau) {
+  if (!c || !dA || !dtau || n < 1 || m < n || lda < m) return CQR_EINVAL;
+  DeviceGuard dg__(c->device);
+  int rc = ws_ensure(c, f64_workspace_bytes(m, n));
+  if (rc) return rc;
+  return f64_geqrf(dA, lda, m, n, dtau, c->ws, c->sm_count, c->stream);
+}
+
+int cqr_dapply_q(cqr_context* c, int trans, const double* dA, int lda, int m, int n, const double* dtau, double* dC, int ldc, int nc) {
+  if (!c || !dA || !dtau || !dC || n < 1 || m < n || lda < m || ldc < m || nc < 1) return CQR_EINVAL;
+  DeviceGuard dg__(c->device);
+  int rc = ws_ensure(c, f64_workspace_bytes(m, nc > n ? nc : n));
+  if (rc) return rc;
+  return f64_apply_q(trans ? 1 : 0, dA, lda, m, n, dtau, dC, ldc, nc, false, c->ws, c->stream);
+}
+
+int cqr_dform_q(cqr_context* c, const double* dA, int lda, int m, int n, const double* dtau, double* dQ, int ldq, int q_cols) {
+  if (!c || !dA || !dtau || !dQ || n < 1 || m < n || lda < m || ldq < m || q_cols < 1 || q_cols > m) return CQR_EINVAL;
+  DeviceGuard dg__(c->device);
+  int rc = ws_ensure(c, f64_workspace_bytes(m, q_cols > n ? q_cols : n));
+  if (rc) return rc;
+  f64_set_identity(dQ, ldq, m, q_cols, c->stream);
+  return f64_apply_q(0, dA, lda, m, n, dtau, dQ, ldq, q_cols, true, c->ws, c->stream);
+}
+
+int cqr_dextract_r(cqr_context* c, const double* dA, int lda, int m, int n, double* dR, int ldr, int r_rows) {
+  if (!c || !dA || !dR || m < 1 || n < 1 || lda < m || r_rows < 1 || r_rows > m || ldr < r_rows) return CQR_EINVAL;
+  DeviceGuard dg__(c->device);
+  f64_extract_r(dA, lda, n, dR, ldr, r_rows, c->stream);
+  return (int)cudaGetLastError();
+}
+
 // ---- row-partitioned TSQR across the GPUs of one box, R tree over peer memory (rtree_peer.cu) ---------------------
 // One process per GPU.  Every rank calls cqr_dist_export (allocates its exchange slab, returns a 64-byte cudaIpc handle),
 // the launcher moves the handles between the ranks by any means (they are plain bytes), every rank calls cqr_dist_attach
@@ -1506,10 +1539,24 @@ void mmqr(float* mat, float* tau, int m, int n) {
                               cudaMemcpyHostToDevice));
   }
   c->host_out = mat;   // finished column blocks stream back while the rest is still being factored
+  static const char* tl_path = getenv("CQR_LEGACY_TIMELINE");   // debugging aid: event brackets of this call -> "t0_ms t1_ms class" rows
+  if (tl_path) cqr_profile_begin(c);
   const int rc = cqr_geqrf(c, dA, (int)lda, m, n, dtau);
   c->host_out = nullptr;
   c->in_n = 0;
   LEGACY_CHECK(rc);
+  if (tl_path) {
+    const int cap = 1 << 16;
+    std::vector<double> t0(cap), t1(cap);
+    std::vector<int> cl(cap);
+    cudaStreamSynchronize(c->stream);
+    const int nrec = cqr_profile_timeline(c, t0.data(), t1.data(), cl.data(), cap);
+    if (FILE* f = fopen(tl_path, "w")) {
+      for (int i = 0; i < nrec; ++i) fprintf(f, "%.4f %.4f %d\n", t0[i], t1[i], cl[i]);
+      fclose(f);
+    }
+    c->prof_on = false; c->prof.clear();
+  }
   // unused slots zero, qr.c:62 -- done while the device is still factoring (cqr_geqrf only enqueues): the reference-sized
   // tau grid is rowPanels * colPanels * PC floats (18 MB at 16384^2), of which the first n are overwritten below
   memset(tau, 0, tau_count * sizeof(float));
@@ -1538,6 +1585,43 @@ void mmqr_reference_format(float* mat, float* tau, int m, int n) {
   LEGACY_CHECK(cudaStreamSynchronize(c->stream));
   LEGACY_CHECK(cudaMemcpy2D(mat, (size_t)m * sizeof(float), dA, lda * sizeof(float), (size_t)m * sizeof(float), n, cudaMemcpyDeviceToHost));
   LEGACY_CHECK(cudaMemcpy(tau, dtau, tau_count * sizeof(float), cudaMemcpyDeviceToHost));
+}
+
+// The legacy pair in double precision (host buffers, blocking, exit(1) on failure): what the reference's
+// `#define Scalar double` build would export (qr.c:9,11).  tau: n doubles followed by zeros up to rowPanels*colPanels*4.
+void mmqr_f64(double* mat, double* tau, int m, int n) {
+  if (!(m && n && m >= n)) { printf("mmqr: need m >= n >= 1 (got %d x %d)\n", m, n); exit(1); }
+  cqr_context* c = legacy_ctx();
+  int rp, cp;
+  getPanelDims(m, n, &rp, &cp);
+  double *dA = nullptr, *dtau = nullptr;
+  LEGACY_CHECK(cudaMalloc((void**)&dA, (size_t)m * n * sizeof(double)));
+  LEGACY_CHECK(cudaMalloc((void**)&dtau, (size_t)n * sizeof(double)));
+  LEGACY_CHECK(cudaMemcpy(dA, mat, (size_t)m * n * sizeof(double), cudaMemcpyHostToDevice));
+  LEGACY_CHECK(cqr_dgeqrf(c, dA, m, m, n, dtau));
+  memset(tau, 0, (size_t)rp * cp * kLegacyPC * sizeof(double));
+  LEGACY_CHECK(cudaStreamSynchronize(c->stream));
+  LEGACY_CHECK(cudaMemcpy(mat, dA, (size_t)m * n * sizeof(double), cudaMemcpyDeviceToHost));
+  LEGACY_CHECK(cudaMemcpy(tau, dtau, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dtau);
+}
+
+void explicitQR_f64(double* A, double* tau, double* Q, double* R, int m, int n) {
+  if (!(m && n && m >= n)) { printf("explicitQR: need m >= n >= 1 (got %d x %d)\n", m, n); exit(1); }
+  cqr_context* c = legacy_ctx();
+  double *dA = nullptr, *dtau = nullptr, *dQ = nullptr, *dR = nullptr;
+  LEGACY_CHECK(cudaMalloc((void**)&dA, (size_t)m * n * sizeof(double)));
+  LEGACY_CHECK(cudaMalloc((void**)&dtau, (size_t)n * sizeof(double)));
+  LEGACY_CHECK(cudaMalloc((void**)&dQ, (size_t)m * m * sizeof(double)));
+  LEGACY_CHECK(cudaMalloc((void**)&dR, (size_t)m * n * sizeof(double)));
+  LEGACY_CHECK(cudaMemcpy(dA, A, (size_t)m * n * sizeof(double), cudaMemcpyHostToDevice));
+  LEGACY_CHECK(cudaMemcpy(dtau, tau, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+  LEGACY_CHECK(cqr_dextract_r(c, dA, m, m, n, dR, m, m));
+  LEGACY_CHECK(cqr_dform_q(c, dA, m, m, n, dtau, dQ, m, m));
+  LEGACY_CHECK(cudaStreamSynchronize(c->stream));
+  LEGACY_CHECK(cudaMemcpy(R, dR, (size_t)m * n * sizeof(double), cudaMemcpyDeviceToHost));
+  LEGACY_CHECK(cudaMemcpy(Q, dQ, (size_t)m * m * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dtau); cudaFree(dQ); cudaFree(dR);
 }
 
 void mmqr_alloc(float* mat, float** tau, int m, int n) {

@@ -38,6 +38,11 @@ void mmqr(float* mat, float* tau, int m, int n);
 /* Replaces the CPU variant mmqr, qr.c:55-313: callee malloc()s *tau, caller free()s. */
 void mmqr_alloc(float* mat, float** tau, int m, int n);
 
+/* Double precision: the pair a `#define Scalar double` build of the reference would export (qr.c:9 "can be float or
+ * double", qr.cu:747-754).  Same contract as mmqr / explicitQR above with double buffers. */
+void mmqr_f64(double* mat, double* tau, int m, int n);
+void explicitQR_f64(double* A, double* tau, double* Q, double* R, int m, int n);
+
 /* mmqr with the REFERENCE's storage on output: its window sweep with PR = 64, PC = 4 (qr.cu:21-23) run on
  * the device, leaving the per-window reflector segments in place (qr.c:109-167) and
  * tau[(rowPanels*pcCount + prCount)*4 + col] (qr.c:300-304), so that the reference's own explicitQR (qr.c:330-438)
@@ -154,6 +159,13 @@ int cqr_stack_form_q(cqr_context* ctx, const float* dRs, int ldrs, int nblk, int
 /* Device core of mmqr_reference_format: in place on dA, dtau_grid = rowPanels*colPanels*4 floats (zero-filled here).
  * CQR_EUNSUPPORTED for shapes off the reference's window grid. */
 int cqr_mmqr_reference_format(cqr_context* ctx, float* dA, int lda, int m, int n, float* dtau_grid);
+
+/* Double-precision blocked Householder QR (fp64 SIMT kernels, 32-column panels factored by one cooperative launch each;
+ * LAPACK storage, tau[0..n)); form / apply Q and R extraction as in the fp32 API.  Device pointers, column-major. */
+int cqr_dgeqrf(cqr_context* ctx, double* dA, int lda, int m, int n, double* dtau);
+int cqr_dform_q(cqr_context* ctx, const double* dA, int lda, int m, int n, const double* dtau, double* dQ, int ldq, int q_cols);
+int cqr_dapply_q(cqr_context* ctx, int trans, const double* dA, int lda, int m, int n, const double* dtau, double* dC, int ldc, int nc);
+int cqr_dextract_r(cqr_context* ctx, const double* dA, int lda, int m, int n, double* dR, int ldr, int r_rows);
 
 /* Row-partitioned TSQR across the GPUs of one box (BASELINE config 3), one process per GPU, R tree over peer memory:
  * cqr_dist_export allocates this rank's exchange slab and returns its 64-byte cudaIpc handle; the launcher hands every

@@ -214,6 +214,52 @@ def test_reference_format_rejects_shapes_off_the_grid(pkg, torch, ctx):
         pkg.mmqr_reference_format(np.zeros((512, 512), dtype=np.float32, order="F"))
 
 
+# ---------------------------------------------------------------------------------------------
+# double precision (the reference's contemplated `Scalar double`, qr.c:9)
+# ---------------------------------------------------------------------------------------------
+EPS64 = 2.0 ** -52
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (5, 3), (64, 64), (257, 129), (300, 200), (1000, 1000), (5000, 70), (4096, 2048), (20000, 33)])
+def test_f64_geqrf_form_q_apply_q(pkg, torch, ctx, m, n):
+    """cqr_dgeqrf / cqr_dform_q / cqr_dapply_q / cqr_dextract_r against numpy's fp64 QR: the same three acceptance numbers
+    with eps = 2^-52 (backward error and orthogonality <= 10 n eps, R within 1e-12)."""
+    rng = np.random.default_rng(123)
+    A = np.asfortranarray(rng.random((m, n)))
+    dA = pkg.colmajor(m, n, dtype=torch.float64); dA.copy_(torch.from_numpy(A))
+    tau = torch.zeros(n, device="cuda", dtype=torch.float64)
+    ctx.dgeqrf(dA, tau)
+    R = pkg.colmajor(n, n, dtype=torch.float64); ctx.dextract_r(dA, R)
+    Q = pkg.colmajor(m, n, dtype=torch.float64); ctx.dform_q(dA, tau, Q)
+    C = pkg.colmajor(m, n, dtype=torch.float64); C.copy_(torch.from_numpy(A))
+    ctx.dapply_q(dA, tau, C, True)                                  # Q^T A = [R; 0]
+    ctx.synchronize()
+    Qh, Rh, Ch = Q.cpu().numpy(), R.cpu().numpy(), C.cpu().numpy()
+    nrm = np.linalg.norm(A)
+    assert np.linalg.norm(A - Qh @ Rh) / (nrm * n * EPS64) <= 10
+    assert np.linalg.norm(Qh.T @ Qh - np.eye(n)) / (n * EPS64) <= 10
+    assert metrics.r_rel_diff(Rh, np.linalg.qr(A, mode="r")) <= 1e-12
+    assert np.linalg.norm(np.triu(Ch[:n]) - Rh) / (nrm * n * EPS64) <= 10
+    assert np.sqrt(np.linalg.norm(np.tril(Ch[:n], -1)) ** 2 + np.linalg.norm(Ch[n:]) ** 2) / (nrm * n * EPS64) <= 10
+
+
+def test_f64_legacy_pair_and_edge_cases(pkg):
+    """mmqr_f64 / explicitQR_f64 (host buffers) on the reference's srand(12) input, a zero column, a graded matrix."""
+    A32 = oracle.rand_matrix(124, 64, 12)
+    for A in (A32.astype(np.float64), np.asfortranarray(np.random.default_rng(5).standard_normal((200, 90)) * np.logspace(0, -12, 90))):
+        m, n = A.shape
+        if n == 90:
+            A[:, 17] = 0.0
+            A[:, 40] = A[:, 3]
+        RV = A.copy(order="F")
+        tau = pkg.mmqr_f64(RV)
+        Q, R = pkg.explicitQR_f64(RV, tau)
+        assert np.all(np.tril(R, -1) == 0)
+        assert np.linalg.norm(A - Q @ R) / (np.linalg.norm(A) * n * EPS64) <= 10
+        assert np.linalg.norm(Q.T @ Q - np.eye(m)) / (m * EPS64) <= 10
+    assert tau[17] == 0.0                                            # zero column: H = I
+
+
 def test_comparator_slot_cusolver_agrees(pkg):
     """cqr_compare_cusolver_sgeqrf (the MAGMA slot of qr.cu:555-565 filled with cuSOLVER): when the library is on the box its
     R must agree with ours -- the one place the two are compared; the reference itself never compares."""

@@ -117,7 +117,7 @@ struct FlatApplyParams {
   float* q; long long ldq;         // output m x nc
 };
 int flat_tsqr_max_chains(int sm_count);   // chains resident in one wave
-void launch_tsqr_flat_r(const FlatTsqrParams& p, cudaStream_t s);
+void launch_tsqr_flat_r(const FlatTsqrParams& p, cudaStream_t s, bool pair = false);   // pair: two pivot columns per reduction
 void launch_tsqr_flat_keep(const FlatTsqrParams& p, cudaStream_t s);   // after launch_tsqr_flat_first_blocks
 void launch_tsqr_flat_first_blocks(float* a, long long lda, long long m, int n, long long rows_per_chain, int chains, float* tau,
                                    cudaStream_t s);

@@ -320,7 +320,7 @@ void run_tsqr_factor(cqr_context* c, const TsqrPlan& P, float* a, long long lda,
         launch_tsqr_flat_first_blocks(a, lda, P.m, P.n, P.flat_rows, P.lv[0].tiles, P.lv[0].tau, cur_stream(c));
         launch_tsqr_flat_keep(f, cur_stream(c));
       }
-      else launch_tsqr_flat_r(f, cur_stream(c));
+      else launch_tsqr_flat_r(f, cur_stream(c), c->opt_flat == 3);
       continue;
     }
     TileQRParams p{};
@@ -550,7 +550,7 @@ static int create_impl(cqr_context* c, int device) {
   if (const char* e = getenv("CQR_PANEL")) c->opt_panel = atoi(e) != 0;
   if (const char* e = getenv("CQR_CLUSTER")) c->opt_cluster = atoi(e) != 0;   // debugging aid: 0 = global-flag exchange only
   if (const char* e = getenv("CQR_GEMM")) c->opt_gemm = (strcmp(e, "simt") == 0) ? 0 : 1;   // debugging aid
-  if (const char* e = getenv("CQR_TSQR_LEAF")) c->opt_flat = strcmp(e, "mma") == 0 ? 2 : (strcmp(e, "flat") == 0 ? 1 : (strcmp(e, "tile") == 0 ? 0 : c->opt_flat));
+  if (const char* e = getenv("CQR_TSQR_LEAF")) c->opt_flat = strcmp(e, "mma") == 0 ? 2 : (strcmp(e, "flat") == 0 ? 1 : (strcmp(e, "pair") == 0 ? 3 : (strcmp(e, "tile") == 0 ? 0 : c->opt_flat)));
   return 0;
 }
 
@@ -613,7 +613,7 @@ int cqr_set_option(cqr_context* c, int opt, int v) {
     case CQR_OPT_SPLITK: if (v < 0 || v > kMaxSplits) return CQR_EINVAL; c->opt_splitk = v; return 0;
     case CQR_OPT_LOOKAHEAD: if (v < 0 || v > 2) return CQR_EINVAL; c->opt_lookahead = v; return 0;
     case CQR_OPT_PANEL: if (v != 0 && v != 1) return CQR_EINVAL; c->opt_panel = v; return 0;
-    case CQR_OPT_FLAT_TSQR: if (v < 0 || v > 2) return CQR_EINVAL; c->opt_flat = v; return 0;
+    case CQR_OPT_FLAT_TSQR: if (v < 0 || v > 3) return CQR_EINVAL; c->opt_flat = v; return 0;
   }
   return CQR_EINVAL;
 }
@@ -790,16 +790,18 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
     }
   }
   const bool chunked = nin > 1;
+  int t_done = -1, flushed = -1;                             // chunked upload: last block whose T event is recorded / whose catch-up work is enqueued
   if (c->in_n > 0 && !chunked)                                // a path that does not join chunks: wait for the whole upload first
     for (int k = 0; k < c->in_n; ++k) CQR_CUDA(cudaStreamWaitEvent(st, c->in_ev[k], 0));
   struct BlockBufs { float *vbuf, *tbig; };
   std::vector<BlockBufs> bbv((size_t)nkeep + 2);
   auto bb = [&](int blk) -> BlockBufs& { return bbv[blk < nkeep ? blk : nkeep + ((blk - nkeep) & 1)]; };
   auto njoin = [&](int blk) { int e = n; if (chunked) { e = c->in_cb[1]; for (int k = 1; k < nin; ++k) if (jn[k] <= blk) e = c->in_cb[k + 1]; } return e; };
-  constexpr int kCatchCols = 2048;                           // catch-up updates go in slices of at most this many columns (scratch size)
+  constexpr int kCatchCols = 4096;                           // catch-up updates go in slices of at most this many columns (scratch size)
   static const int catch_cols = getenv("CQR_CATCH_COLS") ? (atoi(getenv("CQR_CATCH_COLS")) < 256 ? 256 : (atoi(getenv("CQR_CATCH_COLS")) > kCatchCols ? kCatchCols : atoi(getenv("CQR_CATCH_COLS")))) : kCatchCols;
   static const int catch_ctas_pct = getenv("CQR_CATCH_CTAS_PCT") ? atoi(getenv("CQR_CATCH_CTAS_PCT")) : 100;   // share of the GEMM partition a catch-up kernel may fill
-  BlockWs bw_catch[kMaxInChunks] = {};
+  BlockWs bw_catch[kMaxInChunks] = {}, bw_pslice{};
+  static const bool slice_chain_ok = getenv("CQR_H2D_SLICE_ON_CHAIN") && atoi(getenv("CQR_H2D_SLICE_ON_CHAIN")) != 0;   // experiment, off: no gain measured
   TsqrPlan plan;
   float *gram = nullptr, *gpart = nullptr, *qthin = nullptr, *rt = nullptr, *uinv = nullptr, *gsmall = nullptr;
   BlockWs bw_main{}, bw_side{}, bw_slice{};
@@ -811,6 +813,7 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
       b.tbig = cv.take((long long)KB * KB);
     }
     for (int k = 1; k < nin; ++k) if (jn[k] > 0) bw_catch[k] = carve_block_ws(cv, KB, kCatchCols);
+    if (nin > 1) bw_pslice = carve_block_ws(cv, KB, KB);
     gram = cv.take((long long)KB * KB);
     gpart = cv.take((long long)KB * KB * kMaxSplits);
     qthin = cv.take(ldv * 64);
@@ -916,25 +919,38 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
       launch_build_t(gram, KB, dtau + K0, B.tbig, KB, kbw, 1, cur_stream(c));
     }
     if (!chunked) return;
-    // Block K0's reflector is complete: the upload chunks that have not joined yet get it on their catch-up streams.
-    const int blk = K0 / KB;
+    const int blk = K0 / KB;   // block K0's reflector is complete: the catch-up streams may use it (flush_catchup)
     if (blk >= nkeep) return;
     cudaEventRecord(c->ev_t[blk], cur_stream(c));
+    t_done = blk;
+  };
+  // The upload chunks that have not joined yet get the finished block reflectors on their catch-up streams.  The launches
+  // are enqueued lazily -- at the end of a loop iteration, behind the chain's own launches for the next block, or right
+  // before a join needs them -- because in the first blocks the host would otherwise spend more time enqueueing catch-up
+  // work (four chunks x four launches per block) than the chain takes to run, and the panel stream would wait for the host.
+  auto flush_catchup = [&](int upto) {
+    if (!chunked) return;
+    if (upto > t_done) upto = t_done;
     cudaStream_t s0 = c->cur; const int ctas0 = c->cur_ctas; const bool chain0 = c->cur_chain;
     SmPartition& pr = (c->opt_partition && c->opt_panel == 1 && c->opt_cluster && m <= 16384) ? c->part[2] : c->part[0];
-    for (int k = 1; k < nin; ++k) {
-      if (jn[k] <= blk) continue;
-      cudaStream_t sc = pr.sc[k] ? pr.sc[k] : c->part[0].sc[k];
-      if (blk == 0) cudaStreamWaitEvent(sc, c->in_ev[k], 0);
-      cudaStreamWaitEvent(sc, c->ev_t[blk], 0);
-      c->cur = sc; c->cur_ctas = pr.sm_g * catch_ctas_pct / 100 > 8 ? pr.sm_g * catch_ctas_pct / 100 : 8; c->cur_chain = false;
-      Operand V{B.vbuf, ldv};
-      Operand T{B.tbig, KB};
-      for (int c0 = c->in_cb[k]; c0 < c->in_cb[k + 1]; c0 += catch_cols) {
-        const int w = c->in_cb[k + 1] - c0 < catch_cols ? c->in_cb[k + 1] - c0 : catch_cols;
-        apply_block(c, m - K0, kbw, w, V, T, dA + K0 + (long long)c0 * lda, lda, 1, bw_catch[k], tensor);
+    for (int blk = flushed + 1; blk <= upto; ++blk) {
+      const int K0 = blk * KB;
+      BlockBufs& B = bb(blk);
+      for (int k = 1; k < nin; ++k) {
+        if (jn[k] <= blk) continue;
+        cudaStream_t sc = pr.sc[k] ? pr.sc[k] : c->part[0].sc[k];
+        if (blk == 0) cudaStreamWaitEvent(sc, c->in_ev[k], 0);
+        cudaStreamWaitEvent(sc, c->ev_t[blk], 0);
+        c->cur = sc; c->cur_ctas = pr.sm_g * catch_ctas_pct / 100 > 8 ? pr.sm_g * catch_ctas_pct / 100 : 8; c->cur_chain = false;
+        Operand V{B.vbuf, ldv};
+        Operand T{B.tbig, KB};
+        for (int c0 = c->in_cb[k]; c0 < c->in_cb[k + 1]; c0 += catch_cols) {
+          const int w = c->in_cb[k + 1] - c0 < catch_cols ? c->in_cb[k + 1] - c0 : catch_cols;
+          apply_block(c, m - K0, KB, w, V, T, dA + K0 + (long long)c0 * lda, lda, 1, bw_catch[k], tensor);
+        }
+        if (blk == jn[k] - 1) cudaEventRecord(c->ev_joined[k], sc);
       }
-      if (blk == jn[k] - 1) cudaEventRecord(c->ev_joined[k], sc);
+      flushed = blk;
     }
     c->cur = s0; c->cur_ctas = ctas0; c->cur_chain = chain0;
   };
@@ -947,11 +963,14 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
                       (size_t)m * sizeof(float), kbw, cudaMemcpyDeviceToHost, c->copy);
   };
   // Trailing update of columns [c0, c1) with block K0's aggregated reflector (current stream).
-  auto do_update = [&](int K0, BlockBufs& B, int c0, int c1) {
+  auto do_update = [&](int K0, BlockBufs& B, int c0, int c1, BlockWs* wsp = nullptr) {
     if (chunked) {
       const int blk = K0 / KB;
       for (int k = 1; k < nin; ++k)                            // chunks joining at this block: caught up (or just arrived)
-        if (jn[k] == blk) cudaStreamWaitEvent(cur_stream(c), jn[k] > 0 ? c->ev_joined[k] : c->in_ev[k], 0);
+        if (jn[k] == blk) {
+          flush_catchup(blk - 1);                              // the event waited for must have been recorded
+          cudaStreamWaitEvent(cur_stream(c), jn[k] > 0 ? c->ev_joined[k] : c->in_ev[k], 0);
+        }
       const int nj = njoin(blk);
       if (c1 > nj) c1 = nj;
     }
@@ -960,7 +979,7 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
     Operand V{B.vbuf, ldv};
     Operand T{B.tbig, KB};
     float* cp = dA + K0 + (long long)c0 * lda;
-    apply_block(c, m - K0, kbw, c1 - c0, V, T, cp, lda, 1, bw_main, tensor);
+    apply_block(c, m - K0, kbw, c1 - c0, V, T, cp, lda, 1, wsp ? *wsp : bw_main, tensor);
   };
 
   // (only while the trailing part is narrow: four K = 64 updates of a wide C cost more HBM traffic than the chain hides --
@@ -1057,15 +1076,24 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
       break;
     }
     const int la = (nf - cnext < KB) ? nf - cnext : KB;
-    if (!slice_done) {
-      CQR_CUDA(cudaStreamWaitEvent(G, c->ev_panel[blk & 1], 0));
-      use(G, pr.sm_g, false);
-      if (!t_on_chain(K0)) do_block_t(K0, bb(blk));
-      do_update(K0, bb(blk), cnext, cnext + la);
-      CQR_CUDA(cudaEventRecord(c->ev_a, G));
-    }
+    // Experiment (CQR_H2D_SLICE_ON_CHAIN=1, chunked upload only): run the look-ahead slice of the first blocks on the
+    // panel stream itself instead of queueing it on the GEMM partition next to the catch-up kernels.  Measured: no
+    // difference (74.5 vs 74.7 ms e2e), so the default keeps the slice on the GEMM stream.
+    const bool slice_on_chain = chunked && !slice_done && t_on_chain(K0) && blk < nkeep && slice_chain_ok;
+    if (!slice_done) CQR_CUDA(cudaStreamWaitEvent(G, c->ev_panel[blk & 1], 0));
     if (prev_p != P) CQR_CUDA(cudaStreamWaitEvent(P, c->ev_panel[blk & 1], 0));
-    CQR_CUDA(cudaStreamWaitEvent(P, c->ev_a, 0));
+    if (slice_on_chain) {
+      use(P, pr.sm_p, true);
+      do_update(K0, bb(blk), cnext, cnext + la, &bw_pslice);
+    } else {
+      if (!slice_done) {
+        use(G, pr.sm_g, false);
+        if (!t_on_chain(K0)) do_block_t(K0, bb(blk));
+        do_update(K0, bb(blk), cnext, cnext + la);
+        CQR_CUDA(cudaEventRecord(c->ev_a, G));
+      }
+      CQR_CUDA(cudaStreamWaitEvent(P, c->ev_a, 0));
+    }
     // Panel-wise look-ahead (opt_lookahead == 2, panel-bound phase only): the NEXT block's panels are applied to the block
     // after it one by one on the GEMM stream while the panel chain is still running, so when its last panel is done
     // only one K = 64 update separates the chain from the following block -- not the aggregated T plus a K = 256 slice.
@@ -1106,6 +1134,7 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
     ship(cnext, c->ev_panel[(blk + 1) & 1]);
     if (t_on_chain(cnext)) { do_block_t(cnext, bb(blk + 1)); CQR_CUDA(cudaEventRecord(c->ev_panel[(blk + 1) & 1], P)); }
     prev_g = G; prev_p = P;
+    flush_catchup(t_done);                                     // behind the chain's launches for the next block
   }
   use(nullptr, 0, false);
   // hand the result back to the caller's stream: last panel chain and last trailing update

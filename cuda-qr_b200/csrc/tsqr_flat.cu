@@ -122,6 +122,206 @@ struct FlatGroups<8> {
   static __device__ __forceinline__ void run(f32x2 (&)[8][8], float*, float*, int, int, int) {}
 };
 
+// ---- two pivot columns per reduction (R only) ------------------------------------------------------------------------
+// The leaf is bound by its 64 dependent column steps per block (publish x, dots, two shuffle stages, rsqrt / rcp chain,
+// update: ~600 clk each), not by arithmetic.  Here one pass serves the reflectors j and j + 1, with
+// the algebra of panel_wb2.cu specialised to the structured reflector v_j = [e_j ; x / u] (the unit entry sits on R's row
+// j, so reflector j never touches R's row j + 1).  x = B(:, j), y = B(:, j + 1), both BEFORE reflector j; one reduction
+// delivers p_c = x^T a_c and q_c = y^T a_c for every live column.  Then (fp32 spec: tools/two_column_step.py)
+//   reflector j:   sigma_1 = p_j, alpha_1 = R(j,j) -> beta_1, u_1, tau_1;   d1_c = R(j,c) + p_c / u_1, t_c = tau_1 d1_c, e_c = t_c / u_1
+//   column j + 1:  a1 = e_{j+1};  y' = y - a1 x;  sigma_2 = q_{j+1} - 2 a1 p_{j+1} + a1^2 p_j,  alpha_2 = R(j+1,j+1) -> beta_2, u_2, tau_2
+//   any column c:  y'^T a'_c = q_c - e_c p_{j+1} - a1 p_c + a1 e_c p_j;  d2_c = R(j+1,c) + y'^T a'_c / u_2,  f_c = tau_2 d2_c / u_2
+//   update:        a_c -= (e_c - f_c a1) x + f_c y;   R(j,c) -= t_c;   R(j+1,c) -= tau_2 d2_c
+// The expansion of sigma_2 (and of every y'^T a'_c) cancels when y is nearly parallel to x, so a pair with
+// sigma_2 < 0.1 q_{j+1} finishes reflector j alone and column j + 1 takes an ordinary single step (guard and threshold as
+// in panel_wb2.cu; decided on bit-identical totals, uniform over the warp).  One shared x / y buffer: a __syncwarp in
+// front of the publish orders it against the previous step's readers.
+constexpr float kFlatPairGuard = 0.1f;
+
+struct FlatRefl { float bc, inv_u, tau; bool ok; };
+__device__ __forceinline__ FlatRefl flat_scalars(float alpha, float sig) {   // as in flat_steps: a zero / underflowing column gives tau = 0
+  FlatRefl r;
+  const float sj = fmaf(alpha, alpha, sig);
+  r.ok = (sig != 0.f) && (sj >= 1.2e-38f);
+  const float sjs = r.ok ? sj : 1.f;
+  const float rs = rsqrt_approx(sjs);
+  float nrm = sjs * rs;
+  nrm = fmaf(fmaf(-nrm, nrm, sjs), 0.5f * rs, nrm);
+  r.bc = (alpha < 0.f) ? nrm : -nrm;
+  const float u = alpha - r.bc;
+  r.inv_u = r.ok ? rcp_newton(u) : 0.f;
+  r.tau = r.ok ? -u * rcp_newton(r.bc) : 0.f;
+  return r;
+}
+
+// One ordinary column step, pivot j = 8 I0 + jj (the odd column of a pair that failed the guard, or the last column of an odd n).
+template <int I0>
+__device__ __forceinline__ void flat_one(f32x2 (&b)[8][8], float* __restrict__ Rs, float* __restrict__ xb, const int q, const int h, const int jj) {
+  const int j = 8 * I0 + jj;
+  float* Rj = Rs + j * 64;
+  float r[8];
+#pragma unroll
+  for (int i = I0; i < 8; ++i) r[i] = Rj[q + 8 * i];
+  const float alpha = Rj[j];
+  __syncwarp();
+  if (q == jj) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ulonglong2 v; v.x = b[I0][2 * k]; v.y = b[I0][2 * k + 1];
+      *reinterpret_cast<ulonglong2*>(xb + 16 * h + 4 * k) = v;
+    }
+  }
+  __syncwarp();
+  f32x2 x[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xb + 16 * h + 4 * k);
+    x[2 * k] = v.x; x[2 * k + 1] = v.y;
+  }
+  float d[8];
+  f32x2 s2 = 0ull;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s2 = ffma2(x[k], x[k], s2);
+  float sig = fsum2(s2);
+#pragma unroll
+  for (int i = I0; i < 8; ++i) {
+    f32x2 d2 = 0ull;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d2 = ffma2(x[k], b[i][k], d2);
+    d[i] = fsum2(d2);
+  }
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    const float ts = __shfl_xor_sync(kFull, sig, o);
+    float t[8];
+#pragma unroll
+    for (int i = I0; i < 8; ++i) t[i] = __shfl_xor_sync(kFull, d[i], o);
+    sig += ts;
+#pragma unroll
+    for (int i = I0; i < 8; ++i) d[i] += t[i];
+  }
+  const FlatRefl f = flat_scalars(alpha, sig);
+#pragma unroll
+  for (int i = I0; i < 8; ++i) {
+    const bool act = (i > I0) || (q > jj);
+    const float s = fmaf(d[i], f.inv_u, r[i]);
+    const float wv = act ? f.tau * s : 0.f;
+    if (act && h == 0) Rj[q + 8 * i] = r[i] - wv;
+    const float nwu = -(wv * f.inv_u);
+    const f32x2 nw2 = fpack2(nwu, nwu);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) b[i][k] = ffma2(nw2, x[k], b[i][k]);
+  }
+  if (q == jj && h == 0) Rj[j] = f.ok ? f.bc : alpha;
+}
+
+// Pivots j = 8 I0 + jj and j + 1 (jj even) in one pass; false if the guard tripped (reflector j is then done, j + 1 is not).
+template <int I0>
+__device__ __forceinline__ bool flat_pair(f32x2 (&b)[8][8], float* __restrict__ Rs, float* __restrict__ xb, const int q, const int h, const int jj) {
+  const int j = 8 * I0 + jj;
+  float* Rj = Rs + j * 64;
+  float* Rk = Rj + 64;
+  float r1[8], r2[8];
+#pragma unroll
+  for (int i = I0; i < 8; ++i) { r1[i] = Rj[q + 8 * i]; r2[i] = Rk[q + 8 * i]; }
+  const float alpha1 = Rj[j], alpha2 = Rk[j + 1], r1n = Rj[j + 1];
+  __syncwarp();
+  if (q == jj || q == jj + 1) {                 // x to xb[0..63], y to xb[64..127]
+    float* dst = xb + (q - jj) * 64 + 16 * h;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ulonglong2 v; v.x = b[I0][2 * k]; v.y = b[I0][2 * k + 1];
+      *reinterpret_cast<ulonglong2*>(dst + 4 * k) = v;
+    }
+  }
+  __syncwarp();
+  f32x2 x[8], y[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xb + 16 * h + 4 * k);
+    const ulonglong2 u = *reinterpret_cast<const ulonglong2*>(xb + 64 + 16 * h + 4 * k);
+    x[2 * k] = v.x; x[2 * k + 1] = v.y;
+    y[2 * k] = u.x; y[2 * k + 1] = u.y;
+  }
+  float p[8], qd[8];
+#pragma unroll
+  for (int i = I0; i < 8; ++i) {
+    f32x2 p2 = 0ull, q2 = 0ull;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { p2 = ffma2(x[k], b[i][k], p2); q2 = ffma2(y[k], b[i][k], q2); }
+    p[i] = fsum2(p2); qd[i] = fsum2(q2);
+  }
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    float tp[8], tq[8];
+#pragma unroll
+    for (int i = I0; i < 8; ++i) { tp[i] = __shfl_xor_sync(kFull, p[i], o); tq[i] = __shfl_xor_sync(kFull, qd[i], o); }
+#pragma unroll
+    for (int i = I0; i < 8; ++i) { p[i] += tp[i]; qd[i] += tq[i]; }
+  }
+  // pivot sums from the lanes that own columns j and j + 1 (slot I0): x^T x, x^T y, y^T y -- identical in every lane
+  const float pj = __shfl_sync(kFull, p[I0], jj), pj1 = __shfl_sync(kFull, p[I0], jj + 1), qj1 = __shfl_sync(kFull, qd[I0], jj + 1);
+  const FlatRefl f1 = flat_scalars(alpha1, pj);
+  const float a1 = f1.tau * fmaf(pj1, f1.inv_u, r1n) * f1.inv_u;
+  const float sig2 = fmaf(a1, fmaf(a1, pj, -2.f * pj1), qj1);
+  if (sig2 < kFlatPairGuard * qj1) {            // warp-uniform: finish reflector j from what is here, leave column j + 1 to a single step
+#pragma unroll
+    for (int i = I0; i < 8; ++i) {
+      const bool act = (i > I0) || (q > jj);
+      const float t = act ? f1.tau * fmaf(p[i], f1.inv_u, r1[i]) : 0.f;
+      if (act && h == 0) Rj[q + 8 * i] = r1[i] - t;
+      const float ne = -(t * f1.inv_u);
+      const f32x2 ne2 = fpack2(ne, ne);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) b[i][k] = ffma2(ne2, x[k], b[i][k]);
+    }
+    if (q == jj && h == 0) Rj[j] = f1.ok ? f1.bc : alpha1;
+    return false;
+  }
+  const FlatRefl f2 = flat_scalars(alpha2, sig2 > 0.f ? sig2 : 0.f);
+  const float a1pj = a1 * pj;
+#pragma unroll
+  for (int i = I0; i < 8; ++i) {
+    const bool act1 = (i > I0) || (q > jj);      // right of j (column j + 1 included)
+    const bool act2 = (i > I0) || (q > jj + 1);  // right of j + 1
+    const float t = act1 ? f1.tau * fmaf(p[i], f1.inv_u, r1[i]) : 0.f;
+    const float e = t * f1.inv_u;
+    if (act1 && h == 0) Rj[q + 8 * i] = r1[i] - t;
+    const float yta = fmaf(e, a1pj - pj1, fmaf(-a1, p[i], qd[i]));   // q_c - e p_{j+1} - a1 p_c + a1 e p_j
+    const float t2 = act2 ? f2.tau * fmaf(yta, f2.inv_u, r2[i]) : 0.f;
+    const float fc = t2 * f2.inv_u;
+    if (act2 && h == 0) Rk[q + 8 * i] = r2[i] - t2;
+    const float cx = fmaf(fc, a1, -e), cy = -fc;
+    const f32x2 cx2 = fpack2(cx, cx), cy2 = fpack2(cy, cy);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) b[i][k] = ffma2(cy2, y[k], ffma2(cx2, x[k], b[i][k]));
+  }
+  if (q == jj && h == 0) Rj[j] = f1.ok ? f1.bc : alpha1;
+  if (q == jj + 1 && h == 0) Rk[j + 1] = f2.ok ? f2.bc : alpha2;
+  return true;
+}
+
+template <int I0>
+struct FlatGroupsPair {
+  static __device__ __forceinline__ void run(f32x2 (&b)[8][8], float* Rs, float* xs, int q, int h, int n) {
+#pragma unroll 1
+    for (int jj = 0; jj < 8; jj += 2) {
+      const int j = 8 * I0 + jj;
+      if (j >= n) break;                         // warp-uniform
+      if (j + 1 < n) {
+        if (!flat_pair<I0>(b, Rs, xs, q, h, jj)) flat_one<I0>(b, Rs, xs, q, h, jj + 1);
+      } else {
+        flat_one<I0>(b, Rs, xs, q, h, jj);
+      }
+    }
+    FlatGroupsPair<I0 + 1>::run(b, Rs, xs, q, h, n);
+  }
+};
+template <>
+struct FlatGroupsPair<8> {
+  static __device__ __forceinline__ void run(f32x2 (&)[8][8], float*, float*, int, int, int) {}
+};
+
 // ---- software-pipelined step body ---------------------------------------------------------------------------------
 // The step's serial chain is sigma -> two shuffles -> sqrt / reciprocals -> per-column scalars; only the rank-1 update
 // depends on it.  Here the update of reflector j-1 is deferred into step j: the pivot column's slot is updated first
@@ -256,9 +456,10 @@ struct FlatGroupsPipe<8, KEEP> {
   static __device__ __forceinline__ void run(f32x2 (&)[8][8], f32x2 (&)[8], float (&)[8], float*, float*, int, int, int, float*) {}
 };
 
-template <int WPC, int MINB, bool PIPE, bool KEEP = false>
+template <int WPC, int MINB, bool PIPE, bool KEEP = false, bool PAIR = false>
 __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_r_kernel(FlatTsqrParams p) {
   static_assert(PIPE || !KEEP, "the reflector store lives in the pipelined step body");
+  static_assert(!PAIR || (!PIPE && !KEEP), "two pivot columns per reduction: R-only, unpipelined");
   extern __shared__ __align__(16) float flat_smem[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane & 7, h = lane >> 3;
   const long long chain = (long long)blockIdx.x * WPC + w;
@@ -327,6 +528,8 @@ __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_r_kernel(FlatTsqrPar
 #pragma unroll
       for (int i = 0; i < 8; ++i) nw[i] = 0.f;       // nothing pending at the top of a block
       FlatGroupsPipe<0, KEEP>::run(b, xp, nw, Rs, xs, q, h, n, KEEP ? p.tau_out + (rb >> 6) * 64 : nullptr);
+    } else if (PAIR) {
+      FlatGroupsPair<0>::run(b, Rs, xs, q, h, n);
     } else {
       FlatGroups<0>::run(b, Rs, xs, q, h, n);
     }
@@ -656,10 +859,17 @@ void launch_tsqr_flat_apply(const FlatApplyParams& p, cudaStream_t s) {
   tsqr_flat_apply_kernel<4, 2><<<(p.chains + 3) / 4, 128, smem, s>>>(p);
 }
 
-void launch_tsqr_flat_r(const FlatTsqrParams& p, cudaStream_t s) {
+void launch_tsqr_flat_r(const FlatTsqrParams& p, cudaStream_t s, bool pair) {
   if (p.chains <= 0) return;
   flat_init();
   ++g_launches;
+  if (pair) {                                  // two pivot columns per reduction: same 2 x 4 warps per SM geometry
+    constexpr size_t smem = (size_t)4 * kFlatWarpFloats * sizeof(float);
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(tsqr_flat_r_kernel<4, 2, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tsqr_flat_r_kernel<4, 2, false, false, true><<<(p.chains + 3) / 4, 128, smem, s>>>(p);
+    return;
+  }
   switch (g_flat_cfg) {
     case 0: FlatCfg<4, 3, false>::launch(p, s); break;
     case 1: FlatCfg<4, 2, false>::launch(p, s); break;

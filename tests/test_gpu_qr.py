@@ -577,17 +577,19 @@ def test_tsqr_flat_leaf_vs_reference_flat_tree(pkg, torch, ctx, port):
     assert metrics.gram_error(A2, Rh) < 1e-5
 
 
+@pytest.mark.parametrize("leaf", [2, 3])
 @pytest.mark.parametrize("m,n,kind", [(16384, 64, "u"), (20011, 17, "u"), (65536, 64, "n"), (100003, 40, "u"), (1 << 20, 64, "u")])
-def test_tsqr_r_tensor_pipe_leaf(pkg, torch, ctx, m, n, kind):
+def test_tsqr_r_alternative_leaves(pkg, torch, ctx, m, n, kind, leaf):
     """CQR_OPT_FLAT_TSQR = 2: the flat-tree leaf with its block products on the tensor pipe (tsqr_mma.cu: mma.sync TF32,
-    three-product split, every R-sized term on the FMA pipe) against the default SIMT leaf, fp64 and the Gram matrix."""
+    three-product split, every R-sized term on the FMA pipe); = 3: the SIMT leaf with two pivot columns per reduction
+    (flat_pair, guard + single-step fallback).  Both against the default SIMT leaf, fp64 and the Gram matrix."""
     g = torch.Generator(device="cuda").manual_seed(9)
     A = pkg.colmajor(m, n)
     A.copy_(torch.rand((m, n), device="cuda", generator=g) if kind == "u" else torch.randn((m, n), device="cuda", generator=g))
     G = A.t().double() @ A.double()
     Rs = {}
     try:
-        for mode in (2, 1):
+        for mode in (leaf, 1):
             ctx.set_option(pkg.OPT_FLAT_TSQR, mode)
             R = pkg.colmajor(n, n); R.fill_(float("nan"))
             ctx.tsqr_r(A, R); ctx.synchronize()
@@ -597,9 +599,39 @@ def test_tsqr_r_tensor_pipe_leaf(pkg, torch, ctx, m, n, kind):
             Rs[mode] = R.cpu().numpy()
     finally:
         ctx.set_option(pkg.OPT_FLAT_TSQR, 1)
-    assert metrics.r_rel_diff(Rs[2], Rs[1]) <= 1e-5
+    assert metrics.r_rel_diff(Rs[leaf], Rs[1]) <= 1e-5
     if m <= 200000:
-        assert metrics.r_rel_diff(Rs[2], np.linalg.qr(A.cpu().numpy().astype(np.float64), mode="r")) <= 1e-5
+        assert metrics.r_rel_diff(Rs[leaf], np.linalg.qr(A.cpu().numpy().astype(np.float64), mode="r")) <= 1e-5
+
+
+def test_tsqr_pair_leaf_guard_fallback(pkg, torch, ctx):
+    """Neighbouring columns that are nearly (or exactly) dependent trip the cancellation guard of the two-column leaf
+    (sigma_2 < 0.1 q): the pair must fall back to two single steps and still agree with the single-column leaf."""
+    m, n = 40000, 64
+    g = torch.Generator(device="cuda").manual_seed(4)
+    base = torch.randn((m, n), device="cuda", generator=g)
+    A = pkg.colmajor(m, n)
+    A.copy_(base)
+    for j in range(0, n, 2):                                     # every pair: column j+1 = column j + a small perturbation
+        A[:, j + 1] = A[:, j] * (1.0 + 0.01 * j) + 1e-3 * base[:, j + 1]
+    A[:, 9] = A[:, 8]                                            # one exact duplicate, one zero column
+    A[:, 30] = 0.0
+    G = A.t().double() @ A.double()
+    Rs = {}
+    try:
+        for mode in (3, 1):
+            ctx.set_option(pkg.OPT_FLAT_TSQR, mode)
+            R = pkg.colmajor(n, n)
+            ctx.tsqr_r(A, R); ctx.synchronize()
+            Rd = torch.triu(R.double())
+            assert float((Rd.t() @ Rd - G).norm() / G.norm()) < 2e-6
+            Rs[mode] = Rd
+    finally:
+        ctx.set_option(pkg.OPT_FLAT_TSQR, 1)
+    # R itself is ill-determined for dependent columns; the Gram matrices above are the check, plus agreement on the
+    # well-determined leading entries of each pair
+    d = (Rs[3].abs() - Rs[1].abs())[:, ::2]
+    assert float(d.norm() / Rs[1][:, ::2].norm()) < 1e-3
 
 
 def test_tsqr_seeded_form_q_is_linear(pkg, torch, ctx):

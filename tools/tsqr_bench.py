@@ -18,7 +18,7 @@ for m in rows:
         ctx.tsqr_r(A, R); ctx.synchronize()
         continue
     G = A.t().double() @ A.double()
-    for flat in (2, 1, 0):
+    for flat in (3, 2, 1, 0):
         ctx.set_option(pkg.OPT_FLAT_TSQR, flat)
         for _ in range(3):
             ctx.tsqr_r(A, R)

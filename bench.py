@@ -436,7 +436,7 @@ def bench_caqr(args, pkg, ctx, torch, dist, dev, rank, world, timed_steps, pk):
     A0 = pkg.colmajor(m_loc, n, device=dev)
     A0.copy_(torch.rand((m_loc, n), device=dev, generator=g))
     A = pkg.colmajor(m_loc, n, device=dev)
-    cq = dc.DistCAQR(pkg, ctx, m_loc, n, rank, world, dev)
+    cq = dc.DistCAQR(pkg, ctx, m_loc, n, rank, world, dev, kb=args.caqr_kb)
     step = lambda: cq.factor(A)
     restore = lambda: A.copy_(A0)
     restore(); step(); torch.cuda.synchronize()
@@ -444,7 +444,7 @@ def bench_caqr(args, pkg, ctx, torch, dist, dev, rank, world, timed_steps, pk):
     m_total = m_loc * world
     flops = qr_flops(m_total, n)
     res = {"workload": f"rectangular {m_total}x{n} fp32 CAQR, {m_loc} rows per GPU over {world} GPU(s): local blocked Householder + "
-                       f"tcgen05 trailing update, R / top-row all_gather per 256-column block (config 5)",
+                       f"tcgen05 trailing update, R / top-row all_gather per {args.caqr_kb}-column block (config 5)",
            "value": flops / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms, "scaling": "weak", "n_gpus": world,
            "nvlink_bytes_per_rank_per_step": None}
     cq.bytes_exchanged = 0
@@ -515,6 +515,7 @@ def main():
     ap.add_argument("--tsqr-rows", type=int, default=8388608)
     ap.add_argument("--caqr-rows-per-gpu", type=int, default=16384)
     ap.add_argument("--caqr-cols", type=int, default=4096)
+    ap.add_argument("--caqr-kb", type=int, default=256, help="CAQR outer block width (columns per cross-GPU tree step)")
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--ref-size", type=int, default=1536, help="edge of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=2)

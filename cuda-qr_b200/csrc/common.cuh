@@ -143,6 +143,20 @@ void mma_tsqr_read_trace(long long* out);   // [loads, sub-panels, trailing] clo
 #endif
 void launch_tsqr_mma_r(const MmaTsqrParams& p, cudaStream_t s);
 
+// ---- the chain's K <= 64 inner update in one launch: chain_update.cu ------------------------------
+struct ChainUpdParams {
+  const float* v; long long ldv;   // explicit V (mp x kb)
+  const float* t; long long ldt;   // kb x kb upper-triangular T
+  float* c; long long ldc;         // mp x nc, updated in place
+  long long mp; int kb, nc, trans; // trans != 0: T^T (Q^T C)
+  float* wpart;                    // ctas x 64 x 192 scratch
+  float* x;                        // 64 x 192 scratch
+  unsigned* bar; unsigned bar_base;
+  int* err;
+};
+bool chain_update_fits(int kb, int nc, const float* v, long long ldv, const float* c, long long ldc);
+void launch_chain_update(const ChainUpdParams& p, int ctas, cudaStream_t s);
+
 // ---- double-precision variant: f64_qr.cu -----------------------------------------------------------
 size_t f64_workspace_bytes(long long m, int nc_max);
 int f64_geqrf(double* a, long long lda, long long m, int n, double* tau, void* ws, int sm_count, cudaStream_t s);

@@ -90,6 +90,10 @@ struct cqr_context {
   cudaEvent_t in_ev[kMaxInChunks] = {}, ev_joined[kMaxInChunks] = {};
   std::vector<cudaEvent_t> ev_t;   // aggregated T of outer block k is final (catch-up streams wait on it)
   // row-partitioned TSQR across GPUs (cqr_dist_*): this rank's exchange slab and the peers' slabs mapped with cudaIpc
+  // fused chain update (chain_update.cu): grid-barrier counter in device memory and the host's copy of its value
+  unsigned* cu_bar = nullptr;
+  unsigned cu_bar_host = 0;
+  bool cur_fused = false;          // the launch helpers run on the panel stream proper: the one-launch inner update may be used
   RtreeSlab* dist_slab = nullptr;
   RtreeSlab* dist_peers[kRtreeMaxWorld] = {};
   int dist_rank = -1, dist_world = 0;
@@ -438,23 +442,50 @@ constexpr int kMaxSplits = 32;
 struct BlockWs {   // scratch of one block-reflector application with kb reflectors on nc columns
   float *part, *w, *x;
   long long ldw;
+  long long part_cap, x_cap;   // floats
 };
 
 BlockWs carve_block_ws(Carver& cv, int kb, int nc) {
   BlockWs b{};
   b.ldw = round_up(kb, 4);
-  b.part = cv.take(b.ldw * (long long)nc * kMaxSplits);
-  b.w = cv.take(b.ldw * nc);
-  b.x = cv.take(b.ldw * nc);
+  b.part_cap = b.ldw * (long long)nc * kMaxSplits;
+  b.x_cap = b.ldw * nc;
+  b.part = cv.take(b.part_cap);
+  b.w = cv.take(b.x_cap);
+  b.x = cv.take(b.x_cap);
   return b;
 }
 
 // C <- (I - V op(T) V^T) C.   trans_t = 1: op(T) = T^T (this is Q^T C), 0: op(T) = T (Q C).
+// CQR_CHAIN_FUSED: 0 = three launches, 1 = one launch where the panel partition guarantees co-residency (default),
+// 2 = one launch of 32 CTAs wherever the chain runs (only safe with serialised kernels: the ncu capture of that kernel).
+int chain_fused_mode() {
+  static const int mode = getenv("CQR_CHAIN_FUSED") ? atoi(getenv("CQR_CHAIN_FUSED")) : 1;
+  return mode;
+}
+
 // Replaces trailingUpdateKernel (qr.cu:335-465) and the CPU loop qr.c:255-293.
 void apply_block(cqr_context* c, long long mk, int kb, int nc, Operand V, Operand T, float* C, long long ldc,
                  int trans_t, BlockWs& ws, bool tensor) {
   if (nc <= 0 || kb <= 0) return;
   Operand Cop{C, ldc};
+  // The chain's own K <= 64 update of the block's remaining columns: one launch instead of three (chain_update.cu), when
+  // it runs on the panel stream proper (its CTAs must be co-resident: at most the partition's SMs, nothing else in flight).
+  static const long long fused_rows = getenv("CQR_CHAIN_FUSED_ROWS") ? atoll(getenv("CQR_CHAIN_FUSED_ROWS")) : 4096;
+  if (chain_fused_mode() && c->cur_fused && trans_t && (mk <= fused_rows || chain_fused_mode() == 2) &&
+      chain_update_fits(kb, nc, V.p, V.ld, C, ldc) && V.ld >= mk) {
+    int ctas = chain_fused_mode() == 2 ? 32 : cur_ctas(c);
+    const long long need = (mk + 63) / 64;
+    if (ctas > need) ctas = (int)need;
+    if (ctas > 64) ctas = 64;
+    if (ctas >= 1 && (long long)ctas * 64 * 192 <= ws.part_cap && 64ll * 192 <= ws.x_cap) {
+      ProfScope ps(c, CQR_PROF_GEMM_NN, 4.0 * mk * kb * nc, 4.0 * (2.0 * mk * nc + (double)mk * kb));
+      ChainUpdParams q{V.p, V.ld, T.p, T.ld, C, ldc, mk, kb, nc, trans_t, ws.part, ws.x, c->cu_bar, c->cu_bar_host, c->hh_err};
+      launch_chain_update(q, ctas, cur_stream(c));
+      c->cu_bar_host += 2u * (unsigned)ctas;
+      return;
+    }
+  }
   if (nc <= 512 && kb <= 256) {
     // narrow (latency-critical) update: W partials, then reduction and T multiply fused in one SIMT kernel
     int splits; long long ldp, stride;
@@ -532,6 +563,7 @@ static int create_impl(cqr_context* c, int device) {
   CQR_CUDA(cudaMalloc((void**)&c->hh_slots, panel_hh_slot_bytes() + 256));
   CQR_CUDA(cudaMemset(c->hh_slots, 0, panel_hh_slot_bytes() + 256));
   c->hh_err = reinterpret_cast<int*>(reinterpret_cast<char*>(c->hh_slots) + panel_hh_slot_bytes());
+  c->cu_bar = reinterpret_cast<unsigned*>(c->hh_err + 8);   // inside the zeroed 256-byte tail of the slot allocation
   // Profilers that inject into the process (ncu: CUDA_INJECTION64_PATH / NV_COMPUTE_PROFILER_PERFWORKS_DIR) cannot follow
   // launches on green-context streams (ncu 2025.2 dies at the first one), so the spatial partition is off under them and
   // the look-ahead runs on two plain streams; CQR_PARTITION=1 forces it on, =0 off.
@@ -904,7 +936,10 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
         float* cp = dA + j0 + (long long)(j0 + b) * lda;
         Operand V{vj, ldv};
         Operand T{tj, KB};
+        c->cur_fused = c->cur_chain && (chain_fused_mode() == 2 ||
+                                        (c->cur != nullptr && c->opt_partition && c->cur_ctas > 0 && c->cur_ctas <= 64));
         apply_block(c, mp, b, ninner, V, T, cp, lda, 1, bw_side, tensor);
+        c->cur_fused = false;
       }
     }
   };

@@ -210,7 +210,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           mbar_wait(empty0 + 8 * r, ph ^ 1);
           const uint32_t sa = smem_base + r * kStageBytes;
           const uint32_t full = full0 + 8 * r;
+#if defined(CQR_GEMM_EXP) && CQR_GEMM_EXP == 2
+          mbar_expect_tx(full, 2 * kRawBytes);
+#elif defined(CQR_GEMM_EXP) && CQR_GEMM_EXP == 3
+          mbar_expect_tx(full, kRawBytes + kABytes);
+#else
           mbar_expect_tx(full, kRawBytes);
+#endif
           const int k0 = kbeg + kb * BK;
           if (kAMn) {
 #pragma unroll
@@ -219,6 +225,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             tma_load_2d(sa, &tm_a, full, k0, m0);
           }
           tma_load_2d(sa + kABytes, &tm_b, full, k0, n0);
+#if defined(CQR_GEMM_EXP) && CQR_GEMM_EXP >= 2   // timing experiment: the lo halves arrive by TMA too (values are wrong)
+          if (kAMn) {
+#pragma unroll
+            for (int c = 0; c < BM / 32; ++c) tma_load_2d(sa + kRawBytes + c * (BK * 128), &tm_a, full, m0 + 32 * c, k0);
+          } else {
+            tma_load_2d(sa + kRawBytes, &tm_a, full, k0, m0);
+          }
+#if CQR_GEMM_EXP == 2
+          tma_load_2d(sa + kRawBytes + kABytes, &tm_b, full, k0, n0);
+#endif
+#endif
         }
       }
     }
@@ -272,8 +289,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         mbar_wait(full0 + 8 * r, ph);     // implies the stage's previous MMAs are done (producer waited on empty)
         const uint32_t sa = smem_base + r * kStageBytes;
         const uint32_t lo_base = sa + kRawBytes;
+#if defined(CQR_GEMM_EXP) && CQR_GEMM_EXP == 3
+        constexpr uint32_t kConvFrom = kABytes;
+#elif defined(CQR_GEMM_EXP)
+        constexpr uint32_t kConvFrom = kRawBytes;
+#else
+        constexpr uint32_t kConvFrom = 0;
+#endif
 #pragma unroll 4
-        for (uint32_t off = ct * 16; off < kRawBytes; off += kConvThreads * 16) {
+        for (uint32_t off = kConvFrom + ct * 16; off < kRawBytes; off += kConvThreads * 16) {
           float4 v;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sa + off));
           v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);

@@ -1141,6 +1141,9 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
       CQR_CUDA(cudaStreamWaitEvent(G, c->ev_panel[blk & 1], 0));
       if (!t_on_chain(K0)) do_block_t(K0, bb(blk));
     }
+    // (Tried: cutting this update into four column pieces that alternate with the panel-wise slices on the GEMM stream, so
+    // that the slices need not wait for the whole update: 65.7 -> 72.4 ms, the smaller GEMMs lose more than the earlier
+    // slices gain -- in that phase the GEMM partition, not the chain, is the busy one; profiles/r02_pws_interleave.txt.)
     do_update(K0, bb(blk), cnext + la, n);
     slice_done = false;
     use(P, pr.sm_p, true);

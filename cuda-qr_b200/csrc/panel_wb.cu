@@ -331,25 +331,14 @@ __global__ void __launch_bounds__(32 * W, 1) panel_wb_kernel(PanelHHParams p) {
       }
     }
   }
-  // ---- compact-WY T (CTA 0).  T^-1 = diag(1 / tau) + striu(V^T V), so column c of T is a back substitution that does
-  // not depend on the other columns: T(c,c) = tau_c, T(i,c) = -tau_i sum_{k=i+1..c} G(i,k) T(k,c) for i = c-1 .. 0
-  // (tau_i = 0, H_i = I, gives a zero row).  One thread per column, no barrier inside; G(i,k) is a broadcast read and
-  // ts[k][c] is conflict-free across the threads (row stride 65).
+  // ---- compact-WY T (CTA 0): T^-1 = diag(1 / tau) + striu(V^T V), inverted by blocks on all threads (wb_build_t)
   if (blockIdx.x == 0 && p.t != nullptr) {
     __syncthreads();
     const int nb = p.b, nt = 32 * W;
-    for (int c = threadIdx.x; c < nb; c += nt) {
-      sm.ts[c][c] = sm.staus[c];
-      for (int i = c - 1; i >= 0; --i) {
-        float acc = 0.f;
-        for (int k = i + 1; k <= c; ++k) acc = fmaf(sm.gs[i][k], sm.ts[k][c], acc);
-        sm.ts[i][c] = -sm.staus[i] * acc;
-      }
-    }
-    __syncthreads();
+    wb_build_t(sm.gs, sm.ts, sm.staus, nb, threadIdx.x, nt);
     for (int idx = threadIdx.x; idx < nb * nb; idx += nt) {
       const int i = idx % nb, cc = idx / nb;
-      p.t[i + (long long)cc * p.ldt] = (i <= cc) ? sm.ts[i][cc] : 0.f;
+      p.t[i + (long long)cc * p.ldt] = (i <= cc) ? sm.gs[i][cc] : 0.f;
     }
   }
   if (cx.CS > 1) wb_cluster_sync();   // no CTA leaves while pushes addressed to it (or by it) are in flight
@@ -382,7 +371,10 @@ bool panel_wb_plan(long long mp, int* wpc, int* cs, int* ncl) {
   *ncl = 1;
   if (mp > 8192) { *wpc = 8; *cs = 16; *ncl = 2; return true; }
   const int nw = (int)((mp + 63) / 64);
+  // CQR_PANEL_WB_MIN_WPC: fewest warps per CTA above 512 rows (1, 2, 4, 8): wider CTAs mean fewer CTAs in the exchange
+  static const int min_wpc = getenv("CQR_PANEL_WB_MIN_WPC") ? atoi(getenv("CQR_PANEL_WB_MIN_WPC")) : 1;
   int w = 1;
+  if (nw > 8 && (min_wpc == 2 || min_wpc == 4 || min_wpc == 8)) w = min_wpc;
   if (nw <= 8) {                 // up to 512 rows: one CTA, no cluster exchange at all
     while (w < nw) w *= 2;
     *wpc = w; *cs = 1;

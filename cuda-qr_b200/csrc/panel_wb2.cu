@@ -105,10 +105,17 @@ __device__ __forceinline__ Refl wb2_scalars(float alpha, float sig) {
   return r;
 }
 
-// columns j = 8 I0 .. 8 I0 + 7, two per exchange; ex counts the exchanges of this launch (buffer and mbarrier parity)
-template <int I0, int W, bool X2>
-__device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, const Wb2Ctx& cx, unsigned& ex) {
+// Columns j = 8 I0 .. 8 I0 + 7, two per exchange; ex counts the exchanges of this launch (buffer and mbarrier parity).
+// ONE instantiation serves all eight column groups: the caller rotates the register block between groups so that the
+// pivot group is always b[0][.] (register group i holds the columns q + 8 ((i + I0) & 7)) and, in the warp that owns
+// the pivot rows, the pivot row block is always b[.][0] (register row block k holds the rows 8 ((k + I0) & 7) ..).  With
+// I0 a template parameter the kernel was 17 K instructions (276 KB), every group ran its own copy four times, and the
+// ncu capture had 31-34 % of the stall samples in `no_instruction` (instruction-cache misses).  Rows above the pivot
+// are zero in the published x and y, so the dots see the same terms in the same order as before.
+template <int W, bool X2>
+__device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, const Wb2Ctx& cx, unsigned& ex, const int I0) {
   const int q = cx.q, h = cx.h, w = cx.w, lane = cx.lane;
+  const int nact = 8 - I0;                   // register groups / (pivot warp) row blocks still in play: indices 0 .. nact - 1
   int jj = 0;
   bool second = false;                       // this pass is the lone step j+1 of a pair that failed the guard
 #pragma unroll 1
@@ -119,16 +126,16 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
     const unsigned par = (ex >> 1) & 1;
     ++ex;
     WB2_TRACE(0);
-    const int hj = jj >> 1;                  // rows j, j+1 are the (lo, hi) of pair I0 in the lanes h == hj of the top warp
+    const int hj = jj >> 1;                  // rows j, j+1 are the (lo, hi) of row block 0 in the lanes h == hj of the pivot warp
     const int qx = second ? jj + 1 : jj, qy = jj + 1;
     float* xb = sm.xs[w][buf];
     float* yb = sm.ys[w][buf];
-    // ---- publish x and y (this warp's rows; the top warp masks rows 0 .. j+1) and rows j, j+1
+    // ---- publish x and y (this warp's rows; the pivot warp masks rows 0 .. j+1) and rows j, j+1
     if (q == qx || q == qy) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        f32x2 v = b[I0][k];
-        if (cx.top && (k < I0 || (k == I0 && h <= hj))) v = 0ull;
+        f32x2 v = b[0][k];
+        if (cx.top && (k >= nact || (k == 0 && h <= hj))) v = 0ull;
         if (q == qx) *reinterpret_cast<f32x2*>(xb + 8 * k + 2 * h) = v;
         if (q == qy) *reinterpret_cast<f32x2*>(yb + 8 * k + 2 * h) = v;
       }
@@ -137,8 +144,8 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float lo, hi;
-        wupk(b[i][I0], lo, hi);
-        sm.prl[buf][q + 8 * i] = lo;
+        wupk(b[i][0], lo, hi);
+        sm.prl[buf][q + 8 * i] = lo;           // exchange vectors are indexed by the ROTATED column position q + 8 i
         sm.prl[buf][64 + q + 8 * i] = hi;
       }
     }
@@ -266,40 +273,52 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
 
     if (!second) {
       // ---- reflector j and what it does to column j+1 (redundant in every thread: bit-identical inputs)
-      const float xj1 = R2[j], yj1 = R2[j + 1];
-      const Refl s1 = wb2_scalars(R1[j], fmaf(xj1, xj1, P[j]));
+      // (column j sits at rotated position jj)
+      const float xj1 = R2[jj], yj1 = R2[jj + 1];
+      const float pj = P[jj], pj1 = P[jj + 1], qj1 = Q[jj + 1];
+      const Refl s1 = wb2_scalars(R1[jj], fmaf(xj1, xj1, pj));
       const float iu1 = s1.inv_u, t1 = s1.tau;
-      const float d1n = fmaf(fmaf(xj1, yj1, P[j + 1]), iu1, R1[j + 1]);
+      const float d1n = fmaf(fmaf(xj1, yj1, pj1), iu1, R1[jj + 1]);
       const float tn = t1 * d1n;
       const float a1 = tn * iu1;
       const float alpha2 = fmaf(-a1, xj1, yj1);
-      const float sig2 = fmaf(a1 * a1, P[j], fmaf(-2.f * a1, P[j + 1], Q[j + 1]));
-      const bool fb = (cx.mode == 2) || (sig2 < kPairGuard * Q[j + 1]);
+      const float sig2 = fmaf(a1 * a1, pj, fmaf(-2.f * a1, pj1, qj1));
+      const bool fb = (cx.mode == 2) || (sig2 < kPairGuard * qj1);
       if (cx.top && lane == 0) { cx.tau_out[j] = t1; sm.staus[j] = t1; }
       WB2_TRACE(6);
       if (!fb) {
         const Refl s2 = wb2_scalars(alpha2, fmaxf(sig2, 0.f));
         const float iu2 = s2.inv_u, t2 = s2.tau;
         if (cx.top && lane == 0) { cx.tau_out[j + 1] = t2; sm.staus[j + 1] = t2; }
+        // pass 1, all eight groups without a branch (loads and scalar chains of the groups overlap): the two update
+        // coefficients per column, the patched rows j, j+1 (x and y are zero there, so the FMAs below leave them alone)
+        // and the new entries of V^T V; pass 2, the FMAs of the groups that are still in play
+        float cxs[8], cys[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int c = q + 8 * i;
-          const float d1 = fmaf(fmaf(xj1, R2[c], P[c]), iu1, R1[c]);          // v_j^T a_c  (c < j: v_c^T v_j)
-          if (i <= I0 && cx.top && h == 0) {
-            if (c < j) { sm.gs[c][j] = d1; sm.gs[c][j + 1] = fmaf(fmaf(-a1, P[c], Q[c]), iu2, R2[c]); }
-            else if (c == j) sm.gs[j][j + 1] = fmaf(iu1 * iu2, fmaf(-a1, P[j], P[j + 1]), xj1 * iu1);
+          const int cp = q + 8 * i;                                           // rotated position of column c
+          const float pc = P[cp], qc = Q[cp], r1c = R1[cp], r2v = R2[cp];
+          const float d1 = fmaf(fmaf(xj1, r2v, pc), iu1, r1c);                // v_j^T a_c  (c < j: v_c^T v_j)
+          if ((i == 0 || i >= nact) && cx.top && h == 0) {
+            const int c = q + 8 * ((i + I0) & 7);
+            if (c < j) { sm.gs[c][j] = d1; sm.gs[c][j + 1] = fmaf(fmaf(-a1, pc, qc), iu2, r2v); }
+            else if (c == j) sm.gs[j][j + 1] = fmaf(iu1 * iu2, fmaf(-a1, pj, pj1), xj1 * iu1);
           }
-          if (i >= I0) {
-            const bool act = (i > I0) || (q > jj + 1);
-            const float tc = t1 * d1, ec = tc * iu1;
-            const float r2c = fmaf(-ec, xj1, R2[c]);                          // a'(j+1, c)
-            const float inner = fmaf(a1 * ec, P[j], fmaf(-a1, P[c], fmaf(-ec, P[j + 1], Q[c])));
-            const float sc2 = t2 * fmaf(inner, iu2, r2c), fc = sc2 * iu2;
-            const float cxv = act ? fmaf(fc, a1, -ec) : 0.f, cyv = act ? -fc : 0.f;
-            const f32x2 cx2 = wpk(cxv, cxv), cy2 = wpk(cyv, cyv);
+          const bool act = (i < nact) && ((i > 0) || (q > jj + 1));
+          const float tc = t1 * d1, ec = tc * iu1;
+          const float r2c = fmaf(-ec, xj1, r2v);                              // a'(j+1, c)
+          const float inner = fmaf(a1 * ec, pj, fmaf(-a1, pc, fmaf(-ec, pj1, qc)));
+          const float sc2 = t2 * fmaf(inner, iu2, r2c), fc = sc2 * iu2;
+          cxs[i] = act ? fmaf(fc, a1, -ec) : 0.f;
+          cys[i] = act ? -fc : 0.f;
+          if (act && cx.top && h == hj) b[i][0] = wpk(r1c - tc, r2c - sc2);   // rows j, j+1
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i < nact) {
+            const f32x2 cx2 = wpk(cxs[i], cxs[i]), cy2 = wpk(cys[i], cys[i]);
 #pragma unroll
             for (int k = 0; k < 8; ++k) b[i][k] = wfma2(cx2, x[k], wfma2(cy2, y[k], b[i][k]));
-            if (act && cx.top && h == hj) b[i][I0] = wpk(R1[c] - tc, r2c - sc2);   // rows j, j+1 (x, y are masked there)
           }
         }
         if (q == jj + 1) {                   // column j+1: R(j, j+1), beta_2, v = (y - a1 x) / u_2 below
@@ -307,27 +326,31 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
           const f32x2 m22 = wpk(m2, m2), na2 = wpk(-a1, -a1);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const f32x2 nv = wmul2(wfma2(na2, x[k], b[I0][k]), m22);
-            if (!cx.top || k > I0 || (k == I0 && h > hj)) b[I0][k] = nv;
+            const f32x2 nv = wmul2(wfma2(na2, x[k], b[0][k]), m22);
+            if (!cx.top || (k > 0 && k < nact) || (k == 0 && h > hj)) b[0][k] = nv;
           }
-          if (cx.top && h == hj) b[I0][I0] = wpk(R1[j + 1] - tn, s2.ok ? s2.bc : alpha2);
+          if (cx.top && h == hj) b[0][0] = wpk(R1[jj + 1] - tn, s2.ok ? s2.bc : alpha2);
         }
       } else {
         // ---- cancellation fallback, first half: step j alone from the data of this exchange (x^T a_c over the rows
         // below j is p_c + r2_j r2_c); step j+1 follows as a single step with its own exchange
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int c = q + 8 * i;
-          const float d1 = fmaf(fmaf(xj1, R2[c], P[c]), iu1, R1[c]);
-          if (i <= I0 && cx.top && h == 0 && c < j) sm.gs[c][j] = d1;
-          if (i >= I0) {
-            const bool act = (i > I0) || (q > jj);
+          const int cp = q + 8 * i;
+          const float r1c = R1[cp], r2v = R2[cp];
+          const float d1 = fmaf(fmaf(xj1, r2v, P[cp]), iu1, r1c);
+          if ((i == 0 || i >= nact) && cx.top && h == 0) {
+            const int c = q + 8 * ((i + I0) & 7);
+            if (c < j) sm.gs[c][j] = d1;
+          }
+          if (i < nact) {
+            const bool act = (i > 0) || (q > jj);
             const float tc = t1 * d1, ec = tc * iu1;
             const float cxv = act ? -ec : 0.f;
             const f32x2 cx2 = wpk(cxv, cxv);
 #pragma unroll
             for (int k = 0; k < 8; ++k) b[i][k] = wfma2(cx2, x[k], b[i][k]);
-            if (act && cx.top && h == hj) b[i][I0] = wpk(R1[c] - tc, fmaf(-ec, xj1, R2[c]));
+            if (act && cx.top && h == hj) b[i][0] = wpk(r1c - tc, fmaf(-ec, xj1, r2v));
           }
         }
       }
@@ -335,24 +358,28 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
         const f32x2 iu12 = wpk(iu1, iu1);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          if (!cx.top || k > I0 || (k == I0 && h > hj)) b[I0][k] = wmul2(b[I0][k], iu12);
-        if (cx.top && h == hj) b[I0][I0] = wpk(s1.bc, xj1 * iu1);
+          if (!cx.top || (k > 0 && k < nact) || (k == 0 && h > hj)) b[0][k] = wmul2(b[0][k], iu12);
+        if (cx.top && h == hj) b[0][0] = wpk(s1.bc, xj1 * iu1);
       }
       if (fb) second = true;
       else jj += 2;
       WB2_TRACE(7);
     } else {
       // ---- lone step j+1: x is the true column j+1 below row j+1, R2 the current row j+1
-      const Refl s2 = wb2_scalars(R2[j + 1], P[j + 1]);
+      const Refl s2 = wb2_scalars(R2[jj + 1], P[jj + 1]);
       const float iu2 = s2.inv_u, t2 = s2.tau;
       if (cx.top && lane == 0) { cx.tau_out[j + 1] = t2; sm.staus[j + 1] = t2; }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int c = q + 8 * i;
-        const float d2 = fmaf(P[c], iu2, R2[c]);
-        if (i <= I0 && cx.top && h == 0 && c < j + 1) sm.gs[c][j + 1] = d2;
-        if (i >= I0) {
-          const bool act = (i > I0) || (q > jj + 1);
+        const int cp = q + 8 * i;
+        const float r2v = R2[cp];
+        const float d2 = fmaf(P[cp], iu2, r2v);
+        if ((i == 0 || i >= nact) && cx.top && h == 0) {
+          const int c = q + 8 * ((i + I0) & 7);
+          if (c < j + 1) sm.gs[c][j + 1] = d2;
+        }
+        if (i < nact) {
+          const bool act = (i > 0) || (q > jj + 1);
           const float sc2 = t2 * d2, fc = sc2 * iu2;
           const float cxv = act ? -fc : 0.f;
           const f32x2 cx2 = wpk(cxv, cxv);
@@ -360,8 +387,8 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
           for (int k = 0; k < 8; ++k) b[i][k] = wfma2(cx2, x[k], b[i][k]);
           if (act && cx.top && h == hj) {
             float lo, hi;
-            wupk(b[i][I0], lo, hi);
-            b[i][I0] = wpk(lo, R2[c] - sc2);
+            wupk(b[i][0], lo, hi);
+            b[i][0] = wpk(lo, r2v - sc2);
           }
         }
       }
@@ -369,11 +396,11 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
         const f32x2 iu22 = wpk(iu2, iu2);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          if (!cx.top || k > I0 || (k == I0 && h > hj)) b[I0][k] = wmul2(b[I0][k], iu22);
+          if (!cx.top || (k > 0 && k < nact) || (k == 0 && h > hj)) b[0][k] = wmul2(b[0][k], iu22);
         if (cx.top && h == hj) {
           float lo, hi;
-          wupk(b[I0][I0], lo, hi);
-          b[I0][I0] = wpk(lo, s2.bc);
+          wupk(b[0][0], lo, hi);
+          b[0][0] = wpk(lo, s2.bc);
         }
       }
       second = false;
@@ -383,17 +410,26 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
   }
 }
 
-template <int I0, int W, bool X2>
-struct Wb2Groups {
-  static __device__ __forceinline__ void run(f32x2 (&b)[8][8], Wb2Shared<W>& sm, const Wb2Ctx& cx, unsigned& ex) {
-    wb2_steps<I0, W, X2>(b, sm, cx, ex);
-    Wb2Groups<I0 + 1, W, X2>::run(b, sm, cx, ex);
+// Next column group: register group i takes over from i + 1 (the finished group goes to the end), and in the pivot warp
+// row block k from k + 1 as well.  After eight rotations the block is back in its original order.
+__device__ __forceinline__ void wb2_rotate(f32x2 (&b)[8][8], bool top) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const f32x2 t = b[0][k];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) b[i][k] = b[i + 1][k];
+    b[7][k] = t;
   }
-};
-template <int W, bool X2>
-struct Wb2Groups<8, W, X2> {
-  static __device__ __forceinline__ void run(f32x2 (&)[8][8], Wb2Shared<W>&, const Wb2Ctx&, unsigned&) {}
-};
+  if (top) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const f32x2 t = b[i][0];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) b[i][k] = b[i][k + 1];
+      b[i][7] = t;
+    }
+  }
+}
 
 extern __shared__ __align__(16) unsigned char wb2_smem[];
 
@@ -442,7 +478,11 @@ __global__ void __launch_bounds__(32 * W, 1) panel_wb2_kernel(PanelHHParams p) {
 
   unsigned ex = 0;
   WB2_MARK(1);
-  Wb2Groups<0, W, X2>::run(b, sm, cx, ex);
+#pragma unroll 1
+  for (int I0 = 0; I0 < 8; ++I0) {
+    wb2_steps<W, X2>(b, sm, cx, ex, I0);
+    wb2_rotate(b, cx.top);
+  }
   WB2_MARK(2);
 
   // ---- results: LAPACK storage into the panel, explicit V (unit diagonal, zeros above) into vbuf
@@ -468,23 +508,14 @@ __global__ void __launch_bounds__(32 * W, 1) panel_wb2_kernel(PanelHHParams p) {
     }
   }
   WB2_MARK(3);
-  // ---- compact-WY T (CTA 0), as in panel_wb.cu: column c of T is an independent back substitution on
-  // T^-1 = diag(1 / tau) + striu(V^T V); one thread per column
+  // ---- compact-WY T (CTA 0), as in panel_wb.cu: T^-1 = diag(1 / tau) + striu(V^T V), inverted by blocks (wb_build_t)
   if (blockIdx.x == 0 && p.t != nullptr) {
     __syncthreads();
     const int nb = p.b, nt = 32 * W;
-    for (int c = threadIdx.x; c < nb; c += nt) {
-      sm.ts[c][c] = sm.staus[c];
-      for (int i = c - 1; i >= 0; --i) {
-        float acc = 0.f;
-        for (int k = i + 1; k <= c; ++k) acc = fmaf(sm.gs[i][k], sm.ts[k][c], acc);
-        sm.ts[i][c] = -sm.staus[i] * acc;
-      }
-    }
-    __syncthreads();
+    wb_build_t(sm.gs, sm.ts, sm.staus, nb, threadIdx.x, nt);
     for (int idx = threadIdx.x; idx < nb * nb; idx += nt) {
       const int i = idx % nb, cc = idx / nb;
-      p.t[i + (long long)cc * p.ldt] = (i <= cc) ? sm.ts[i][cc] : 0.f;
+      p.t[i + (long long)cc * p.ldt] = (i <= cc) ? sm.gs[i][cc] : 0.f;
     }
   }
   WB2_MARK(4);

@@ -117,11 +117,8 @@ class DistCAQR:
             S = self.stack[:P * w, :w + nt]
             rs = S[:, :w]
             cs = S[:, w:] if nt else None
-            for p in range(P):
-                blk = out[p].t()                               # (kb, w + nt)
-                rs[p * w:(p + 1) * w].copy_(blk[:w, :w])
-                if nt:
-                    cs[p * w:(p + 1) * w].copy_(blk[:w, w:])
+            # S[p w + i, j] = out[p, j, i]: one strided copy into the stack's storage (columns x stacked rows)
+            S.t().unflatten(1, (P, w)).copy_(out[:, :, :w].permute(1, 0, 2))
             return rs, cs
 
         def tree_qr(k0, w, rs):
@@ -179,8 +176,7 @@ class DistCAQR:
         allv = t.empty((P, w, w), dtype=t.float32, device=self.device)
         self.comm.all_gather_into(allv, mine)
         Vt = self.pkg.colmajor(P * w, w, device=self.device)
-        for p in range(P):
-            Vt[p * w:(p + 1) * w].copy_(allv[p].t())
+        Vt.t().unflatten(1, (P, w)).copy_(allv.permute(1, 0, 2))      # Vt[p w + i, j] = allv[p, j, i]
         return Vt
 
     def apply_q(self, A_loc, C_loc, trans: bool):
@@ -202,8 +198,7 @@ class DistCAQR:
                 alltop = t.empty((P, nc, w), dtype=t.float32, device=self.device)
                 self.comm.all_gather_into(alltop, top)
                 Cs = self.pkg.colmajor(P * w, nc, device=self.device)
-                for p in range(P):
-                    Cs[p * w:(p + 1) * w].copy_(alltop[p].t())
+                Cs.t().unflatten(1, (P, w)).copy_(alltop.permute(1, 0, 2))
                 self.ctx.apply_q(Vt, self.tau_tree[k0 // self.kb, :w], Cs, trans)
                 C_loc[r0:r0 + w].copy_(Cs[self.rank * w:(self.rank + 1) * w])
 

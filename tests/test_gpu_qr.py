@@ -629,9 +629,10 @@ def test_tsqr_pair_leaf_guard_fallback(pkg, torch, ctx):
     finally:
         ctx.set_option(pkg.OPT_FLAT_TSQR, 1)
     # R itself is ill-determined for dependent columns; the Gram matrices above are the check, plus agreement on the
-    # well-determined leading entries of each pair
-    d = (Rs[3].abs() - Rs[1].abs())[:, ::2]
-    assert float(d.norm() / Rs[1][:, ::2].norm()) < 1e-3
+    # well-determined entries: first column of each pair against the reflectors of first columns (an odd row belongs to
+    # the direction of a 1e-3 perturbation, which is only determined to ~1e-3 / eps)
+    d = (Rs[3].abs() - Rs[1].abs())[::2, ::2]
+    assert float(d.norm() / Rs[1][::2, ::2].norm()) < 1e-3
 
 
 def test_tsqr_seeded_form_q_is_linear(pkg, torch, ctx):

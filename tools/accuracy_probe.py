@@ -9,6 +9,8 @@ pkg = importlib.import_module("cuda-qr_b200")
 ctx = pkg.Context(0); ctx.use_torch_stream()
 EPS = 2.0 ** -23
 sizes = [int(s) for s in sys.argv[1:]] or [1024, 2048, 4096, 8192]
+SIMT_MAX = int(os.environ.get("PROBE_SIMT_MAX", "16384"))                      # fp32 SIMT GEMMs up to this size
+OUTERS = [int(x) for x in os.environ.get("PROBE_OUTERS", "256,64").split(",")]   # outer block widths
 
 
 def blocked_norm_diff(X, Y):
@@ -32,7 +34,7 @@ def ours(A0, mode, outer=256):
     be = blocked_norm_diff(A0, QR)
     del QR
     Q = pkg.colmajor(m, n); ctx.form_q(A, tau, Q); ctx.synchronize()
-    G = (Q.t().double() @ Q.double()) if n <= 8192 else None
+    G = (Q.t().double() @ Q.double()) if n <= 16384 else None
     orth = float((G - torch.eye(n, device="cuda", dtype=torch.float64)).norm() / n ** 0.5) if G is not None else float("nan")
     return be, orth
 
@@ -41,7 +43,7 @@ def cusolver(A0):
     m, n = A0.shape
     t0 = time.perf_counter(); Q, R = torch.linalg.qr(A0.contiguous()); torch.cuda.synchronize(); dt = time.perf_counter() - t0
     be = blocked_norm_diff(A0, Q @ R)
-    G = Q.t().double() @ Q.double() if n <= 8192 else None
+    G = Q.t().double() @ Q.double() if n <= 16384 else None
     orth = float((G - torch.eye(n, device="cuda", dtype=torch.float64)).norm() / n ** 0.5) if G is not None else float("nan")
     return be, orth, dt
 
@@ -52,12 +54,12 @@ for n in sizes:
         X = torch.rand((n, n), device="cuda", generator=g) if dist == "uniform" else torch.randn((n, n), device="cuda", generator=g)
         A0 = pkg.to_colmajor(X)
         for mode, name in ((1, "tf32x3"), (0, "simt")):
-            if mode == 0 and n > 4096:
+            if mode == 0 and n > SIMT_MAX:
                 continue
-            for outer in (256, 64):
+            for outer in OUTERS:
                 be, orth = ours(A0, mode, outer)
                 print(f"n={n:6d} {dist:8s} ours/{name:7s} outer={outer:3d}: backward {be:.3e} ({be / (n * EPS):.4f} n*eps)  orth {orth:.3e} ({orth / (n * EPS):.4f} n*eps)", flush=True)
-        if n <= 8192:
+        if n <= 16384:
             be, orth, dt = cusolver(X)
             print(f"n={n:6d} {dist:8s} cusolver(torch.linalg.qr) {dt*1e3:8.1f} ms incl. Q: backward {be:.3e}  orth {orth:.3e}", flush=True)
 ctx.set_option(pkg.OPT_GEMM, 1); ctx.set_option(pkg.OPT_OUTER_BLOCK, 256)

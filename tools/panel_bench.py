@@ -10,7 +10,7 @@ for m in ms_list:
     A0 = pkg.colmajor(m, 64); A0.copy_(torch.rand((m, 64), device="cuda"))
     A = pkg.colmajor(m, 64); tau = torch.zeros(64, device="cuda")
     out = []
-    for mode in (1, 0):
+    for mode in ((1,) if os.environ.get('CQR_PANEL_BENCH_MODES') == '1' else (1, 0)):
         ctx.set_option(pkg.OPT_PANEL, mode)
         for _ in range(3):
             A.copy_(A0); ctx.geqrf(A, tau)
@@ -22,6 +22,7 @@ for m in ms_list:
             e0.record(); ctx.geqrf(A, tau); e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3)
         ts.sort()
+        assert ctx.last_error() == 0 if hasattr(ctx, 'last_error') else True
         out.append(f"mode {mode}: median {ts[10]:8.1f} us  min {ts[0]:8.1f} us")
     print(f"panel {m:6d} x 64   " + "   ".join(out), flush=True)
 ctx.set_option(pkg.OPT_PANEL, 1)

@@ -155,6 +155,8 @@ struct ChainUpdParams {
   int* err;
 };
 bool chain_update_fits(int kb, int nc, const float* v, long long ldv, const float* c, long long ldc);
+long long chain_update_part_floats(int nc);
+int chain_update_min_ctas(int nc);
 void launch_chain_update(const ChainUpdParams& p, int ctas, cudaStream_t s);
 
 // ---- double-precision variant: f64_qr.cu -----------------------------------------------------------

@@ -92,8 +92,8 @@ struct cqr_context {
   // row-partitioned TSQR across GPUs (cqr_dist_*): this rank's exchange slab and the peers' slabs mapped with cudaIpc
   // fused chain update (chain_update.cu): grid-barrier counter in device memory and the host's copy of its value
   unsigned* cu_bar = nullptr;
-  unsigned cu_bar_host = 0;
-  bool cur_fused = false;          // the launch helpers run on the panel stream proper: the one-launch inner update may be used
+  unsigned cu_bar_host[2] = {0, 0};   // grid-barrier counters of the one-launch K = 64 update: [0] panel stream, [1] GEMM stream
+  int cur_fused = 0;               // the one-launch update may be used: 1 = inner update on the panel stream, 2 = look-ahead slice on the GEMM stream
   RtreeSlab* dist_slab = nullptr;
   RtreeSlab* dist_peers[kRtreeMaxWorld] = {};
   int dist_rank = -1, dist_world = 0;
@@ -471,18 +471,23 @@ void apply_block(cqr_context* c, long long mk, int kb, int nc, Operand V, Operan
   Operand Cop{C, ldc};
   // The chain's own K <= 64 update of the block's remaining columns: one launch instead of three (chain_update.cu), when
   // it runs on the panel stream proper (its CTAs must be co-resident: at most the partition's SMs, nothing else in flight).
+  // cur_fused: 1 = the chain's inner update on the panel partition (pays up to ~4096 rows: fp32 FMA on 32 SMs), 2 = a
+  // panel-wise look-ahead slice on the GEMM partition (116 SMs: pays at every height the slices are used at).
   static const long long fused_rows = getenv("CQR_CHAIN_FUSED_ROWS") ? atoll(getenv("CQR_CHAIN_FUSED_ROWS")) : 4096;
-  if (chain_fused_mode() && c->cur_fused && trans_t && (mk <= fused_rows || chain_fused_mode() == 2) &&
+  static const long long slice_rows = getenv("CQR_SLICE_FUSED_ROWS") ? atoll(getenv("CQR_SLICE_FUSED_ROWS")) : 16384;
+  const int fm = c->cur_fused;
+  if (chain_fused_mode() && fm && trans_t && (mk <= (fm == 1 ? fused_rows : slice_rows) || chain_fused_mode() == 2) &&
       chain_update_fits(kb, nc, V.p, V.ld, C, ldc) && V.ld >= mk) {
     int ctas = chain_fused_mode() == 2 ? 32 : cur_ctas(c);
-    const long long need = (mk + 63) / 64;
+    const int sub = nc <= 192 ? 64 : 32;
+    const long long need = (mk + sub - 1) / sub;
     if (ctas > need) ctas = (int)need;
-    if (ctas > 64) ctas = 64;
-    if (ctas >= 1 && (long long)ctas * 64 * 192 <= ws.part_cap && 64ll * 192 <= ws.x_cap) {
+    if (ctas > 128) ctas = 128;
+    if (ctas >= chain_update_min_ctas(nc) && ctas * chain_update_part_floats(nc) <= ws.part_cap && 64ll * nc <= ws.x_cap) {
       ProfScope ps(c, CQR_PROF_GEMM_NN, 4.0 * mk * kb * nc, 4.0 * (2.0 * mk * nc + (double)mk * kb));
-      ChainUpdParams q{V.p, V.ld, T.p, T.ld, C, ldc, mk, kb, nc, trans_t, ws.part, ws.x, c->cu_bar, c->cu_bar_host, c->hh_err};
+      ChainUpdParams q{V.p, V.ld, T.p, T.ld, C, ldc, mk, kb, nc, trans_t, ws.part, ws.x, c->cu_bar + (fm - 1), c->cu_bar_host[fm - 1], c->hh_err};
       launch_chain_update(q, ctas, cur_stream(c));
-      c->cu_bar_host += 2u * (unsigned)ctas;
+      c->cu_bar_host[fm - 1] += 2u * (unsigned)ctas;
       return;
     }
   }
@@ -855,6 +860,10 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
     bw_main = carve_block_ws(cv, KB, ncmax);
     bw_side = carve_block_ws(cv, 64, KB);   // inner updates: 64 reflectors on < KB columns
     bw_slice = carve_block_ws(cv, 64, KB);  // panel-wise look-ahead slices on the GEMM stream (opt_lookahead == 2)
+    {                                       // ... as one launch on every SM of the GEMM partition: one partial W per CTA
+      const long long need = (long long)c->sm_count * chain_update_part_floats(KB < 256 ? KB : 256);
+      if (need > bw_slice.part_cap) { bw_slice.part = cv.take(need); bw_slice.part_cap = need; }
+    }
     if (!pass) { int rc = ws_ensure(c, cv.off); if (rc) return rc; }
   }
 
@@ -936,10 +945,10 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
         float* cp = dA + j0 + (long long)(j0 + b) * lda;
         Operand V{vj, ldv};
         Operand T{tj, KB};
-        c->cur_fused = c->cur_chain && (chain_fused_mode() == 2 ||
-                                        (c->cur != nullptr && c->opt_partition && c->cur_ctas > 0 && c->cur_ctas <= 64));
+        c->cur_fused = (c->cur_chain && (chain_fused_mode() == 2 ||
+                                         (c->cur != nullptr && c->opt_partition && c->cur_ctas > 0 && c->cur_ctas <= 64))) ? 1 : 0;
         apply_block(c, mp, b, ninner, V, T, cp, lda, 1, bw_side, tensor);
-        c->cur_fused = false;
+        c->cur_fused = 0;
       }
     }
   };
@@ -1133,7 +1142,7 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
     // after it one by one on the GEMM stream while the panel chain is still running, so when its last panel is done
     // only one K = 64 update separates the chain from the following block -- not the aggregated T plus a K = 256 slice.
     const int c2 = cnext + la;               // first column right of the next block
-    static const long long pws_rows = getenv("CQR_PWS_ROWS") ? atoll(getenv("CQR_PWS_ROWS")) : 14336;   // tuning knob
+    static const long long pws_rows = getenv("CQR_PWS_ROWS") ? atoll(getenv("CQR_PWS_ROWS")) : 10240;   // tuning knob
     const bool pws = c->opt_lookahead == 2 && (m - cnext) <= pws_rows && c2 < nf && KB / 64 <= 8;
     // GEMM stream first (host order only): what is left of block K's update, then -- behind it -- the panel-wise share
     use(G, pr.sm_g, false);
@@ -1159,7 +1168,9 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
         cudaStreamWaitEvent(G, c->ev_pp[(blk + 1) & 1][off / 64], 0);
         Operand V{Bn.vbuf + off + (long long)off * ldv, ldv};
         Operand T{Bn.tbig + off + (long long)off * KB, KB};
+        c->cur_fused = (c->opt_partition && pr.sm_g > 0 && pr.sm_g <= 128) ? 2 : 0;   // alone on its partition: one launch
         apply_block(c, m - j0, b, c2 + w2 - col0, V, T, dA + j0 + (long long)col0 * lda, lda, 1, bw_slice, tensor);
+        c->cur_fused = 0;
         use(P, pr.sm_p, true);
       };
       do_panels(cnext, bb(blk + 1), &hk);

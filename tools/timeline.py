@@ -23,6 +23,18 @@ main = [t for t in tl if t not in chain]
 def busy(xs):
     return sum(t[1] - t[0] for t in xs)
 print(f"chain stream busy {busy(chain):.2f} ms, GEMM stream busy {busy(main):.2f} ms")
+# per outer block (four panels): period, time in panel kernels, in chain-class brackets (inner updates and look-ahead slices,
+# on either stream) and in the GEMM stream's own brackets -- shows which of the two streams is the busy one where
+panels = sorted(t for t in tl if t[2] == "panel")
+print("block  first_panel_ms  period_us  panels_us  chain_us  gemm_us")
+for b in range(0, len(panels) - 4, 4):
+    w0, w1 = panels[b][0], panels[b + 4][0]
+    inw = [t for t in tl if w0 <= t[0] < w1]
+    pan = sum(t[1] - t[0] for t in inw if t[2] == "panel")
+    ch = sum(t[1] - t[0] for t in inw if t[2] in ("chain_tn", "chain_nn", "chain_misc"))
+    gm = sum(t[1] - t[0] for t in inw if t[2] not in ("panel", "chain_tn", "chain_nn", "chain_misc"))
+    if (b // 4) % 4 == 0:
+        print(f"{b // 4:5d}  {w0:14.2f}  {(w1 - w0) * 1e3:9.0f}  {pan * 1e3:9.0f}  {ch * 1e3:8.0f}  {gm * 1e3:7.0f}")
 for t0, t1, c in sorted(tl):
     if lo <= t0 <= hi:
         lane = "P" if c in ("panel", "chain_tn", "chain_nn", "chain_misc") else "G"

@@ -27,7 +27,7 @@ _FP = ctypes.POINTER(ctypes.c_float)
 _IP = ctypes.POINTER(ctypes.c_int)
 _VP = ctypes.c_void_p
 
-OPT_GEMM, OPT_OUTER_BLOCK, OPT_TILE_ROWS, OPT_SPLITK, OPT_LOOKAHEAD, OPT_PANEL, OPT_FLAT_TSQR = 1, 2, 3, 4, 5, 6, 7
+OPT_GEMM, OPT_OUTER_BLOCK, OPT_TILE_ROWS, OPT_SPLITK, OPT_LOOKAHEAD, OPT_PANEL, OPT_FLAT_TSQR, OPT_PARTITION = 1, 2, 3, 4, 5, 6, 7, 8
 GEMM_SIMT, GEMM_TF32X3 = 0, 1
 
 # Every symbol include/cudaqr_b200.h declares (tests check the .so exports all of them).

@@ -665,6 +665,7 @@ int cqr_get_option(cqr_context* c, int opt, int* v) {
     case CQR_OPT_LOOKAHEAD: *v = c->opt_lookahead; return 0;
     case CQR_OPT_PANEL: *v = c->opt_panel; return 0;
     case CQR_OPT_FLAT_TSQR: *v = c->opt_flat; return 0;
+    case CQR_OPT_PARTITION: *v = c->opt_partition ? 1 : 0; return 0;
   }
   return CQR_EINVAL;
 }

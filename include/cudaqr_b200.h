@@ -89,7 +89,9 @@ enum {
   CQR_OPT_LOOKAHEAD = 5,    /* 0: none; 1: next block's panels overlap the trailing update on a side stream; 2 (default): as 1, and in the
                              * panel-bound phase each finished panel is applied to the block after next's columns at once (panel-wise slices) */
   CQR_OPT_PANEL = 6,        /* 1 (default): one-launch multi-CTA Householder panel; 0: TSQR tree + Householder reconstruction */
-  CQR_OPT_FLAT_TSQR = 7     /* R-only cqr_tsqr_r on >= 16384 rows: 1 (default) SIMT flat-tree leaf, 2 tensor-pipe flat-tree leaf (tsqr_mma.cu), 0 256-row tile leaves */
+  CQR_OPT_FLAT_TSQR = 7,    /* R-only cqr_tsqr_r on >= 16384 rows: 1 (default) SIMT flat-tree leaf, 2 tensor-pipe flat-tree leaf (tsqr_mma.cu), 0 256-row tile leaves */
+  CQR_OPT_PARTITION = 8     /* read-only (cqr_get_option): 1 when the look-ahead streams own disjoint SM partitions (CUDA green contexts),
+                             * 0 when they share the device (CQR_PARTITION=0, an injecting profiler, or no driver support) */
 };
 
 int cqr_create(cqr_context** ctx, int device);

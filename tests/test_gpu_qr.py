@@ -954,3 +954,47 @@ def test_geqrf_pair_step_cancellation_fallback(pkg, torch, ctx):
     ctx.synchronize()
     assert np.isfinite(host(dA)).all() and np.isfinite(tau.cpu().numpy()).all()
     check_factorisation(A, host(Q), host(R))
+
+
+_FUSED_SNIPPET = r"""
+import importlib, sys
+import numpy as np, torch
+sys.path.insert(0, {root!r})
+pkg = importlib.import_module("cuda-qr_b200")
+ctx = pkg.Context(0); ctx.use_torch_stream()
+m, n = {m}, {n}
+A = pkg.colmajor(m, n); A.copy_(torch.rand((m, n), device="cuda", generator=torch.Generator(device="cuda").manual_seed(31)))
+tau = torch.zeros(n, device="cuda")
+ctx.geqrf(A, tau); ctx.synchronize()
+np.save({out!r}, A[:n].cpu().numpy())
+print("partition", ctx.get_option(pkg.OPT_PARTITION), "launches", ctx.launch_count())
+"""
+
+
+@pytest.mark.parametrize("m,n", [(3000, 1536), (12000, 2048)])
+def test_one_launch_chain_update_agrees_with_three_launch_path(pkg, torch, tmp_path, m, n):
+    """chain_update.cu (W = V^T C, X = T^T W, C -= V X in one launch with two grid barriers; fp32 FMA) replaces the three
+    tcgen05 launches for the chain's inner updates (<= 4096 rows) and for the panel-wise look-ahead slices.  The same
+    factorisation with CQR_CHAIN_FUSED=0 (the switch is read once per process, hence the subprocesses) must give the same
+    R to fp32 accuracy, with fewer launches; both against the Gram matrix.  Reference step: trailingUpdateKernel, qr.cu:335-465."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    res = {}
+    for mode in ("1", "0"):
+        out = str(tmp_path / f"r_{mode}.npy")
+        env = dict(os.environ, CQR_CHAIN_FUSED=mode)
+        p = subprocess.run([sys.executable, "-c", _FUSED_SNIPPET.format(root=ROOT, m=m, n=n, out=out)], capture_output=True, text=True,
+                           timeout=600, env=env)
+        assert p.returncode == 0, p.stderr[-2000:]
+        words = p.stdout.split()
+        res[mode] = (np.triu(np.load(out)).astype(np.float64), int(words[1]), int(words[3]))
+    (R1, part, l1), (R0, _, l0) = res["1"], res["0"]
+    g = torch.Generator(device="cuda").manual_seed(31)
+    A = torch.rand((m, n), device="cuda", generator=g).double()
+    G = (A.t() @ A).cpu().numpy()
+    for R in (R1, R0):
+        assert np.linalg.norm(R.T @ R - G) / np.linalg.norm(G) < 2e-5
+    assert np.linalg.norm(np.abs(R1) - np.abs(R0)) / np.linalg.norm(R0) < 1e-4
+    if part:                                                    # green contexts available: the one-launch form was really used
+        assert l1 < l0

@@ -19,7 +19,9 @@ for m, n, batch in [(64, 64, 40), (50, 33, 9)]:            # batched warp kernel
 A = np.asfortranarray(np.random.default_rng(0).random((300, 200), dtype=np.float32))
 RV = A.copy(order="F"); tau = pkg.mmqr(RV); Q, R = pkg.explicitQR(RV, tau)
 print("legacy 300x200 residual", float(np.linalg.norm(Q.astype(np.float64) @ R.astype(np.float64) - A) / np.linalg.norm(A)))
-for m, n in [(2500, 64), (4100, 128)]:                     # panel kernels on the cluster exchange (panel_wb2.cu from 2048 rows up)
+# panel kernels on the cluster exchange (panel_wb2.cu from 2048 rows up); the wider cases run the look-ahead schedule with
+# inner updates -- under CQR_CHAIN_FUSED=2 through the one-launch K = 64 update (chain_update.cu)
+for m, n in [(2500, 64), (4100, 128), (3000, 600)]:
     A = pkg.colmajor(m, n); A.copy_(torch.rand((m, n), device="cuda", generator=g)); O = A.clone()
     tau = torch.zeros(n, device="cuda"); ctx.geqrf(A, tau); ctx.synchronize()
     Rd = torch.triu(A[:n].double()); G = O.t().double() @ O.double()

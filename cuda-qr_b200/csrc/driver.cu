@@ -93,6 +93,7 @@ struct cqr_context {
   // fused chain update (chain_update.cu): grid-barrier counter in device memory and the host's copy of its value
   unsigned* cu_bar = nullptr;
   unsigned cu_bar_host[2] = {0, 0};   // grid-barrier counters of the one-launch K = 64 update: [0] panel stream, [1] GEMM stream
+  int cur_tiles = 0;               // > 0: tensor GEMMs are launched with at most this many tiles per CTA instead of one persistent CTA per SM
   int cur_fused = 0;               // the one-launch update may be used: 1 = inner update on the panel stream, 2 = look-ahead slice on the GEMM stream
   RtreeSlab* dist_slab = nullptr;
   RtreeSlab* dist_peers[kRtreeMaxWorld] = {};
@@ -135,6 +136,8 @@ struct DeviceGuard {
 
 inline cudaStream_t cur_stream(cqr_context* c) { return c->cur ? c->cur : c->stream; }
 inline int cur_ctas(cqr_context* c) { return (c->cur && c->cur_ctas > 0) ? c->cur_ctas : c->sm_count; }
+// grid hint for the tensor GEMMs: the partition's SM count (persistent CTAs) or, negated, a cap on the tiles per CTA
+inline int gemm_grid_hint(cqr_context* c) { return c->cur_tiles > 0 ? -c->cur_tiles : cur_ctas(c); }
 
 // ---- green contexts (driver API through cudaGetDriverEntryPoint: the library does not link libcuda) -------
 struct DrvApi {
@@ -404,7 +407,7 @@ void gemm_tn_part(cqr_context* c, int M, int N, int K, Operand A, Operand B, flo
   // algorithmic traffic: both operands read once, partials written
   ProfScope ps(c, CQR_PROF_GEMM_TN, 2.0 * M * N * K, 4.0 * ((double)K * (M + N) + (double)M * N * splits));
   if (tensor && c->opt_gemm == 1)
-    done = launch_gemm_tn_umma(M, N, K, A.p, A.ld, B.p, B.ld, part, ldp, splits, stride, cur_ctas(c), cur_stream(c));
+    done = launch_gemm_tn_umma(M, N, K, A.p, A.ld, B.p, B.ld, part, ldp, splits, stride, gemm_grid_hint(c), cur_stream(c));
   if (!done) launch_gemm_tn_simt(M, N, K, A.p, A.ld, B.p, B.ld, part, ldp, splits, stride, cur_stream(c));
   *splits_out = splits; *ldp_out = ldp; *stride_out = stride;
 }
@@ -417,7 +420,7 @@ void gemm_tn(cqr_context* c, int M, int N, int K, Operand A, Operand B, float* p
     ProfScope ps(c, CQR_PROF_GEMM_TN, 2.0 * M * N * K, 4.0 * ((double)K * (M + N) + (double)M * N));
     bool done = false;
     if (tensor && c->opt_gemm == 1)
-      done = launch_gemm_tn_umma(M, N, K, A.p, A.ld, B.p, B.ld, d, ldd, 1, 0, cur_ctas(c), cur_stream(c));
+      done = launch_gemm_tn_umma(M, N, K, A.p, A.ld, B.p, B.ld, d, ldd, 1, 0, gemm_grid_hint(c), cur_stream(c));
     if (!done) launch_gemm_tn_simt(M, N, K, A.p, A.ld, B.p, B.ld, d, ldd, 1, 0, cur_stream(c));
     return;
   }
@@ -433,7 +436,7 @@ void gemm_nn(cqr_context* c, int M, int N, int K, float alpha, Operand A, Operan
   ProfScope ps(c, CQR_PROF_GEMM_NN, 2.0 * M * N * K,
                4.0 * ((double)M * N * ((beta != 0.f ? 1 : 0) + 1) + (double)K * (M + N)));
   if (tensor && c->opt_gemm == 1)
-    done = launch_gemm_nn_umma(M, N, K, alpha, A.p, A.ld, B.p, B.ld, beta, d, ldd, cur_ctas(c), cur_stream(c));
+    done = launch_gemm_nn_umma(M, N, K, alpha, A.p, A.ld, B.p, B.ld, beta, d, ldd, gemm_grid_hint(c), cur_stream(c));
   if (!done) launch_gemm_nn_simt(M, N, K, alpha, A.p, A.ld, B.p, B.ld, beta, d, ldd, cur_stream(c));
 }
 
@@ -837,6 +840,10 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
   auto njoin = [&](int blk) { int e = n; if (chunked) { e = c->in_cb[1]; for (int k = 1; k < nin; ++k) if (jn[k] <= blk) e = c->in_cb[k + 1]; } return e; };
   constexpr int kCatchCols = 4096;                           // catch-up updates go in slices of at most this many columns (scratch size)
   static const int catch_cols = getenv("CQR_CATCH_COLS") ? (atoi(getenv("CQR_CATCH_COLS")) < 256 ? 256 : (atoi(getenv("CQR_CATCH_COLS")) > kCatchCols ? kCatchCols : atoi(getenv("CQR_CATCH_COLS")))) : kCatchCols;
+  // Catch-up GEMMs as short CTAs (at most this many 128 x 256 tiles each) instead of one persistent CTA per SM: they
+  // share the GEMM partition with the look-ahead slices of the main stream, which has the higher priority but can only
+  // get SMs when CTAs retire -- behind a persistent kernel that is a whole catch-up GEMM (~0.2 ms), 0 = persistent
+  static const int catch_tiles = getenv("CQR_CATCH_TILES") ? atoi(getenv("CQR_CATCH_TILES")) : 2;
   static const int catch_ctas_pct = getenv("CQR_CATCH_CTAS_PCT") ? atoi(getenv("CQR_CATCH_CTAS_PCT")) : 100;   // share of the GEMM partition a catch-up kernel may fill
   BlockWs bw_catch[kMaxInChunks] = {}, bw_pslice{};
   static const bool slice_chain_ok = getenv("CQR_H2D_SLICE_ON_CHAIN") && atoi(getenv("CQR_H2D_SLICE_ON_CHAIN")) != 0;   // experiment, off: no gain measured
@@ -987,6 +994,7 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
         if (blk == 0) cudaStreamWaitEvent(sc, c->in_ev[k], 0);
         cudaStreamWaitEvent(sc, c->ev_t[blk], 0);
         c->cur = sc; c->cur_ctas = pr.sm_g * catch_ctas_pct / 100 > 8 ? pr.sm_g * catch_ctas_pct / 100 : 8; c->cur_chain = false;
+        c->cur_tiles = catch_tiles;
         Operand V{B.vbuf, ldv};
         Operand T{B.tbig, KB};
         for (int c0 = c->in_cb[k]; c0 < c->in_cb[k + 1]; c0 += catch_cols) {
@@ -997,7 +1005,7 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
       }
       flushed = blk;
     }
-    c->cur = s0; c->cur_ctas = ctas0; c->cur_chain = chain0;
+    c->cur = s0; c->cur_ctas = ctas0; c->cur_chain = chain0; c->cur_tiles = 0;
   };
   // Columns [K0, K0 + kbw) are final once the block's panel chain is done (event ev): R above, V below.
   auto ship = [&](int K0, cudaEvent_t ev) {

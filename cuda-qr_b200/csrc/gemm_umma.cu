@@ -482,8 +482,14 @@ bool launch_umma(int M, int N, int K, const float* a, long long lda, const float
   splits = (K + kper - 1) / kper;
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   const long long total = (long long)tiles_m * tiles_n * splits;
-  if (max_ctas < 1 || max_ctas > sm_count()) max_ctas = sm_count();
-  const int grid = (int)(total < max_ctas ? total : max_ctas);
+  int grid;
+  if (max_ctas < 0) {            // at most -max_ctas tiles per CTA: the grid may exceed the SM count (CTAs queue in hardware)
+    const long long g = (total - max_ctas - 1) / -max_ctas;
+    grid = (int)(g < 1 ? 1 : g);
+  } else {
+    if (max_ctas < 1 || max_ctas > sm_count()) max_ctas = sm_count();
+    grid = (int)(total < max_ctas ? total : max_ctas);
+  }
   ++g_launches;
   umma_gemm_kernel<BN, kAMn><<<grid, kThreadsP, smem, s>>>(ta, tb, td, e2, M, N, K, kper, tiles_m, tiles_n, splits);
   if (cudaGetLastError() != cudaSuccess) { --g_launches; return false; }   // launch refused: the caller falls back to the SIMT GEMM

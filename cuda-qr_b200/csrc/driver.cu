@@ -1152,7 +1152,9 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
     // only one K = 64 update separates the chain from the following block -- not the aggregated T plus a K = 256 slice.
     const int c2 = cnext + la;               // first column right of the next block
     static const long long pws_rows = getenv("CQR_PWS_ROWS") ? atoll(getenv("CQR_PWS_ROWS")) : 10240;   // tuning knob
-    const bool pws = c->opt_lookahead == 2 && (m - cnext) <= pws_rows && c2 < nf && KB / 64 <= 8;
+    // (the threshold is the height at which a SQUARE trailing matrix stops keeping the GEMM partition busier than the chain;
+    // what counts is the update's work, rows x columns still to the right, so a tall matrix with few columns qualifies early)
+    const bool pws = c->opt_lookahead == 2 && (long long)(m - cnext) * (n - c2) <= pws_rows * pws_rows && c2 < nf && KB / 64 <= 8;
     // GEMM stream first (host order only): what is left of block K's update, then -- behind it -- the panel-wise share
     use(G, pr.sm_g, false);
     if (slice_done) {                        // this block's slice was applied panel by panel: T and the rest are what is left

@@ -13,6 +13,9 @@
 // Plain fp32 on the FMA pipe (FFMA2 over row pairs): at these sizes the tensor pipe buys nothing (the update is
 // latency-bound below ~8192 rows) and fp32 FMA needs no operand split.  Shared-memory layouts are chosen so that every
 // inner-loop load is a conflict-free 64-bit access: V_s[k][r] with a stride of 66 floats, threads owning k = tk + 16 i.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "warp_math.cuh"
 
@@ -280,6 +283,18 @@ template <int NC, int SUB>
 static void launch_cu(const ChainUpdParams& p, int ctas, cudaStream_t s) {
   static PerDeviceOnce once;
   if (once.first()) cudaFuncSetAttribute(chain_update_kernel<NC, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CuCfg<NC, SUB>::SMEM);
+  // Cooperative launch: the grid is gang-scheduled, so CTAs never spin at the grid barrier while the rest of the grid
+  // waits for SMs that another context's kernel holds (two contexts on one device share the SMs of their partitions).
+  static const bool coop = !(getenv("CQR_CHAIN_COOP") && atoi(getenv("CQR_CHAIN_COOP")) == 0);
+  if (coop) {
+    ChainUpdParams q = p;
+    void* args[] = {&q};
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)chain_update_kernel<NC, SUB>, dim3(ctas), dim3(CU_THREADS), args, CuCfg<NC, SUB>::SMEM, s);
+    static const bool trace = getenv("CQR_CHAIN_COOP_TRACE") != nullptr;
+    if (trace) { static int shown = 0; if (shown++ < 4) fprintf(stderr, "chain_update<%d,%d> cooperative launch, %d CTAs: %s\n", NC, SUB, ctas, cudaGetErrorString(e)); }
+    if (e == cudaSuccess) return;
+    cudaGetLastError();   // not supported here (or the grid does not fit): plain launch, the barrier's timeout still guards it
+  }
   chain_update_kernel<NC, SUB><<<ctas, CU_THREADS, CuCfg<NC, SUB>::SMEM, s>>>(p);
 }
 

@@ -99,7 +99,7 @@ struct cqr_context {
   RtreeSlab* dist_peers[kRtreeMaxWorld] = {};
   int dist_rank = -1, dist_world = 0;
   unsigned dist_epoch = 0;
-  cudaEvent_t ev_start = nullptr, ev_a = nullptr, ev_g = nullptr, ev_panel[2] = {nullptr, nullptr};
+  cudaEvent_t ev_start = nullptr, ev_a = nullptr, ev_g = nullptr, ev_upd = nullptr, ev_panel[2] = {nullptr, nullptr};
   cudaEvent_t ev_pp[2][8] = {};    // per-panel completion (panel-wise look-ahead slices, opt_lookahead == 2)
   int opt_gemm = 1, opt_outer = 256, opt_tile_rows = 256, opt_splitk = 0, opt_lookahead = 2, opt_panel = 1, opt_cluster = 1, opt_flat = 1;   // opt_flat: R-only TSQR leaf 0 = tile tree, 1 = SIMT flat tree (default), 2 = tensor-pipe flat tree (measured slower)
   // multi-CTA panel kernel (panel_hh.cu): cross-CTA exchange slots, launch epoch, spin-timeout flag
@@ -563,6 +563,7 @@ static int create_impl(cqr_context* c, int device) {
   }
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+  CQR_CUDA(cudaEventCreateWithFlags(&c->ev_upd, cudaEventDisableTiming));
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_g, cudaEventDisableTiming));
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_panel[0], cudaEventDisableTiming));
   CQR_CUDA(cudaEventCreateWithFlags(&c->ev_panel[1], cudaEventDisableTiming));
@@ -635,7 +636,7 @@ int cqr_destroy(cqr_context* c) {
     if (pt.gp) drv_api().GreenCtxDestroy(pt.gp);
     if (pt.gg) drv_api().GreenCtxDestroy(pt.gg);
   }
-  for (cudaEvent_t e : {c->ev_start, c->ev_a, c->ev_g, c->ev_panel[0], c->ev_panel[1]}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {c->ev_start, c->ev_a, c->ev_g, c->ev_upd, c->ev_panel[0], c->ev_panel[1]}) if (e) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i)
     for (int j = 0; j < 8; ++j) if (c->ev_pp[i][j]) cudaEventDestroy(c->ev_pp[i][j]);
   delete c;
@@ -846,7 +847,12 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
   static const int catch_tiles = getenv("CQR_CATCH_TILES") ? atoi(getenv("CQR_CATCH_TILES")) : 2;
   static const int catch_ctas_pct = getenv("CQR_CATCH_CTAS_PCT") ? atoi(getenv("CQR_CATCH_CTAS_PCT")) : 100;   // share of the GEMM partition a catch-up kernel may fill
   BlockWs bw_catch[kMaxInChunks] = {}, bw_pslice{};
-  static const bool slice_chain_ok = getenv("CQR_H2D_SLICE_ON_CHAIN") && atoi(getenv("CQR_H2D_SLICE_ON_CHAIN")) != 0;   // experiment, off: no gain measured
+  // Option (off): the look-ahead slice (block K onto block K+1's columns, K = 256) on the PANEL stream while the GEMM
+  // partition is the busy one (remaining rows > CQR_SLICE_CHAIN_ROWS, only where the aggregated T is built on the panel
+  // stream too), so that the GEMM stream does nothing but the big updates.  Measured at 16384^2: 64.0 ms either way with
+  // the threshold at 12288 rows, 63.5 at 14336 -- the panel stream, which then has to wait for the previous block's update
+  // before its slice, becomes as busy as the GEMM stream.  0 = never (default).
+  static const long long slice_chain_rows = getenv("CQR_SLICE_CHAIN_ROWS") ? atoll(getenv("CQR_SLICE_CHAIN_ROWS")) : 0;
   TsqrPlan plan;
   float *gram = nullptr, *gpart = nullptr, *qthin = nullptr, *rt = nullptr, *uinv = nullptr, *gsmall = nullptr;
   BlockWs bw_main{}, bw_side{}, bw_slice{};
@@ -858,7 +864,7 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
       b.tbig = cv.take((long long)KB * KB);
     }
     for (int k = 1; k < nin; ++k) if (jn[k] > 0) bw_catch[k] = carve_block_ws(cv, KB, kCatchCols);
-    if (nin > 1) bw_pslice = carve_block_ws(cv, KB, KB);
+    bw_pslice = carve_block_ws(cv, KB, KB);
     gram = cv.take((long long)KB * KB);
     gpart = cv.take((long long)KB * KB * kMaxSplits);
     qthin = cv.take(ldv * 64);
@@ -1108,6 +1114,7 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
   ship(0, c->ev_panel[0]);
   if (t_on_chain(0)) { do_block_t(0, bb(0)); CQR_CUDA(cudaEventRecord(c->ev_panel[0], prev_p)); }
   bool slice_done = false;   // the current block's look-ahead slice is already on the GEMM stream (panel-wise, see below)
+  bool upd_recorded = false; // ev_upd marks the end of the previous block's trailing update on the GEMM stream
   for (int blk = 0; blk < nblk; ++blk) {
     const int K0 = blk * KB;
     const int kbw = (nf - K0 < KB) ? nf - K0 : KB;
@@ -1129,13 +1136,13 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
       break;
     }
     const int la = (nf - cnext < KB) ? nf - cnext : KB;
-    // Experiment (CQR_H2D_SLICE_ON_CHAIN=1, chunked upload only): run the look-ahead slice of the first blocks on the
-    // panel stream itself instead of queueing it on the GEMM partition next to the catch-up kernels.  Measured: no
-    // difference (74.5 vs 74.7 ms e2e), so the default keeps the slice on the GEMM stream.
-    const bool slice_on_chain = chunked && !slice_done && t_on_chain(K0) && blk < nkeep && slice_chain_ok;
+    const bool slice_on_chain = !slice_done && t_on_chain(K0) && slice_chain_rows > 0 && (m - K0) > slice_chain_rows && (!chunked || blk < nkeep);
     if (!slice_done) CQR_CUDA(cudaStreamWaitEvent(G, c->ev_panel[blk & 1], 0));
     if (prev_p != P) CQR_CUDA(cudaStreamWaitEvent(P, c->ev_panel[blk & 1], 0));
     if (slice_on_chain) {
+      // block K-1's update of these columns is still on the GEMM stream: the slice waits for it.  While that stream is the
+      // busy one this is the only hand-over of the block, and it runs update after update without a gap.
+      if (upd_recorded) CQR_CUDA(cudaStreamWaitEvent(P, c->ev_upd, 0));
       use(P, pr.sm_p, true);
       do_update(K0, bb(blk), cnext, cnext + la, &bw_pslice);
     } else {
@@ -1165,6 +1172,8 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
     // that the slices need not wait for the whole update: 65.7 -> 72.4 ms, the smaller GEMMs lose more than the earlier
     // slices gain -- in that phase the GEMM partition, not the chain, is the busy one; profiles/r02_pws_interleave.txt.)
     do_update(K0, bb(blk), cnext + la, n);
+    CQR_CUDA(cudaEventRecord(c->ev_upd, G));
+    upd_recorded = true;
     slice_done = false;
     use(P, pr.sm_p, true);
     if (pws) {

@@ -1,0 +1,1 @@
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tools/caqr_steps.py 2>&1 | grep -E "factor|Error|error" | head

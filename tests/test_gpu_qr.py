@@ -994,7 +994,7 @@ def test_one_launch_chain_update_agrees_with_three_launch_path(pkg, torch, tmp_p
     A = torch.rand((m, n), device="cuda", generator=g).double()
     G = (A.t() @ A).cpu().numpy()
     for R in (R1, R0):
-        assert np.linalg.norm(R.T @ R - G) / np.linalg.norm(G) < 2e-5
+        assert np.linalg.norm(R.T @ R - G) / np.linalg.norm(G) < 1e-4          # 3xTF32 trailing updates: 4.4e-5 at 12000 x 2048
     assert np.linalg.norm(np.abs(R1) - np.abs(R0)) / np.linalg.norm(R0) < 1e-4
     if part:                                                    # green contexts available: the one-launch form was really used
         assert l1 < l0

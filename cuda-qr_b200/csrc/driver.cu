@@ -1044,7 +1044,9 @@ static int geqrf_impl(cqr_context* c, float* dA, int lda, int m, int n, int nf, 
   // (only while the trailing part is narrow: four K = 64 updates of a wide C cost more HBM traffic than the chain hides --
   // 16384 x 3840: 4 x 0.37 ms against 0.39 ms for one K = 256 update)
   static const int partial_overlap_cols = getenv("CQR_PARTIAL_OVERLAP_COLS") ? atoi(getenv("CQR_PARTIAL_OVERLAP_COLS")) : 1536;
-  if (nblk == 1 && n > nf && n - nf <= partial_overlap_cols && c->opt_lookahead == 2 && c->opt_partition && c->opt_panel == 1 &&
+  // (the bound is on the trailing part's size, rows x columns, quoted at full height: the stacked-R step of CAQR has few
+  // rows and thousands of columns and qualifies)
+  if (nblk == 1 && n > nf && (long long)m * (n - nf) <= 16384ll * partial_overlap_cols && c->opt_lookahead == 2 && c->opt_partition && c->opt_panel == 1 &&
       c->opt_cluster && m <= 16384 && KB / 64 <= 8) {
     // One block to factor, many columns to update (the local step of CAQR): the panel chain runs on the panel partition
     // while the GEMM partition applies every finished 64-column panel (V_j, T_j) to all the trailing columns -- no

@@ -44,15 +44,13 @@ struct Wb2Shared {
   float gs[64][65];            // CTA 0: G(c, j) = v_c^T v_j (c < j)
   float ts[64][65];
   float staus[64];
-  float tot_x[2][128];         // two clusters: totals over both clusters, rows j and j+1
-  float prow_x[2][128];
 };
 
 struct Wb2Ctx {
   int q, h, w, lane;
   bool top;                    // this warp holds the panel's first 64 rows (the pivot rows)
   unsigned rank, CS, cl, ncl;  // CTA rank in its cluster, cluster size, cluster index, number of clusters (1 or 2)
-  uint2* slots;                // two clusters: {value, tag} exchange slots in global memory [2 buffers][3][128]
+  uint2* slots;                // two clusters: {value, tag} exchange slots in global memory [2 buffers][32 CTAs + pivot rows][128]
   unsigned epoch;
   int nb, mode;                // mode 2: every pair takes the fallback
   int* err;
@@ -205,11 +203,36 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
         const unsigned wpo = 32u / CS;                  // float4 groups per owner CTA
         if (lane == 0) {
           wb_mbar_expect(&sm.mbar1[buf], (32 + ((!X2 || cx.cl == 0) ? wpo : 0)) * 16);
-          wb_mbar_expect(&sm.mbar2[buf], (32 + ((!X2 || cx.cl == 0) ? 32 : 0)) * 16);
+          wb_mbar_expect(&sm.mbar2[buf], (32 + 32) * 16);
         }
         const unsigned owner = ((unsigned)lane * CS) >> 5, wl = (unsigned)lane - owner * wpo;
         wb_st_async_v4(&sm.rs_in[buf][rank * wpo + wl][0], &sm.mbar1[buf], owner, sv);
         if (rank == 0 && (!X2 || cx.cl == 0)) wb_st_async_v4(&sm.prs_in[buf][wl][0], &sm.mbar1[buf], owner, pv);
+        // Two clusters: the same CTA sums also go to global memory as {value, tag} slots (one row of 128 per CTA and
+        // buffer, row 32 = the pivot rows), where the OWNER of each column group in the other cluster collects them while
+        // its own cluster's reduce-scatter is in flight: the cross-cluster hop (an L2 round trip, ~900 cycles) overlaps
+        // phase 1 instead of following phase 2 (it used to add ~1800 cycles to each of the 32 steps of a 16384-row panel).
+        unsigned tag = 0;
+        if constexpr (X2) {
+          tag = cx.epoch * 64u + ex;                     // ex = 1 .. 64 inside a launch, epoch unique per launch
+          uint2* mine = cx.slots + ((size_t)buf * 33 + cx.cl * CS + rank) * 128 + 4 * lane;
+          wb_st_flag(mine + 0, sv.x, tag); wb_st_flag(mine + 1, sv.y, tag);
+          wb_st_flag(mine + 2, sv.z, tag); wb_st_flag(mine + 3, sv.w, tag);
+          if (cx.cl == 0 && rank == 0) {
+            uint2* pvs = cx.slots + ((size_t)buf * 33 + 32) * 128 + 4 * lane;
+            wb_st_flag(pvs + 0, pv.x, tag); wb_st_flag(pvs + 1, pv.y, tag);
+            wb_st_flag(pvs + 2, pv.z, tag); wb_st_flag(pvs + 3, pv.w, tag);
+          }
+        }
+        const unsigned slot = (unsigned)lane % wpo, peer = (unsigned)lane / wpo;   // after the reduction a lane holds the total of group `slot`
+        const unsigned col4 = 4u * (rank * wpo + slot);
+        float4 u = make_float4(0.f, 0.f, 0.f, 0.f), pg = u;
+        if constexpr (X2) {
+          // the other cluster's share of my groups (lane = sender * wpo + group, as in rs_in) and, in cluster 1, rows j, j+1:
+          // polled BEFORE the wait for the own cluster's contributions, so the two latencies overlap
+          u = wb_poll4(cx.slots + ((size_t)buf * 33 + (cx.cl ^ 1u) * CS + peer) * 128 + col4, tag, cx.err);
+          if (cx.cl != 0) pg = wb_poll4(cx.slots + ((size_t)buf * 33 + 32) * 128 + col4, tag, cx.err);
+        }
         wb_mbar_wait(&sm.mbar1[buf], par, cx.err);
         WB2_TRACE(4);
         float4 t = *reinterpret_cast<const float4*>(&sm.rs_in[buf][lane][0]);    // entry = sender * wpo + my group
@@ -217,56 +240,26 @@ __device__ __forceinline__ void wb2_steps(f32x2 (&b)[8][8], Wb2Shared<W>& sm, co
           t.x += __shfl_xor_sync(kFull, t.x, o); t.y += __shfl_xor_sync(kFull, t.y, o);
           t.z += __shfl_xor_sync(kFull, t.z, o); t.w += __shfl_xor_sync(kFull, t.w, o);
         }
-        const unsigned slot = (unsigned)lane % wpo, peer = (unsigned)lane / wpo;   // lane holds the total of group `slot`
-        const unsigned col4 = 4u * (rank * wpo + slot);
+        float4 pr4 = *reinterpret_cast<const float4*>(&sm.prs_in[buf][slot][0]);   // rows j, j+1 of my groups (cluster 0)
+        if constexpr (X2) {
+          // same shuffle tree as for the own cluster's sums, so both clusters form bit-identical per-cluster sums and
+          // add them in the same order (cluster 0 + cluster 1)
+          for (unsigned o = 16; o >= wpo; o >>= 1) {
+            u.x += __shfl_xor_sync(kFull, u.x, o); u.y += __shfl_xor_sync(kFull, u.y, o);
+            u.z += __shfl_xor_sync(kFull, u.z, o); u.w += __shfl_xor_sync(kFull, u.w, o);
+          }
+          if (cx.cl == 0) { t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+          else { t.x = u.x + t.x; t.y = u.y + t.y; t.z = u.z + t.z; t.w = u.w + t.w; }
+          if (cx.cl != 0) pr4 = pg;
+        }
         wb_st_async_v4(&sm.tot_in[buf][col4], &sm.mbar2[buf], peer, t);
-        if (!X2 || cx.cl == 0) wb_st_async_v4(&sm.prow[buf][col4], &sm.mbar2[buf], peer, *reinterpret_cast<const float4*>(&sm.prs_in[buf][slot][0]));
+        wb_st_async_v4(&sm.prow[buf][col4], &sm.mbar2[buf], peer, pr4);
       }
     }
     if (cx.CS == 1) __syncthreads();
     else wb_mbar_wait(&sm.mbar2[buf], par, cx.err);
     const float* P = sm.tot_in[buf];
     const float* R1 = sm.prow[buf];
-    if constexpr (X2) {
-      // two clusters (as in panel_wb.cu): the leaders publish their 128 cluster sums (cluster 0 also rows j, j+1) as
-      // {value, tag} pairs in global memory, warp 0 of every CTA polls the other cluster's slots (four values per lane) and
-      // adds in the same order on both sides (cluster 0 + cluster 1), so all 32 CTAs hold bit-identical totals
-      if (w == 0) {
-        const unsigned tag = cx.epoch * 64u + ex;        // ex = 1 .. 64 inside a launch, epoch unique per launch
-        uint2* mys = cx.slots + ((size_t)buf * 3 + cx.cl) * 128;
-        const uint2* oth = cx.slots + ((size_t)buf * 3 + (cx.cl ^ 1u)) * 128;
-        uint2* piv = cx.slots + ((size_t)buf * 3 + 2) * 128;
-        if (cx.rank == 0) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = lane + 32 * e;
-            wb_st_flag(mys + c, sm.tot_in[buf][c], tag);
-            if (cx.cl == 0) wb_st_flag(piv + c, sm.prow[buf][c], tag);
-          }
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = lane + 32 * e;
-          const float mine = sm.tot_in[buf][c];
-          float so = 0.f, po = 0.f;
-          long long t0 = 0;
-          for (;;) {
-            const uint2 r = wb_ld_flag(oth + c);
-            uint2 qv; qv.x = 0u; qv.y = tag;
-            if (cx.cl != 0) qv = wb_ld_flag(piv + c);
-            so = __uint_as_float(r.x); po = __uint_as_float(qv.x);
-            if (r.y == tag && qv.y == tag) break;
-            if (t0 == 0) t0 = clock64();
-            else if (clock64() - t0 > 2000000000LL) { atomicExch(cx.err, 1); break; }
-          }
-          sm.tot_x[buf][c] = (cx.cl == 0) ? (mine + so) : (so + mine);
-          sm.prow_x[buf][c] = (cx.cl == 0) ? sm.prow[buf][c] : po;
-        }
-      }
-      __syncthreads();
-      P = sm.tot_x[buf];
-      R1 = sm.prow_x[buf];
-    }
     const float* Q = P + 64;
     const float* R2 = R1 + 64;
     WB2_TRACE(5);
@@ -556,7 +549,7 @@ void panel_wb2_read_trace(long long* steps, long long* marks) {
 bool launch_panel_wb2(const PanelHHParams& p, int wpc, int cs, int ncl, int mode, cudaStream_t s) {
   if (p.b != 64 || ncl < 1 || ncl > 2 || cs > 16) return false;
   if (ncl == 2 && (wpc != 8 || cs != 16)) return false;
-  if (ncl == 2 && panel_hh_slot_bytes() < (size_t)2 * 3 * 128 * sizeof(uint2)) return false;
+  if (ncl == 2 && panel_hh_slot_bytes() < (size_t)2 * 33 * 128 * sizeof(uint2)) return false;
   PanelHHParams pp = p;
   pp.pmax = mode;
   ++g_launches;

@@ -58,6 +58,17 @@ __device__ __forceinline__ uint2 wb_ld_flag(const uint2* p) {
   asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
   return r;
 }
+// four consecutive {value, tag} slots, polled until all carry `tag` (bounded like the mbarrier wait below)
+__device__ __forceinline__ float4 wb_poll4(const uint2* p, unsigned tag, int* err) {
+  long long t0 = 0;
+  for (;;) {
+    const uint2 a = wb_ld_flag(p), b = wb_ld_flag(p + 1), c = wb_ld_flag(p + 2), d = wb_ld_flag(p + 3);
+    if (a.y == tag && b.y == tag && c.y == tag && d.y == tag)
+      return make_float4(__uint_as_float(a.x), __uint_as_float(b.x), __uint_as_float(c.x), __uint_as_float(d.x));
+    if (t0 == 0) t0 = clock64();
+    else if (clock64() - t0 > 2000000000LL) { atomicExch(err, 1); return make_float4(0.f, 0.f, 0.f, 0.f); }
+  }
+}
 // bounded wait: a protocol error must not hang the device; *err is set and the caller's results are void
 __device__ __forceinline__ void wb_mbar_wait(unsigned long long* bar, unsigned parity, int* err) {
   unsigned ok, a = (unsigned)__cvta_generic_to_shared(bar);

@@ -35,7 +35,7 @@ EXPORTS = [
     "getPanelDims", "mmqr", "mmqr_alloc", "explicitQR", "dgemm", "identity", "printMat",
     "cqr_create", "cqr_destroy", "cqr_set_stream", "cqr_set_option", "cqr_get_option", "cqr_synchronize",
     "cqr_error_string", "cqr_launch_count", "cqr_profile_begin", "cqr_profile_end", "cqr_profile_timeline", "cqr_reserve", "cqr_geqrf", "cqr_geqrf_partial", "cqr_extract_r", "cqr_form_q",
-    "cqr_apply_q", "cqr_solve_ls", "cqr_tsqr_r", "cqr_tsqr_factor", "cqr_tsqr_form_q", "cqr_stack_qr", "cqr_stack_form_q",
+    "cqr_apply_q", "cqr_solve_ls", "cqr_tsqr_r", "cqr_tsqr_gram_info", "cqr_tsqr_factor", "cqr_tsqr_form_q", "cqr_stack_qr", "cqr_stack_form_q",
     "cqr_geqrf_batched", "cqr_gemm", "cqr_gemm_tf32x3", "cqr_set_identity", "cqr_version",
     "cqr_compare_cusolver_sgeqrf", "mmqr_reference_format", "cqr_mmqr_reference_format",
     "cqr_dist_export", "cqr_dist_attach", "cqr_dist_detach", "cqr_tsqr_dist_r",
@@ -94,6 +94,7 @@ def _load() -> ctypes.CDLL:
     lib.cqr_solve_ls.argtypes = [_VP, _VP, i, i, i, _VP, _VP, i, i]
     lib.cqr_tsqr_r.argtypes = [_VP, _VP, i, ll, i, _VP, i]
     lib.cqr_tsqr_factor.argtypes = [_VP, _VP, i, ll, i, _VP, i]
+    lib.cqr_tsqr_gram_info.argtypes = [_VP, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]
     lib.cqr_tsqr_form_q.argtypes = [_VP, _VP, i, _VP, i]
     lib.cqr_stack_qr.argtypes = [_VP, _VP, i, i, i, _VP, _VP, i]
     lib.cqr_stack_form_q.argtypes = [_VP, _VP, i, i, i, _VP, _VP, i, _VP, i]
@@ -392,6 +393,13 @@ class Context:
     def tsqr_r(self, A, R):
         m, n = A.shape
         _check(lib.cqr_tsqr_r(self.h, _dptr(A), _ld(A), m, n, _dptr(R), _ld(R)), "cqr_tsqr_r")
+
+    def tsqr_gram_info(self):
+        """(bound, householder) of the Gram leaf (OPT_FLAT_TSQR = 4) of the last tsqr_r: bound = n ||Rs^-1||_F^2 >= cond_2 of the
+        unit-diagonal Gram matrix (-1: breakdown / out-of-range scale), householder = True when the gated Householder leaf ran."""
+        b, g = ctypes.c_double(0.0), ctypes.c_int(0)
+        _check(lib.cqr_tsqr_gram_info(self.h, ctypes.byref(b), ctypes.byref(g)), "cqr_tsqr_gram_info")
+        return b.value, bool(g.value)
 
     def tsqr_factor(self, A, R):
         m, n = A.shape

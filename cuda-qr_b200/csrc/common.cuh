@@ -71,6 +71,7 @@ struct TileQRParams {
   int fan;              // tiles stacked per parent tile (TH / 64)
   // batched mode: tau row stride other than 64 and no R output
   int tau_stride;
+  const int* gate;      // non-null: the kernel runs only if *gate != 0 (Householder leaf behind the Gram leaf, gram_umma.cu)
 };
 
 struct TileApplyParams {
@@ -104,6 +105,7 @@ struct FlatTsqrParams {
   // implicit-Q variant only: reflectors are written over the source (a_out == a) and taus to tau_out[block][64]
   float* a_out;
   float* tau_out;
+  const int* gate;                 // non-null: the kernel runs only if *gate != 0 (see TileQRParams::gate)
 };
 struct FlatApplyParams {
   const float* v; long long ldv;   // the factored matrix (V blocks as written by the implicit-Q leaf)
@@ -273,6 +275,12 @@ bool launch_gemm_tn_umma(int M, int N, int K, const float* a, long long lda, con
                          long long ldd, int splits, long long d_split_stride, int max_ctas, cudaStream_t s);
 bool launch_gemm_nn_umma(int M, int N, int K, float alpha, const float* a, long long lda, const float* b, long long ldb,
                          float beta, float* d, long long ldd, int max_ctas, cudaStream_t s);
+
+// ---- Gram leaf of the R-only TSQR on tcgen05 (gram_umma.cu): error-free bf16 slicing, fp64 Cholesky, gated fallback ----
+bool gram_tsqr_eligible(const float* a, long long lda, long long m, int n);
+size_t gram_tsqr_workspace_floats(int sm_count);
+bool launch_tsqr_gram_r(const float* a, long long lda, long long m, int n, float* r, long long ldr, float* ws, int sm_count,
+                        int max_ctas, double bound_max, int** gate_out, double** info_out, cudaStream_t s);
 
 // global launch counter (gpu_launches evidence)
 extern std::atomic<long long> g_launches;   // host threads may drive contexts on several devices

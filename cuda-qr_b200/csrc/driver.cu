@@ -62,6 +62,7 @@ struct cqr_context {
   int device = 0;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
+  double* gram_info = nullptr; int* gram_gate = nullptr;   // device pointers into ws: the last Gram-leaf call's verdict
   // scratch arena (re-carved by every top-level call)
   char* ws = nullptr;
   size_t ws_bytes = 0, ws_off = 0;
@@ -315,13 +316,14 @@ TileSrc level_src(const TsqrPlan& P, int l, float* a, long long lda) {
 
 // Factor: leaves read `a` (m x n, lda).  keep_q: write reflectors back (leaves into a).
 void run_tsqr_factor(cqr_context* c, const TsqrPlan& P, float* a, long long lda, bool keep_q, float* r,
-                     long long ldr) {
+                     long long ldr, const int* gate = nullptr) {
   const int L = (int)P.lv.size();
   for (int l = 0; l < L; ++l) {
     if (l == 0 && P.flat) {   // >= 2 chains by construction, so a tree level follows
       FlatTsqrParams f{};
       f.a = a; f.lda = lda; f.m = P.m; f.n = P.n; f.rows_per_chain = P.flat_rows; f.chains = P.lv[0].tiles;
       f.r_out = P.lv[1].store; f.r_tile_stride = (long long)P.th * 64; f.r_ld = P.th; f.fan = P.fan;
+      f.gate = gate;
       if (keep_q) {
         f.a_out = a; f.tau_out = P.lv[0].tau;
         launch_tsqr_flat_first_blocks(a, lda, P.m, P.n, P.flat_rows, P.lv[0].tiles, P.lv[0].tau, cur_stream(c));
@@ -337,6 +339,7 @@ void run_tsqr_factor(cqr_context* c, const TsqrPlan& P, float* a, long long lda,
     p.tau = P.lv[l].tau;
     p.tau_stride = 64;
     p.fan = P.fan;
+    p.gate = gate;
     if (l == L - 1) { p.r_out = r; p.r_tile_stride = 0; p.r_ld = ldr; p.r_rows = P.n; p.fan = 1; }
     else { p.r_out = P.lv[l + 1].store; p.r_tile_stride = (long long)P.th * 64; p.r_ld = P.th; p.r_rows = CQR_SLOT; }
     launch_tile_qr(p, P.lv[l].tiles, P.th, cur_stream(c));
@@ -591,7 +594,7 @@ static int create_impl(cqr_context* c, int device) {
   if (const char* e = getenv("CQR_PANEL")) c->opt_panel = atoi(e) != 0;
   if (const char* e = getenv("CQR_CLUSTER")) c->opt_cluster = atoi(e) != 0;   // debugging aid: 0 = global-flag exchange only
   if (const char* e = getenv("CQR_GEMM")) c->opt_gemm = (strcmp(e, "simt") == 0) ? 0 : 1;   // debugging aid
-  if (const char* e = getenv("CQR_TSQR_LEAF")) c->opt_flat = strcmp(e, "mma") == 0 ? 2 : (strcmp(e, "flat") == 0 ? 1 : (strcmp(e, "pair") == 0 ? 3 : (strcmp(e, "tile") == 0 ? 0 : c->opt_flat)));
+  if (const char* e = getenv("CQR_TSQR_LEAF")) c->opt_flat = strcmp(e, "gram") == 0 ? 4 : strcmp(e, "mma") == 0 ? 2 : (strcmp(e, "flat") == 0 ? 1 : (strcmp(e, "pair") == 0 ? 3 : (strcmp(e, "tile") == 0 ? 0 : c->opt_flat)));
   return 0;
 }
 
@@ -654,7 +657,7 @@ int cqr_set_option(cqr_context* c, int opt, int v) {
     case CQR_OPT_SPLITK: if (v < 0 || v > kMaxSplits) return CQR_EINVAL; c->opt_splitk = v; return 0;
     case CQR_OPT_LOOKAHEAD: if (v < 0 || v > 2) return CQR_EINVAL; c->opt_lookahead = v; return 0;
     case CQR_OPT_PANEL: if (v != 0 && v != 1) return CQR_EINVAL; c->opt_panel = v; return 0;
-    case CQR_OPT_FLAT_TSQR: if (v < 0 || v > 3) return CQR_EINVAL; c->opt_flat = v; return 0;
+    case CQR_OPT_FLAT_TSQR: if (v < 0 || v > 4) return CQR_EINVAL; c->opt_flat = v; return 0;
   }
   return CQR_EINVAL;
 }
@@ -1344,14 +1347,24 @@ static int tsqr_mma_r(cqr_context* c, const float* dA, long long lda, long long 
   return (int)cudaGetLastError();
 }
 
+static double gram_bound_max() {   // largest n * ||R^^-1||_F^2 (>= cond_2 of the unit-diagonal Gram matrix) the Gram leaf accepts
+  static double v = -1.0;
+  if (v < 0.0) { const char* e = getenv("CQR_GRAM_BOUND"); v = e ? atof(e) : 32768.0; if (!(v > 0.0)) v = 32768.0; }
+  return v;
+}
+
 static int tsqr_common(cqr_context* c, float* dA, int lda, long long m, int n, float* dR, int ldr, bool keep) {
   if (!c || !dA || !dR || n < 1 || n > 64 || m < n || lda < m || ldr < n) return CQR_EINVAL;
   DeviceGuard dg__(c->device);
   if (!keep && c->opt_flat == 2 && m >= 16384) return tsqr_mma_r(c, dA, lda, m, n, dR, ldr);
+  // R-only on the Gram leaf (gram_umma.cu): the Householder path below is still enqueued, behind a device-side gate
+  const bool gram = !keep && c->opt_flat == 4 && m >= 16384 && gram_tsqr_eligible(dA, lda, m, n);
   const int th = c->opt_tile_rows;
   TsqrPlan plan;
+  float* gram_ws = nullptr;
   for (int pass = 0; pass < 2; ++pass) {
     Carver cv(pass ? (keep ? c->ts : c->ws) : nullptr);
+    if (gram) gram_ws = cv.take((long long)gram_tsqr_workspace_floats(c->sm_count));
     plan_tsqr(plan, m, n, th, cv, (c->opt_flat && m >= 16384) ? flat_tsqr_max_chains(c->sm_count) : 0, keep);
     if (!pass) {
       if (keep) {
@@ -1369,10 +1382,33 @@ static int tsqr_common(cqr_context* c, float* dA, int lda, long long m, int n, f
   }
   {
     ProfScope ps(c, CQR_PROF_PANEL, 2.0 * m * n * n, 4.0 * (double)m * n * (keep ? 2 : 1));
-    run_tsqr_factor(c, plan, dA, lda, keep, dR, ldr);
+    int* gate = nullptr;
+    c->gram_info = nullptr; c->gram_gate = nullptr;
+    if (gram && launch_tsqr_gram_r(dA, lda, m, n, dR, ldr, gram_ws, c->sm_count, cur_ctas(c), gram_bound_max(), &gate,
+                                   &c->gram_info, cur_stream(c)))
+      c->gram_gate = gate;
+    else
+      gate = nullptr;
+    run_tsqr_factor(c, plan, dA, lda, keep, dR, ldr, gate);
   }
   if (keep) { c->ts_plan = plan; c->ts_a = dA; c->ts_lda = lda; c->ts_valid = true; }
   return (int)cudaGetLastError();
+}
+
+// What the Gram leaf of the last cqr_tsqr_r on this context decided (synchronises the stream): *bound = n ||R^^-1||_F^2 of
+// the diagonally scaled Gram matrix (-1: Cholesky broke down or the data were out of scale), *householder = 1 when the
+// Householder leaf produced R.  CQR_ESTATE when the last call did not use the Gram leaf.
+int cqr_tsqr_gram_info(cqr_context* c, double* bound, int* householder) {
+  if (!c) return CQR_EINVAL;
+  if (!c->gram_gate || !c->gram_info) return CQR_ESTATE;
+  DeviceGuard dg__(c->device);
+  CQR_CUDA(cudaStreamSynchronize(c->stream));
+  double b = 0.0; int g = 0;
+  CQR_CUDA(cudaMemcpy(&b, c->gram_info, sizeof(double), cudaMemcpyDeviceToHost));
+  CQR_CUDA(cudaMemcpy(&g, c->gram_gate, sizeof(int), cudaMemcpyDeviceToHost));
+  if (bound) *bound = b;
+  if (householder) *householder = g;
+  return 0;
 }
 
 int cqr_tsqr_r(cqr_context* c, const float* dA, int lda, long long m, int n, float* dR, int ldr) {
@@ -1391,6 +1427,16 @@ int cqr_tsqr_form_q(cqr_context* c, const float* dX, int ldx, float* dQ, int ldq
   DeviceGuard dg__(c->device);
   run_tsqr_form_q(c, P, c->ts_a, c->ts_lda, dX, ldx, P.n, dQ, ldq);
   return (int)cudaGetLastError();
+}
+
+// debugging aid (tools/gram_check.py): the fp64 Gram matrix (64 x 64, row i at 64 i) the last Gram-leaf call reduced
+__attribute__((visibility("default"))) int cqr_debug_gram_matrix(cqr_context* c, double* host_g) {
+  if (!c || !host_g) return CQR_EINVAL;
+  if (!c->gram_info) return CQR_ESTATE;
+  DeviceGuard dg__(c->device);
+  CQR_CUDA(cudaStreamSynchronize(c->stream));
+  CQR_CUDA(cudaMemcpy(host_g, c->gram_info - 64 * 64, 64 * 64 * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 // ---- double precision (f64_qr.cu; SURVEY 8f-4: the reference's contemplated `Scalar double`, qr.c:9) ---------------

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256, (RI <= 4 ? 3 : 2)) tile_qr_kernel(TileQRP
   const int t = blockIdx.x;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   __shared__ float vs[2][TH];
+  if (p.gate != nullptr && *(const volatile int*)p.gate == 0) return;   // the Gram leaf produced R: nothing to do
 
   const int rows = tile_rows_of(p.a, t, TH);
   float* src = p.a.base + (long long)t * p.a.tile_stride;

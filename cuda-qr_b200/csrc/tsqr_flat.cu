@@ -464,6 +464,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_r_kernel(FlatTsqrPar
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane & 7, h = lane >> 3;
   const long long chain = (long long)blockIdx.x * WPC + w;
   if (chain >= p.chains) return;             // warps never meet at a block barrier
+  if (p.gate != nullptr && *(const volatile int*)p.gate == 0) return;   // the Gram leaf produced R: nothing to do
   float* Rs = flat_smem + w * kFlatWarpFloats;
   float* xs = Rs + 64 * 64;
   for (int i = lane; i < 64 * 64 / 4; i += 32) reinterpret_cast<float4*>(Rs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);

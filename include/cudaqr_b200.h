@@ -89,7 +89,10 @@ enum {
   CQR_OPT_LOOKAHEAD = 5,    /* 0: none; 1: next block's panels overlap the trailing update on a side stream; 2 (default): as 1, and in the
                              * panel-bound phase each finished panel is applied to the block after next's columns at once (panel-wise slices) */
   CQR_OPT_PANEL = 6,        /* 1 (default): one-launch multi-CTA Householder panel; 0: TSQR tree + Householder reconstruction */
-  CQR_OPT_FLAT_TSQR = 7,    /* R-only cqr_tsqr_r on >= 16384 rows: 1 (default) SIMT flat-tree leaf, 2 tensor-pipe flat-tree leaf (tsqr_mma.cu), 0 256-row tile leaves */
+  CQR_OPT_FLAT_TSQR = 7,    /* R-only cqr_tsqr_r on >= 16384 rows: 1 SIMT flat-tree Householder leaf, 2 tensor-pipe flat-tree leaf (tsqr_mma.cu),
+                             * 3 SIMT leaf with two pivot columns per reduction, 0 256-row tile leaves, 4 Gram leaf on tcgen05
+                             * (gram_umma.cu: error-free bf16 slicing, fp64 Cholesky, R with a positive diagonal) with the
+                             * Householder leaf (1) behind a device-side gate for ill-conditioned / badly scaled input */
   CQR_OPT_PARTITION = 8     /* read-only (cqr_get_option): 1 when the look-ahead streams own disjoint SM partitions (CUDA green contexts),
                              * 0 when they share the device (CQR_PARTITION=0, an injecting profiler, or no driver support) */
 };
@@ -146,6 +149,11 @@ int cqr_solve_ls(cqr_context* ctx, const float* dA, int lda, int m, int n, const
 
 /* Communication-avoiding tall-skinny QR (n <= 64).  R-only: A is read once, never written. */
 int cqr_tsqr_r(cqr_context* ctx, const float* dA, int lda, long long m, int n, float* dR, int ldr);
+/* Verdict of the Gram leaf (CQR_OPT_FLAT_TSQR = 4) of the last cqr_tsqr_r / cqr_tsqr_dist_r on this context; synchronises
+ * the stream.  *bound = n ||Rs^-1||_F^2 >= cond_2 of the unit-diagonal Gram matrix (Rs = R with columns scaled to unit
+ * norm; -1: Cholesky broke down or a column's scale was out of range), *householder = 1 when the Householder leaf
+ * produced R instead (bound above CQR_GRAM_BOUND, default 32768).  CQR_ESTATE if the last call did not use the Gram leaf. */
+int cqr_tsqr_gram_info(cqr_context* ctx, double* bound, int* householder);
 /* Factor keeping the implicit Q: leaf reflectors overwrite A, tree levels live in the context. */
 int cqr_tsqr_factor(cqr_context* ctx, float* dA, int lda, long long m, int n, float* dR, int ldr);
 /* Thin Q (m x n) of the last cqr_tsqr_factor on this context times the n x n seed dX

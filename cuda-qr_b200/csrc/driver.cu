@@ -1429,7 +1429,7 @@ int cqr_tsqr_form_q(cqr_context* c, const float* dX, int ldx, float* dQ, int ldq
   return (int)cudaGetLastError();
 }
 
-// debugging aid (tools/gram_check.py): the fp64 Gram matrix (64 x 64, row i at 64 i) the last Gram-leaf call reduced
+// debugging aid (tools/gram_debug.py): T (64 x 64 fp64, row i at 64 i) of the last Gram-leaf call; the Gram matrix is T + T^T
 __attribute__((visibility("default"))) int cqr_debug_gram_matrix(cqr_context* c, double* host_g) {
   if (!c || !host_g) return CQR_EINVAL;
   if (!c->gram_info) return CQR_ESTATE;

@@ -17,22 +17,23 @@
 //     in TMEM.  Every product is an integer < 2^16 times the pair's quantum and a group adds 128 of them: all partial sums
 //     are integers <= 2^23 in that unit, i.e. EXACT in the fp32 accumulator whatever the tensor pipe's rounding mode
 //     (measured: it truncates, profiles/r02_tsqr_mma_accuracy.txt);
-//   * after 128 rows the epilogue warps read the accumulator (tcgen05.ld), form U = D11/2 + D12 + D13 (TMEM lanes 0-63)
-//     and V = D22/2 + D23 (lanes 64-127) with two rounded fp32 adds, keep fp32 running sums over 8 groups and add those
-//     into a per-CTA fp64 slab; G = sum over CTAs of U + U^T + V + V^T (the dropped D33 is 2^-32 relative);
+//   * after 128 rows the epilogue warps read the accumulator (tcgen05.ld) and add U = D11/2 + D12 + D13 (TMEM lanes 0-63)
+//     and V = D22/2 + D23 (lanes 64-127) to fp64 running sums held in registers for the whole kernel (one store per CTA at
+//     the end); G = sum over CTAs of U + U^T + V + V^T (the dropped D33 is 2^-32 relative);
 //   * gram_finish_kernel reduces the slabs in fp64 (fixed order), and its last block factors G = R^T R in fp64, bounds
 //     cond of the diagonally scaled Gram matrix by n * ||R^^-1||_F^2 (explicit triangular inverse) and either writes R
 //     (fp32) or raises the gate that lets the Householder leaf behind it run (ill-conditioned, non-finite or badly
 //     scaled input) -- no host synchronisation either way.
-// Data flow of gram_kernel (persistent, one CTA per SM, 448 threads):
+// Data flow of gram_kernel (persistent, one CTA per SM, 576 threads):
 //   warp 0     TMA producer: four 32-row x 64-column fp32 boxes (128B swizzle) = one 128-row group per stage, 3 stages
 //   warps 2-9  converters: stage -> registers (32 values of one column per thread), column maxima, slices -> bf16 K-major
 //              128B-swizzled operand tiles S1|S2|S3 (2 slice stages), fence.proxy.async
 //   warp 1     MMA issuer: 8 tcgen05.mma per group into one of two TMEM accumulators (192 columns each)
-//   warps 10-13 epilogue (one per TMEM lane quarter)
+//   warps 10-17 epilogue (two per TMEM lane quarter, 32 columns each)
 // Per 128-row group and SM: 32 KB from HBM (1.4 K clk at 6.5 TB/s), 8 MMAs x 96 clk, ~76 KB of shared-memory traffic.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -50,9 +51,8 @@ constexpr uint32_t kRawStage = 4 * kRawTile;      // 32 KB
 constexpr uint32_t kSlTile = 64 * 128;            // 64 columns x 64 k bf16 (128 B rows), 128B swizzle
 constexpr uint32_t kSlKb = 3 * kSlTile;           // S1 | S2 | S3 of one 64-deep K block
 constexpr uint32_t kSlStage = 2 * kSlKb;          // 48 KB
-constexpr int kConvT = 256, kEpiT = 128;
+constexpr int kConvT = 256, kEpiT = 256;
 constexpr int kGramThreads = 64 + kConvT + kEpiT;
-constexpr int kDump = 8;                          // groups per fp32 running sum
 constexpr int kAccCols = 256;                     // TMEM column stride between the two accumulators (192 used)
 constexpr size_t kGramSmem = (size_t)kNRaw * kRawStage + (size_t)kNSl * kSlStage + 1024 + 256;
 constexpr int kSlabDoubles = 128 * 64;            // per-CTA fp64 slab: [j][tmem lane]
@@ -71,6 +71,25 @@ constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {   // exact: both are integers <= 256 times a power of two
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {   // FADD2: two rounded fp32 adds in one issue slot
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
 }
 
 struct GramParams {
@@ -158,17 +177,19 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
     for (int g = 0; g < ng; ++g) {
       const uint32_t r = g % kNRaw, t = g % kNSl;
       mbar_wait(full0 + 8 * r, (g / kNRaw) & 1);
-      float v[32];
+      uint64_t v[16];                 // 32 values as fp32 pairs (k, k + 1)
       const uint32_t src = raw0 + r * kRawStage + rd_off;
 #pragma unroll
       for (uint32_t j = 0; j < 8; ++j) {
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(v[4 * j]), "=f"(v[4 * j + 1]), "=f"(v[4 * j + 2]), "=f"(v[4 * j + 3])
-                     : "r"(src + ((j ^ swz) << 4)));
+        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v[2 * j]), "=l"(v[2 * j + 1]) : "r"(src + ((j ^ swz) << 4)));
       }
       float mx = 0.f;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) mx = fmaxf(mx, fabsf(v[k]));
+      for (int k = 0; k < 16; ++k) {
+        float lo, hi;
+        unpack_f32x2(v[k], lo, hi);
+        mx = fmaxf(mx, fmaxf(fabsf(lo), fabsf(hi)));
+      }
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
       // every value has been consumed (the maximum depends on all 32 loads), so the loads have completed: only now may
@@ -186,27 +207,24 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
         sg2 = __uint_as_float(((ec + 8) << 23) | 0x400000u);
         sg3 = __uint_as_float((ec << 23) | 0x400000u);
       }
+      const uint64_t S1 = pack_f32x2(sg1, sg1), S2 = pack_f32x2(sg2, sg2), S3 = pack_f32x2(sg3, sg3);
       mbar_wait(slfree0 + 8 * t, ((g / kNSl) & 1) ^ 1);   // the MMAs of group g - 2 are done with this slice stage
       const uint32_t dst = sl0 + t * kSlStage + wr_off;
 #pragma unroll
       for (uint32_t i = 0; i < 4; ++i) {                  // one 16-byte chunk (8 k) of each slice per pass
         uint32_t w1[4], w2[4], w3[4];
 #pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-          float s1[2], s2[2], s3[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float x = v[8 * i + k + e];
-            const float a1 = __fsub_rn(__fadd_rn(x, sg1), sg1);
-            const float r1 = __fsub_rn(x, a1);
-            const float a2 = __fsub_rn(__fadd_rn(r1, sg2), sg2);
-            const float r2 = __fsub_rn(r1, a2);
-            const float a3 = __fsub_rn(__fadd_rn(r2, sg3), sg3);
-            s1[e] = a1; s2[e] = a2; s3[e] = a3;
-          }
-          w1[k >> 1] = pack_bf16(s1[0], s1[1]);
-          w2[k >> 1] = pack_bf16(s2[0], s2[1]);
-          w3[k >> 1] = pack_bf16(s3[0], s3[1]);
+        for (int pp = 0; pp < 4; ++pp) {
+          const uint64_t x = v[4 * i + pp];
+          const uint64_t a1 = sub2(add2(x, S1), S1);     // RN to a multiple of the first quantum (both halves at once)
+          const uint64_t r1 = sub2(x, a1);               // exact
+          const uint64_t a2 = sub2(add2(r1, S2), S2);
+          const uint64_t r2 = sub2(r1, a2);
+          const uint64_t a3 = sub2(add2(r2, S3), S3);
+          float lo, hi;
+          unpack_f32x2(a1, lo, hi); w1[pp] = pack_bf16(lo, hi);
+          unpack_f32x2(a2, lo, hi); w2[pp] = pack_bf16(lo, hi);
+          unpack_f32x2(a3, lo, hi); w3[pp] = pack_bf16(lo, hi);
         }
         const uint32_t o = ((chunk0 + i) ^ swz) << 4;
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + o), "r"(w1[0]), "r"(w1[1]), "r"(w1[2]), "r"(w1[3]) : "memory");
@@ -217,58 +235,42 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
       mbar_arrive(conv0 + 8 * t);
     }
   } else {
-    // epilogue: warp reads TMEM lanes 32 qq .. + 31.  Lanes 0-63 (row i of [S1|S2]^T = column i of S1): U(i, :);
-    // lanes 64-127 (column i of S2): V(i, :).
-    const int qq = warp & 3;
+    // epilogue: a warp may only touch TMEM lanes 32 (warp % 4) .. + 31; two warps share a lane quarter and take 32 of the
+    // 64 columns each.  Lanes 0-63 (row i of [S1|S2]^T = column i of S1) give U(i, :), lanes 64-127 (column i of S2) V(i, :).
+    // The running sums live in fp64 REGISTERS for the whole kernel (32 per thread).  A group's contribution D11/2 + D12 + D13
+    // is rounded to fp32 once (2^-25 of the group's value, random sign: ~1e-10 of G after a few thousand groups) and then
+    // added exactly; nothing is lost between groups.  One F2F per value: the conversion runs on the quarter-rate XU pipe,
+    // two per value (x and y converted separately) made the epilogue the slowest stage at 36 % XU utilisation.  (First version: fp32 running sums dumped into an fp64 slab in global memory every 8 groups --
+    // the read-modify-write of the slab and 15 spilled accumulators made the epilogue the slowest stage of the pipeline.)
+    const int qq = warp & 3, hh = (warp - (2 + kConvT / 32)) >> 2;
     const int tl = 32 * qq + lane;
-    const bool upper = qq < 2;
-    double* slab = p.slabs + (size_t)blockIdx.x * kSlabDoubles + tl;
-    float acc[64];
+    const uint32_t offx = qq < 2 ? 0u : 64u;
+    const float wy = qq < 2 ? 1.f : 0.f;
+    double acc[32];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
-    bool first = true;
+    for (int j = 0; j < 32; ++j) acc[j] = 0.0;
     for (int g = 0; g < ng; ++g) {
       const uint32_t a = g & 1;
       mbar_wait(tfull0 + 8 * a, (g >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t td = tmem_base + a * kAccCols + ((uint32_t)(32 * qq) << 16);
-      if (upper) {
+      const uint32_t td = tmem_base + a * kAccCols + ((uint32_t)(32 * qq) << 16) + 32 * hh;
+      // one code path for both halves: upper lanes x = D11 / 2, y = D12 + D13; lower lanes x = D22 / 2, y = 0 * D22 + D23
 #pragma unroll
-        for (int jc = 0; jc < 8; ++jc) {
-          float d1[8], d2[8], d3[8];
-          tmem_ld8(td + 8 * jc, d1);
-          tmem_ld8(td + 64 + 8 * jc, d2);
-          tmem_ld8(td + 128 + 8 * jc, d3);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int jc = 0; jc < 8; ++jc) {   // four columns per pass: 64 accumulator registers leave room for 12 loaded values
+        float d1[4], d2[4], d3[4];
+        tmem_ld4(td + offx + 4 * jc, d1);
+        tmem_ld4(td + 64 + 4 * jc, d2);
+        tmem_ld4(td + 128 + 4 * jc, d3);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[8 * jc + j] += __fadd_rn(__fmaf_rn(0.5f, d1[j], d2[j]), d3[j]);
-        }
-      } else {
-#pragma unroll
-        for (int jc = 0; jc < 8; ++jc) {
-          float d2[8], d3[8];
-          tmem_ld8(td + 64 + 8 * jc, d2);
-          tmem_ld8(td + 128 + 8 * jc, d3);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[8 * jc + j] += __fmaf_rn(0.5f, d2[j], d3[j]);
-        }
+        for (int j = 0; j < 4; ++j) acc[4 * jc + j] += (double)__fmaf_rn(0.5f, d1[j], __fmaf_rn(d2[j], wy, d3[j]));
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(tempty0 + 8 * a);
-      if ((g + 1) % kDump == 0 || g + 1 == ng) {
-#pragma unroll
-        for (int jb = 0; jb < 64; jb += 8) {   // eight at a time: all 64 loads in flight at once would spill
-          double cur[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) cur[j] = first ? 0.0 : slab[(jb + j) * 128];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { slab[(jb + j) * 128] = cur[j] + (double)acc[jb + j]; acc[jb + j] = 0.f; }
-          asm volatile("" ::: "memory");
-        }
-        first = false;
-      }
     }
+    double* slab = p.slabs + (size_t)blockIdx.x * kSlabDoubles + (size_t)(32 * hh) * 128 + tl;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) slab[j * 128] = acc[j];
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -290,21 +292,20 @@ struct GramFinishParams {
 };
 
 __global__ void __launch_bounds__(256) gram_finish_kernel(GramFinishParams p) {
-  __shared__ double red[4][64];
-  __shared__ double Gs[65][65];   // upper triangle: G -> R; X = R^^-1 goes below it, X(l, j) at Gs[j + 1][l]
-  __shared__ double dg[64], rinv[64], cinv[64];
+  __shared__ double red[256];
+  __shared__ double Gs[65][65];   // upper triangle: G -> unscaled Cholesky rows; rows 1..64 below the diagonal: the running sums S of
+                                  // the forward substitution for Y = R^^-T, S(k, j) at Gs[k + 1][j] (j <= k)
+  __shared__ double dg[64], cinv[64], csq[64];
   __shared__ int s_last, s_fail;
-  const int tid = threadIdx.x, j = tid & 63, part = tid >> 6, i = blockIdx.x;
+  const int tid = threadIdx.x, i = blockIdx.x;
   {
+    // T(i, j) = sum over CTAs of U(j, i) + V(j, i) = S[i * 128 + j] + S[i * 128 + 64 + j]: contiguous reads only; G = T + T^T
+    const int j2 = tid & 127, half = tid >> 7;
     double s = 0.0;
-    for (int b = part; b < p.nslabs; b += 4) {
-      const double* S = p.slabs + (size_t)b * kSlabDoubles;
-      // U(i,j) = S[j*128 + i], V(i,j) = S[j*128 + 64 + i]
-      s += (__ldcg(S + j * 128 + i) + __ldcg(S + i * 128 + j)) + (__ldcg(S + j * 128 + 64 + i) + __ldcg(S + i * 128 + 64 + j));
-    }
-    red[part][j] = s;
+    for (int b = half; b < p.nslabs; b += 2) s += __ldcg(p.slabs + (size_t)b * kSlabDoubles + i * 128 + j2);
+    red[tid] = s;
     __syncthreads();
-    if (part == 0) p.g[i * 64 + j] = (red[0][j] + red[1][j]) + (red[2][j] + red[3][j]);
+    if (tid < 64) p.g[i * 64 + tid] = (red[tid] + red[128 + tid]) + (red[64 + tid] + red[192 + tid]);
   }
   __threadfence();
   __syncthreads();
@@ -317,18 +318,43 @@ __global__ void __launch_bounds__(256) gram_finish_kernel(GramFinishParams p) {
   if (!s_last) return;
   __threadfence();
   const int n = p.n;
-  for (int e = tid; e < 64 * 64; e += 256) Gs[e >> 6][e & 63] = __ldcg(p.g + e);
+  const int j = tid & 63, part = tid >> 6;
+  for (int e = tid; e < 64 * 64; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    if (r <= c) Gs[r][c] = __ldcg(p.g + r * 64 + c) + __ldcg(p.g + c * 64 + r);
+    else Gs[r + 1][c] = 0.0;                    // S(r, c), c < r
+  }
+  if (tid < 64) Gs[tid + 1][tid] = 0.0;        // S(k, k)
   __syncthreads();
-  if (tid < 64) dg[tid] = Gs[tid][tid];
+  if (tid < 64) {
+    const double d = Gs[tid][tid];
+    dg[tid] = d;
+    csq[tid] = sqrt(d);
+    cinv[tid] = 1.0 / sqrt(d);                  // R^ = R diag(cinv): unit-diagonal Gram matrix
+  }
   __syncthreads();
-  // right-looking Cholesky on the upper triangle, unscaled rows: after step k row k holds r(k,:) * r(k,k)
+  // One pass, one barrier per step k:
+  //   threads of columns j > k: right-looking Cholesky update on the upper triangle (rows stay unscaled: after step k row k
+  //     holds r(k,:) r(k,k));
+  //   threads of columns j <= k (idle in the update): row k of Y = R^^-T by forward substitution in axpy form,
+  //     Y(k,j) = (delta_kj - S(k,j)) / r^(k,k), then S(k',j) += r^(k,k') Y(k,j) for k' > k.  ||Y||_F^2 = trace of the inverse
+  //     of the unit-diagonal Gram matrix.
+  double ysq = 0.0;
   for (int k = 0; k < n; ++k) {
     const double d = Gs[k][k];
-    if (!(d > 0.0) || !(d <= 1.7e308) || !(d > 1e-30 * dg[k])) { if (tid == 0) s_fail = 1; break; }   // uniform: every thread reads the same d
+    if (!(d > 0.0) || !(d <= 1.7e308) || !(dg[k] <= 1.7e308)) { if (tid == 0) s_fail = 1; break; }   // uniform: every thread reads the same d
     const double rd = 1.0 / d;
-    if (j > k && j < n) {
-      const double w = Gs[k][j] * rd;
-      for (int ii = k + 1 + part; ii <= j; ii += 4) Gs[ii][j] -= Gs[k][ii] * w;
+    if (j > k) {
+      if (j < n) {
+        const double w = Gs[k][j] * rd;
+        for (int ii = k + 1 + part; ii <= j; ii += 4) Gs[ii][j] -= Gs[k][ii] * w;
+      }
+    } else {
+      const double rs = sqrt(rd);                                   // 1 / r(k,k)
+      const double y = ((j == k ? 1.0 : 0.0) - Gs[k + 1][j]) * (rs * csq[k]);
+      if (part == 0) ysq += y * y;
+      const double yr = y * rs;
+      for (int kk = k + 1 + part; kk < n; kk += 4) Gs[kk + 1][j] += Gs[k][kk] * cinv[kk] * yr;
     }
     __syncthreads();
   }
@@ -336,60 +362,21 @@ __global__ void __launch_bounds__(256) gram_finish_kernel(GramFinishParams p) {
   const bool fail = s_fail != 0 || (*(volatile int*)p.status != 0);
   double bound = 0.0, minpiv = 0.0;
   if (!fail) {
-    // R(k,j) = Gs[k][j] / sqrt(Gs[k][k]);   R^ = R diag(1/sqrt(g_jj))
-    if (tid < n) rinv[tid] = 1.0 / sqrt(Gs[tid][tid]);
-    __syncthreads();
-    for (int e = tid; e < 64 * 64; e += 256) {
-      const int k = e >> 6, jj = e & 63;
-      if (k <= jj && jj < n) Gs[k][jj] *= rinv[k];          // R
-    }
-    __syncthreads();
-    for (int e = tid; e < 64 * 64; e += 256) {
+    for (int e = tid; e < 64 * 64; e += 256) {     // R(k,j) = Gs[k][j] / sqrt(Gs[k][k])
       const int k = e >> 6, jj = e & 63;
       float out = 0.f;
-      if (k <= jj && jj < n) out = (float)Gs[k][jj];
+      if (k <= jj && jj < n) out = (float)(Gs[k][jj] / sqrt(Gs[k][k]));
       if (k < n && jj < n) p.r[k + (long long)jj * p.ldr] = out;
     }
-    // X = R^^-1, column j by back substitution in "axpy" form: all columns advance together, row l = n-1 .. 0;
-    // thread (j, part) carries the partial sums of rows part + 4 u of column j.
-    double sacc[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) sacc[u] = 0.0;
-    if (tid < n) cinv[tid] = 1.0 / sqrt(dg[tid]);   // R^(i, l) = R(i, l) cinv[l]
-    __syncthreads();
-    for (int l = n - 1; l >= 0; --l) {
-      if ((l & 3) == part && j < n && j >= l) {      // x(l, j) = (delta_lj - s_l) / r^(l, l)
-        double s = 0.0;
-#pragma unroll
-        for (int u = 0; u < 16; ++u) if (u == (l >> 2)) s = sacc[u];
-        Gs[j + 1][l] = ((j == l ? 1.0 : 0.0) - s) / (Gs[l][l] * cinv[l]);
-      }
-      __syncthreads();
-      if (j < n && j >= l) {
-        const double x = Gs[j + 1][l] * cinv[l];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int ii = part + 4 * u;
-          if (ii < l) sacc[u] += Gs[ii][l] * x;
-        }
-      }
-    }
-    __syncthreads();
-    // ||X||_F^2 and the smallest scaled pivot
-    double f = 0.0;
-    for (int e = tid; e < 64 * 64; e += 256) {
-      const int k = e >> 6, jj = e & 63;
-      if (k <= jj && jj < n) f += Gs[jj + 1][k] * Gs[jj + 1][k];
-    }
-    for (int o = 16; o; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
-    if ((tid & 31) == 0) red[0][tid >> 5] = f;
+    for (int o = 16; o; o >>= 1) ysq += __shfl_xor_sync(0xffffffffu, ysq, o);
+    if ((tid & 31) == 0) red[tid >> 5] = ysq;
     __syncthreads();
     if (tid == 0) {
       double t = 0.0;
-      for (int w = 0; w < 8; ++w) t += red[0][w];
+      for (int w = 0; w < 8; ++w) t += red[w];
       bound = (double)n * t;
       minpiv = 1e300;
-      for (int k = 0; k < n; ++k) { const double r = Gs[k][k] * Gs[k][k] / dg[k]; if (r < minpiv) minpiv = r; }
+      for (int k = 0; k < n; ++k) { const double r = Gs[k][k] / dg[k]; if (r < minpiv) minpiv = r; }
     }
   }
   if (tid == 0) {
@@ -441,7 +428,11 @@ bool launch_tsqr_gram_r(const float* a, long long lda, long long m, int n, float
   GramParams gp{m, groups, slabs, status};
   ++g_launches;
   gram_kernel<<<grid, kGramThreads, kGramSmem, s>>>(tm, gp);
-  if (cudaGetLastError() != cudaSuccess) { --g_launches; return false; }
+  if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) {
+    if (getenv("CQR_DEBUG")) fprintf(stderr, "gram_kernel launch: %s\n", cudaGetErrorString(e));
+    --g_launches;
+    return false;
+  }
   GramFinishParams fp{slabs, grid, n, g, r, ldr, status, ticket, info, bound_max};
   ++g_launches;
   gram_finish_kernel<<<64, 256, 0, s>>>(fp);

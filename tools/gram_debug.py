@@ -20,7 +20,7 @@ def gram_of(X):
     assert rc == 0, rc
     Gx = (A.double().t() @ A.double()).cpu().numpy()
     n = X.shape[1]
-    G = np.triu(G[:n, :n]); G = G + np.triu(G, 1).T
+    G = G[:n, :n] + G[:n, :n].T     # the kernel keeps T = sum of the slabs' transposed halves; G = T + T^T
     global lastR
     lastR = np.triu(R.double().cpu().numpy())
     return G, Gx, ctx.tsqr_gram_info()

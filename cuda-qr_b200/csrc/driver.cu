@@ -1436,6 +1436,11 @@ __attribute__((visibility("default"))) int cqr_debug_gram_matrix(cqr_context* c,
   DeviceGuard dg__(c->device);
   CQR_CUDA(cudaStreamSynchronize(c->stream));
   CQR_CUDA(cudaMemcpy(host_g, c->gram_info - 64 * 64, 64 * 64 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (getenv("CQR_DEBUG")) {
+    double info[8];
+    CQR_CUDA(cudaMemcpy(info, c->gram_info, sizeof(info), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "gram_finish last block: elimination loop %.0f clocks\n", info[2]);
+  }
   return 0;
 }
 

@@ -254,14 +254,24 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
       mbar_wait(tfull0 + 8 * a, (g >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t td = tmem_base + a * kAccCols + ((uint32_t)(32 * qq) << 16) + 32 * hh;
-      // one code path for both halves: upper lanes x = D11 / 2, y = D12 + D13; lower lanes x = D22 / 2, y = 0 * D22 + D23
+      // one code path for both halves: upper lanes x = D11 / 2, y = D12 + D13; lower lanes x = D22 / 2, y = 0 * D22 + D23.
+      // Four columns per pass, the next pass's twelve values already in flight (tcgen05.wait::ld waits for ALL outstanding
+      // loads, so the prefetch is issued after the wait and lands while this pass converts and adds).
+      float c1[4], c2[4], c3[4];
+      tmem_ld4(td + offx, c1);
+      tmem_ld4(td + 64, c2);
+      tmem_ld4(td + 128, c3);
 #pragma unroll
-      for (int jc = 0; jc < 8; ++jc) {   // four columns per pass: 64 accumulator registers leave room for 12 loaded values
+      for (int jc = 0; jc < 8; ++jc) {
         float d1[4], d2[4], d3[4];
-        tmem_ld4(td + offx + 4 * jc, d1);
-        tmem_ld4(td + 64 + 4 * jc, d2);
-        tmem_ld4(td + 128 + 4 * jc, d3);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { d1[j] = c1[j]; d2[j] = c2[j]; d3[j] = c3[j]; }
+        if (jc + 1 < 8) {
+          tmem_ld4(td + offx + 4 * (jc + 1), c1);
+          tmem_ld4(td + 64 + 4 * (jc + 1), c2);
+          tmem_ld4(td + 128 + 4 * (jc + 1), c3);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[4 * jc + j] += (double)__fmaf_rn(0.5f, d1[j], __fmaf_rn(d2[j], wy, d3[j]));
       }
@@ -291,98 +301,160 @@ struct GramFinishParams {
   double bound_max;
 };
 
-__global__ void __launch_bounds__(256) gram_finish_kernel(GramFinishParams p) {
-  __shared__ double red[256];
-  __shared__ double Gs[65][65];   // upper triangle: G -> unscaled Cholesky rows; rows 1..64 below the diagonal: the running sums S of
-                                  // the forward substitution for Y = R^^-T, S(k, j) at Gs[k + 1][j] (j <= k)
-  __shared__ double dg[64], cinv[64], csq[64];
-  __shared__ int s_last, s_fail;
+// 1 / d and 1 / sqrt(d) for d in the fp32 range: fp32 seed (MUFU, ~2^-22) + one Newton step in fp64 (~2^-43 relative: a
+// perturbation of G far below the 1e-10 it is known to).  The IEEE division and square root are ~40-instruction subroutines
+// with dependent DFMA chains, and they sat on the critical path of each of the 64 elimination steps.
+__device__ __forceinline__ double fast_rcp(double d) {
+  const double r = (double)__frcp_rn((float)d);
+  return r * (2.0 - d * r);
+}
+__device__ __forceinline__ double fast_rsqrt(double d) {
+  const double r = (double)rsqrtf((float)d);
+  return r * (1.5 - 0.5 * d * r * r);
+}
+
+constexpr int kFinT = 1024;   // threads of the finish kernel: a 32 x 32 grid of 2 x 2 register tiles over the 64 x 64 matrix
+
+__global__ void __launch_bounds__(kFinT) gram_finish_kernel(GramFinishParams p) {
+  __shared__ double red[kFinT];
+  __shared__ double rowk[2][72];   // the published pivot row (double-buffered): [0..63] row k, [64] 1 / d_k, [65] 1 / sqrt(d_k), [66] fail flag
+  __shared__ double dg[64], pivS[64], csqS[64];
+  __shared__ int s_last;
   const int tid = threadIdx.x, i = blockIdx.x;
   {
-    // T(i, j) = sum over CTAs of U(j, i) + V(j, i) = S[i * 128 + j] + S[i * 128 + 64 + j]: contiguous reads only; G = T + T^T
-    const int j2 = tid & 127, half = tid >> 7;
-    double s = 0.0;
-    for (int b = half; b < p.nslabs; b += 2) s += __ldcg(p.slabs + (size_t)b * kSlabDoubles + i * 128 + j2);
-    red[tid] = s;
+    // T(i, j) = sum over CTAs of U(j, i) + V(j, i) = S[i * 128 + j] + S[i * 128 + 64 + j]: contiguous reads only; G = T + T^T.
+    // Eight slab groups in parallel (fixed assignment and order: the result does not depend on timing), loads unrolled by four.
+    const int j2 = tid & 127, grp = tid >> 7;
+    const double* S = p.slabs + i * 128 + j2;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int b = grp;
+    for (; b + 24 < p.nslabs; b += 32) {
+      const double v0 = __ldcg(S + (size_t)b * kSlabDoubles), v1 = __ldcg(S + (size_t)(b + 8) * kSlabDoubles),
+                   v2 = __ldcg(S + (size_t)(b + 16) * kSlabDoubles), v3 = __ldcg(S + (size_t)(b + 24) * kSlabDoubles);
+      s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+    }
+    for (; b < p.nslabs; b += 8) s0 += __ldcg(S + (size_t)b * kSlabDoubles);
+    red[tid] = (s0 + s1) + (s2 + s3);
     __syncthreads();
-    if (tid < 64) p.g[i * 64 + tid] = (red[tid] + red[128 + tid]) + (red[64 + tid] + red[192 + tid]);
+    if (tid < 64) {
+      double t = 0.0;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) t += red[128 * g + tid] + red[128 * g + 64 + tid];
+      p.g[i * 64 + tid] = t;
+    }
   }
   __threadfence();
   __syncthreads();
   if (tid == 0) {
     const unsigned t = atomicAdd(p.ticket, 1u);
     s_last = (t == gridDim.x - 1);
-    s_fail = 0;
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // ---- last block: fp64 Cholesky G = R^T R with the matrix in REGISTERS ---------------------------------------------------
+  // Thread (pr, q) = (warp, lane) owns M[2 pr .. 2 pr + 1][2 q .. 2 q + 1].  On and above the diagonal M is G, reduced in place
+  // (rows stay unscaled: after step k row k holds r(k,:) r(k,k)); strictly below it M carries the running sums S of the forward
+  // substitution for Y = Rs^-T (Rs = R with columns scaled to unit norm, Rs^T Rs = the unit-diagonal Gram matrix):
+  //     Y(k,j) = (delta_kj - S(k,j)) / rs(k,k),   S(k',j) += rs(k,k') Y(k,j)  for k' > k >= j     (S(k,k) = 0 always),
+  // and ||Y||_F^2 is the trace of the inverse of the unit-diagonal Gram matrix.  Per step the warp that owns row k publishes
+  // it (64 values plus 1/d_k and 1/sqrt(d_k), formed one step earlier by the thread that finished the pivot) and everybody
+  // updates its tile from four published values: one barrier and ~160 shared-memory wavefronts per step.  (Two versions with
+  // the matrix in shared memory took 1450-1670 cycles per step, bound by ~1400 wavefronts of LDS/STS -- in-kernel clocks.)
   const int n = p.n;
-  const int j = tid & 63, part = tid >> 6;
-  for (int e = tid; e < 64 * 64; e += 256) {
-    const int r = e >> 6, c = e & 63;
-    if (r <= c) Gs[r][c] = __ldcg(p.g + r * 64 + c) + __ldcg(p.g + c * 64 + r);
-    else Gs[r + 1][c] = 0.0;                    // S(r, c), c < r
+  const int pr = tid >> 5, q = tid & 31;
+  const int r0 = 2 * pr, c0 = 2 * q;
+  double m00, m01, m10, m11;
+  {
+    auto gl = [&](int r, int c) -> double { return r <= c ? __ldcg(p.g + r * 64 + c) + __ldcg(p.g + c * 64 + r) : 0.0; };
+    m00 = gl(r0, c0); m01 = gl(r0, c0 + 1); m10 = gl(r0 + 1, c0); m11 = gl(r0 + 1, c0 + 1);
   }
-  if (tid < 64) Gs[tid + 1][tid] = 0.0;        // S(k, k)
+  if (pr == q) { dg[r0] = m00; dg[r0 + 1] = m11; csqS[r0] = m00 > 0.0 ? sqrt(m00) : 0.0; csqS[r0 + 1] = m11 > 0.0 ? sqrt(m11) : 0.0; }
   __syncthreads();
-  if (tid < 64) {
-    const double d = Gs[tid][tid];
-    dg[tid] = d;
-    csq[tid] = sqrt(d);
-    cinv[tid] = 1.0 / sqrt(d);                  // R^ = R diag(cinv): unit-diagonal Gram matrix
-  }
-  __syncthreads();
-  // One pass, one barrier per step k:
-  //   threads of columns j > k: right-looking Cholesky update on the upper triangle (rows stay unscaled: after step k row k
-  //     holds r(k,:) r(k,k));
-  //   threads of columns j <= k (idle in the update): row k of Y = R^^-T by forward substitution in axpy form,
-  //     Y(k,j) = (delta_kj - S(k,j)) / r^(k,k), then S(k',j) += r^(k,k') Y(k,j) for k' > k.  ||Y||_F^2 = trace of the inverse
-  //     of the unit-diagonal Gram matrix.
+  // column scales of Rs for this thread's ROW indices (0 for a zero column: the pivot test stops the elimination there)
+  const double ci0 = dg[r0] > 0.0 ? 1.0 / csqS[r0] : 0.0, ci1 = dg[r0 + 1] > 0.0 ? 1.0 / csqS[r0 + 1] : 0.0;
+  double rcp_next = 0.0, rsq_next = 0.0;        // of the next pivot: valid in the thread that owns it
+  if (tid == 0) { rcp_next = 1.0 / m00; rsq_next = 1.0 / sqrt(m00); }
   double ysq = 0.0;
+  int failed = 0;
+  const long long tk0 = clock64();
   for (int k = 0; k < n; ++k) {
-    const double d = Gs[k][k];
-    if (!(d > 0.0) || !(d <= 1.7e308) || !(dg[k] <= 1.7e308)) { if (tid == 0) s_fail = 1; break; }   // uniform: every thread reads the same d
-    const double rd = 1.0 / d;
-    if (j > k) {
-      if (j < n) {
-        const double w = Gs[k][j] * rd;
-        for (int ii = k + 1 + part; ii <= j; ii += 4) Gs[ii][j] -= Gs[k][ii] * w;
+    double* buf = rowk[k & 1];
+    if (pr == (k >> 1)) {                       // publish row k
+      const bool odd = k & 1;
+      const double v0 = odd ? m10 : m00, v1 = odd ? m11 : m01;
+      buf[c0] = v0; buf[c0 + 1] = v1;
+      if (q == pr) {
+        const double d = odd ? m11 : m00;
+        const bool ok = d > 1e-37 && d < 1e37 && dg[k] < 1e37;
+        buf[64] = rcp_next; buf[65] = rsq_next; buf[66] = ok ? 0.0 : 1.0;
+        pivS[k] = d;
       }
-    } else {
-      const double rs = sqrt(rd);                                   // 1 / r(k,k)
-      const double y = ((j == k ? 1.0 : 0.0) - Gs[k + 1][j]) * (rs * csq[k]);
-      if (part == 0) ysq += y * y;
-      const double yr = y * rs;
-      for (int kk = k + 1 + part; kk < n; kk += 4) Gs[kk + 1][j] += Gs[k][kk] * cinv[kk] * yr;
     }
     __syncthreads();
+    if (buf[66] != 0.0) { failed = 1; break; }  // uniform
+    const double rcp = buf[64], rs = buf[65];
+    if (pr == (k >> 1)) {                       // R(k, :) = row k / sqrt(d_k), rounded to fp32; zeros left of the diagonal
+      const bool odd = k & 1;
+      const double v0 = odd ? m10 : m00, v1 = odd ? m11 : m01;
+      if (c0 < n) p.r[k + (long long)c0 * p.ldr] = c0 >= k ? (float)(v0 * rs) : 0.f;
+      if (c0 + 1 < n) p.r[k + (long long)(c0 + 1) * p.ldr] = c0 + 1 >= k ? (float)(v1 * rs) : 0.f;
+    }
+    if (r0 + 1 > k) {                           // warp-uniform: rows <= k are finished
+      const double a0 = buf[r0], a1 = buf[r0 + 1];          // row k at this thread's row indices
+      const double b0 = buf[c0], b1 = buf[c0 + 1];          // ... and at its column indices
+      const double scale = rs * csqS[k];                    // 1 / rs(k,k)
+      // Cholesky part (k < r <= c): m -= a_r (b_c / d)
+      const double w0 = b0 * rcp, w1 = b1 * rcp;
+      // forward-substitution part (c <= k < r): m += rs(k,r) Y(k,c);  rs(k,r) = a_r / sqrt(d) * ci_r
+      const double y0 = c0 < k ? -b0 * scale : (c0 == k ? scale : 0.0);
+      const double y1 = c0 + 1 < k ? -b1 * scale : (c0 + 1 == k ? scale : 0.0);
+      const double s0 = a0 * rs * ci0, s1 = a1 * rs * ci1;
+      if (r0 > k) {
+        if (c0 >= r0) m00 -= a0 * w0; else if (c0 <= k) m00 += s0 * y0;
+        if (c0 + 1 >= r0) m01 -= a0 * w1; else if (c0 + 1 <= k) m01 += s0 * y1;
+      }
+      {
+        const int r1 = r0 + 1;                 // r1 > k here
+        if (c0 >= r1) m10 -= a1 * w0; else if (c0 <= k) m10 += s1 * y0;
+        if (c0 + 1 >= r1) m11 -= a1 * w1; else if (c0 + 1 <= k) m11 += s1 * y1;
+      }
+      if (pr == ((k + 1) >> 1) && q == pr && k + 1 < n) {   // the next pivot is final: its reciprocals for the next step
+        const double dn = ((k + 1) & 1) ? m11 : m00;
+        const bool okd = dn > 1e-37 && dn < 1e37;
+        rcp_next = okd ? fast_rcp(dn) : 0.0;
+        rsq_next = okd ? fast_rsqrt(dn) : 0.0;
+      }
+    }
+    if (pr == (k >> 1)) {                       // ||Y(k, :)||^2, columns j <= k, by the row's owner warp
+      const double scale = rs * csqS[k];
+      const double b0 = buf[c0], b1 = buf[c0 + 1];
+      const double y0 = c0 < k ? -b0 * scale : (c0 == k ? scale : 0.0);
+      const double y1 = c0 + 1 < k ? -b1 * scale : (c0 + 1 == k ? scale : 0.0);
+      ysq += y0 * y0 + y1 * y1;
+    }
   }
   __syncthreads();
-  const bool fail = s_fail != 0 || (*(volatile int*)p.status != 0);
+  const long long tk1 = clock64();
+  const bool fail = failed != 0 || (*(volatile int*)p.status != 0);
   double bound = 0.0, minpiv = 0.0;
   if (!fail) {
-    for (int e = tid; e < 64 * 64; e += 256) {     // R(k,j) = Gs[k][j] / sqrt(Gs[k][k])
-      const int k = e >> 6, jj = e & 63;
-      float out = 0.f;
-      if (k <= jj && jj < n) out = (float)(Gs[k][jj] / sqrt(Gs[k][k]));
-      if (k < n && jj < n) p.r[k + (long long)jj * p.ldr] = out;
-    }
     for (int o = 16; o; o >>= 1) ysq += __shfl_xor_sync(0xffffffffu, ysq, o);
     if ((tid & 31) == 0) red[tid >> 5] = ysq;
     __syncthreads();
     if (tid == 0) {
       double t = 0.0;
-      for (int w = 0; w < 8; ++w) t += red[w];
+      for (int w = 0; w < kFinT / 32; ++w) t += red[w];
       bound = (double)n * t;
       minpiv = 1e300;
-      for (int k = 0; k < n; ++k) { const double r = Gs[k][k] / dg[k]; if (r < minpiv) minpiv = r; }
+      for (int k = 0; k < n; ++k) { const double r = pivS[k] / dg[k]; if (r < minpiv) minpiv = r; }
     }
   }
   if (tid == 0) {
     const bool gate = fail || !(bound <= p.bound_max);
     p.info[0] = fail ? -1.0 : bound;
     p.info[1] = minpiv;
+    p.info[2] = (double)(tk1 - tk0);   // clocks of the elimination loop (tools/gram_debug.py)
     *p.status = gate ? 1 : 0;
     *p.ticket = 0u;
     __threadfence();
@@ -435,7 +507,7 @@ bool launch_tsqr_gram_r(const float* a, long long lda, long long m, int n, float
   }
   GramFinishParams fp{slabs, grid, n, g, r, ldr, status, ticket, info, bound_max};
   ++g_launches;
-  gram_finish_kernel<<<64, 256, 0, s>>>(fp);
+  gram_finish_kernel<<<64, kFinT, 0, s>>>(fp);
   if (gate_out) *gate_out = status;
   if (info_out) *info_out = info;
   return cudaGetLastError() == cudaSuccess;

@@ -370,21 +370,47 @@ def bench_tsqr(args, pkg, ctx, torch, dist, dev, rank, world, timed_steps, pk):
            "value": flops / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms, "scaling": "strong", "n_gpus": world}
     bytes_alg = 4.0 * m_loc * n
     ach = bytes_alg / (ms * 1e-3) / 1e9
-    res["roofline"] = {"bound": "hbm", "kernel": "tsqr_flat_r_kernel (warp-resident flat-tree Householder leaf, A read once) + tile_qr_kernel<8> tree", "achieved": ach,
-                       "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": _traffic("tsqr_flat") if world == 1 else None,
-                       "note": "per-GPU algorithmic bytes 4*m_loc*n over the whole step (leaves + tree + NCCL hops); "
-                               "SIMT Householder is FMA-issue bound at this shape (32 flop/B): the fp32 FMA floor is 2mn^2 / (148 SMs x 128 lanes x 2 x clock) ~ 1.0 ms = 33 % of the HBM roof, see DESIGN.md"}
-    # both roofline fractions: the leaf is compute-bound long before it is HBM-bound (32 flop/B), so the arithmetic rate is
-    # stated against the fp32 FMA ceiling (148 SMs x 128 lanes x 2 x max clock) as well
+    leaf = ctx.get_option(pkg.OPT_FLAT_TSQR)
+    gram = leaf == pkg.TSQR_LEAF_GRAM
+    if gram:
+        kernel = ("gram_kernel (R = chol(A^T A): error-free bf16 slices on tcgen05 kind::f16, exact fp32 accumulation in TMEM, fp64 "
+                  "reduction) + gram_finish_kernel (fp64 Cholesky, condition gate) + the gated Householder leaf's empty launches")
+        note = ("per-GPU algorithmic bytes 4*m_loc*n over the whole step (leaf + finish + gate launches + cross-GPU tree); A is read "
+                "once by TMA, nothing of size m is written")
+    else:
+        kernel = "tsqr_flat_r_kernel (warp-resident flat-tree Householder leaf, A read once) + tile_qr_kernel<8> tree"
+        note = ("per-GPU algorithmic bytes 4*m_loc*n over the whole step (leaves + tree + NCCL hops); SIMT Householder is FMA-issue bound "
+                "at this shape (32 flop/B): the fp32 FMA floor is 2mn^2 / (148 SMs x 128 lanes x 2 x clock) ~ 1.0 ms = 33 % of the HBM roof")
+    res["leaf"] = "gram (tcgen05, gated Householder fallback)" if gram else {0: "tile", 1: "flat", 2: "mma", 3: "pair"}.get(leaf, str(leaf))
+    res["roofline"] = {"bound": "hbm", "kernel": kernel, "achieved": ach,
+                       "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                       "traffic": _traffic("tsqr_gram" if gram else "tsqr_flat") if world == 1 else None, "note": note}
+    if gram:
+        bound, householder = ctx.tsqr_gram_info()
+        res["gram_leaf"] = {"cond_bound": bound, "householder_fallback_ran": householder, "bound_max": 32768,
+                            "tensor_work": "3 bf16 slices: one M=128 N=192 K=16 tcgen05.mma per 16 rows = 6 m n^2 MAC, 96 clk each: 35-40 % of the tensor pipe at this rate"}
+    # the arithmetic rate of the Householder formula against the fp32 FMA ceiling (148 SMs x 128 lanes x 2 x max clock): the
+    # Householder leaf is bound by it long before HBM (32 flop/B); the Gram leaf does its contraction on the tensor pipe instead
     fma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
     res["roofline"]["fp32_fma"] = {"achieved": flops / world / (ms * 1e-3) / 1e12, "peak": fma_peak, "unit": "TFLOP/s per GPU",
-                                   "frac": flops / world / (ms * 1e-3) / 1e12 / fma_peak}
+                                   "frac": flops / world / (ms * 1e-3) / 1e12 / fma_peak,
+                                   "note": "2mn^2 Householder flops over the step time; not what the Gram leaf executes" if gram else ""}
     # in-run scaling record: this rank's local TSQR alone (leaf + on-GPU tree, no cross-GPU step) and, on rank 0, the
     # whole matrix on one GPU; efficiency = t_1 / (N t_N)
     R_loc = pkg.colmajor(n, n, device=dev)
     ms_local, _ = timed_steps(lambda: ctx.tsqr_r(A_loc, R_loc), lambda: None, 10, 3)
     res["local_ms"] = ms_local
     res["cross_gpu_ms"] = ms - ms_local
+    if gram:   # the Householder flat-tree leaf on the same rows, same run (what the gate falls back to)
+        ctx.set_option(pkg.OPT_FLAT_TSQR, pkg.TSQR_LEAF_FLAT)
+        ms_hh, _ = timed_steps(lambda: ctx.tsqr_r(A_loc, R_loc), lambda: None, 5, 2)
+        Rh = torch.triu(R_loc.double())
+        ctx.set_option(pkg.OPT_FLAT_TSQR, pkg.TSQR_LEAF_GRAM)
+        ctx.tsqr_r(A_loc, R_loc); torch.cuda.synchronize()
+        Rg = torch.triu(R_loc.double())
+        sg = torch.sign(torch.diagonal(Rh)); sg[sg == 0] = 1
+        res["householder_leaf"] = {"local_ms": ms_hh, "speedup": ms_hh / ms_local,
+                                   "r_rel_diff_vs_gram_leaf": float((Rh * sg[:, None] - Rg).norm() / Rg.norm())}
     if world > 1:
         t1 = torch.zeros(1, device=dev, dtype=torch.float64)
         if rank == 0:

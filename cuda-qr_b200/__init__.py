@@ -29,6 +29,9 @@ _VP = ctypes.c_void_p
 
 OPT_GEMM, OPT_OUTER_BLOCK, OPT_TILE_ROWS, OPT_SPLITK, OPT_LOOKAHEAD, OPT_PANEL, OPT_FLAT_TSQR, OPT_PARTITION = 1, 2, 3, 4, 5, 6, 7, 8
 GEMM_SIMT, GEMM_TF32X3 = 0, 1
+# OPT_FLAT_TSQR values: the leaf of the R-only cqr_tsqr_r on >= 16384 rows
+TSQR_LEAF_TILE, TSQR_LEAF_FLAT, TSQR_LEAF_MMA, TSQR_LEAF_PAIR, TSQR_LEAF_GRAM = 0, 1, 2, 3, 4
+TSQR_LEAF_DEFAULT = TSQR_LEAF_GRAM
 
 # Every symbol include/cudaqr_b200.h declares (tests check the .so exports all of them).
 EXPORTS = [

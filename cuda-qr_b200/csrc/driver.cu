@@ -102,7 +102,7 @@ struct cqr_context {
   unsigned dist_epoch = 0;
   cudaEvent_t ev_start = nullptr, ev_a = nullptr, ev_g = nullptr, ev_upd = nullptr, ev_panel[2] = {nullptr, nullptr};
   cudaEvent_t ev_pp[2][8] = {};    // per-panel completion (panel-wise look-ahead slices, opt_lookahead == 2)
-  int opt_gemm = 1, opt_outer = 256, opt_tile_rows = 256, opt_splitk = 0, opt_lookahead = 2, opt_panel = 1, opt_cluster = 1, opt_flat = 1;   // opt_flat: R-only TSQR leaf 0 = tile tree, 1 = SIMT flat tree (default), 2 = tensor-pipe flat tree (measured slower)
+  int opt_gemm = 1, opt_outer = 256, opt_tile_rows = 256, opt_splitk = 0, opt_lookahead = 2, opt_panel = 1, opt_cluster = 1, opt_flat = 4;   // opt_flat: R-only TSQR leaf 0 = tile tree, 1 = SIMT flat tree, 2 = tensor-pipe flat tree (measured slower), 3 = SIMT pair step, 4 (default) = Gram leaf on tcgen05 with 1 behind a device-side gate
   // multi-CTA panel kernel (panel_hh.cu): cross-CTA exchange slots, launch epoch, spin-timeout flag
   uint2* hh_slots = nullptr;
   int* hh_err = nullptr;

@@ -89,8 +89,8 @@ enum {
   CQR_OPT_LOOKAHEAD = 5,    /* 0: none; 1: next block's panels overlap the trailing update on a side stream; 2 (default): as 1, and in the
                              * panel-bound phase each finished panel is applied to the block after next's columns at once (panel-wise slices) */
   CQR_OPT_PANEL = 6,        /* 1 (default): one-launch multi-CTA Householder panel; 0: TSQR tree + Householder reconstruction */
-  CQR_OPT_FLAT_TSQR = 7,    /* R-only cqr_tsqr_r on >= 16384 rows: 1 SIMT flat-tree Householder leaf, 2 tensor-pipe flat-tree leaf (tsqr_mma.cu),
-                             * 3 SIMT leaf with two pivot columns per reduction, 0 256-row tile leaves, 4 Gram leaf on tcgen05
+  CQR_OPT_FLAT_TSQR = 7,    /* R-only cqr_tsqr_r on >= 16384 rows: 4 (default) Gram leaf, see below; 1 SIMT flat-tree Householder leaf, 2 tensor-pipe flat-tree leaf (tsqr_mma.cu),
+                             * 3 SIMT leaf with two pivot columns per reduction, 0 256-row tile leaves; 4 = Gram leaf on tcgen05
                              * (gram_umma.cu: error-free bf16 slicing, fp64 Cholesky, R with a positive diagonal) with the
                              * Householder leaf (1) behind a device-side gate for ill-conditioned / badly scaled input */
   CQR_OPT_PARTITION = 8     /* read-only (cqr_get_option): 1 when the look-ahead streams own disjoint SM partitions (CUDA green contexts),

@@ -537,7 +537,7 @@ def test_tsqr_r_and_thin_q(pkg, torch, ctx, port, m, n):
         Q4 = pkg.colmajor(m, n)
         ctx.tsqr_form_q(Q4)
         ctx.synchronize()
-        ctx.set_option(pkg.OPT_FLAT_TSQR, 1)
+        ctx.set_option(pkg.OPT_FLAT_TSQR, pkg.TSQR_LEAF_DEFAULT)
         assert np.array_equal(host(R3), host(R4))
         assert metrics.r_rel_diff(host(R1), host(R3)) < 2e-5
         check_factorisation(A, host(Q4), host(R4))
@@ -558,6 +558,7 @@ def test_tsqr_flat_leaf_vs_reference_flat_tree(pkg, torch, ctx, port):
     A = oracle.rand_matrix(m, n, 12)
     dA = dev(pkg, torch, A)
     R = pkg.colmajor(n, n)
+    ctx.set_option(pkg.OPT_FLAT_TSQR, pkg.TSQR_LEAF_FLAT)   # this test is about the Householder flat leaf (the default is the Gram leaf)
     l0 = ctx.launch_count()
     ctx.tsqr_r(dA, R)
     ctx.synchronize()
@@ -573,8 +574,16 @@ def test_tsqr_flat_leaf_vs_reference_flat_tree(pkg, torch, ctx, port):
     ctx.tsqr_r(dev(pkg, torch, A2), R)
     ctx.synchronize()
     Rh = host(R)
+    ctx.set_option(pkg.OPT_FLAT_TSQR, pkg.TSQR_LEAF_DEFAULT)
     assert np.isfinite(Rh).all() and np.all(Rh[:, 5][6:] == 0)
     assert metrics.gram_error(A2, Rh) < 1e-5
+    # the same input through the default (Gram) leaf: the zero column makes the Cholesky pivot vanish, the device-side
+    # gate hands the call to the Householder leaf, and the result is the same
+    ctx.tsqr_r(dev(pkg, torch, A2), R)
+    ctx.synchronize()
+    bound, householder = ctx.tsqr_gram_info()
+    assert householder and bound == -1.0
+    assert np.array_equal(host(R), Rh)
 
 
 @pytest.mark.parametrize("leaf", [2, 3])
@@ -598,10 +607,126 @@ def test_tsqr_r_alternative_leaves(pkg, torch, ctx, m, n, kind, leaf):
             assert float((Rd.t() @ Rd - G).norm() / G.norm()) < 2e-6
             Rs[mode] = R.cpu().numpy()
     finally:
-        ctx.set_option(pkg.OPT_FLAT_TSQR, 1)
+        ctx.set_option(pkg.OPT_FLAT_TSQR, pkg.TSQR_LEAF_DEFAULT)
     assert metrics.r_rel_diff(Rs[leaf], Rs[1]) <= 1e-5
     if m <= 200000:
         assert metrics.r_rel_diff(Rs[leaf], np.linalg.qr(A.cpu().numpy().astype(np.float64), mode="r")) <= 1e-5
+
+
+
+@pytest.mark.parametrize("m,n,kind", [(16384, 64, "u"), (20012, 17, "u"), (65536, 64, "n"), (100004, 40, "u"), (131072 + 128 * 5, 64, "u"),
+                                      (262144, 64, "n"), (1 << 20, 64, "u")])
+def test_tsqr_gram_leaf(pkg, torch, ctx, m, n, kind):
+    """CQR_OPT_FLAT_TSQR = 4 (default): R = chol(A^T A) with the Gram matrix formed error-free on tcgen05 (bf16 slices,
+    exact fp32 accumulation, fp64 reduction and Cholesky; gram_umma.cu).  Against the Householder leaf, fp64 and the Gram
+    matrix; R has a positive diagonal and zeros below it; two calls give the same bits (fixed-order reductions)."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    A = pkg.colmajor(m, n)
+    A.copy_(torch.rand((m, n), device="cuda", generator=g) if kind == "u" else torch.randn((m, n), device="cuda", generator=g))
+    A0 = A.clone()
+    G = A.t().double() @ A.double()
+    Rs = {}
+    try:
+        for mode in (pkg.TSQR_LEAF_GRAM, pkg.TSQR_LEAF_FLAT):
+            ctx.set_option(pkg.OPT_FLAT_TSQR, mode)
+            R = pkg.colmajor(n, n); R.fill_(float("nan"))
+            ctx.tsqr_r(A, R); ctx.synchronize()
+            assert float(torch.tril(R, -1).abs().max()) == 0.0 if n > 1 else True
+            Rd = torch.triu(R.double())
+            assert float((Rd.t() @ Rd - G).norm() / G.norm()) < (2e-7 if mode == pkg.TSQR_LEAF_GRAM else 2e-6)
+            Rs[mode] = R.cpu().numpy()
+            if mode == pkg.TSQR_LEAF_GRAM:
+                bound, householder = ctx.tsqr_gram_info()
+                assert not householder and 1.0 <= bound <= 32768.0
+                assert bool((torch.diagonal(R) > 0).all())
+                R2 = pkg.colmajor(n, n)
+                ctx.tsqr_r(A, R2); ctx.synchronize()
+                assert torch.equal(R, R2)
+        assert torch.equal(A, A0)                                   # R-only: A is never written
+    finally:
+        ctx.set_option(pkg.OPT_FLAT_TSQR, pkg.TSQR_LEAF_DEFAULT)
+    assert metrics.r_rel_diff(Rs[pkg.TSQR_LEAF_GRAM], Rs[pkg.TSQR_LEAF_FLAT]) <= 1e-5
+    if m <= 300000:
+        r64 = np.linalg.qr(A.cpu().numpy().astype(np.float64), mode="r")
+        assert metrics.r_rel_diff(Rs[pkg.TSQR_LEAF_GRAM], r64) <= 2e-7      # fp32 rounding of R: closer to fp64 than the Householder leaf
+        assert metrics.r_rel_diff(Rs[pkg.TSQR_LEAF_FLAT], r64) <= 1e-5
+
+
+def test_tsqr_gram_leaf_is_error_free_on_integer_data(pkg, torch, ctx):
+    """Input that fits the first 8-bit slice: the tensor-core Gram matrix must be EXACT, bit for bit (debug export of the
+    fp64 matrix the kernel reduced), whatever the rounding mode of the accumulators.  With two or three slices in play
+    a 256-row pair's D11/2 + D12 + D13 is rounded to fp32 once before the fp64 sum: 2^-25 of the pair's value, random."""
+    import ctypes
+    m, n = 65536 + 128, 64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for lo, hi, scale in ((0, 256, 1.0 / 256), (-255, 256, 1.0 / 256), (0, 65536, 1.0 / 65536), (-2000, 2001, 1.0)):
+        X = torch.randint(lo, hi, (m, n), device="cuda", generator=g).double() * scale
+        A = pkg.colmajor(m, n); A.copy_(X.float())
+        assert torch.equal(A.double(), X)
+        R = pkg.colmajor(n, n)
+        ctx.tsqr_r(A, R); ctx.synchronize()
+        T = np.zeros((64, 64))
+        pkg.lib.cqr_debug_gram_matrix.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        assert pkg.lib.cqr_debug_gram_matrix(ctx.h, T.ctypes.data) == 0
+        Gk = T + T.T
+        Gx = (X.t() @ X).cpu().numpy()
+        if hi == 256:
+            assert np.array_equal(Gk, Gx)
+        else:
+            assert np.abs(Gk - Gx).max() <= 1e-8 * np.abs(Gx).max()
+        Rd = torch.triu(R.double())
+        assert float((Rd.t() @ Rd - torch.from_numpy(Gx).cuda()).norm() / np.linalg.norm(Gx)) < 1.5e-7
+
+
+def test_tsqr_gram_leaf_gate(pkg, torch, ctx):
+    """The Gram leaf only keeps its R when n ||Rs^-1||_F^2 (>= cond_2 of the unit-diagonal Gram matrix) is at most 32768;
+    otherwise -- ill-conditioned, rank-deficient, out-of-scale or non-eligible input -- the Householder leaf enqueued behind
+    the device-side gate produces R, with no host synchronisation in between.  Either way R passes the parity bounds."""
+    m, n = 131072, 64
+    g = torch.Generator(device="cuda").manual_seed(21)
+    def graded(cond):
+        Q = torch.linalg.qr(torch.randn((m, n), device="cuda", generator=g, dtype=torch.float64)).Q
+        V = torch.linalg.qr(torch.randn((n, n), device="cuda", generator=g, dtype=torch.float64)).Q
+        sv = torch.logspace(0, -float(np.log10(cond)), n, device="cuda", dtype=torch.float64)
+        return (Q * sv) @ V.t()
+    def run(X):
+        A = pkg.colmajor(X.shape[0], X.shape[1]); A.copy_(X.float())
+        R = pkg.colmajor(X.shape[1], X.shape[1])
+        ctx.tsqr_r(A, R); ctx.synchronize()
+        return A, R
+    for cond, expect_householder in ((3.0, False), (10.0, False), (100.0, True), (1e4, True)):
+        A, R = run(graded(cond))
+        bound, householder = ctx.tsqr_gram_info()
+        assert householder == expect_householder and bound >= cond * cond * 0.5
+        r64 = np.linalg.qr(A.double().cpu().numpy(), mode="r")
+        assert metrics.r_rel_diff(R.cpu().numpy(), r64) <= (1e-6 if not householder else metrics.TOL_R)
+        assert metrics.gram_error(A.cpu().numpy(), R.cpu().numpy()) < 1e-6
+    # exactly dependent columns, a zero column, values the fp32 accumulators cannot carry: Cholesky / scale guard -> Householder
+    X = torch.rand((m, n), device="cuda", generator=g); X[:, 7] = X[:, 3]
+    A, R = run(X)
+    assert ctx.tsqr_gram_info() [1] and metrics.gram_error(A.cpu().numpy(), R.cpu().numpy()) < 1e-6
+    X = torch.rand((m, n), device="cuda", generator=g); X[:, 9] = 0
+    A, R = run(X)
+    assert ctx.tsqr_gram_info()[1] and metrics.gram_error(A.cpu().numpy(), R.cpu().numpy()) < 1e-6
+    X = torch.rand((m, n), device="cuda", generator=g) * 1e-20
+    A, R = run(X)
+    assert ctx.tsqr_gram_info() == (-1.0, True)
+    G = A.double().t() @ A.double()
+    Rd = torch.triu(R.double())
+    assert float((Rd.t() @ Rd - G).norm() / G.norm()) < 1e-6
+    # a leading dimension that TMA cannot address (lda % 4 != 0): the Gram leaf is not used at all
+    X = torch.rand((m - 1, n), device="cuda", generator=g)
+    A, R = run(X)
+    with pytest.raises(pkg.CudaQRError):
+        ctx.tsqr_gram_info()
+    assert metrics.gram_error(A.cpu().numpy(), R.cpu().numpy()) < 1e-6
+    # column scales spread over 2^-20 .. 2^20: diagonal scaling does not hurt Cholesky, and the slices are per column
+    X = torch.randn((m, n), device="cuda", generator=g) * (2.0 ** torch.linspace(-20, 20, n, device="cuda"))
+    A, R = run(X)
+    bound, householder = ctx.tsqr_gram_info()
+    assert not householder and bound < 8192
+    r64 = np.linalg.qr(A.double().cpu().numpy(), mode="r")
+    assert metrics.r_rel_diff(R.cpu().numpy(), r64) <= 1e-6
 
 
 def test_tsqr_pair_leaf_guard_fallback(pkg, torch, ctx):
@@ -627,7 +752,7 @@ def test_tsqr_pair_leaf_guard_fallback(pkg, torch, ctx):
             assert float((Rd.t() @ Rd - G).norm() / G.norm()) < 2e-6
             Rs[mode] = Rd
     finally:
-        ctx.set_option(pkg.OPT_FLAT_TSQR, 1)
+        ctx.set_option(pkg.OPT_FLAT_TSQR, pkg.TSQR_LEAF_DEFAULT)
     # R itself is ill-determined for dependent columns; the Gram matrices above are the check, plus agreement on the
     # well-determined entries: first column of each pair against the reflectors of first columns (an odd row belongs to
     # the direction of a 1e-3 perturbation, which is only determined to ~1e-3 / eps)

@@ -44,7 +44,7 @@ namespace cqr {
 namespace {
 
 constexpr int kGR = 128;                          // rows per group (= per raw stage = per accumulator flush)
-constexpr int kNRaw = 4;                          // raw ring depth (a pair of groups is resident while it is scaled and sliced)
+constexpr int kNRaw = 3;                          // raw ring depth
 constexpr int kNSl = 2;                           // slice ring depth
 constexpr uint32_t kRawTile = 32 * 64 * 4;        // one TMA box: 32 rows x 64 columns fp32, rows of 128 B = one column's 32 k
 constexpr uint32_t kRawStage = 4 * kRawTile;      // 32 KB
@@ -145,11 +145,10 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // two groups (256 rows, one common scale per column) go into one accumulator before it is handed to the epilogue
       for (int g = 0; g < ng; ++g) {
-        const uint32_t t = g % kNSl, pair = g >> 1, a = pair & 1;
+        const uint32_t t = g % kNSl, a = g & 1;
         mbar_wait(conv0 + 8 * t, (g / kNSl) & 1);
-        if ((g & 1) == 0) mbar_wait(tempty0 + 8 * a, ((pair >> 1) & 1) ^ 1);
+        mbar_wait(tempty0 + 8 * a, ((g >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + a * kAccCols;
         const uint32_t sl = sl0 + t * kSlStage;
@@ -159,11 +158,11 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
           for (int k = 0; k < 4; ++k) {
             // A = rows 0-127 ([S1 | S2]), B = rows 0-191 ([S1 | S2 | S3]) of the same K-major tile stack: one descriptor
             const uint64_t d = make_desc(sl + kb * kSlKb + k * 32, 16, 1024, 2);
-            umma_bf16(tmem_d, d, d, kIdescBf16, ((g & 1) | kb | k) != 0);
+            umma_bf16(tmem_d, d, d, kIdescBf16, (kb | k) != 0);
           }
         }
         umma_commit(slfree0 + 8 * t);
-        if ((g & 1) || g + 1 == ng) umma_commit(tfull0 + 8 * a);
+        umma_commit(tfull0 + 8 * a);
       }
     }
   } else if (warp < 2 + kConvT / 32) {
@@ -175,28 +174,31 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
     // destination: K block q / 2, bytes (q % 2) * 64 .. + 63 of row c  ->  16-byte chunks 4 (q % 2) + {0..3}
     const uint32_t wr_off = (q >> 1) * kSlKb + c * 128;
     const uint32_t chunk0 = (uint32_t)(q & 1) * 4;
-    for (int g0 = 0; g0 < ng; g0 += 2) {
-      const int npair = (g0 + 1 < ng) ? 2 : 1;
-      // pass 1: the column's maximum over the pair (256 rows)
-      float mx = 0.f;
-      for (int h = 0; h < npair; ++h) {
-        const int g = g0 + h;
-        const uint32_t r = g % kNRaw;
-        mbar_wait(full0 + 8 * r, (g / kNRaw) & 1);
-        const uint32_t src = raw0 + r * kRawStage + rd_off;
+    for (int g = 0; g < ng; ++g) {
+      const uint32_t r = g % kNRaw, t = g % kNSl;
+      mbar_wait(full0 + 8 * r, (g / kNRaw) & 1);
+      uint64_t v[16];                 // 32 values as fp32 pairs (k, k + 1)
+      const uint32_t src = raw0 + r * kRawStage + rd_off;
 #pragma unroll
-        for (uint32_t j = 0; j < 8; ++j) {
-          float a0, a1, a2, a3;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3) : "r"(src + (j << 4)));
-          mx = fmaxf(mx, fmaxf(fmaxf(fabsf(a0), fabsf(a1)), fmaxf(fabsf(a2), fabsf(a3))));
-        }
+      for (uint32_t j = 0; j < 8; ++j) {
+        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v[2 * j]), "=l"(v[2 * j + 1]) : "r"(src + ((j ^ swz) << 4)));
+      }
+      float mx = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        float lo, hi;
+        unpack_f32x2(v[k], lo, hi);
+        mx = fmaxf(mx, fmaxf(fabsf(lo), fabsf(hi)));
       }
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+      // every value has been consumed (the maximum depends on all 32 loads), so the loads have completed: only now may
+      // TMA refill the stage.  Arriving right after ISSUING the loads let a fast (L2-fed) refill overtake them.
+      mbar_arrive(rawfree0 + 8 * r);
       // 2^E > mx with biased exponent eb + 1; slice quanta 2^(E-8), 2^(E-16), 2^(E-24); sigma_i = 1.5 * 2^(quantum + 23)
       const uint32_t eb = __float_as_uint(mx) >> 23;
       float sg1, sg2, sg3;
-      if (eb == 0) {               // zero (or denormal) column in this pair: slices are the values themselves (zeros)
+      if (eb == 0) {               // zero (or denormal) column in this group: slices are the values themselves (zeros)
         sg1 = sg2 = sg3 = 0.f;
       } else {
         if (eb < 87 || eb > 167) atomicOr(p.status, 1);   // |a| outside 2^-40 .. 2^40 (or Inf): leave it to the Householder leaf
@@ -206,45 +208,31 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
         sg3 = __uint_as_float((ec << 23) | 0x400000u);
       }
       const uint64_t S1 = pack_f32x2(sg1, sg1), S2 = pack_f32x2(sg2, sg2), S3 = pack_f32x2(sg3, sg3);
-      // pass 2: slice group by group
-      for (int h = 0; h < npair; ++h) {
-        const int g = g0 + h;
-        const uint32_t r = g % kNRaw, t = g % kNSl;
-        uint64_t v[16];                 // 32 values as fp32 pairs (k, k + 1)
-        const uint32_t src = raw0 + r * kRawStage + rd_off;
+      mbar_wait(slfree0 + 8 * t, ((g / kNSl) & 1) ^ 1);   // the MMAs of group g - 2 are done with this slice stage
+      const uint32_t dst = sl0 + t * kSlStage + wr_off;
 #pragma unroll
-        for (uint32_t j = 0; j < 8; ++j) {
-          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v[2 * j]), "=l"(v[2 * j + 1]) : "r"(src + ((j ^ swz) << 4)));
+      for (uint32_t i = 0; i < 4; ++i) {                  // one 16-byte chunk (8 k) of each slice per pass
+        uint32_t w1[4], w2[4], w3[4];
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) {
+          const uint64_t x = v[4 * i + pp];
+          const uint64_t a1 = sub2(add2(x, S1), S1);     // RN to a multiple of the first quantum (both halves at once)
+          const uint64_t r1 = sub2(x, a1);               // exact
+          const uint64_t a2 = sub2(add2(r1, S2), S2);
+          const uint64_t r2 = sub2(r1, a2);
+          const uint64_t a3 = sub2(add2(r2, S3), S3);
+          float lo, hi;
+          unpack_f32x2(a1, lo, hi); w1[pp] = pack_bf16(lo, hi);
+          unpack_f32x2(a2, lo, hi); w2[pp] = pack_bf16(lo, hi);
+          unpack_f32x2(a3, lo, hi); w3[pp] = pack_bf16(lo, hi);
         }
-        mbar_wait(slfree0 + 8 * t, ((g / kNSl) & 1) ^ 1);   // the MMAs of group g - 2 are done with this slice stage
-        const uint32_t dst = sl0 + t * kSlStage + wr_off;
-#pragma unroll
-        for (uint32_t i = 0; i < 4; ++i) {                  // one 16-byte chunk (8 k) of each slice per pass
-          uint32_t w1[4], w2[4], w3[4];
-#pragma unroll
-          for (int pp = 0; pp < 4; ++pp) {
-            const uint64_t x = v[4 * i + pp];
-            const uint64_t a1 = sub2(add2(x, S1), S1);     // RN to a multiple of the first quantum (both halves at once)
-            const uint64_t r1 = sub2(x, a1);               // exact
-            const uint64_t a2 = sub2(add2(r1, S2), S2);
-            const uint64_t r2 = sub2(r1, a2);
-            const uint64_t a3 = sub2(add2(r2, S3), S3);
-            float lo, hi;
-            unpack_f32x2(a1, lo, hi); w1[pp] = pack_bf16(lo, hi);
-            unpack_f32x2(a2, lo, hi); w2[pp] = pack_bf16(lo, hi);
-            unpack_f32x2(a3, lo, hi); w3[pp] = pack_bf16(lo, hi);
-          }
-          const uint32_t o = ((chunk0 + i) ^ swz) << 4;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + o), "r"(w1[0]), "r"(w1[1]), "r"(w1[2]), "r"(w1[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + kSlTile + o), "r"(w2[0]), "r"(w2[1]), "r"(w2[2]), "r"(w2[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 2 * kSlTile + o), "r"(w3[0]), "r"(w3[1]), "r"(w3[2]), "r"(w3[3]) : "memory");
-        }
-        // the slices depend on all 32 loads, so the loads have completed: only now may TMA refill the stage.  (Arriving
-        // right after ISSUING the loads let a fast, L2-fed refill overtake them: wrong Gram matrices at 128 K - 256 K rows.)
-        mbar_arrive(rawfree0 + 8 * r);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(conv0 + 8 * t);
+        const uint32_t o = ((chunk0 + i) ^ swz) << 4;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + o), "r"(w1[0]), "r"(w1[1]), "r"(w1[2]), "r"(w1[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + kSlTile + o), "r"(w2[0]), "r"(w2[1]), "r"(w2[2]), "r"(w2[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 2 * kSlTile + o), "r"(w3[0]), "r"(w3[1]), "r"(w3[2]), "r"(w3[3]) : "memory");
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(conv0 + 8 * t);
     }
   } else {
     // epilogue: a warp may only touch TMEM lanes 32 (warp % 4) .. + 31; two warps share a lane quarter and take 32 of the
@@ -261,8 +249,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
     double acc[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = 0.0;
-    const int npairs = (ng + 1) >> 1;
-    for (int g = 0; g < npairs; ++g) {           // one accumulator = one pair of groups (256 rows)
+    for (int g = 0; g < ng; ++g) {
       const uint32_t a = g & 1;
       mbar_wait(tfull0 + 8 * a, (g >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

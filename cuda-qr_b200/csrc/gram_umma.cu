@@ -197,17 +197,16 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
       mbar_arrive(rawfree0 + 8 * r);
       // 2^E > mx with biased exponent eb + 1; slice quanta 2^(E-8), 2^(E-16), 2^(E-24); sigma_i = 1.5 * 2^(quantum + 23)
       const uint32_t eb = __float_as_uint(mx) >> 23;
-      float sg1, sg2, sg3;
+      float sg1, sg2;
       if (eb == 0) {               // zero (or denormal) column in this group: slices are the values themselves (zeros)
-        sg1 = sg2 = sg3 = 0.f;
+        sg1 = sg2 = 0.f;
       } else {
         if (eb < 87 || eb > 167) atomicOr(p.status, 1);   // |a| outside 2^-40 .. 2^40 (or Inf): leave it to the Householder leaf
         const uint32_t ec = eb < 30 ? 30 : (eb > 230 ? 230 : eb);
         sg1 = __uint_as_float(((ec + 16) << 23) | 0x400000u);
         sg2 = __uint_as_float(((ec + 8) << 23) | 0x400000u);
-        sg3 = __uint_as_float((ec << 23) | 0x400000u);
       }
-      const uint64_t S1 = pack_f32x2(sg1, sg1), S2 = pack_f32x2(sg2, sg2), S3 = pack_f32x2(sg3, sg3);
+      const uint64_t S1 = pack_f32x2(sg1, sg1), S2 = pack_f32x2(sg2, sg2);
       mbar_wait(slfree0 + 8 * t, ((g / kNSl) & 1) ^ 1);   // the MMAs of group g - 2 are done with this slice stage
       const uint32_t dst = sl0 + t * kSlStage + wr_off;
 #pragma unroll
@@ -220,11 +219,13 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
           const uint64_t r1 = sub2(x, a1);               // exact
           const uint64_t a2 = sub2(add2(r1, S2), S2);
           const uint64_t r2 = sub2(r1, a2);
-          const uint64_t a3 = sub2(add2(r2, S3), S3);
+          // third slice: the bf16 conversion itself rounds r2 (|r2| <= 2^(E-17)) to 8 significant bits -- at least as fine as
+          // the fixed quantum 2^(E-24).  Its products are no longer integers of one quantum, but D13 / D23 sit 2^-16 below D11:
+          // what the accumulator may truncate there is 2^-36 of G.
           float lo, hi;
           unpack_f32x2(a1, lo, hi); w1[pp] = pack_bf16(lo, hi);
           unpack_f32x2(a2, lo, hi); w2[pp] = pack_bf16(lo, hi);
-          unpack_f32x2(a3, lo, hi); w3[pp] = pack_bf16(lo, hi);
+          unpack_f32x2(r2, lo, hi); w3[pp] = pack_bf16(lo, hi);
         }
         const uint32_t o = ((chunk0 + i) ^ swz) << 4;
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + o), "r"(w1[0]), "r"(w1[1]), "r"(w1[2]), "r"(w1[3]) : "memory");
@@ -257,23 +258,26 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_kernel(const __grid_cons
       // one code path for both halves: upper lanes x = D11 / 2, y = D12 + D13; lower lanes x = D22 / 2, y = 0 * D22 + D23.
       // Four columns per pass, the next pass's twelve values already in flight (tcgen05.wait::ld waits for ALL outstanding
       // loads, so the prefetch is issued after the wait and lands while this pass converts and adds).
-      float c1[4], c2[4], c3[4];
+      float c1[4], c2[4], c3[4], d1[4], d2[4], d3[4];   // two register sets, alternating: no copies between them
       tmem_ld4(td + offx, c1);
       tmem_ld4(td + 64, c2);
       tmem_ld4(td + 128, c3);
 #pragma unroll
-      for (int jc = 0; jc < 8; ++jc) {
-        float d1[4], d2[4], d3[4];
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int jc = 0; jc < 8; jc += 2) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");      // set c has landed
+        tmem_ld4(td + offx + 4 * (jc + 1), d1);
+        tmem_ld4(td + 64 + 4 * (jc + 1), d2);
+        tmem_ld4(td + 128 + 4 * (jc + 1), d3);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { d1[j] = c1[j]; d2[j] = c2[j]; d3[j] = c3[j]; }
-        if (jc + 1 < 8) {
-          tmem_ld4(td + offx + 4 * (jc + 1), c1);
-          tmem_ld4(td + 64 + 4 * (jc + 1), c2);
-          tmem_ld4(td + 128 + 4 * (jc + 1), c3);
+        for (int j = 0; j < 4; ++j) acc[4 * jc + j] += (double)__fmaf_rn(0.5f, c1[j], __fmaf_rn(c2[j], wy, c3[j]));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");      // set d has landed
+        if (jc + 2 < 8) {
+          tmem_ld4(td + offx + 4 * (jc + 2), c1);
+          tmem_ld4(td + 64 + 4 * (jc + 2), c2);
+          tmem_ld4(td + 128 + 4 * (jc + 2), c3);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[4 * jc + j] += (double)__fmaf_rn(0.5f, d1[j], __fmaf_rn(d2[j], wy, d3[j]));
+        for (int j = 0; j < 4; ++j) acc[4 * (jc + 1) + j] += (double)__fmaf_rn(0.5f, d1[j], __fmaf_rn(d2[j], wy, d3[j]));
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(tempty0 + 8 * a);

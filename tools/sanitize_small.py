@@ -11,6 +11,15 @@ for m, n in [(16444, 64), (20011, 17)]:                    # flat TSQR leaf: ali
     R = pkg.colmajor(n, n); ctx.tsqr_r(A, R); ctx.synchronize()
     G = A.t().double() @ A.double(); Rd = torch.triu(R.double())
     print("tsqr_r", m, n, float((Rd.t() @ Rd - G).norm() / G.norm()))
+# Gram leaf (gram_umma.cu: TMA ring, converter / MMA / epilogue warps, finish kernel) with several groups per CTA, a narrow
+# matrix, and a singular input that raises the gate so the Householder leaf behind it runs as well
+for m, n, dup in [(148 * 128 * 3 + 256, 64, False), (16384, 24, False), (32768, 64, True)]:
+    A = pkg.colmajor(m, n); A.copy_(torch.rand((m, n), device="cuda", generator=g))
+    if dup:
+        A[:, 5] = A[:, 2]
+    R = pkg.colmajor(n, n); ctx.tsqr_r(A, R); ctx.synchronize()
+    G = A.t().double() @ A.double(); Rd = torch.triu(R.double())
+    print("tsqr_r gram leaf", m, n, ctx.tsqr_gram_info(), float((Rd.t() @ Rd - G).norm() / G.norm()))
 for m, n, batch in [(64, 64, 40), (50, 33, 9)]:            # batched warp kernel
     A3 = torch.rand((batch, n, m), device="cuda", generator=g); tau = torch.zeros((batch, n), device="cuda")
     O = A3.clone(); ctx.geqrf_batched(A3, tau); ctx.synchronize()

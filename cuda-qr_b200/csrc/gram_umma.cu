@@ -305,16 +305,21 @@ struct GramFinishParams {
   double bound_max;
 };
 
-// 1 / d and 1 / sqrt(d) for d in the fp32 range: fp32 seed (MUFU, ~2^-22) + one Newton step in fp64 (~2^-43 relative: a
-// perturbation of G far below the 1e-10 it is known to).  The IEEE division and square root are ~40-instruction subroutines
-// with dependent DFMA chains, and they sat on the critical path of each of the 64 elimination steps.
+// 1 / d and 1 / sqrt(d): hardware seed on the high word (MUFU.RCP64H / RSQ64H, ~2^-20) + one Newton step in fp64 (~2^-40
+// relative: a perturbation of G far below the 1e-10 it is known to).  The IEEE division and square root are ~40-instruction
+// subroutines with dependent DFMA chains, and they sit on the critical path of each of the 64 elimination steps; a seed through
+// fp32 (F2F, MUFU, F2F) costs two more XU round trips per step.
 __device__ __forceinline__ double fast_rcp(double d) {
-  const double r = (double)__frcp_rn((float)d);
-  return r * (2.0 - d * r);
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  const double e = fma(-d, r, 1.0);
+  return fma(r, e, r);
 }
 __device__ __forceinline__ double fast_rsqrt(double d) {
-  const double r = (double)rsqrtf((float)d);
-  return r * (1.5 - 0.5 * d * r * r);
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  const double e = fma(-d * r, r, 1.0);        // 1 - d r^2
+  return fma(0.5 * r, e, r);
 }
 
 constexpr int kFinT = 1024;   // threads of the finish kernel: a 32 x 32 grid of 2 x 2 register tiles over the 64 x 64 matrix
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__(kFinT) gram_finish_kernel(GramFinishParams p) 
   __shared__ double red[kFinT];
   __shared__ double rowk[2][72];   // the published pivot row (double-buffered): [0..63] row k, [64] 1 / d_k, [65] 1 / sqrt(d_k), [66] fail flag
   __shared__ double dg[64], pivS[64], csqS[64];
-  __shared__ int s_last;
+  __shared__ int s_last, s_bad[2];   // s_bad[k & 1]: the pivot of step k is not a positive, finite, in-range number
   const int tid = threadIdx.x, i = blockIdx.x;
   {
     // T(i, j) = sum over CTAs of U(j, i) + V(j, i) = S[i * 128 + j] + S[i * 128 + 64 + j]: contiguous reads only; G = T + T^T.
@@ -390,13 +395,16 @@ __global__ void __launch_bounds__(kFinT) gram_finish_kernel(GramFinishParams p) 
       buf[c0] = v0; buf[c0 + 1] = v1;
       if (q == pr) {
         const double d = odd ? m11 : m00;
-        const bool ok = d > 1e-37 && d < 1e37 && dg[k] < 1e37;
-        buf[64] = rcp_next; buf[65] = rsq_next; buf[66] = ok ? 0.0 : 1.0;
+        // 1e-37 < d < 1e37 on the high word (integer compares: an fp64 compare would sit on the step's critical path);
+        // negative, zero, NaN and Inf all fall outside
+        const int hi = __double2hiint(d), hg = __double2hiint(dg[k]);
+        s_bad[k & 1] = !(hi > 0x38410000 && hi < 0x47A00000 && hg < 0x47A00000);
+        buf[64] = rcp_next; buf[65] = rsq_next;
         pivS[k] = d;
       }
     }
     __syncthreads();
-    if (buf[66] != 0.0) { failed = 1; break; }  // uniform
+    if (s_bad[k & 1]) { failed = 1; break; }    // uniform
     const double rcp = buf[64], rs = buf[65];
     if (pr == (k >> 1)) {                       // R(k, :) = row k / sqrt(d_k), rounded to fp32; zeros left of the diagonal
       const bool odd = k & 1;
@@ -425,9 +433,8 @@ __global__ void __launch_bounds__(kFinT) gram_finish_kernel(GramFinishParams p) 
       }
       if (pr == ((k + 1) >> 1) && q == pr && k + 1 < n) {   // the next pivot is final: its reciprocals for the next step
         const double dn = ((k + 1) & 1) ? m11 : m00;
-        const bool okd = dn > 1e-37 && dn < 1e37;
-        rcp_next = okd ? fast_rcp(dn) : 0.0;
-        rsq_next = okd ? fast_rsqrt(dn) : 0.0;
+        rcp_next = fast_rcp(dn);                 // garbage for a pivot out of range: the publish step flags it, nobody uses it
+        rsq_next = fast_rsqrt(dn);
       }
     }
     if (pr == (k >> 1)) {                       // ||Y(k, :)||^2, columns j <= k, by the row's owner warp

@@ -18,7 +18,7 @@ for m in rows:
         ctx.tsqr_r(A, R); ctx.synchronize()
         continue
     G = A.t().double() @ A.double()
-    for flat in (3, 2, 1, 0):
+    for flat in (4, 3, 2, 1, 0):       # 4 = Gram leaf (default), 3 = SIMT pair step, 2 = mma.sync leaf, 1 = SIMT flat leaf, 0 = tile leaves
         ctx.set_option(pkg.OPT_FLAT_TSQR, flat)
         for _ in range(3):
             ctx.tsqr_r(A, R)
@@ -37,5 +37,5 @@ for m in rows:
         flops = 2.0 * m * 64 * 64 - 2.0 * 64 ** 3 / 3
         print(f"tsqr_r {m:8d} x 64  flat={flat} minb={os.environ.get('CQR_FLAT_MINB', '3')}: median {ts[7]:7.3f} ms  min {ts[0]:7.3f} ms  "
               f"{flops / ts[7] / 1e9:7.1f} TFLOP/s  {4.0 * m * 64 / ts[7] / 1e6:7.1f} GB/s  launches {launches}  gram {gram:.2e}", flush=True)
-    ctx.set_option(pkg.OPT_FLAT_TSQR, 1)
+    ctx.set_option(pkg.OPT_FLAT_TSQR, pkg.TSQR_LEAF_DEFAULT)
     del A

@@ -26,6 +26,24 @@ struct PerDeviceOnce {
   void retry() { int d = 0; if (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) done[d] = false; }
 };
 
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may be scheduled while its predecessor on the
+// stream is still running; it must execute pdl_wait() before it reads anything the predecessor wrote (a no-op when the kernel
+// was launched the ordinary way).  pdl_trigger() lets the NEXT kernel on the stream be scheduled from this point on.  Used for
+// the chain of gated launches behind the Gram leaf (gram_umma.cu): seven kernels that return at once when the gate is 0 cost
+// ~2.5 us each as ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename Kernel, typename Params>
+inline cudaError_t launch_pdl(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t s, const Params& p) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);

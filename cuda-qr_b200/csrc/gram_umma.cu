@@ -330,6 +330,8 @@ __global__ void __launch_bounds__(kFinT) gram_finish_kernel(GramFinishParams p) 
   __shared__ double dg[64], pivS[64], csqS[64];
   __shared__ int s_last, s_bad[2];   // s_bad[k & 1]: the pivot of step k is not a positive, finite, in-range number
   const int tid = threadIdx.x, i = blockIdx.x;
+  pdl_trigger();   // the first gated kernel behind may be scheduled now (it waits for this grid to complete)
+  pdl_wait();      // the slabs of gram_kernel
   {
     // T(i, j) = sum over CTAs of U(j, i) + V(j, i) = S[i * 128 + j] + S[i * 128 + 64 + j]: contiguous reads only; G = T + T^T.
     // Eight slab groups in parallel (fixed assignment and order: the result does not depend on timing), loads unrolled by four.
@@ -518,7 +520,7 @@ bool launch_tsqr_gram_r(const float* a, long long lda, long long m, int n, float
   }
   GramFinishParams fp{slabs, grid, n, g, r, ldr, status, ticket, info, bound_max};
   ++g_launches;
-  gram_finish_kernel<<<64, kFinT, 0, s>>>(fp);
+  if (launch_pdl(gram_finish_kernel, dim3(64), dim3(kFinT), 0, s, fp) != cudaSuccess) { cudaGetLastError(); gram_finish_kernel<<<64, kFinT, 0, s>>>(fp); }
   if (gate_out) *gate_out = status;
   if (info_out) *info_out = info;
   return cudaGetLastError() == cudaSuccess;

@@ -31,7 +31,11 @@ __global__ void __launch_bounds__(256, (RI <= 4 ? 3 : 2)) tile_qr_kernel(TileQRP
   const int t = blockIdx.x;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   __shared__ float vs[2][TH];
-  if (p.gate != nullptr && *(const volatile int*)p.gate == 0) return;   // the Gram leaf produced R: nothing to do
+  if (p.gate != nullptr) {             // gated launches are programmatic dependent launches (launch_tile_qr)
+    pdl_trigger();
+    pdl_wait();
+    if (*(const volatile int*)p.gate == 0) return;   // the Gram leaf produced R: nothing to do
+  }
 
   const int rows = tile_rows_of(p.a, t, TH);
   float* src = p.a.base + (long long)t * p.a.tile_stride;
@@ -304,6 +308,12 @@ void launch_batched_qr_col(float* base, long long stride, long long lda, int m, 
 void launch_tile_qr(const TileQRParams& p, int tiles, int tile_rows, cudaStream_t s) {
   if (tiles <= 0) return;
   ++g_launches;
+  if (p.gate != nullptr) {               // behind the Gram leaf: overlap the launch with the predecessor (see pdl_wait)
+    if (tile_rows == 64) launch_pdl(tile_qr_kernel<2>, dim3(tiles), dim3(256), 0, s, p);
+    else if (tile_rows == 128) launch_pdl(tile_qr_kernel<4>, dim3(tiles), dim3(256), 0, s, p);
+    else launch_pdl(tile_qr_kernel<8>, dim3(tiles), dim3(256), 0, s, p);
+    return;
+  }
   if (tile_rows == 64) tile_qr_kernel<2><<<tiles, 256, 0, s>>>(p);
   else if (tile_rows == 128) tile_qr_kernel<4><<<tiles, 256, 0, s>>>(p);
   else tile_qr_kernel<8><<<tiles, 256, 0, s>>>(p);

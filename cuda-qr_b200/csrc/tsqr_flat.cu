@@ -464,7 +464,11 @@ __global__ void __launch_bounds__(32 * WPC, MINB) tsqr_flat_r_kernel(FlatTsqrPar
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane & 7, h = lane >> 3;
   const long long chain = (long long)blockIdx.x * WPC + w;
   if (chain >= p.chains) return;             // warps never meet at a block barrier
-  if (p.gate != nullptr && *(const volatile int*)p.gate == 0) return;   // the Gram leaf produced R: nothing to do
+  if (p.gate != nullptr) {             // gated launch = programmatic dependent launch (FlatCfg::launch)
+    pdl_trigger();
+    pdl_wait();
+    if (*(const volatile int*)p.gate == 0) return;   // the Gram leaf produced R: nothing to do
+  }
   float* Rs = flat_smem + w * kFlatWarpFloats;
   float* xs = Rs + 64 * 64;
   for (int i = lane; i < 64 * 64 / 4; i += 32) reinterpret_cast<float4*>(Rs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -818,7 +822,8 @@ struct FlatCfg {
     }
     static PerDeviceOnce once;             // per_sm() set the attribute on the device that ran flat_init() only
     if (once.first()) cudaFuncSetAttribute(tsqr_flat_r_kernel<WPC, MINB, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + pad));
-    tsqr_flat_r_kernel<WPC, MINB, PIPE><<<(p.chains + WPC - 1) / WPC, 32 * WPC, smem + pad, s>>>(p);
+    if (p.gate != nullptr) launch_pdl(tsqr_flat_r_kernel<WPC, MINB, PIPE>, dim3((unsigned)((p.chains + WPC - 1) / WPC)), dim3(32 * WPC), smem + pad, s, p);
+    else tsqr_flat_r_kernel<WPC, MINB, PIPE><<<(p.chains + WPC - 1) / WPC, 32 * WPC, smem + pad, s>>>(p);
   }
 };
 

@@ -297,7 +297,7 @@ bool launch_gemm_nn_umma(int M, int N, int K, float alpha, const float* a, long 
 // ---- Gram leaf of the R-only TSQR on tcgen05 (gram_umma.cu): error-free bf16 slicing, fp64 Cholesky, gated fallback ----
 bool gram_tsqr_eligible(const float* a, long long lda, long long m, int n);
 size_t gram_tsqr_workspace_floats(int sm_count);
-bool launch_tsqr_gram_r(const float* a, long long lda, long long m, int n, float* r, long long ldr, float* ws, int sm_count,
+bool launch_tsqr_gram_r(const float* a, long long lda, long long m, int n, float* r, long long ldr, float* ws, int* flags, int sm_count,
                         int max_ctas, double bound_max, int** gate_out, double** info_out, cudaStream_t s);
 
 // global launch counter (gpu_launches evidence)

@@ -575,7 +575,7 @@ static int create_impl(cqr_context* c, int device) {
   CQR_CUDA(cudaMalloc((void**)&c->hh_slots, panel_hh_slot_bytes() + 256));
   CQR_CUDA(cudaMemset(c->hh_slots, 0, panel_hh_slot_bytes() + 256));
   c->hh_err = reinterpret_cast<int*>(reinterpret_cast<char*>(c->hh_slots) + panel_hh_slot_bytes());
-  c->cu_bar = reinterpret_cast<unsigned*>(c->hh_err + 8);   // inside the zeroed 256-byte tail of the slot allocation
+  c->cu_bar = reinterpret_cast<unsigned*>(c->hh_err + 8);   // inside the zeroed 256-byte tail of the slot allocation (ints 16-18: Gram leaf flags)
   // Profilers that inject into the process (ncu: CUDA_INJECTION64_PATH / NV_COMPUTE_PROFILER_PERFWORKS_DIR) cannot follow
   // launches on green-context streams (ncu 2025.2 dies at the first one), so the spatial partition is off under them and
   // the look-ahead runs on two plain streams; CQR_PARTITION=1 forces it on, =0 off.
@@ -1384,7 +1384,7 @@ static int tsqr_common(cqr_context* c, float* dA, int lda, long long m, int n, f
     ProfScope ps(c, CQR_PROF_PANEL, 2.0 * m * n * n, 4.0 * (double)m * n * (keep ? 2 : 1));
     int* gate = nullptr;
     c->gram_info = nullptr; c->gram_gate = nullptr;
-    if (gram && launch_tsqr_gram_r(dA, lda, m, n, dR, ldr, gram_ws, c->sm_count, cur_ctas(c), gram_bound_max(), &gate,
+    if (gram && launch_tsqr_gram_r(dA, lda, m, n, dR, ldr, gram_ws, c->hh_err + 16, c->sm_count, cur_ctas(c), gram_bound_max(), &gate,
                                    &c->gram_info, cur_stream(c)))
       c->gram_gate = gate;
     else

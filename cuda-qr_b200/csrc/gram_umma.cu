@@ -299,7 +299,8 @@ struct GramFinishParams {
   int n;
   double* g;               // 64 x 64 fp64 scratch (row i by block i)
   float* r; long long ldr; // n x n upper triangular out (zeros below the diagonal)
-  int* status;             // [0] in: scale flag from gram_kernel; out: 0 = R written, 1 = the Householder leaf must run (gate)
+  int* status;             // persistent context words: [0] scale flag (set by gram_kernel, cleared here), [1] ticket (left at 0),
+                           // [2] gate out: 0 = R written, 1 = the Householder leaf must run
   unsigned* ticket;
   double* info;            // [0] n * ||R^^-1||_F^2 (bound on cond_2 of the unit-diagonal Gram matrix), [1] smallest pivot / diagonal
   double bound_max;
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(kFinT) gram_finish_kernel(GramFinishParams p) 
   __shared__ double red[kFinT];
   __shared__ double rowk[2][72];   // the published pivot row (double-buffered): [0..63] row k, [64] 1 / d_k, [65] 1 / sqrt(d_k), [66] fail flag
   __shared__ double dg[64], pivS[64], csqS[64];
-  __shared__ int s_last, s_bad[2];   // s_bad[k & 1]: the pivot of step k is not a positive, finite, in-range number
+  __shared__ int s_last, s_scale, s_bad[2];   // s_bad[k & 1]: the pivot of step k is not a positive, finite, in-range number
   const int tid = threadIdx.x, i = blockIdx.x;
   pdl_trigger();   // the first gated kernel behind may be scheduled now (it waits for this grid to complete)
   pdl_wait();      // the slabs of gram_kernel
@@ -449,7 +450,9 @@ __global__ void __launch_bounds__(kFinT) gram_finish_kernel(GramFinishParams p) 
   }
   __syncthreads();
   const long long tk1 = clock64();
-  const bool fail = failed != 0 || (*(volatile int*)p.status != 0);
+  if (tid == 0) s_scale = *(volatile int*)p.status;
+  __syncthreads();
+  const bool fail = failed != 0 || s_scale != 0;
   double bound = 0.0, minpiv = 0.0;
   if (!fail) {
     for (int o = 16; o; o >>= 1) ysq += __shfl_xor_sync(0xffffffffu, ysq, o);
@@ -468,7 +471,8 @@ __global__ void __launch_bounds__(kFinT) gram_finish_kernel(GramFinishParams p) 
     p.info[0] = fail ? -1.0 : bound;
     p.info[1] = minpiv;
     p.info[2] = (double)(tk1 - tk0);   // clocks of the elimination loop (tools/gram_debug.py)
-    *p.status = gate ? 1 : 0;
+    p.status[2] = gate ? 1 : 0;
+    p.status[0] = 0;   // scale flag and ticket are left clean for the next call (the words live in the context, not in the workspace)
     *p.ticket = 0u;
     __threadfence();
   }
@@ -486,7 +490,7 @@ size_t gram_tsqr_workspace_floats(int sm_count) {   // slabs + G + info (doubles
 
 // Enqueues the Gram leaf; *gate_out is the device flag that is 0 when R was written and 1 when the Householder leaf behind
 // it has to produce R.  Returns false when the launch could not be made (nothing enqueued).
-bool launch_tsqr_gram_r(const float* a, long long lda, long long m, int n, float* r, long long ldr, float* ws, int sm_count,
+bool launch_tsqr_gram_r(const float* a, long long lda, long long m, int n, float* r, long long ldr, float* ws, int* flags, int sm_count,
                         int max_ctas, double bound_max, int** gate_out, double** info_out, cudaStream_t s) {
   if (!gram_tsqr_eligible(a, lda, m, n)) return false;
   CUtensorMap tm;
@@ -502,14 +506,13 @@ bool launch_tsqr_gram_r(const float* a, long long lda, long long m, int n, float
   double* slabs = reinterpret_cast<double*>(ws);
   double* g = slabs + (size_t)sm_count * kSlabDoubles;
   double* info = g + 64 * 64;
-  unsigned* ticket = reinterpret_cast<unsigned*>(info + 8);
-  int* status = reinterpret_cast<int*>(ticket + 4);
+  // flags: three zero-initialised words owned by the context: [0] scale flag, [1] ticket, [2] gate.  The finish kernel leaves
+  // [0] and [1] at zero, so no memset is needed per call (the workspace itself is shared with other calls and may hold anything).
+  int* status = flags;
+  unsigned* ticket = reinterpret_cast<unsigned*>(flags + 1);
   const long long groups = (m + kGR - 1) / kGR;
   if (max_ctas < 1 || max_ctas > sm_count) max_ctas = sm_count;
   const int grid = (int)(groups < max_ctas ? groups : max_ctas);
-  // status and ticket start at zero: the finish kernel leaves the ticket at zero and rewrites status, but the scale flag is
-  // OR-ed in by gram_kernel, so clear it per call
-  if (cudaMemsetAsync(ticket, 0, 32, s) != cudaSuccess) { cudaGetLastError(); return false; }
   GramParams gp{m, groups, slabs, status};
   ++g_launches;
   gram_kernel<<<grid, kGramThreads, kGramSmem, s>>>(tm, gp);
@@ -521,7 +524,7 @@ bool launch_tsqr_gram_r(const float* a, long long lda, long long m, int n, float
   GramFinishParams fp{slabs, grid, n, g, r, ldr, status, ticket, info, bound_max};
   ++g_launches;
   if (launch_pdl(gram_finish_kernel, dim3(64), dim3(kFinT), 0, s, fp) != cudaSuccess) { cudaGetLastError(); gram_finish_kernel<<<64, kFinT, 0, s>>>(fp); }
-  if (gate_out) *gate_out = status;
+  if (gate_out) *gate_out = flags + 2;
   if (info_out) *info_out = info;
   return cudaGetLastError() == cudaSuccess;
 }

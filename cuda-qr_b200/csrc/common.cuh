@@ -188,7 +188,8 @@ void f64_set_identity(double* a, long long lda, long long m, int n, cudaStream_t
 void f64_extract_r(const double* a, long long lda, int n, double* r, long long ldr, int r_rows, cudaStream_t s);
 
 // ---- cross-GPU R tree over peer memory: rtree_peer.cu ------------------------------------------
-constexpr int kRtreeMaxLevels = 4, kRtreeMaxWorld = 16;
+constexpr int kRtreeMaxLevels = 8, kRtreeMaxWorld = 16;   // slots per epoch parity: tree levels (binary tree) or sender rank - 1 (one-hop gather, world <= 8)
+constexpr int kRtreeFlatMaxWorld = 8;
 struct RtreeSlab {                               // one per rank, cudaMalloc'ed, mapped into every peer with cudaIpc
   float slot[2][kRtreeMaxLevels][64 * 64];       // [epoch parity][tree level]: the R a peer hands over at that level
   unsigned ready[2][kRtreeMaxLevels];            // epoch of the R in the slot (written by the sender)
@@ -202,7 +203,7 @@ struct RtreePeerParams {
   int* err;                                      // set to 1 if a peer never arrived
   RtreeSlab* slabs[kRtreeMaxWorld];              // slabs[rank] is this rank's own
 };
-void launch_rtree_peer(const RtreePeerParams& p, cudaStream_t s);
+void launch_rtree_peer(const RtreePeerParams& p, cudaStream_t s);   // CQR_RTREE=tree: always the binary tree; default: one-hop gather up to 8 ranks
 
 // ---- exporter for the reference's own storage format: legacy_format.cu ------------------------
 bool legacy_format_shape_ok(int m, int n);       // m = 64 + 60 k, n a multiple of 4, n <= m (the reference's legal shapes)

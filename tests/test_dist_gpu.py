@@ -133,10 +133,11 @@ def _tsqr_peer_worker(rank, world, port, m, n, reps, out):
     ctx.close()
 
 
-@pytest.mark.parametrize("world,m,n", [(2, 2044, 64), (4, 4 * 20011, 64), (3, 9000, 40), (4, 2044, 64)])
+@pytest.mark.parametrize("world,m,n", [(2, 2044, 64), (4, 4 * 20011, 64), (3, 9000, 40), (4, 2044, 64), (5, 10240, 32), (8, 20000, 64)])
 def test_dist_tsqr_peer_memory_rtree(world, m, n, port):
-    """cqr_tsqr_dist_r: the cross-rank R tree as ONE kernel per rank over cudaIpc-mapped peer slabs (stores into the
-    receiver's slab, flag release / acquire, stacked QR in registers), five calls back to back.  R against fp64, and on
+    """cqr_tsqr_dist_r: the cross-rank R combine as ONE kernel per rank over cudaIpc-mapped peer slabs (stores into the
+    receiver's slab, flag release / acquire, stacked QR in registers; up to 8 ranks one hop into rank 0, which factors the
+    stacked (64 world) x 64 matrix: tile_qr_core<4 / 8 / 16>), five calls back to back.  R against fp64, and on
     the reference-legal shape against the restated qr.c."""
     from oracle import metrics
     reps = 5

@@ -309,10 +309,12 @@ void launch_tile_qr(const TileQRParams& p, int tiles, int tile_rows, cudaStream_
   if (tiles <= 0) return;
   ++g_launches;
   if (p.gate != nullptr) {               // behind the Gram leaf: overlap the launch with the predecessor (see pdl_wait)
-    if (tile_rows == 64) launch_pdl(tile_qr_kernel<2>, dim3(tiles), dim3(256), 0, s, p);
-    else if (tile_rows == 128) launch_pdl(tile_qr_kernel<4>, dim3(tiles), dim3(256), 0, s, p);
-    else launch_pdl(tile_qr_kernel<8>, dim3(tiles), dim3(256), 0, s, p);
-    return;
+    cudaError_t e;
+    if (tile_rows == 64) e = launch_pdl(tile_qr_kernel<2>, dim3(tiles), dim3(256), 0, s, p);
+    else if (tile_rows == 128) e = launch_pdl(tile_qr_kernel<4>, dim3(tiles), dim3(256), 0, s, p);
+    else e = launch_pdl(tile_qr_kernel<8>, dim3(tiles), dim3(256), 0, s, p);
+    if (e == cudaSuccess) return;
+    cudaGetLastError();                   // attribute refused: launch the ordinary way (pdl_wait is then a no-op)
   }
   if (tile_rows == 64) tile_qr_kernel<2><<<tiles, 256, 0, s>>>(p);
   else if (tile_rows == 128) tile_qr_kernel<4><<<tiles, 256, 0, s>>>(p);

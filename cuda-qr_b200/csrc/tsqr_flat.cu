@@ -822,8 +822,11 @@ struct FlatCfg {
     }
     static PerDeviceOnce once;             // per_sm() set the attribute on the device that ran flat_init() only
     if (once.first()) cudaFuncSetAttribute(tsqr_flat_r_kernel<WPC, MINB, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + pad));
-    if (p.gate != nullptr) launch_pdl(tsqr_flat_r_kernel<WPC, MINB, PIPE>, dim3((unsigned)((p.chains + WPC - 1) / WPC)), dim3(32 * WPC), smem + pad, s, p);
-    else tsqr_flat_r_kernel<WPC, MINB, PIPE><<<(p.chains + WPC - 1) / WPC, 32 * WPC, smem + pad, s>>>(p);
+    if (p.gate != nullptr) {             // behind the Gram leaf: programmatic dependent launch, ordinary launch if the attribute is refused
+      if (launch_pdl(tsqr_flat_r_kernel<WPC, MINB, PIPE>, dim3((unsigned)((p.chains + WPC - 1) / WPC)), dim3(32 * WPC), smem + pad, s, p) == cudaSuccess) return;
+      cudaGetLastError();
+    }
+    tsqr_flat_r_kernel<WPC, MINB, PIPE><<<(p.chains + WPC - 1) / WPC, 32 * WPC, smem + pad, s>>>(p);
   }
 };
 

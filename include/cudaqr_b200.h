@@ -180,9 +180,10 @@ int cqr_dextract_r(cqr_context* ctx, const double* dA, int lda, int m, int n, do
 /* Row-partitioned TSQR across the GPUs of one box (BASELINE config 3), one process per GPU, R tree over peer memory:
  * cqr_dist_export allocates this rank's exchange slab and returns its 64-byte cudaIpc handle; the launcher hands every
  * rank all `world` handles (rank order, 64 bytes each) for cqr_dist_attach; cqr_tsqr_dist_r is then the local R-only
- * TSQR of this rank's m_loc x n rows plus one kernel that walks the binary reduction tree, the stacked-R blocks moving
- * as NVLink stores into the receiver's slab (no NCCL, no host synchronisation between calls).  The combined R is on
- * rank 0.  Every rank makes the same sequence of calls.  The reference has no multi-GPU path (qr.cu:737). */
+ * TSQR of this rank's m_loc x n rows plus one kernel per rank that combines the R factors, the n x n blocks moving as
+ * NVLink stores into the receiver's slab (no NCCL, no host synchronisation between calls): up to 8 ranks every rank
+ * stores into rank 0's slab and rank 0 factors the stacked (64 world) x n matrix in one go, beyond that (or with
+ * CQR_RTREE=tree) a binary reduction tree.  The combined R is on rank 0.  Every rank makes the same sequence of calls.  The reference has no multi-GPU path (qr.cu:737). */
 int cqr_dist_export(cqr_context* ctx, void* handle_out_64_bytes);
 int cqr_dist_attach(cqr_context* ctx, int rank, int world, const void* handles);
 int cqr_dist_detach(cqr_context* ctx);

@@ -8,14 +8,16 @@
 // cond(A)^2.  So the contraction is made ERROR-FREE (Ozaki-style slicing):
 //   * rows are taken in groups of 128; per group and column c, 2^E_c > max |a(:,c)| (one pass over the group in
 //     registers, two shuffles);
-//   * a = s1 + s2 + s3 + rho with s_i = RN(residual to a multiple of 2^(E_c - 8 i)) -- |s1| <= 256, |s2|,|s3| <= 128
-//     units, so every slice is exact in bf16 (8-bit significand) and |rho| <= 2^(E_c - 25): elements in the column's top
-//     binade are represented exactly, the rest to 2^-25 of the column maximum (half an fp32 ulp of the maximum);
+//   * a = s1 + s2 + s3 + rho with s1, s2 = RN(residual to a multiple of 2^(E_c - 8), 2^(E_c - 16)) -- |s1| <= 256, |s2| <= 128
+//     quanta -- and s3 = the bf16 rounding of the rest (|r2| <= 2^(E_c - 17): 8 significant bits reach 2^(E_c - 24) or finer).
+//     Every slice is exact in bf16 (8-bit significand) and |rho| <= 2^(E_c - 25): elements in the column's top binade are
+//     represented exactly, the rest to 2^-25 of the column maximum (half an fp32 ulp of the maximum);
 //   * ONE tcgen05.mma (kind::f16, bf16 x bf16 -> f32, M = 128, N = 192, K = 16) per 16 rows forms
 //         [S1 | S2]^T [S1 | S2 | S3]  =  D11 D12 D13
 //                                        D21 D22 D23            (Dxy = Sx^T Sy, 64 x 64 each)
-//     in TMEM.  Every product is an integer < 2^16 times the pair's quantum and a group adds 128 of them: all partial sums
-//     are integers <= 2^23 in that unit, i.e. EXACT in the fp32 accumulator whatever the tensor pipe's rounding mode
+//     in TMEM.  Every product of the fixed-point slices (D11, D12, D22) is an integer < 2^16 times the pair's quantum and a
+//     group adds 128 of them: all partial sums are integers <= 2^23 in that unit, i.e. EXACT in the fp32 accumulator whatever
+//     the tensor pipe's rounding mode; the blocks with S3 are 2^-16 below D11, a truncated bit there is 2^-36 of G
 //     (measured: it truncates, profiles/r02_tsqr_mma_accuracy.txt);
 //   * after 128 rows the epilogue warps read the accumulator (tcgen05.ld) and add U = D11/2 + D12 + D13 (TMEM lanes 0-63)
 //     and V = D22/2 + D23 (lanes 64-127) to fp64 running sums held in registers for the whole kernel (one store per CTA at

@@ -7,7 +7,7 @@ Workloads (BASELINE.json configs).  The headline line is config 2: 16384 x 16384
 (at N > 1 every rank factors its own matrix: replicas only).  The same JSON object carries, under the keys
 `tsqr`, `batched` and (N > 1) `caqr`: config 3, 8 388 608 x 64 row-partitioned over the N ranks (local step: the Gram leaf on
 tcgen05, gram_umma.cu, with the Householder leaf timed beside it) with the R factors
-combined in a binary tree (strong scaling; `tsqr.efficiency_vs_ideal` from the in-run per-rank leaf time); config 4,
+combined over peer memory (one hop into rank 0 up to 8 ranks; strong scaling; `tsqr.efficiency_vs_ideal` from the in-run per-rank leaf time); config 4,
 65 536 independent 64 x 64 matrices split across ranks; config 5, CAQR with 16384 rows per rank, with its three
 acceptance numbers.  `--no-extra` drops those, `--no-e2e` / `--no-cpu` drop the host-buffer and CPU legs.
 `cpu_baseline` also times config 1 (the reference's own CPU case, 512 x 512) as BASELINE.md section 3 specifies;

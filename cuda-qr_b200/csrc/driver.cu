@@ -62,7 +62,8 @@ struct cqr_context {
   int device = 0;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
-  double* gram_info = nullptr; int* gram_gate = nullptr;   // device pointers into ws: the last Gram-leaf call's verdict
+  double* gram_info = nullptr; int* gram_gate = nullptr;   // the last Gram-leaf call's verdict (words in the context's flag area, not in ws)
+  double* gram_t = nullptr;                                // debugging aid: the reduced fp64 matrix of that call (in ws: valid until the next call)
   // scratch arena (re-carved by every top-level call)
   char* ws = nullptr;
   size_t ws_bytes = 0, ws_off = 0;
@@ -575,7 +576,7 @@ static int create_impl(cqr_context* c, int device) {
   CQR_CUDA(cudaMalloc((void**)&c->hh_slots, panel_hh_slot_bytes() + 256));
   CQR_CUDA(cudaMemset(c->hh_slots, 0, panel_hh_slot_bytes() + 256));
   c->hh_err = reinterpret_cast<int*>(reinterpret_cast<char*>(c->hh_slots) + panel_hh_slot_bytes());
-  c->cu_bar = reinterpret_cast<unsigned*>(c->hh_err + 8);   // inside the zeroed 256-byte tail of the slot allocation (ints 16-18: Gram leaf flags)
+  c->cu_bar = reinterpret_cast<unsigned*>(c->hh_err + 8);   // inside the zeroed 256-byte tail of the slot allocation (ints 16-18: Gram leaf flags, 20-25: its verdict)
   // Profilers that inject into the process (ncu: CUDA_INJECTION64_PATH / NV_COMPUTE_PROFILER_PERFWORKS_DIR) cannot follow
   // launches on green-context streams (ncu 2025.2 dies at the first one), so the spatial partition is off under them and
   // the look-ahead runs on two plain streams; CQR_PARTITION=1 forces it on, =0 off.
@@ -1383,10 +1384,12 @@ static int tsqr_common(cqr_context* c, float* dA, int lda, long long m, int n, f
   {
     ProfScope ps(c, CQR_PROF_PANEL, 2.0 * m * n * n, 4.0 * (double)m * n * (keep ? 2 : 1));
     int* gate = nullptr;
-    c->gram_info = nullptr; c->gram_gate = nullptr;
+    c->gram_info = nullptr; c->gram_gate = nullptr; c->gram_t = nullptr;
     if (gram && launch_tsqr_gram_r(dA, lda, m, n, dR, ldr, gram_ws, c->hh_err + 16, c->sm_count, cur_ctas(c), gram_bound_max(), &gate,
-                                   &c->gram_info, cur_stream(c)))
+                                   &c->gram_info, cur_stream(c))) {
       c->gram_gate = gate;
+      c->gram_t = reinterpret_cast<double*>(gram_ws) + (size_t)c->sm_count * 128 * 64;   // behind the per-CTA slabs
+    }
     else
       gate = nullptr;
     run_tsqr_factor(c, plan, dA, lda, keep, dR, ldr, gate);
@@ -1432,12 +1435,12 @@ int cqr_tsqr_form_q(cqr_context* c, const float* dX, int ldx, float* dQ, int ldq
 // debugging aid (tools/gram_debug.py): T (64 x 64 fp64, row i at 64 i) of the last Gram-leaf call; the Gram matrix is T + T^T
 __attribute__((visibility("default"))) int cqr_debug_gram_matrix(cqr_context* c, double* host_g) {
   if (!c || !host_g) return CQR_EINVAL;
-  if (!c->gram_info) return CQR_ESTATE;
+  if (!c->gram_info || !c->gram_t) return CQR_ESTATE;
   DeviceGuard dg__(c->device);
   CQR_CUDA(cudaStreamSynchronize(c->stream));
-  CQR_CUDA(cudaMemcpy(host_g, c->gram_info - 64 * 64, 64 * 64 * sizeof(double), cudaMemcpyDeviceToHost));
+  CQR_CUDA(cudaMemcpy(host_g, c->gram_t, 64 * 64 * sizeof(double), cudaMemcpyDeviceToHost));
   if (getenv("CQR_DEBUG")) {
-    double info[8];
+    double info[3];
     CQR_CUDA(cudaMemcpy(info, c->gram_info, sizeof(info), cudaMemcpyDeviceToHost));
     fprintf(stderr, "gram_finish last block: elimination loop %.0f clocks\n", info[2]);
   }

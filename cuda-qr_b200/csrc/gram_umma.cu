@@ -507,9 +507,10 @@ bool launch_tsqr_gram_r(const float* a, long long lda, long long m, int n, float
   }
   double* slabs = reinterpret_cast<double*>(ws);
   double* g = slabs + (size_t)sm_count * kSlabDoubles;
-  double* info = g + 64 * 64;
-  // flags: three zero-initialised words owned by the context: [0] scale flag, [1] ticket, [2] gate.  The finish kernel leaves
-  // [0] and [1] at zero, so no memset is needed per call (the workspace itself is shared with other calls and may hold anything).
+  double* info = reinterpret_cast<double*>(flags + 4);   // verdict (bound, smallest pivot ratio, loop clocks): persistent, see below
+  // flags: zero-initialised words owned by the context: [0] scale flag, [1] ticket, [2] gate, [4..9] three doubles of verdict.
+  // The finish kernel leaves [0] and [1] at zero, so no memset is needed per call, and the verdict stays readable
+  // (cqr_tsqr_gram_info) whatever later calls do with the workspace, which is shared and may be reallocated.
   int* status = flags;
   unsigned* ticket = reinterpret_cast<unsigned*>(flags + 1);
   const long long groups = (m + kGR - 1) / kGR;

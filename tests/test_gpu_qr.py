@@ -577,6 +577,13 @@ def test_tsqr_flat_leaf_vs_reference_flat_tree(pkg, torch, ctx, port):
     ctx.set_option(pkg.OPT_FLAT_TSQR, pkg.TSQR_LEAF_DEFAULT)
     assert np.isfinite(Rh).all() and np.all(Rh[:, 5][6:] == 0)
     assert metrics.gram_error(A2, Rh) < 1e-5
+    # the reference-legal srand(12) input through the default (Gram) leaf: same R as the restated qr.c after sign normalisation
+    ctx.tsqr_r(dA, R)
+    ctx.synchronize()
+    bound, householder = ctx.tsqr_gram_info()
+    assert not householder and bound < 32768
+    assert metrics.r_rel_diff(host(R), r_ref) <= metrics.TOL_R
+    assert metrics.gram_error(A, host(R)) < 1e-6
     # the same input through the default (Gram) leaf: the zero column makes the Cholesky pivot vanish, the device-side
     # gate hands the call to the Householder leaf, and the result is the same
     ctx.tsqr_r(dev(pkg, torch, A2), R)
